@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py - train meshes/s of cheb_VAE (files/default.cfg, 4998-vertex template) on N B200s.
+
+One "step" = one pass of the hot path over one batch of synthetic meshes: forward + backward +
+(gradient all-reduce) + Adam (main.py:67-85).  Workload at N=1: BASELINE.json configs[1]
+("cheb_VAE default.cfg training, batch 64 fp32, single B200"); for N>1 every rank keeps a 64-mesh
+shard (weak scaling; N=8 is configs[2], global batch 512).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (see the task contract): `value` = device-resident throughput (CUDA events,
+max over ranks, L2 flushed between steps), `e2e` = the same through TrainEngine.step() with HOST
+buffers (H2D of the batch + D2H of the loss inside the timed region), `roofline` for the dominant
+kernel (the level-0 Chebyshev recurrence SpMM) timed live, `cpu_baseline` = the CPU oracle port of
+the reference step timed on this box's host cores.  `--impl reference` times that CPU port alone.
+"""
+import argparse
+import copy
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "train_meshes_per_sec"
+UNIT = "meshes/s"
+PER_GPU_BATCH = 64
+OPERATORS_NPZ = os.path.join(ROOT, "tests", "golden", "operators_template5k.npz")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline: the oracle port of the reference training step
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step_rate(batch: int, steps: int, warmup: int, threads: int):
+    """meshes/s of the CPU port of main.py:67-85 (forward, backward, Adam) with the oracle
+    restatement of cheb_VAE; default.cfg hyper-parameters, dropout 0.2, x_gt fp64, seed 666."""
+    from oracle import mesh_vae_oracle as O     # the checker, used here ONLY as the timed CPU baseline
+    torch.set_num_threads(threads)
+    torch.manual_seed(666)
+    A, D, U, nn_ = O.load_operators(OPERATORS_NPZ)
+    cfg = copy.deepcopy(O.DEFAULT_CONFIG)
+    net = O.OracleChebVAE(3, cfg, D, U, A, nn_)
+    net.train()
+    opt = torch.optim.Adam(net.parameters(), lr=cfg["learning_rate"], weight_decay=cfg["weight_decay"])
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(batch, nn_[0], 3, generator=g)
+    x_gt = x.double()
+    y = torch.nn.functional.one_hot(torch.randint(0, 2, (batch,), generator=g), 2)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss, *_ = net(x, x_gt, y, m_type="train")
+        loss.backward()
+        opt.step()
+        float(loss)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return batch * len(times) / total, 1e3 * total / len(times)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    sample_batch = 16       # files/default.cfg:26 batch_size - the reference's own CPU-runnable case
+    val, ms = cpu_reference_step_rate(sample_batch, args.steps, args.warmup, threads)
+    sample = (f"{sample_batch}-mesh steps (files/default.cfg batch_size) of the cheb_VAE train step "
+              f"(fwd+bwd+Adam), oracle CPU port of the reference, {args.steps} timed steps")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cheb_VAE default.cfg train step, 4998-vertex template, fp32 (x_gt fp64)",
+                       "batch_per_step": sample_batch, "device": "host CPU"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def build_model(dev):
+    import meshvae_b200 as mvb
+    d = np.load(OPERATORS_NPZ)
+    nn_ = [int(v) for v in d["num_nodes"]]
+
+    def mk(name, i):
+        idx = torch.from_numpy(np.vstack((d[f"{name}{i}_row"], d[f"{name}{i}_col"]))).long()
+        val = torch.from_numpy(d[f"{name}{i}_val"]).float()
+        return torch.sparse_coo_tensor(idx, val, tuple(int(s) for s in d[f"{name}{i}_shape"]),
+                                       check_invariants=False).to(dev)
+
+    A = [mk("A", i) for i in range(5)]
+    D = [mk("D", i) for i in range(4)]
+    U = [mk("U", i) for i in range(4)]
+    cfg = {"n_layers": 4, "num_hidden": 512, "polygon_order": [6, 6, 6, 6, 6],
+           "num_conv_filters": [16, 16, 16, 32, 32], "num_classes": 2, "num_style": 16, "dropout": 0.2,
+           "model": "optimal_sigma_VAE"}
+    torch.manual_seed(666)          # files/default.cfg:13 random_seeds
+    net = mvb.cheb_VAE(3, cfg, D, U, A, nn_, model=cfg["model"]).to(dev)
+    return mvb, net, A, nn_
+
+
+def spmm_roofline(mvb, A, nn_, batch, dev, peaks, reps=30):
+    """Time the dominant kernel alone: one Chebyshev recurrence step T_k = 2 L T_{k-1} - T_{k-2}
+    on the level-0 operator with B*16 columns (the dec3 layer).  Algorithmic bytes per launch =
+    3*u + csr, u = N*B*F*4; L2 flushed before every launch."""
+    L = mvb._lib
+    n = nn_[0]
+    f = 16
+    ei, norm = mvb.ChebConv_batch.norm(A[0]._indices(), n)
+    op = mvb.operators.from_edges(ei, norm, n, dev)
+    x = torch.randn(n, batch, f, device=dev)
+    z = torch.randn(n, batch, f, device=dev)
+    y = torch.empty_like(x)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    st = torch.cuda.current_stream()
+    ms = []
+    for i in range(reps + 3):
+        flush.fill_(float(i))
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(st)
+        L.check(L.lib.mvb_spmm(n, L.ptr(op.rowptr), L.ptr(op.colidx), L.ptr(op.vals), L.ptr(x), L.ptr(y), L.ptr(z),
+                               None, 2.0, -1.0, batch * f, L.stream_ptr()))
+        e.record(st)
+        e.synchronize()
+        if i >= 3:
+            ms.append(s.elapsed_time(e))
+    u = n * batch * f * 4
+    alg = 3 * u + op.csr_bytes()
+    avg_ms = sum(ms) / len(ms)
+    achieved = alg / (avg_ms * 1e-3) / 1e9
+    peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("spmm_v4_level0_b64_f16_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            traffic = None
+    return {"bound": "hbm", "kernel": "spmm_v4_kernel<z> level-0 recurrence step, B*F=%d cols" % (batch * f),
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
+
+
+def run_ours(args, rank, world, local_rank):
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - this framework has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    mvb, net, A, nn_ = build_model(dev)
+    from meshvae_b200.engine import TrainEngine
+    B = args.batch
+    eng = TrainEngine(net, B, lr=1e-3, weight_decay=5e-4, x_gt_dtype=torch.float64, use_graph=not args.no_graph)
+    eng.capture(warmup=3)
+
+    # synthetic batch in pinned host memory (z-score-like vertices)
+    g = torch.Generator().manual_seed(1000 + rank)
+    x_h = torch.randn(B, nn_[0], 3, generator=g).pin_memory()
+    xgt_h = x_h.double().pin_memory()
+    y_h = torch.randint(0, 2, (B,), generator=g).pin_memory()
+    eng.step(x_h, xgt_h, y_h)        # loads the static device buffers once
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    st = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        eng.device_step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    # ---- device-resident timing: K steps, CUDA events per step, L2 flushed between steps ----------
+    evs = []
+    for i in range(args.steps):
+        flush.fill_(float(i))
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(st)
+        eng.device_step()
+        e.record(st)
+        evs.append((s, e))
+    barrier()
+    dev_ms = sum(s.elapsed_time(e) for s, e in evs)
+    # ---- end-to-end timing through the public call, host buffers, loss read back ------------------
+    for _ in range(min(3, args.warmup)):
+        eng.step(x_h, xgt_h, y_h)
+    barrier()
+    e2e_ms = 0.0
+    last_loss = None
+    for i in range(args.steps):
+        flush.fill_(float(i))
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(st)
+        last_loss = eng.step(x_h, xgt_h, y_h)
+        e.record(st)
+        e.synchronize()
+        e2e_ms += s.elapsed_time(e)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        return 0
+    if not np.isfinite(last_loss):
+        raise SystemExit(f"bench.py: loss is not finite ({last_loss})")
+
+    peaks = {}
+    ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(ppath):
+        peaks = json.load(open(ppath))
+    roof = spmm_roofline(mvb, A, nn_, B, dev, peaks)
+    total_meshes = B * world * args.steps
+    value = total_meshes / (dev_ms * 1e-3)
+    e2e_val = total_meshes / (e2e_ms * 1e-3)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cv, cms = cpu_reference_step_rate(16, 12, 2, threads)
+        cpu = {"value": cv, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "12 timed 16-mesh train steps (fwd+bwd+Adam) of the oracle CPU port, %.0f ms/step" % cms}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cheb_VAE files/default.cfg training step (fwd+bwd+allreduce+Adam), "
+                                   "4998-vertex template, K=6, filters 16,16,16,32,32, dropout 0.2, x_gt fp64",
+                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": "flushed between timed steps (256 MiB write, outside the event pairs)",
+                       "cuda_graph": not args.no_graph, "final_loss": last_loss},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": eng.h2d_bytes(),
+                    "d2h_bytes_per_step": eng.d2h_bytes(), "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(eng.launches_per_step) * args.steps,
+            "gpu_launches_per_step": int(eng.launches_per_step),
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="meshes per GPU per step")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if args.steps > 40:
+            args.steps = 40
+        return run_reference(args, rank)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        return run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    sys.exit(main())

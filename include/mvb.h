@@ -1,0 +1,168 @@
+/*
+ * mvb.h  --  C ABI of libmvb_sm100a.so, the B200-native (sm_100a) kernels for the Mesh-VAE hot path.
+ *
+ * The reference (ZOUKaifeng/Mesh-VAE) is pure Python and has NO FFI layer: its boundary for this
+ * path is the Python module namespace.  Every entry point below therefore names
+ * the reference Python symbol (file:line under the reference tree) whose arithmetic it replaces;
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every `float*` / `int*` / `double*` / `void*` data pointer is a DEVICE pointer owned by the
+ *     caller (mvb_csr_from_coo_host is the one exception: HOST pointers, runs on the CPU);
+ *   - kernels are enqueue-only on `stream` (a cudaStream_t passed as void*): no allocation, no
+ *     synchronisation, CUDA-graph capturable; scratch memory is an explicit `workspace` whose
+ *     size the matching *_workspace_bytes() query returns;
+ *   - activations are VERTEX-MAJOR: a logical [B, N, F] reference tensor is stored as
+ *     [N, B, F] contiguous (row = (vertex, mesh), B*F contiguous floats per vertex);
+ *   - sparse operators are CSR with int32 indices and fp32 values, entries of a row kept in the
+ *     COO order the reference hands over (deterministic summation order);
+ *   - return value: MVB_OK (0) or a negative MVB_E* code; mvb_last_error() gives the text
+ *     (thread-local).  There is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with MVB_ECUDA.
+ */
+#ifndef MVB_H_
+#define MVB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVB_OK 0
+#define MVB_EINVAL (-1) /* bad size / null pointer / unsupported combination */
+#define MVB_ECUDA (-2)  /* CUDA runtime error (launch failure, no device)   */
+#define MVB_EALIGN (-3) /* pointer not aligned as documented                */
+#define MVB_EWORKSPACE (-4) /* workspace too small                          */
+
+#define MVB_VERSION 100
+
+/* ---- library info ------------------------------------------------------------------------ */
+int mvb_version(void);             /* MVB_VERSION */
+int mvb_sm_arch(void);             /* 100: the only architecture compiled in (sm_100a) */
+const char *mvb_last_error(void);  /* text of the last error on this thread ("" if none) */
+/* compute capability (major*10+minor) of the current device, or MVB_ECUDA when there is none */
+int mvb_device_cc(void);
+/* number of CUDA kernels this library has launched (or captured) in this process so far; bench.py
+ * reports the per-step delta as "gpu_launches" */
+int64_t mvb_launch_count(void);
+
+/* ---- operator hand-off: COO -> CSR (HOST function) ---------------------------------------
+ * Replaces the implicit operator format of the reference: model.py:24-32 `scipy_to_torch_sparse`
+ * (uncoalesced COO, int64 / f32), consumed via `_indices()/_values()` at nn/pool.py:19 and
+ * models/cheb_VAE.py:118, and the (edge_index, norm) pair of nn/conv.py:541-555.
+ * Builds CSR of P (transpose == 0: out rows = P rows) or of P^T (transpose != 0: out rows =
+ * P columns) by a STABLE counting sort, so entries of one output row keep their COO order;
+ * duplicates are kept (they sum).  n_out_rows may exceed the largest index (empty rows):
+ * this is how the 20-node operator acts on a 4998-vertex tensor (models/cheb_VAE.py:288).
+ * rowptr has n_out_rows+1 entries; colidx / vals have nnz entries.  HOST pointers. */
+int mvb_csr_from_coo_host(int64_t n_out_rows, int64_t n_out_cols, int64_t nnz,
+                          const int64_t *coo_row, const int64_t *coo_col, const float *coo_val,
+                          int transpose, int32_t *rowptr, int32_t *colidx, float *vals);
+
+/* ---- A1: sparse propagate  (nn/conv.py:242-331 MessagePassing.propagate = index_select
+ *          :199-200, message :579-581, scatter-add :363-364) -------------------------------
+ * y[r, :] = alpha * sum_{j in row r} vals[j] * x[colidx[j], :]  +  beta * z[r, :]  +  w[r, :]
+ * x: [n_src_rows, ncols], y/z/w: [n_rows, ncols]; z and w may be NULL; y may alias z or w
+ * (each row only reads its own z/w row) but must not alias x.  The 16-byte vector path is used
+ * when ncols % 4 == 0 and all pointers are 16-byte aligned, else a scalar path. */
+int mvb_spmm(int n_rows, const int32_t *rowptr, const int32_t *colidx, const float *vals,
+             const float *x, float *y, const float *z, const float *w, float alpha, float beta,
+             int64_t ncols, void *stream);
+
+/* ---- A5/A6: mesh pooling  (nn/pool.py:13-23 SurfacePool.forward; models/cheb_cls.py:22-27 Pool)
+ * forward : y[M, B*F] = P x[N, B*F]      with CSR(P)   (n_out_rows = M)
+ * backward: dx[N, B*F] = P^T dy[M, B*F]  with CSR(P^T) (n_out_rows = N)  - no atomics. */
+int mvb_pool_fwd(int n_out_rows, const int32_t *rowptr, const int32_t *colidx, const float *vals,
+                 const float *x, float *y, int64_t ncols, void *stream);
+int mvb_pool_bwd(int n_in_rows, const int32_t *rowptr_t, const int32_t *colidx_t,
+                 const float *vals_t, const float *dy, float *dx, int64_t ncols, void *stream);
+
+/* ---- A3: Chebyshev convolution forward  (nn/conv.py:557-577 ChebConv_batch.forward; the PyG
+ *          ChebConv used at models/cheb_cls.py:95 is the same operator with W_k = lins[k].weight^T)
+ * T_0 = x, T_1 = L x, T_k = 2 L T_{k-1} - T_{k-2};  y = sum_k T_k W_k (+ bias) (ReLU if relu != 0;
+ * the reference applies F.relu at the call site, models/cheb_VAE.py:264,285).
+ * x [N,B,Fin]; weight [K,Fin,Fout]; bias [Fout] or NULL; basis [(K-1),N,B,Fin] receives
+ * T_1..T_{K-1} (saved for the backward pass; may be NULL only when K == 1); y [N,B,Fout].
+ * CSR (rowptr/colidx/vals) is L_hat with N rows (rows without entries are legal). */
+int mvb_cheb_fwd(int N, int B, int Fin, int Fout, int K, const int32_t *rowptr,
+                 const int32_t *colidx, const float *vals, const float *x, const float *weight,
+                 const float *bias, int relu, float *basis, float *y, void *stream);
+
+/* ---- A13: Chebyshev convolution backward (autograd of nn/conv.py:557-577) ------------------
+ * dW_k = sum_{v,b} T_k^T dY ; db = sum dY ; G_{K-1} = dY W_{K-1}^T ;
+ * G_k = dY W_k^T + 2 L^T G_{k+1} - G_{k+2} ; dX = dY W_0^T + L^T G_1 - G_2.
+ * CSR arguments are L^T (for the symmetric L_hat of nn/conv.py:541-555 this equals L).
+ * y_for_relu: the forward output when the forward ran with relu != 0 (dY is masked by y > 0),
+ * else NULL.  dx may be NULL (first encoder layer: the input needs no gradient), dbias may be
+ * NULL.  dweight [K,Fin,Fout] and dbias [Fout] are OVERWRITTEN (deterministic two-pass
+ * reduction, no atomics).  workspace: mvb_cheb_bwd_workspace_bytes(...) bytes, 16-byte aligned. */
+size_t mvb_cheb_bwd_workspace_bytes(int N, int B, int Fin, int Fout, int K, int need_dx);
+int mvb_cheb_bwd(int N, int B, int Fin, int Fout, int K, const int32_t *rowptr_t,
+                 const int32_t *colidx_t, const float *vals_t, const float *x, const float *basis,
+                 const float *weight, const float *y_for_relu, const float *dy, float *dx,
+                 float *dweight, float *dbias, void *workspace, size_t workspace_bytes,
+                 void *stream);
+
+/* ---- A9: reparameterisation  (models/cheb_VAE.py:309-319) ----------------------------------
+ * z = eps * exp(0.5 * logvar) + mu  on n = B*Z elements; eps is supplied by the caller (the
+ * reference draws it with the CPU generator, :316).  Backward: dmu = dz, dlogvar = dz*eps*0.5*std. */
+int mvb_vae_reparam_fwd(int64_t n, const float *mu, const float *logvar, const float *eps,
+                        float *z, void *stream);
+int mvb_vae_reparam_bwd(int64_t n, const float *logvar, const float *eps, const float *dz,
+                        float *dmu, float *dlogvar, void *stream);
+
+/* ---- A10/A11: loss epilogue  (models/cheb_VAE.py:321-346 loss_function; logpdf.py:7-8 KLD,
+ *          :22-23 gaussian_nll, :24-28 softclip) -----------------------------------------------
+ * recon  [N,B,C] fp32 VERTEX-MAJOR (the decoder output as the kernels produce it);
+ * x_gt   [B,N,C] mesh-major as main.py:70 delivers it, fp64 (x_is_f64 != 0; data.py:107) or fp32
+ *        (inference.py:87);  mu/logvar [B,Z];  y_hat [B,ncls] softmax;  y [B,ncls] int64 one-hot;
+ * log_sigma = softclip(1, -6) = 1.0009117 by default (models/cheb_VAE.py:328-329).
+ * Outputs: loss[1] (fp64; mean_b(kld + rec - 2 log sum_c(y_hat*y))), kld[B] fp32, rec[B] fp64,
+ * correct[1] int64, dnll [N,B,C] fp32 = (recon - x_gt)/sigma^2 (saved for backward).
+ * Arithmetic is fp64 when x_gt is fp64 (as torch type promotion makes the reference do),
+ * per-element fp32 with fp64 accumulation otherwise.  Deterministic (fixed-order reductions).
+ * workspace: mvb_vae_loss_workspace_bytes(B, N) bytes. */
+size_t mvb_vae_loss_workspace_bytes(int B, int N);
+int mvb_vae_loss_fwd(int B, int N, int C, int Z, int ncls, const float *recon, const void *x_gt,
+                     int x_is_f64, const float *mu, const float *logvar, const float *y_hat,
+                     const int64_t *y, float log_sigma, double *loss, float *kld, double *rec,
+                     int64_t *correct, float *dnll, void *workspace, size_t workspace_bytes,
+                     void *stream);
+/* gloss: DEVICE pointer to the fp64 upstream gradient of `loss` (a scalar).
+ * d_recon[N,B,C] = gloss/B * dnll ; d_mu = gloss/B * mu ; d_logvar = gloss/B * 0.5 (exp(logvar) - 1);
+ * d_yhat[b,c] = gloss/B * (-2) * y[b,c] / sum_c(y_hat*y). Any output pointer may be NULL. */
+int mvb_vae_loss_bwd(int B, int N, int C, int Z, int ncls, const float *dnll, const float *mu,
+                     const float *logvar, const float *y_hat, const int64_t *y,
+                     const double *gloss, float *d_recon, float *d_mu, float *d_logvar,
+                     float *d_yhat, void *stream);
+
+/* ---- logpdf.py drop-ins used when the reference's own loss_function runs unchanged ----------
+ * KLD (logpdf.py:7-8): out[b] = -0.5 sum_j (1 + logvar - mu^2 - exp(logvar)); bwd as above.
+ * gaussian_nll (logpdf.py:22-23), elementwise on n values with scalar log_sigma:
+ *   out = 0.5 ((x - mu)/exp(log_sigma))^2 + log_sigma + 0.5 log(2 pi); out/x are fp64 when
+ *   x_is_f64 != 0 else fp32; mu (the reconstruction) is fp32.  d_mu = g * (mu - x)/sigma^2. */
+int mvb_kld_fwd(int B, int Z, const float *mu, const float *logvar, float *out, void *stream);
+int mvb_kld_bwd(int B, int Z, const float *mu, const float *logvar, const float *gout,
+                float *d_mu, float *d_logvar, void *stream);
+int mvb_gaussian_nll_fwd(int64_t n, const float *mu, const void *x, int x_is_f64, float log_sigma,
+                         void *out, void *stream);
+int mvb_gaussian_nll_bwd(int64_t n, const float *mu, const void *x, int x_is_f64, float log_sigma,
+                         const void *gout, float *d_mu, void *stream);
+
+/* ---- next row f2: fused Adam on a flat parameter buffer  (main.py:251 torch.optim.Adam(lr,
+ *          weight_decay), L2-style decay; main.py:81 optimizer.step()) --------------------------
+ * step: DEVICE int64 counter, incremented by one inside the call (graph-capturable, no host state).
+ * g <- g*grad_scale + wd*p ; m <- b1 m + (1-b1) g ; v <- b2 v + (1-b2) g^2 ;
+ * p <- p - lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).   grad_scale = 1/world_size folds the
+ * data-parallel gradient average into the update. */
+int mvb_adam_step(int64_t n, float *p, const float *g, float *m, float *v, int64_t *step, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                  void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVB_H_ */

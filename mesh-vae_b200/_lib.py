@@ -1,0 +1,84 @@
+"""ctypes binding of libmvb_sm100a.so (the C ABI declared in include/mvb.h).
+
+There is no CPU fallback: if the library is missing it is built with nvcc, and if that fails the
+import raises.  Every compute call goes through `check()`, which raises MvbError with the
+library's own message on a non-zero return code."""
+import ctypes
+import os
+from ctypes import c_int, c_int64, c_float, c_void_p, c_size_t, c_char_p
+
+from . import build as _build
+
+_vp = c_void_p
+
+
+class MvbError(RuntimeError):
+    pass
+
+
+def _load():
+    path = _build.LIB
+    if not os.path.exists(path) or _build._stale():
+        try:
+            path = _build.build()
+        except Exception as e:  # noqa: BLE001
+            if not os.path.exists(_build.LIB):
+                raise MvbError(f"libmvb_sm100a.so is missing and could not be built: {e}") from e
+            path = _build.LIB
+    return ctypes.CDLL(path)
+
+
+lib = _load()
+
+# name -> (restype, argtypes)   -- mirrors include/mvb.h one to one
+SIGNATURES = {
+    "mvb_version": (c_int, []),
+    "mvb_sm_arch": (c_int, []),
+    "mvb_last_error": (c_char_p, []),
+    "mvb_device_cc": (c_int, []),
+    "mvb_launch_count": (c_int64, []),
+    "mvb_csr_from_coo_host": (c_int, [c_int64, c_int64, c_int64, _vp, _vp, _vp, c_int, _vp, _vp, _vp]),
+    "mvb_spmm": (c_int, [c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_float, c_float, c_int64, _vp]),
+    "mvb_pool_fwd": (c_int, [c_int, _vp, _vp, _vp, _vp, _vp, c_int64, _vp]),
+    "mvb_pool_bwd": (c_int, [c_int, _vp, _vp, _vp, _vp, _vp, c_int64, _vp]),
+    "mvb_cheb_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp, c_int, _vp, _vp, _vp]),
+    "mvb_cheb_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    "mvb_cheb_bwd": (c_int, [c_int, c_int, c_int, c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                             _vp, c_size_t, _vp]),
+    "mvb_vae_reparam_fwd": (c_int, [c_int64, _vp, _vp, _vp, _vp, _vp]),
+    "mvb_vae_reparam_bwd": (c_int, [c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mvb_vae_loss_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "mvb_vae_loss_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, _vp, _vp, c_int, _vp, _vp, _vp, _vp, c_float,
+                                 _vp, _vp, _vp, _vp, _vp, _vp, c_size_t, _vp]),
+    "mvb_vae_loss_bwd": (c_int, [c_int, c_int, c_int, c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mvb_kld_fwd": (c_int, [c_int, c_int, _vp, _vp, _vp, _vp]),
+    "mvb_kld_bwd": (c_int, [c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mvb_gaussian_nll_fwd": (c_int, [c_int64, _vp, _vp, c_int, c_float, _vp, _vp]),
+    "mvb_gaussian_nll_bwd": (c_int, [c_int64, _vp, _vp, c_int, c_float, _vp, _vp, _vp]),
+    "mvb_adam_step": (c_int, [c_int64, _vp, _vp, _vp, _vp, _vp, c_float, c_float, c_float, c_float, c_float, c_float,
+                              _vp]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)          # AttributeError here == header/library mismatch: fail loudly
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def last_error() -> str:
+    return (lib.mvb_last_error() or b"").decode()
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        raise MvbError(f"{what or 'mvb call'} failed (code {rc}): {last_error()}")
+
+
+def ptr(t):
+    """device (or host) pointer of a tensor, None -> NULL"""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,128 @@
+"""Host-side mirror of the reference model `cheb_VAE` (models/cheb_VAE.py:104-351) composed from the
+native modules: same constructor signature, method names, return tuple and state-dict keys
+(`cheb.{i}.weight/.bias`, `cheb_dec.{i}.weight/.bias` with `cheb_dec.4.bias` absent, `enc_lin`,
+`dec_lin`, `dec_lin_1` (dead, quirk 7), `dec_lin_2`, `z_mean`, `z_log_var`, `classifier_layer`),
+so checkpoints written by main.py:32-39 load unchanged.  The reference file itself also runs
+unchanged on top of the `compat/` import shims; this mirror exists because the reference tree is
+not present on the GPU box and because it can use the fused entry points:
+
+  * ReLU fused into the contraction epilogue of every conv that the reference follows with
+    F.relu (models/cheb_VAE.py:264,285);
+  * the loss epilogue (models/cheb_VAE.py:321-346) as one fused kernel pair on the vertex-major
+    reconstruction;
+  * reparameterisation noise either from the CPU generator as the reference draws it
+    (models/cheb_VAE.py:316, `noise="cpu"`) or from the device generator (`noise="device"`,
+    CUDA-graph capturable).
+"""
+from typing import Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as Fn
+from . import operators
+from .conv import ChebConv_batch
+from .pool import SurfacePool
+
+
+class cheb_VAE(nn.Module):
+    def __init__(self, num_features, config, downsample_matrices, upsample_matrices, adjacency_matrices, num_nodes,
+                 model="MSE_VAE"):
+        super().__init__()
+        self.n_layers = config["n_layers"]
+        self.filters = [num_features] + list(config["num_conv_filters"])
+        self.K = config["polygon_order"]
+        self.downsample_matrices = downsample_matrices
+        self.upsample_matrices = upsample_matrices
+        self.adjacency_matrices = adjacency_matrices
+        pairs = [ChebConv_batch.norm(adjacency_matrices[i]._indices(), num_nodes[i]) for i in range(len(num_nodes))]
+        self.A_edge_index = tuple(p[0] for p in pairs)
+        self.A_norm = tuple(p[1] for p in pairs)
+
+        f = self.filters
+        self.cheb = nn.ModuleList([ChebConv_batch(f[i], f[i + 1], self.K[i]) for i in range(len(f) - 2)])
+        self.cheb_dec = nn.ModuleList([ChebConv_batch(f[-i - 1], f[-i - 2], self.K[i]) for i in range(len(f) - 1)])
+        self.cheb_dec[-1].bias = None          # no bias on the output conv (models/cheb_VAE.py:135)
+        for conv in list(self.cheb) + list(self.cheb_dec)[:-1]:
+            conv.fuse_relu = True              # every one of these is followed by F.relu in the reference
+        self.pool = SurfacePool()
+
+        self.num_class = config["num_classes"]
+        self.z = config["num_style"]
+        self.num_hidden = config["num_hidden"]
+        flat = downsample_matrices[-1].shape[0] * f[-1]
+        self.classifier_layer = nn.Linear(self.num_hidden, self.num_class)
+        self.z_mean = nn.Linear(self.num_hidden + self.num_class, self.z)
+        self.z_log_var = nn.Linear(self.num_hidden + self.num_class, self.z)
+        self.enc_lin = nn.Linear(flat, self.num_hidden)
+        self.dec_lin = nn.Linear(self.z + self.num_class, self.num_hidden)
+        self.dec_lin_1 = nn.Linear(self.z + self.num_class, self.num_hidden)
+        self.dec_lin_2 = nn.Linear(self.num_hidden, flat)
+        self.dropout = nn.Dropout(p=config["dropout"])
+        self.reset_parameters()
+        self.type = model
+        self.noise = "cpu"
+        self.log_sigma = Fn.LOG_SIGMA_DEFAULT
+
+    def reset_parameters(self):
+        nn.init.normal_(self.enc_lin.weight, 0, 0.1)
+        nn.init.normal_(self.dec_lin.weight, 0, 0.1)
+
+    def set_param(self, alpha, beta):
+        self.alpha, self.beta = alpha, beta
+
+    # ---- sub-networks (logical [B, N, F] tensors; physically vertex-major views) -----------------
+    def encoder(self, x):
+        for i in range(self.n_layers):
+            x = F.relu(self.cheb[i](x, self.A_edge_index[i], self.A_norm[i]))   # relu already fused: no-op pass
+            x = self.pool(x, self.downsample_matrices[i])
+        x = x.reshape(x.shape[0], self.enc_lin.in_features)
+        return self.dropout(F.relu(self.enc_lin(x)))
+
+    def classifier(self, x):
+        return F.softmax(self.classifier_layer(self.dropout(x)), dim=1)
+
+    def decoder(self, z):
+        x = self.dropout(F.relu(self.dec_lin(z)))
+        x = self.dropout(F.relu(self.dec_lin_2(x)))
+        x = x.reshape(x.shape[0], -1, self.filters[-1])
+        for i in range(self.n_layers):
+            lvl = self.n_layers - i - 1
+            x = self.pool(x, self.upsample_matrices[lvl])
+            x = F.relu(self.cheb_dec[i](x, self.A_edge_index[lvl], self.A_norm[lvl]))
+        # quirk 1: the output conv runs the COARSEST operator on the finest mesh (models/cheb_VAE.py:288)
+        return self.cheb_dec[-1](x, self.A_edge_index[-1], self.A_norm[-1])
+
+    def sample(self, y, z):
+        x = self.decoder(torch.cat([y, z], -1))
+        return x.reshape(z.shape[0], -1, self.filters[0])
+
+    def reparameterize(self, mu, logvar, eps: Optional[torch.Tensor] = None):
+        if eps is None:
+            if self.noise == "device":
+                eps = torch.randn(mu.shape, device=mu.device, dtype=mu.dtype)
+            else:
+                eps = torch.normal(mean=0, std=1, size=tuple(mu.shape)).to(mu.device)
+        return Fn.reparameterize(mu, logvar, eps)
+
+    def loss_function(self, x, recon_x, z, mu_z, logvar_z, y, y_hat):
+        loss, kld, rec, correct = Fn.vae_loss(Fn.to_vertex_major(recon_x), x, mu_z, logvar_z, y_hat, y, self.log_sigma)
+        return loss, correct, kld, rec
+
+    def forward(self, data, x_gt, y, supervise=True, m_type="test", eps: Optional[torch.Tensor] = None):
+        self.supervise = supervise
+        if isinstance(data, torch.Tensor):
+            x, batch_size = data, data.shape[0]
+        else:
+            x, batch_size = data.x, data.num_graphs
+        x = x.reshape(batch_size, -1, self.filters[0])
+        h = self.encoder(x)
+        y_hat = self.classifier(h)
+        h = torch.cat([y, h], -1)
+        x_mean, x_var = self.z_mean(h), self.z_log_var(h)
+        z_ = self.reparameterize(x_mean, x_var, eps) if m_type == "train" else x_mean
+        z = torch.cat([y, z_], -1)
+        recon = self.decoder(z).reshape(batch_size, -1, self.filters[0])
+        loss, correct, kld, rec_loss = self.loss_function(x_gt, recon, z, x_mean, x_var, y, y_hat)
+        return loss, correct, recon, [kld, rec_loss, z_], y_hat

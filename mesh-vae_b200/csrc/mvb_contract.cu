@@ -1,0 +1,363 @@
+// Dense per-row contractions of the Chebyshev convolution, FP32 FFMA path (strict 1e-4 parity):
+//
+//  * contract_kernel : out[row, :] = act( [T_0 | T_1 | ... | T_{K-1}][row, :] . W + bias )
+//      forward  : K input planes of width Fin, W = weight[K*Fin, Fout]      (nn/conv.py:559,566,571,575)
+//      backward : 1 input plane (dY, width Fout), W = weight^T [Fout, K*Fin], K output planes
+//                 P_k = dY W_k^T  (autograd of the K matmuls)
+//  * wgrad_kernel    : dW[K*Fin, Fout] = [T_0|...|T_{K-1}]^T dY, db = 1^T dY, reduced over the
+//      N*B rows with a fixed tile->CTA map and an ordered second pass (deterministic, no atomics).
+//
+// Both stage a tile of rows in shared memory with fully coalesced 16-byte loads (a tile of R
+// consecutive (vertex, mesh) rows of one plane is one contiguous R*Fin*4-byte run in the
+// vertex-major layout), rows padded to a stride == 4 (mod 32) words so the 128-bit shared loads
+// of 8 consecutive rows hit 32 distinct banks.  Each thread owns a TR x 4 (resp. 4 x 4) register
+// tile.  Roofline: reads K*u, writes o; at 6.9 FLOP/B the FFMA pipe, not HBM,
+// is the practical bound - the tcgen05 kind::tf32 variant is the planned replacement.
+#include "mvb_internal.cuh"
+
+namespace mvb {
+
+static inline int round4(int v) { return (v + 3) & ~3; }
+static inline int pad_ld(int m4) {  // smallest ld >= m4 with ld % 32 == 4
+    int ld = (m4 / 32) * 32 + 4;
+    while (ld < m4) ld += 32;
+    return ld;
+}
+
+// Stage nr rows of all input planes into Ts[r*LD + p*in_w + i]; plane 0 optionally masked.
+__device__ __forceinline__ void stage_planes(float *Ts, int LD, int64_t rows, int64_t row0, int nr,
+                                             int in_planes, int in_w, const float *in0,
+                                             const float *in_rest, const float *mask, bool vec,
+                                             int tid, int nthreads) {
+    for (int p = 0; p < in_planes; ++p) {
+        const float *src = (p == 0 ? in0 : in_rest + (int64_t)(p - 1) * rows * in_w) + row0 * in_w;
+        const float *msk = (p == 0 && mask) ? mask + row0 * in_w : nullptr;
+        if (vec) {
+            const int q4 = in_w >> 2;
+            const int n4 = nr * q4;
+            const float4 *s4 = reinterpret_cast<const float4 *>(src);
+            const float4 *m4 = reinterpret_cast<const float4 *>(msk);
+            for (int i = tid; i < n4; i += nthreads) {
+                const int r = i / q4, q = i - r * q4;
+                float4 v = __ldg(s4 + i);
+                if (msk) {
+                    const float4 mk = __ldg(m4 + i);
+                    v.x = mk.x > 0.f ? v.x : 0.f;
+                    v.y = mk.y > 0.f ? v.y : 0.f;
+                    v.z = mk.z > 0.f ? v.z : 0.f;
+                    v.w = mk.w > 0.f ? v.w : 0.f;
+                }
+                *reinterpret_cast<float4 *>(Ts + r * LD + p * in_w + 4 * q) = v;
+            }
+        } else {
+            const int n = nr * in_w;
+            for (int i = tid; i < n; i += nthreads) {
+                const int r = i / in_w, q = i - r * in_w;
+                float v = __ldg(src + i);
+                if (msk) v = __ldg(msk + i) > 0.f ? v : 0.f;
+                Ts[r * LD + p * in_w + q] = v;
+            }
+        }
+    }
+}
+
+template <int TR>
+__global__ void __launch_bounds__(512, 1)
+contract_kernel(ContractArgs a, int M, int Nn, int M4, int N4, int LD, int R, int NT,
+                int in_vec, int out_vec) {
+    extern __shared__ float4 smem4[];
+    float *Ws = reinterpret_cast<float *>(smem4);  // [M4][N4]
+    float *Ts = Ws + M4 * N4;                      // [R][LD]
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int RG = R / TR;
+    const int ni = tid % NT, rg = tid / NT;
+
+    for (int i = tid; i < M4 * N4; i += nthreads) {
+        const int m = i / N4, n = i - m * N4;
+        float v = 0.f;
+        if (m < M && n < Nn) v = a.w_transposed ? __ldg(a.wmat + (int64_t)n * M + m) : __ldg(a.wmat + (int64_t)m * Nn + n);
+        Ws[i] = v;
+    }
+    if (M4 > M) {
+        const int padw = M4 - M;
+        for (int i = tid; i < R * padw; i += nthreads) Ts[(i / padw) * LD + M + (i % padw)] = 0.f;
+    }
+    float bv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (a.bias) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (4 * ni + j < Nn) bv[j] = __ldg(a.bias + 4 * ni + j);
+    }
+
+    const int64_t ntiles = (a.rows + R - 1) / R;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t row0 = t * R;
+        const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
+        __syncthreads();
+        stage_planes(Ts, LD, a.rows, row0, nr, a.in_planes, a.in_w, a.in0, a.in_rest, a.mask,
+                     in_vec != 0, tid, nthreads);
+        __syncthreads();
+
+        float acc[TR][4];
+#pragma unroll
+        for (int j = 0; j < TR; ++j) {
+            acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        }
+        const float *wp = Ws + 4 * ni;
+        const float *tp = Ts + rg * LD;
+#pragma unroll 2
+        for (int m0 = 0; m0 < M4; m0 += 4) {
+            const float4 w0 = *reinterpret_cast<const float4 *>(wp + (m0 + 0) * N4);
+            const float4 w1 = *reinterpret_cast<const float4 *>(wp + (m0 + 1) * N4);
+            const float4 w2 = *reinterpret_cast<const float4 *>(wp + (m0 + 2) * N4);
+            const float4 w3 = *reinterpret_cast<const float4 *>(wp + (m0 + 3) * N4);
+#pragma unroll
+            for (int j = 0; j < TR; ++j) {
+                const float4 tv = *reinterpret_cast<const float4 *>(tp + j * RG * LD + m0);
+                acc[j][0] = fmaf(tv.x, w0.x, acc[j][0]);
+                acc[j][1] = fmaf(tv.x, w0.y, acc[j][1]);
+                acc[j][2] = fmaf(tv.x, w0.z, acc[j][2]);
+                acc[j][3] = fmaf(tv.x, w0.w, acc[j][3]);
+                acc[j][0] = fmaf(tv.y, w1.x, acc[j][0]);
+                acc[j][1] = fmaf(tv.y, w1.y, acc[j][1]);
+                acc[j][2] = fmaf(tv.y, w1.z, acc[j][2]);
+                acc[j][3] = fmaf(tv.y, w1.w, acc[j][3]);
+                acc[j][0] = fmaf(tv.z, w2.x, acc[j][0]);
+                acc[j][1] = fmaf(tv.z, w2.y, acc[j][1]);
+                acc[j][2] = fmaf(tv.z, w2.z, acc[j][2]);
+                acc[j][3] = fmaf(tv.z, w2.w, acc[j][3]);
+                acc[j][0] = fmaf(tv.w, w3.x, acc[j][0]);
+                acc[j][1] = fmaf(tv.w, w3.y, acc[j][1]);
+                acc[j][2] = fmaf(tv.w, w3.z, acc[j][2]);
+                acc[j][3] = fmaf(tv.w, w3.w, acc[j][3]);
+            }
+        }
+
+        const int n0 = 4 * ni;
+#pragma unroll
+        for (int j = 0; j < TR; ++j) {
+            const int rl = rg + j * RG;
+            if (rl >= nr) continue;
+            const int64_t row = row0 + rl;
+            float o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                o[q] = acc[j][q] + bv[q];
+                if (a.relu) o[q] = o[q] > 0.f ? o[q] : 0.f;
+            }
+            if (out_vec) {
+                const int p = n0 / a.out_w, jj = n0 - p * a.out_w;
+                float *dst = a.out + ((int64_t)p * a.rows + row) * a.out_w + jj;
+                *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int n = n0 + q;
+                    if (n < Nn) {
+                        const int p = n / a.out_w, jj = n - p * a.out_w;
+                        a.out[((int64_t)p * a.rows + row) * a.out_w + jj] = o[q];
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int TR>
+static int launch_contract_t(const ContractArgs &a, int M, int Nn, int M4, int N4, int LD, int R,
+                             int NT, int in_vec, int out_vec, int grid, int threads, size_t smem,
+                             cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(contract_kernel<TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return set_err(MVB_ECUDA, "contract: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    contract_kernel<TR><<<grid, threads, smem, st>>>(a, M, Nn, M4, N4, LD, R, NT, in_vec, out_vec);
+    return check_launch("mvb contract");
+}
+
+int launch_contract(const ContractArgs &a, cudaStream_t st) {
+    if (a.rows == 0) return MVB_OK;
+    const int M = a.in_planes * a.in_w, Nn = a.out_planes * a.out_w;
+    MVB_REQUIRE(M > 0 && Nn > 0, "contract: empty shape");
+    const int M4 = round4(M), N4 = round4(Nn), LD = pad_ld(M4), NT = N4 / 4;
+    int TR = 4, R = 128;
+    while ((R / TR) * NT > 512 && R > 32) R /= 2;
+    MVB_REQUIRE((R / TR) * NT <= 512, "contract: output width %d too large", Nn);
+    size_t smem = ((size_t)M4 * N4 + (size_t)R * LD) * sizeof(float);
+    while (smem > 200 * 1024 && R > 8) {
+        R /= 2;
+        smem = ((size_t)M4 * N4 + (size_t)R * LD) * sizeof(float);
+    }
+    MVB_REQUIRE(smem <= 200 * 1024, "contract: K*Fin x Fout = %d x %d does not fit shared memory", M, Nn);
+    if (R < 4 * TR) TR = 1;
+    if ((R / TR) * NT < 128 && TR == 4) TR = 2;
+    if ((R / TR) * NT < 128 && TR == 2) TR = 1;
+    const int threads = (R / TR) * NT;
+    const int in_vec = (a.in_w % 4 == 0) && aligned16(a.in0) && (a.in_planes == 1 || aligned16(a.in_rest)) &&
+                       (!a.mask || aligned16(a.mask));
+    const int out_vec = (a.out_w % 4 == 0) && aligned16(a.out);
+    const int64_t ntiles = (a.rows + R - 1) / R;
+    int64_t grid = ntiles;
+    const int64_t cap = (int64_t)num_sms() * 4;
+    if (grid > cap) grid = cap;
+    switch (TR) {
+        case 4: return launch_contract_t<4>(a, M, Nn, M4, N4, LD, R, NT, in_vec, out_vec, (int)grid, threads, smem, st);
+        case 2: return launch_contract_t<2>(a, M, Nn, M4, N4, LD, R, NT, in_vec, out_vec, (int)grid, threads, smem, st);
+        default: return launch_contract_t<1>(a, M, Nn, M4, N4, LD, R, NT, in_vec, out_vec, (int)grid, threads, smem, st);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight / bias gradient
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+wgrad_kernel(WgradArgs a, int M, int has_bias, int M4, int N4, int LDT, int R, int MT, int NT,
+             int ngroups, int in_vec, int dy_vec) {
+    extern __shared__ float4 smem4[];
+    float *Ts = reinterpret_cast<float *>(smem4);  // [R][LDT]
+    float *Ds = Ts + R * LDT;                      // [R][N4]
+    float *red = Ds + R * N4;                      // [ngroups][M4*N4]
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int G = MT * NT;
+    const int g = tid / G, tg = tid - g * G;
+    const int mi = tg / NT, ni = tg - mi * NT;
+
+    // constant columns of the T tile: the "ones" column that yields db, then zero padding
+    {
+        const int padw = M4 - M;
+        for (int i = tid; i < R * padw; i += nthreads) {
+            const int r = i / padw, c = M + (i - r * padw);
+            Ts[r * LDT + c] = (has_bias && c == M) ? 1.f : 0.f;
+        }
+        const int padn = N4 - a.n_out;
+        for (int i = tid; i < R * padn; i += nthreads) Ds[(i / padn) * N4 + a.n_out + (i % padn)] = 0.f;
+    }
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const int64_t ntiles = (a.rows + R - 1) / R;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t row0 = t * R;
+        const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
+        __syncthreads();
+        stage_planes(Ts, LDT, a.rows, row0, nr, a.in_planes, a.in_w, a.in0, a.in_rest, nullptr,
+                     in_vec != 0, tid, nthreads);
+        stage_planes(Ds, N4, a.rows, row0, nr, 1, a.n_out, a.dy, nullptr, a.mask, dy_vec != 0, tid,
+                     nthreads);
+        __syncthreads();
+        if (g < ngroups) {
+            for (int r = g; r < nr; r += ngroups) {
+                const float4 tv = *reinterpret_cast<const float4 *>(Ts + r * LDT + 4 * mi);
+                const float4 dv = *reinterpret_cast<const float4 *>(Ds + r * N4 + 4 * ni);
+                acc[0][0] = fmaf(tv.x, dv.x, acc[0][0]);
+                acc[0][1] = fmaf(tv.x, dv.y, acc[0][1]);
+                acc[0][2] = fmaf(tv.x, dv.z, acc[0][2]);
+                acc[0][3] = fmaf(tv.x, dv.w, acc[0][3]);
+                acc[1][0] = fmaf(tv.y, dv.x, acc[1][0]);
+                acc[1][1] = fmaf(tv.y, dv.y, acc[1][1]);
+                acc[1][2] = fmaf(tv.y, dv.z, acc[1][2]);
+                acc[1][3] = fmaf(tv.y, dv.w, acc[1][3]);
+                acc[2][0] = fmaf(tv.z, dv.x, acc[2][0]);
+                acc[2][1] = fmaf(tv.z, dv.y, acc[2][1]);
+                acc[2][2] = fmaf(tv.z, dv.z, acc[2][2]);
+                acc[2][3] = fmaf(tv.z, dv.w, acc[2][3]);
+                acc[3][0] = fmaf(tv.w, dv.x, acc[3][0]);
+                acc[3][1] = fmaf(tv.w, dv.y, acc[3][1]);
+                acc[3][2] = fmaf(tv.w, dv.z, acc[3][2]);
+                acc[3][3] = fmaf(tv.w, dv.w, acc[3][3]);
+            }
+        }
+    }
+    // ordered cross-group reduction, then one partial [M4*N4] per CTA
+    if (g < ngroups) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) red[(size_t)g * M4 * N4 + (4 * mi + i) * N4 + 4 * ni + j] = acc[i][j];
+    }
+    __syncthreads();
+    float *part = a.partials + (size_t)blockIdx.x * M4 * N4;
+    for (int i = tid; i < M4 * N4; i += nthreads) {
+        float s = 0.f;
+        for (int q = 0; q < ngroups; ++q) s += red[(size_t)q * M4 * N4 + i];
+        part[i] = s;
+    }
+}
+
+__global__ void wgrad_finalize_kernel(const float *__restrict__ partials, int nparts, int M,
+                                      int n_out, int M4, int N4, float *dweight, float *dbias) {
+    const int total = (M + (dbias ? 1 : 0)) * n_out;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int m = i / n_out, n = i - m * n_out;
+        float s = 0.f;
+        for (int p = 0; p < nparts; ++p) s += partials[(size_t)p * M4 * N4 + m * N4 + n];
+        if (m < M)
+            dweight[(size_t)m * n_out + n] = s;
+        else
+            dbias[n] = s;
+    }
+}
+
+static void wgrad_shape(int M, int n_out, int has_bias, int &M4, int &N4, int &LDT, int &MT, int &NT,
+                        int &ngroups, int &R) {
+    M4 = round4(M + (has_bias ? 1 : 0));
+    N4 = round4(n_out);
+    LDT = pad_ld(M4);
+    MT = M4 / 4;
+    NT = N4 / 4;
+    const int G = MT * NT;
+    ngroups = 256 / G;
+    if (ngroups < 1) ngroups = 1;
+    if (ngroups > 16) ngroups = 16;
+    R = 64;
+}
+
+static int wgrad_grid(int64_t rows, int R) {
+    int64_t ntiles = (rows + R - 1) / R;
+    int64_t cap = (int64_t)num_sms() * 2;
+    return (int)(ntiles < cap ? (ntiles < 1 ? 1 : ntiles) : cap);
+}
+
+size_t wgrad_partial_bytes(int M, int n_out) {
+    int M4, N4, LDT, MT, NT, ng, R;
+    wgrad_shape(M, n_out, 1, M4, N4, LDT, MT, NT, ng, R);
+    return (size_t)num_sms() * 2 * M4 * N4 * sizeof(float);
+}
+
+int launch_wgrad(const WgradArgs &a, cudaStream_t st) {
+    const int M = a.in_planes * a.in_w;
+    const int has_bias = a.dbias != nullptr;
+    int M4, N4, LDT, MT, NT, ngroups, R;
+    wgrad_shape(M, a.n_out, has_bias, M4, N4, LDT, MT, NT, ngroups, R);
+    const int G = MT * NT;
+    MVB_REQUIRE(G <= 512, "wgrad: K*Fin x Fout = %d x %d too large for the register-tiled reduction", M, a.n_out);
+    const int threads = G * ngroups;
+    const int grid = wgrad_grid(a.rows, R);
+    MVB_REQUIRE((size_t)grid * M4 * N4 * sizeof(float) <= a.partial_bytes, "wgrad: workspace too small");
+    const size_t smem = ((size_t)R * LDT + (size_t)R * N4 + (size_t)ngroups * M4 * N4) * sizeof(float);
+    MVB_REQUIRE(smem <= 200 * 1024, "wgrad: shared memory %zu too large", smem);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return set_err(MVB_ECUDA, "wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int in_vec = (a.in_w % 4 == 0) && aligned16(a.in0) && (a.in_planes == 1 || aligned16(a.in_rest));
+    const int dy_vec = (a.n_out % 4 == 0) && aligned16(a.dy) && (!a.mask || aligned16(a.mask));
+    if (a.rows > 0) {
+        wgrad_kernel<<<grid, threads, smem, st>>>(a, M, has_bias, M4, N4, LDT, R, MT, NT, ngroups, in_vec, dy_vec);
+        int rc = check_launch("mvb wgrad");
+        if (rc) return rc;
+    }
+    const int total = (M + has_bias) * a.n_out;
+    wgrad_finalize_kernel<<<(total + 127) / 128, 128, 0, st>>>(a.partials, a.rows > 0 ? grid : 0, M, a.n_out, M4, N4, a.dweight, a.dbias);
+    return check_launch("mvb wgrad finalize");
+}
+
+}  // namespace mvb

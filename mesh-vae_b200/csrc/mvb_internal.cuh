@@ -1,0 +1,78 @@
+// Internal helpers shared by the libmvb_sm100a translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "mvb.h"
+
+namespace mvb {
+
+// thread-local last-error text (mvb_last_error)
+char *err_buf();
+int set_err(int code, const char *fmt, ...);
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+#define MVB_REQUIRE(cond, ...)                          \
+    do {                                                \
+        if (!(cond)) return mvb::set_err(MVB_EINVAL, __VA_ARGS__); \
+    } while (0)
+
+// after a kernel launch: report launch-configuration errors without synchronising
+void count_launch();
+inline int check_launch(const char *what) {
+    count_launch();
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(MVB_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+    }
+    return MVB_OK;
+}
+
+int num_sms();  // cached multiprocessor count of the current device (148 on B200)
+
+// ---- launchers implemented in the .cu files ------------------------------------------------
+int launch_spmm(int n_rows, const int32_t *rowptr, const int32_t *colidx, const float *vals,
+                const float *x, float *y, const float *z, const float *w, float alpha, float beta,
+                int64_t ncols, cudaStream_t st);
+
+// Generic small-matrix contraction over the rows of vertex-major activations:
+//   out[p_out][row][j] = act( sum_{p_in,i} in[p_in][row][i] * Wm[p_in*in_w + i][p_out*out_w + j] + bias )
+// in plane 0 = in0, planes 1.. = in_rest + (p-1)*rows*in_w.  Wm is [M, Nn] row-major in global
+// memory, or [Nn, M] row-major when w_transposed.  mask (optional, same layout as plane 0 of the
+// input): input values of plane 0 are zeroed where mask <= 0 (fused ReLU backward).
+struct ContractArgs {
+    int64_t rows;
+    int in_planes, in_w;
+    const float *in0, *in_rest;
+    const float *mask;
+    const float *wmat;
+    int w_transposed;
+    const float *bias;
+    int relu;
+    int out_planes, out_w;
+    float *out;
+};
+int launch_contract(const ContractArgs &a, cudaStream_t st);
+
+// dW/db reduction:  dwm[m][n] = sum_rows tcat[row][m] * dy[row][n],  db[n] = sum_rows dy[row][n]
+// tcat planes as above (K planes of width Fin), dy [rows, Fout] (optionally masked by mask > 0).
+// Deterministic: fixed tile->CTA assignment, per-CTA partials in workspace, ordered final sum.
+struct WgradArgs {
+    int64_t rows;
+    int in_planes, in_w;
+    const float *in0, *in_rest;
+    const float *dy;
+    const float *mask;
+    int n_out;            // Fout
+    float *dweight;       // [in_planes*in_w, n_out]
+    float *dbias;         // [n_out] or nullptr
+    float *partials;      // workspace
+    size_t partial_bytes;
+};
+size_t wgrad_partial_bytes(int M, int n_out);
+int launch_wgrad(const WgradArgs &a, cudaStream_t st);
+
+}  // namespace mvb

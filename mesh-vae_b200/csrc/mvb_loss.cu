@@ -1,0 +1,351 @@
+// VAE loss epilogue and the small elementwise pieces around the latent code
+// (models/cheb_VAE.py:309-346, logpdf.py:7-8,22-28) as fused, deterministic CUDA kernels.
+//
+// The reconstruction arrives VERTEX-MAJOR [N,B,C] (as the decoder kernels write it) while the
+// ground truth arrives mesh-major [B,N,C] (fp64 in training, main.py:70 / data.py:107): the
+// forward kernel stages a (32 vertices x 32 meshes) tile of each through shared memory so both
+// global reads are coalesced, emits (recon - x)/sigma^2 for the backward pass in the same sweep
+// and reduces the NLL per mesh with a fixed-order warp reduction -> per-(vertex-chunk, mesh)
+// partials -> ordered final sum.  No atomics anywhere, bit-reproducible run to run.
+// Roofline: HBM; algorithmic bytes = N*B*C*(4 + sizeof(x) + 4).
+#include "mvb_internal.cuh"
+
+namespace mvb {
+
+#define MVB_HALF_LOG_2PI 0.91893853320467274178
+
+template <typename XT>
+struct AccT { typedef float type; };
+template <>
+struct AccT<double> { typedef double type; };
+
+template <typename XT>
+__global__ void __launch_bounds__(256)
+vae_rec_partial_kernel(int B, int N, int C, int VCH, int BCH, const float *__restrict__ recon,
+                       const XT *__restrict__ xgt, float log_sigma, float sigma,
+                       double *__restrict__ partial, float *__restrict__ dnll) {
+    typedef typename AccT<XT>::type AT;
+    extern __shared__ double smem_d[];
+    XT *Xs = reinterpret_cast<XT *>(smem_d);                     // [BCH][VCH*C]
+    float *Rs = reinterpret_cast<float *>(Xs + (size_t)BCH * VCH * C);  // [VCH][BCH*C]
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const int v0 = blockIdx.x * VCH, b0 = blockIdx.y * BCH;
+    const int nv = min(VCH, N - v0), nb = min(BCH, B - b0);
+    const int rw = nb * C;  // contiguous run per vertex in recon
+    const int xw = nv * C;  // contiguous run per mesh in x_gt
+    for (int i = tid; i < nv * rw; i += nthreads) {
+        const int v = i / rw, rem = i - v * rw;
+        Rs[v * (BCH * C) + rem] = __ldg(recon + ((int64_t)(v0 + v) * B + b0) * C + rem);
+    }
+    for (int i = tid; i < nb * xw; i += nthreads) {
+        const int b = i / xw, rem = i - b * xw;
+        Xs[b * (VCH * C) + rem] = xgt[((int64_t)(b0 + b) * N + v0) * C + rem];
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+    const AT sg = (AT)sigma;
+    const AT sg2 = sg * sg;
+    const AT cst = (AT)log_sigma + (AT)MVB_HALF_LOG_2PI;
+    for (int b = warp; b < nb; b += nwarps) {
+        double s = 0.0;
+        for (int e = lane; e < xw; e += 32) {
+            const int v = e / C, c = e - v * C;
+            float *rp = Rs + v * (BCH * C) + b * C + c;
+            const AT d = (AT)(*rp) - (AT)Xs[b * (VCH * C) + e];   // recon - x
+            const AT t = d / sg;
+            const AT nll = (AT)0.5 * t * t + cst;
+            s += (double)nll;
+            *rp = (float)(d / sg2);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+        if (lane == 0) partial[(int64_t)blockIdx.x * B + b0 + b] = s;
+    }
+    __syncthreads();
+    for (int i = tid; i < nv * rw; i += nthreads) {
+        const int v = i / rw, rem = i - v * rw;
+        dnll[((int64_t)(v0 + v) * B + b0) * C + rem] = Rs[v * (BCH * C) + rem];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+vae_loss_finalize_kernel(int B, int Z, int ncls, int nchunks, const double *__restrict__ partial,
+                         const float *__restrict__ mu, const float *__restrict__ logvar,
+                         const float *__restrict__ y_hat, const int64_t *__restrict__ y,
+                         double *loss, float *kld, double *rec, int64_t *correct) {
+    __shared__ double s_sum[256];
+    __shared__ int s_cnt[256];
+    const int tid = threadIdx.x;
+    double lsum = 0.0;
+    int lcnt = 0;
+    for (int b = tid; b < B; b += blockDim.x) {
+        double r = 0.0;
+        for (int ch = 0; ch < nchunks; ++ch) r += partial[(int64_t)ch * B + b];
+        rec[b] = r;
+        float k = 0.f;
+        for (int j = 0; j < Z; ++j) {
+            const float m = mu[b * Z + j], lv = logvar[b * Z + j];
+            k += 1.f + lv - m * m - expf(lv);
+        }
+        k *= -0.5f;
+        kld[b] = k;
+        float q = 0.f;
+        int am_h = 0, am_y = 0;
+        float best_h = y_hat[b * ncls];
+        int64_t best_y = y[b * ncls];
+        for (int c = 0; c < ncls; ++c) {
+            const float h = y_hat[b * ncls + c];
+            const int64_t yy = y[b * ncls + c];
+            q += h * (float)yy;
+            if (h > best_h) { best_h = h; am_h = c; }
+            if (yy > best_y) { best_y = yy; am_y = c; }
+        }
+        const float logqy = logf(q);
+        lsum += (double)k + r - (double)(2.f * logqy);
+        lcnt += (am_h == am_y) ? 1 : 0;
+    }
+    s_sum[tid] = lsum;
+    s_cnt[tid] = lcnt;
+    __syncthreads();
+    for (int off = blockDim.x >> 1; off > 0; off >>= 1) {
+        if (tid < off) {
+            s_sum[tid] += s_sum[tid + off];
+            s_cnt[tid] += s_cnt[tid + off];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        *loss = s_sum[0] / (double)B;
+        *correct = (int64_t)s_cnt[0];
+    }
+}
+
+__global__ void scale_by_gloss_kernel(int64_t n, const float *__restrict__ src,
+                                      const double *__restrict__ gloss, double inv_b, float *dst) {
+    const float s = (float)(*gloss * inv_b);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = s * src[i];
+}
+
+__global__ void scale4_by_gloss_kernel(int64_t n4, const float4 *__restrict__ src,
+                                       const double *__restrict__ gloss, double inv_b, float4 *dst) {
+    const float s = (float)(*gloss * inv_b);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(src + i);
+        dst[i] = make_float4(s * v.x, s * v.y, s * v.z, s * v.w);
+    }
+}
+
+__global__ void vae_loss_bwd_small_kernel(int B, int Z, int ncls, const float *__restrict__ mu,
+                                          const float *__restrict__ logvar,
+                                          const float *__restrict__ y_hat,
+                                          const int64_t *__restrict__ y,
+                                          const double *__restrict__ gloss, float *d_mu,
+                                          float *d_logvar, float *d_yhat) {
+    const float s = (float)(*gloss / (double)B);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B * Z) {
+        if (d_mu) d_mu[i] = s * mu[i];
+        if (d_logvar) d_logvar[i] = s * 0.5f * (expf(logvar[i]) - 1.f);
+    }
+    if (d_yhat && i < B) {
+        float q = 0.f;
+        for (int c = 0; c < ncls; ++c) q += y_hat[i * ncls + c] * (float)y[i * ncls + c];
+        for (int c = 0; c < ncls; ++c) d_yhat[i * ncls + c] = s * (-2.f) * (float)y[i * ncls + c] / q;
+    }
+}
+
+// ---- reparameterisation ----------------------------------------------------------------------
+__global__ void reparam_fwd_kernel(int64_t n, const float *__restrict__ mu,
+                                   const float *__restrict__ logvar, const float *__restrict__ eps,
+                                   float *z) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) z[i] = fmaf(eps[i], expf(0.5f * logvar[i]), mu[i]);
+}
+__global__ void reparam_bwd_kernel(int64_t n, const float *__restrict__ logvar,
+                                   const float *__restrict__ eps, const float *__restrict__ dz,
+                                   float *dmu, float *dlogvar) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float g = dz[i];
+        if (dmu) dmu[i] = g;
+        if (dlogvar) dlogvar[i] = g * eps[i] * 0.5f * expf(0.5f * logvar[i]);
+    }
+}
+
+// ---- logpdf drop-ins ---------------------------------------------------------------------------
+__global__ void kld_fwd_kernel(int B, int Z, const float *__restrict__ mu,
+                               const float *__restrict__ logvar, float *out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float k = 0.f;
+    for (int j = 0; j < Z; ++j) {
+        const float m = mu[b * Z + j], lv = logvar[b * Z + j];
+        k += 1.f + lv - m * m - expf(lv);
+    }
+    out[b] = -0.5f * k;
+}
+__global__ void kld_bwd_kernel(int B, int Z, const float *__restrict__ mu,
+                               const float *__restrict__ logvar, const float *__restrict__ gout,
+                               float *d_mu, float *d_logvar) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * Z) return;
+    const float g = gout[i / Z];
+    if (d_mu) d_mu[i] = g * mu[i];
+    if (d_logvar) d_logvar[i] = g * 0.5f * (expf(logvar[i]) - 1.f);
+}
+
+template <typename XT>
+__global__ void nll_fwd_kernel(int64_t n, const float *__restrict__ mu, const XT *__restrict__ x,
+                               float log_sigma, float sigma, XT *out) {
+    typedef typename AccT<XT>::type AT;
+    const AT sg = (AT)sigma, cst = (AT)log_sigma + (AT)MVB_HALF_LOG_2PI;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const AT t = ((AT)x[i] - (AT)mu[i]) / sg;
+        out[i] = (XT)((AT)0.5 * t * t + cst);
+    }
+}
+template <typename XT>
+__global__ void nll_bwd_kernel(int64_t n, const float *__restrict__ mu, const XT *__restrict__ x,
+                               float sigma, const XT *__restrict__ gout, float *d_mu) {
+    typedef typename AccT<XT>::type AT;
+    const AT sg2 = (AT)sigma * (AT)sigma;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        d_mu[i] = (float)((AT)gout[i] * ((AT)mu[i] - (AT)x[i]) / sg2);
+}
+
+static inline unsigned ew_grid(int64_t n, int threads) {
+    int64_t b = (n + threads - 1) / threads;
+    const int64_t cap = (int64_t)num_sms() * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+static void loss_tiles(int C, size_t xsize, int &VCH, int &BCH, size_t &smem) {
+    VCH = 32;
+    BCH = 32;
+    smem = (size_t)VCH * BCH * C * (xsize + 4);
+    while (smem > 48 * 1024 && VCH > 1) {
+        VCH /= 2;
+        smem = (size_t)VCH * BCH * C * (xsize + 4);
+    }
+}
+
+}  // namespace mvb
+
+using namespace mvb;
+
+extern "C" size_t mvb_vae_loss_workspace_bytes(int B, int N) {
+    // worst case VCH = 1 never happens for C <= 12; size for VCH >= 8 chunks, generous and tiny
+    const size_t nch = (size_t)(N + 7) / 8;
+    return nch * (size_t)B * sizeof(double);
+}
+
+extern "C" int mvb_vae_loss_fwd(int B, int N, int C, int Z, int ncls, const float *recon,
+                                const void *x_gt, int x_is_f64, const float *mu,
+                                const float *logvar, const float *y_hat, const int64_t *y,
+                                float log_sigma, double *loss, float *kld, double *rec,
+                                int64_t *correct, float *dnll, void *workspace,
+                                size_t workspace_bytes, void *stream) {
+    MVB_REQUIRE(B > 0 && N > 0 && C > 0 && Z > 0 && ncls > 0, "vae_loss_fwd: bad sizes");
+    MVB_REQUIRE(recon && x_gt && mu && logvar && y_hat && y && loss && kld && rec && correct && dnll && workspace,
+                "vae_loss_fwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int VCH, BCH;
+    size_t smem;
+    loss_tiles(C, x_is_f64 ? 8 : 4, VCH, BCH, smem);
+    MVB_REQUIRE(VCH >= 8, "vae_loss_fwd: C=%d too large", C);
+    const int nch = (N + VCH - 1) / VCH;
+    if ((size_t)nch * B * sizeof(double) > workspace_bytes)
+        return set_err(MVB_EWORKSPACE, "vae_loss_fwd: workspace %zu < %zu", workspace_bytes, (size_t)nch * B * sizeof(double));
+    dim3 grid(nch, (B + BCH - 1) / BCH);
+    const float sigma = expf(log_sigma);
+    double *partial = reinterpret_cast<double *>(workspace);
+    if (x_is_f64)
+        vae_rec_partial_kernel<double><<<grid, 256, smem, st>>>(B, N, C, VCH, BCH, recon, (const double *)x_gt, log_sigma, sigma, partial, dnll);
+    else
+        vae_rec_partial_kernel<float><<<grid, 256, smem, st>>>(B, N, C, VCH, BCH, recon, (const float *)x_gt, log_sigma, sigma, partial, dnll);
+    int rc = check_launch("mvb_vae_loss_fwd partial");
+    if (rc) return rc;
+    vae_loss_finalize_kernel<<<1, 256, 0, st>>>(B, Z, ncls, nch, partial, mu, logvar, y_hat, y, loss, kld, rec, correct);
+    return check_launch("mvb_vae_loss_fwd finalize");
+}
+
+extern "C" int mvb_vae_loss_bwd(int B, int N, int C, int Z, int ncls, const float *dnll,
+                                const float *mu, const float *logvar, const float *y_hat,
+                                const int64_t *y, const double *gloss, float *d_recon, float *d_mu,
+                                float *d_logvar, float *d_yhat, void *stream) {
+    MVB_REQUIRE(B > 0 && N > 0 && C > 0 && gloss, "vae_loss_bwd: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_recon) {
+        MVB_REQUIRE(dnll, "vae_loss_bwd: dnll is null");
+        const int64_t n = (int64_t)N * B * C;
+        if (n % 4 == 0 && aligned16(dnll) && aligned16(d_recon))
+            scale4_by_gloss_kernel<<<ew_grid(n / 4, 256), 256, 0, st>>>(n / 4, (const float4 *)dnll, gloss, 1.0 / B, (float4 *)d_recon);
+        else
+            scale_by_gloss_kernel<<<ew_grid(n, 256), 256, 0, st>>>(n, dnll, gloss, 1.0 / B, d_recon);
+        int rc = check_launch("mvb_vae_loss_bwd recon");
+        if (rc) return rc;
+    }
+    if (d_mu || d_logvar || d_yhat) {
+        MVB_REQUIRE(mu && logvar && y_hat && y, "vae_loss_bwd: null latent pointers");
+        const int n = B * (Z > 1 ? Z : 1);
+        vae_loss_bwd_small_kernel<<<(n + 127) / 128, 128, 0, st>>>(B, Z, ncls, mu, logvar, y_hat, y, gloss, d_mu, d_logvar, d_yhat);
+        return check_launch("mvb_vae_loss_bwd latent");
+    }
+    return MVB_OK;
+}
+
+extern "C" int mvb_vae_reparam_fwd(int64_t n, const float *mu, const float *logvar,
+                                   const float *eps, float *z, void *stream) {
+    MVB_REQUIRE(n >= 0 && mu && logvar && eps && z, "reparam_fwd: bad arguments");
+    if (n == 0) return MVB_OK;
+    reparam_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, mu, logvar, eps, z);
+    return check_launch("mvb_vae_reparam_fwd");
+}
+
+extern "C" int mvb_vae_reparam_bwd(int64_t n, const float *logvar, const float *eps,
+                                   const float *dz, float *dmu, float *dlogvar, void *stream) {
+    MVB_REQUIRE(n >= 0 && logvar && eps && dz, "reparam_bwd: bad arguments");
+    if (n == 0) return MVB_OK;
+    reparam_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, logvar, eps, dz, dmu, dlogvar);
+    return check_launch("mvb_vae_reparam_bwd");
+}
+
+extern "C" int mvb_kld_fwd(int B, int Z, const float *mu, const float *logvar, float *out, void *stream) {
+    MVB_REQUIRE(B > 0 && Z > 0 && mu && logvar && out, "kld_fwd: bad arguments");
+    kld_fwd_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, Z, mu, logvar, out);
+    return check_launch("mvb_kld_fwd");
+}
+
+extern "C" int mvb_kld_bwd(int B, int Z, const float *mu, const float *logvar, const float *gout,
+                           float *d_mu, float *d_logvar, void *stream) {
+    MVB_REQUIRE(B > 0 && Z > 0 && mu && logvar && gout, "kld_bwd: bad arguments");
+    kld_bwd_kernel<<<(B * Z + 127) / 128, 128, 0, (cudaStream_t)stream>>>(B, Z, mu, logvar, gout, d_mu, d_logvar);
+    return check_launch("mvb_kld_bwd");
+}
+
+extern "C" int mvb_gaussian_nll_fwd(int64_t n, const float *mu, const void *x, int x_is_f64,
+                                    float log_sigma, void *out, void *stream) {
+    MVB_REQUIRE(n >= 0 && mu && x && out, "gaussian_nll_fwd: bad arguments");
+    if (n == 0) return MVB_OK;
+    const float sigma = expf(log_sigma);
+    if (x_is_f64)
+        nll_fwd_kernel<double><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(n, mu, (const double *)x, log_sigma, sigma, (double *)out);
+    else
+        nll_fwd_kernel<float><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(n, mu, (const float *)x, log_sigma, sigma, (float *)out);
+    return check_launch("mvb_gaussian_nll_fwd");
+}
+
+extern "C" int mvb_gaussian_nll_bwd(int64_t n, const float *mu, const void *x, int x_is_f64,
+                                    float log_sigma, const void *gout, float *d_mu, void *stream) {
+    MVB_REQUIRE(n >= 0 && mu && x && gout && d_mu, "gaussian_nll_bwd: bad arguments");
+    if (n == 0) return MVB_OK;
+    const float sigma = expf(log_sigma);
+    if (x_is_f64)
+        nll_bwd_kernel<double><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(n, mu, (const double *)x, sigma, (const double *)gout, d_mu);
+    else
+        nll_bwd_kernel<float><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(n, mu, (const float *)x, sigma, (const float *)gout, d_mu);
+    return check_launch("mvb_gaussian_nll_bwd");
+}

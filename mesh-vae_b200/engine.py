@@ -1,0 +1,161 @@
+"""Training-step engine for `cheb_VAE`: the per-batch body of main.py:67-85 (H2D of the batch,
+forward, backward, optimizer step, loss read-back) with every device operation captured once in
+CUDA graphs and replayed, one process per GPU.
+
+Data parallel (new - the reference is single device, main.py:194-195): each rank owns a
+contiguous slice of the global batch; the gradient of the global-batch mean loss is the average
+of the per-rank gradients, exchanged as ONE flat fp32 buffer with one NCCL all-reduce over
+NVLink / NVSwitch between the backward graph and the optimizer graph; the 1/world_size scaling is
+folded into the fused Adam kernel (`mvb_adam_step`).  `dec_lin_1` never receives a gradient
+(quirk 7) and is excluded from the flat buffers, exactly as torch's Adam skips it.
+"""
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import lib, check, ptr, stream_ptr
+
+
+class FlatAdam:
+    """Adam(lr, betas, eps, weight_decay) with torch.optim.Adam's arithmetic (main.py:251) as one
+    fused kernel over a flat parameter buffer; parameters are re-pointed to views of that buffer."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        self.params = [p for p in params]
+        dev = self.params[0].device
+        self.n = sum(p.numel() for p in self.params)
+        self.flat_p = torch.empty(self.n, device=dev, dtype=torch.float32)
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat_p[off:off + k].copy_(p.detach().reshape(-1))
+            p.data = self.flat_p[off:off + k].view_as(p)
+            off += k
+        self.flat_g = torch.zeros(self.n, device=dev, dtype=torch.float32)
+        self.m = torch.zeros_like(self.flat_p)
+        self.v = torch.zeros_like(self.flat_p)
+        self.step_count = torch.zeros((), device=dev, dtype=torch.int64)
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+
+    def pack_grads(self):
+        """one concatenation of the per-parameter gradients into the flat exchange buffer"""
+        torch.cat([p.grad.reshape(-1) for p in self.params], out=self.flat_g)
+
+    def step(self, grad_scale: float = 1.0):
+        check(lib.mvb_adam_step(self.n, ptr(self.flat_p), ptr(self.flat_g), ptr(self.m), ptr(self.v),
+                                ptr(self.step_count), self.lr, self.betas[0], self.betas[1], self.eps,
+                                self.weight_decay, grad_scale, stream_ptr()), "mvb_adam_step")
+
+
+class TrainEngine:
+    def __init__(self, net, batch: int, lr=1e-3, weight_decay=5e-4, x_gt_dtype=torch.float64, use_graph=True,
+                 distributed: Optional[bool] = None):
+        self.net = net
+        self.dev = next(net.parameters()).device
+        self.batch = batch
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.distributed = (self.world > 1) if distributed is None else distributed
+        self.n_vert = net.adjacency_matrices[0].shape[0]
+        self.feat = net.filters[0]
+        # which parameters receive gradients is a property of the graph (dec_lin_1 is dead): probe once
+        self.x = torch.zeros(batch, self.n_vert, self.feat, device=self.dev)
+        self.x_gt = torch.zeros(batch, self.n_vert, self.feat, device=self.dev, dtype=x_gt_dtype)
+        self.y_hot = torch.zeros(batch, net.num_class, device=self.dev, dtype=torch.int64)
+        self.y_hot[:, 0] = 1
+        self.eps = torch.zeros(batch, net.z, device=self.dev)
+        net.train()
+        net.zero_grad(set_to_none=True)
+        loss, *_ = net(self.x, self.x_gt, self.y_hot, m_type="train", eps=self.eps)
+        loss.backward()
+        live = [p for p in net.parameters() if p.grad is not None]
+        net.zero_grad(set_to_none=True)
+        self.opt = FlatAdam(live, lr=lr, weight_decay=weight_decay)
+        self.loss = torch.zeros((), device=self.dev, dtype=torch.float64)
+        self.stats = torch.zeros(3, device=self.dev, dtype=torch.float64)   # kld mean, rec mean, correct
+        self.use_graph = use_graph
+        self.g_fb = self.g_opt = None
+        self.launches_per_step = None
+        self._pinned = None
+
+    # ---- device work of one step -------------------------------------------------------------
+    def _fwd_bwd(self):
+        self.net.zero_grad(set_to_none=True)
+        loss, correct, recon, (kld, rec, z_), y_hat = self.net(self.x, self.x_gt, self.y_hot, m_type="train",
+                                                                eps=self.eps)
+        loss.backward()
+        self.opt.pack_grads()
+        self.loss.copy_(loss.detach())
+        self.stats[0] = kld.mean()
+        self.stats[1] = rec.mean()
+        self.stats[2] = correct
+
+    def _optim(self):
+        self.opt.step(1.0 / self.world)
+
+    def capture(self, warmup: int = 3):
+        """warm up on a side stream (lazy init, cuBLAS workspaces), then capture the graphs"""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        state = (self.opt.flat_p.clone(), self.opt.m.clone(), self.opt.v.clone(), self.opt.step_count.clone())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._fwd_bwd()
+                self._optim()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        # warm-up must not train: restore parameters and optimizer state
+        self.opt.flat_p.copy_(state[0]); self.opt.m.copy_(state[1]); self.opt.v.copy_(state[2])
+        self.opt.step_count.copy_(state[3])
+        if not self.use_graph:
+            c0 = lib.mvb_launch_count()
+            self._fwd_bwd(); self._optim()
+            self.launches_per_step = lib.mvb_launch_count() - c0
+            self.opt.flat_p.copy_(state[0]); self.opt.m.copy_(state[1]); self.opt.v.copy_(state[2])
+            self.opt.step_count.copy_(state[3])
+            return
+        c0 = lib.mvb_launch_count()
+        self.g_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fb):
+            self._fwd_bwd()
+        self.g_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_opt, pool=self.g_fb.pool()):
+            self._optim()
+        self.launches_per_step = lib.mvb_launch_count() - c0
+        torch.cuda.synchronize()
+
+    def device_step(self):
+        """one training step on inputs already resident in the static device buffers"""
+        if self.use_graph:
+            self.g_fb.replay()
+        else:
+            self._fwd_bwd()
+        if self.distributed:
+            dist.all_reduce(self.opt.flat_g, op=dist.ReduceOp.SUM)
+        if self.use_graph:
+            self.g_opt.replay()
+        else:
+            self._optim()
+
+    # ---- the public per-batch call (host buffers in, loss out) ---------------------------------
+    def step(self, x_host: torch.Tensor, x_gt_host: torch.Tensor, y_host: torch.Tensor,
+             eps_host: Optional[torch.Tensor] = None) -> float:
+        """x_host [B,N,3] f32, x_gt_host [B,N,3] f64/f32, y_host [B] int64 labels (pinned host memory for
+        asynchronous copies).  Mirrors main.py:69-85: H2D, one-hot, step, loss read-back."""
+        self.x.copy_(x_host, non_blocking=True)
+        self.x_gt.copy_(x_gt_host, non_blocking=True)
+        if eps_host is None:   # the reference draws the noise on the CPU generator (cheb_VAE.py:316)
+            eps_host = torch.normal(mean=0, std=1, size=(self.batch, self.net.z))
+        self.eps.copy_(eps_host, non_blocking=True)
+        # one-hot on the host, then H2D, as main.py:71 does
+        self.y_hot.copy_(torch.nn.functional.one_hot(y_host, self.net.num_class), non_blocking=True)
+        self.device_step()
+        return float(self.loss)          # D2H read of the step's loss (synchronises)
+
+    def h2d_bytes(self) -> int:
+        return (self.x.numel() * self.x.element_size() + self.x_gt.numel() * self.x_gt.element_size()
+                + self.eps.numel() * 4 + self.y_hot.numel() * 8)
+
+    def d2h_bytes(self) -> int:
+        return 8
