@@ -48,6 +48,9 @@ int mvb_device_cc(void);
 /* number of CUDA kernels this library has launched (or captured) in this process so far; bench.py
  * reports the per-step delta as "gpu_launches" */
 int64_t mvb_launch_count(void);
+/* enable (default) / disable the tcgen05 3xTF32 tensor-core kernels for the dense contractions;
+ * disabled, the strict-fp32 FFMA kernels run everywhere.  Returns the previous setting. */
+int mvb_set_tensor_cores(int enable);
 
 /* ---- operator hand-off: COO -> CSR (HOST function) ---------------------------------------
  * Replaces the implicit operator format of the reference: model.py:24-32 `scipy_to_torch_sparse`
@@ -84,10 +87,16 @@ int mvb_pool_bwd(int n_in_rows, const int32_t *rowptr_t, const int32_t *colidx_t
  *          ChebConv used at models/cheb_cls.py:95 is the same operator with W_k = lins[k].weight^T)
  * T_0 = x, T_1 = L x, T_k = 2 L T_{k-1} - T_{k-2};  y = sum_k T_k W_k (+ bias) (ReLU if relu != 0;
  * the reference applies F.relu at the call site, models/cheb_VAE.py:264,285).
- * x [N,B,Fin]; weight [K,Fin,Fout]; bias [Fout] or NULL; basis [(K-1),N,B,Fin] receives
- * T_1..T_{K-1} (saved for the backward pass; may be NULL only when K == 1); y [N,B,Fout].
- * CSR (rowptr/colidx/vals) is L_hat with N rows (rows without entries are legal). */
-int mvb_cheb_fwd(int N, int B, int Fin, int Fout, int K, const int32_t *rowptr,
+ * x [N,B,Fin]; weight [K,Fin,Fout]; bias [Fout] or NULL; y [N,B,Fout].
+ * CSR (rowptr/colidx/vals) is L_hat with N rows; rows without entries are legal.
+ * n_active (0..N): the caller's promise that rows >= n_active have no entries and that no entry
+ * references a column >= n_active (pass N when unknown).  Those rows have the closed form
+ * T_k = cos(k pi/2) x, so they are contracted once with sum_k cos(k pi/2) W_k instead of running
+ * the recurrence - the reference's output layer applies the 20-vertex operator to the
+ * 4998-vertex mesh (models/cheb_VAE.py:288) and is 99.6 % such rows.
+ * basis [(K-1), n_active, B, Fin] receives T_1..T_{K-1} of the active prefix (saved for the
+ * backward pass; may be NULL when K == 1 or n_active == 0). */
+int mvb_cheb_fwd(int N, int B, int Fin, int Fout, int K, int n_active, const int32_t *rowptr,
                  const int32_t *colidx, const float *vals, const float *x, const float *weight,
                  const float *bias, int relu, float *basis, float *y, void *stream);
 
@@ -99,8 +108,9 @@ int mvb_cheb_fwd(int N, int B, int Fin, int Fout, int K, const int32_t *rowptr,
  * else NULL.  dx may be NULL (first encoder layer: the input needs no gradient), dbias may be
  * NULL.  dweight [K,Fin,Fout] and dbias [Fout] are OVERWRITTEN (deterministic two-pass
  * reduction, no atomics).  workspace: mvb_cheb_bwd_workspace_bytes(...) bytes, 16-byte aligned. */
-size_t mvb_cheb_bwd_workspace_bytes(int N, int B, int Fin, int Fout, int K, int need_dx);
-int mvb_cheb_bwd(int N, int B, int Fin, int Fout, int K, const int32_t *rowptr_t,
+size_t mvb_cheb_bwd_workspace_bytes(int N, int B, int Fin, int Fout, int K, int n_active,
+                                    int need_dx);
+int mvb_cheb_bwd(int N, int B, int Fin, int Fout, int K, int n_active, const int32_t *rowptr_t,
                  const int32_t *colidx_t, const float *vals_t, const float *x, const float *basis,
                  const float *weight, const float *y_for_relu, const float *dy, float *dx,
                  float *dweight, float *dbias, void *workspace, size_t workspace_bytes,

@@ -38,7 +38,9 @@ class cheb_GCN(nn.Module):
         b = x.shape[0]
         x = x.reshape(b, -1, self.filters[0])
         for i in range(self.n_layers):
-            x = F.relu(self.cheb[i](x, self.A_edge_index[i]))
+            x = self.cheb[i](x, self.A_edge_index[i])
+            if not self.cheb[i].fuse_relu:      # F.relu of cheb_cls.py:97, fused into the conv epilogue otherwise
+                x = F.relu(x)
             x = Pool(x, self.downsample_matrices[i])
         x = x.reshape(b, self.enc_lin.in_features)
         return self.cls_layer(F.relu(self.enc_lin(x)))

@@ -72,10 +72,15 @@ class cheb_VAE(nn.Module):
     def set_param(self, alpha, beta):
         self.alpha, self.beta = alpha, beta
 
+    @staticmethod
+    def _act(conv, y):
+        """F.relu of models/cheb_VAE.py:264,285 - already applied inside the conv epilogue when fused"""
+        return y if conv.fuse_relu else F.relu(y)
+
     # ---- sub-networks (logical [B, N, F] tensors; physically vertex-major views) -----------------
     def encoder(self, x):
         for i in range(self.n_layers):
-            x = F.relu(self.cheb[i](x, self.A_edge_index[i], self.A_norm[i]))   # relu already fused: no-op pass
+            x = self._act(self.cheb[i], self.cheb[i](x, self.A_edge_index[i], self.A_norm[i]))
             x = self.pool(x, self.downsample_matrices[i])
         x = x.reshape(x.shape[0], self.enc_lin.in_features)
         return self.dropout(F.relu(self.enc_lin(x)))
@@ -90,7 +95,7 @@ class cheb_VAE(nn.Module):
         for i in range(self.n_layers):
             lvl = self.n_layers - i - 1
             x = self.pool(x, self.upsample_matrices[lvl])
-            x = F.relu(self.cheb_dec[i](x, self.A_edge_index[lvl], self.A_norm[lvl]))
+            x = self._act(self.cheb_dec[i], self.cheb_dec[i](x, self.A_edge_index[lvl], self.A_norm[lvl]))
         # quirk 1: the output conv runs the COARSEST operator on the finest mesh (models/cheb_VAE.py:288)
         return self.cheb_dec[-1](x, self.A_edge_index[-1], self.A_norm[-1])
 

@@ -114,70 +114,112 @@ extern "C" int mvb_pool_bwd(int n_in_rows, const int32_t *rowptr_t, const int32_
 // ---------------------------------------------------------------------------------------------
 // Chebyshev convolution
 // ---------------------------------------------------------------------------------------------
-extern "C" int mvb_cheb_fwd(int N, int B, int Fin, int Fout, int K, const int32_t *rowptr,
-                            const int32_t *colidx, const float *vals, const float *x,
-                            const float *weight, const float *bias, int relu, float *basis, float *y,
-                            void *stream) {
+// n_active: rows >= n_active of L have no entries and no entry references a column >= n_active
+// (n_active == N for an ordinary operator).  For the empty rows the recurrence has the closed form
+// T_k = c_k x, c_k = cos(k pi/2), so they collapse to ONE plane with the folded weight
+// sum_k c_k W_k; only the first n_active vertices (a contiguous prefix in the vertex-major layout)
+// run the SpMM recurrence.  This is what makes the reference's output layer - the 20-vertex
+// operator applied to the 4998-vertex mesh, models/cheb_VAE.py:288 - a streaming pass.
+static void fill_contract(ContractArgs &a) {
+    memset(&a, 0, sizeof(a));
+}
+
+extern "C" int mvb_cheb_fwd(int N, int B, int Fin, int Fout, int K, int n_active,
+                            const int32_t *rowptr, const int32_t *colidx, const float *vals,
+                            const float *x, const float *weight, const float *bias, int relu,
+                            float *basis, float *y, void *stream) {
     MVB_REQUIRE(N > 0 && B > 0 && Fin > 0 && Fout > 0 && K > 0, "cheb_fwd: bad sizes N=%d B=%d Fin=%d Fout=%d K=%d", N, B, Fin, Fout, K);
-    MVB_REQUIRE(x && weight && y && (K == 1 || (basis && rowptr)), "cheb_fwd: null pointer");
+    MVB_REQUIRE(n_active >= 0 && n_active <= N, "cheb_fwd: n_active=%d outside [0,%d]", n_active, N);
+    MVB_REQUIRE(x && weight && y && (K == 1 || n_active == 0 || (basis && rowptr)), "cheb_fwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t ncols = (int64_t)B * Fin;
-    const int64_t plane = (int64_t)N * ncols;
-    // recurrence: T_1 = L x ; T_k = 2 L T_{k-1} - T_{k-2}     (nn/conv.py:564, 568-569)
-    for (int k = 1; k < K; ++k) {
-        float *tk = basis + (int64_t)(k - 1) * plane;
-        const float *tkm1 = (k == 1) ? x : basis + (int64_t)(k - 2) * plane;
-        const float *tkm2 = (k == 1) ? nullptr : (k == 2 ? x : basis + (int64_t)(k - 3) * plane);
-        int rc = launch_spmm(N, rowptr, colidx, vals, tkm1, tk, tkm2, nullptr, k == 1 ? 1.f : 2.f, -1.f, ncols, st);
+    const int64_t plane = (int64_t)n_active * ncols;
+    int rc;
+    if (n_active > 0) {
+        // recurrence: T_1 = L x ; T_k = 2 L T_{k-1} - T_{k-2}     (nn/conv.py:564, 568-569)
+        for (int k = 1; k < K; ++k) {
+            float *tk = basis + (int64_t)(k - 1) * plane;
+            const float *tkm1 = (k == 1) ? x : basis + (int64_t)(k - 2) * plane;
+            const float *tkm2 = (k == 1) ? nullptr : (k == 2 ? x : basis + (int64_t)(k - 3) * plane);
+            rc = launch_spmm(n_active, rowptr, colidx, vals, tkm1, tk, tkm2, nullptr, k == 1 ? 1.f : 2.f, -1.f, ncols, st);
+            if (rc) return rc;
+        }
+        ContractArgs a;
+        fill_contract(a);
+        a.rows = (int64_t)n_active * B;
+        a.in_planes = K;
+        a.in_w = Fin;
+        a.in0 = x;
+        a.in_rest = basis;
+        a.wmat = weight;
+        a.bias = bias;
+        a.relu = relu;
+        a.out_planes = 1;
+        a.out_w = Fout;
+        a.out = y;
+        rc = launch_contract(a, st);
         if (rc) return rc;
     }
-    ContractArgs a;
-    a.rows = (int64_t)N * B;
-    a.in_planes = K;
-    a.in_w = Fin;
-    a.in0 = x;
-    a.in_rest = basis;
-    a.mask = nullptr;
-    a.wmat = weight;
-    a.w_transposed = 0;
-    a.bias = bias;
-    a.relu = relu;
-    a.out_planes = 1;
-    a.out_w = Fout;
-    a.out = y;
-    return launch_contract(a, st);
+    if (n_active < N) {
+        ContractArgs a;
+        fill_contract(a);
+        const int64_t off = (int64_t)n_active * B;
+        a.rows = (int64_t)(N - n_active) * B;
+        a.in_planes = 1;
+        a.in_w = Fin;
+        a.in0 = x + off * Fin;
+        a.wmat = weight;
+        a.w_fold = K;
+        a.bias = bias;
+        a.relu = relu;
+        a.out_planes = 1;
+        a.out_w = Fout;
+        a.out = y + off * Fout;
+        rc = launch_contract(a, st);
+        if (rc) return rc;
+    }
+    return MVB_OK;
 }
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-extern "C" size_t mvb_cheb_bwd_workspace_bytes(int N, int B, int Fin, int Fout, int K, int need_dx) {
+extern "C" size_t mvb_cheb_bwd_workspace_bytes(int N, int B, int Fin, int Fout, int K, int n_active, int need_dx) {
     size_t bytes = align_up(wgrad_partial_bytes(K * Fin, Fout), 256);
-    if (need_dx) bytes += align_up((size_t)K * N * B * Fin * sizeof(float), 256);
+    if (n_active < N) bytes += align_up(wgrad_partial_bytes(Fin, Fout), 256);
+    if (need_dx) bytes += align_up((size_t)K * n_active * B * Fin * sizeof(float), 256);
     return bytes;
 }
 
-extern "C" int mvb_cheb_bwd(int N, int B, int Fin, int Fout, int K, const int32_t *rowptr_t,
-                            const int32_t *colidx_t, const float *vals_t, const float *x,
-                            const float *basis, const float *weight, const float *y_for_relu,
-                            const float *dy, float *dx, float *dweight, float *dbias,
-                            void *workspace, size_t workspace_bytes, void *stream) {
+extern "C" int mvb_cheb_bwd(int N, int B, int Fin, int Fout, int K, int n_active,
+                            const int32_t *rowptr_t, const int32_t *colidx_t, const float *vals_t,
+                            const float *x, const float *basis, const float *weight,
+                            const float *y_for_relu, const float *dy, float *dx, float *dweight,
+                            float *dbias, void *workspace, size_t workspace_bytes, void *stream) {
     MVB_REQUIRE(N > 0 && B > 0 && Fin > 0 && Fout > 0 && K > 0, "cheb_bwd: bad sizes");
-    MVB_REQUIRE(x && weight && dy && dweight && workspace && (K == 1 || basis), "cheb_bwd: null pointer");
-    MVB_REQUIRE(!dx || K == 1 || rowptr_t, "cheb_bwd: dx requested without L^T");
+    MVB_REQUIRE(n_active >= 0 && n_active <= N, "cheb_bwd: n_active=%d outside [0,%d]", n_active, N);
+    MVB_REQUIRE(x && weight && dy && dweight && workspace && (K == 1 || n_active == 0 || basis), "cheb_bwd: null pointer");
+    MVB_REQUIRE(!dx || K == 1 || n_active == 0 || rowptr_t, "cheb_bwd: dx requested without L^T");
     if (!aligned16(workspace)) return set_err(MVB_EALIGN, "cheb_bwd: workspace not 16-byte aligned");
-    if (workspace_bytes < mvb_cheb_bwd_workspace_bytes(N, B, Fin, Fout, K, dx != nullptr))
-        return set_err(MVB_EWORKSPACE, "cheb_bwd: workspace %zu < %zu", workspace_bytes,
-                       mvb_cheb_bwd_workspace_bytes(N, B, Fin, Fout, K, dx != nullptr));
+    const size_t need = mvb_cheb_bwd_workspace_bytes(N, B, Fin, Fout, K, n_active, dx != nullptr);
+    if (workspace_bytes < need) return set_err(MVB_EWORKSPACE, "cheb_bwd: workspace %zu < %zu", workspace_bytes, need);
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t rows = (int64_t)N * B;
+    const int64_t rows_act = (int64_t)n_active * B;
+    const int64_t rows_in = (int64_t)(N - n_active) * B;
     const int64_t ncols = (int64_t)B * Fin;
-    const int64_t plane = (int64_t)N * ncols;
+    const int64_t plane = (int64_t)n_active * ncols;
     char *ws = reinterpret_cast<char *>(workspace);
-    const size_t part_bytes = align_up(wgrad_partial_bytes(K * Fin, Fout), 256);
+    const size_t partA_bytes = align_up(wgrad_partial_bytes(K * Fin, Fout), 256);
+    const size_t partB_bytes = (n_active < N) ? align_up(wgrad_partial_bytes(Fin, Fout), 256) : 0;
+    float *partA = reinterpret_cast<float *>(ws);
+    float *partB = reinterpret_cast<float *>(ws + partA_bytes);
+    float *P = reinterpret_cast<float *>(ws + partA_bytes + partB_bytes);
+    const int has_bias = dbias != nullptr;
+    int rc, nA = 0, m4A = 0, nB = 0, m4B = 0;
 
-    // dW_k = T_k^T dY, db = 1^T dY
+    // dW_k = T_k^T dY, db = 1^T dY over the active prefix ...
     WgradArgs wa;
-    wa.rows = rows;
+    memset(&wa, 0, sizeof(wa));
+    wa.rows = rows_act;
     wa.in_planes = K;
     wa.in_w = Fin;
     wa.in0 = x;
@@ -185,45 +227,77 @@ extern "C" int mvb_cheb_bwd(int N, int B, int Fin, int Fout, int K, const int32_
     wa.dy = dy;
     wa.mask = y_for_relu;
     wa.n_out = Fout;
-    wa.dweight = dweight;
-    wa.dbias = dbias;
-    wa.partials = reinterpret_cast<float *>(ws);
-    wa.partial_bytes = part_bytes;
-    int rc = launch_wgrad(wa, st);
-    if (rc || !dx) return rc;
-
-    // P_k = dY W_k^T for all k in one pass (plane k of the workspace); P_0 lands in a scratch plane
-    float *P = reinterpret_cast<float *>(ws + part_bytes);
-    ContractArgs a;
-    a.rows = rows;
-    a.in_planes = 1;
-    a.in_w = Fout;
-    a.in0 = dy;
-    a.in_rest = nullptr;
-    a.mask = y_for_relu;
-    a.wmat = weight;          // [K*Fin, Fout] row-major == [Nn, M] -> transposed view
-    a.w_transposed = 1;
-    a.bias = nullptr;
-    a.relu = 0;
-    a.out_planes = K;
-    a.out_w = Fin;
-    a.out = P;
-    rc = launch_contract(a, st);
+    wa.partials = partA;
+    wa.partial_bytes = partA_bytes;
+    rc = launch_wgrad_partials(wa, has_bias, &nA, &m4A, st);
     if (rc) return rc;
-
-    // reverse recurrence, in place on the P planes (G_k overwrites P_k):
-    //   G_{K-1} = P_{K-1};  G_k = P_k + 2 L^T G_{k+1} - G_{k+2}  (k >= 1);  dX = P_0 + L^T G_1 - G_2
-    for (int k = K - 2; k >= 0; --k) {
-        float *pk = P + (int64_t)k * plane;
-        const float *gk1 = P + (int64_t)(k + 1) * plane;
-        const float *gk2 = (k + 2 <= K - 1) ? P + (int64_t)(k + 2) * plane : nullptr;
-        float *dst = (k == 0) ? dx : pk;
-        rc = launch_spmm(N, rowptr_t, colidx_t, vals_t, gk1, dst, gk2, pk, k == 0 ? 1.f : 2.f, -1.f, ncols, st);
+    // ... plus S = x^T dY over the empty rows (dW_k += c_k S)
+    if (rows_in > 0) {
+        WgradArgs wb;
+        memset(&wb, 0, sizeof(wb));
+        wb.rows = rows_in;
+        wb.in_planes = 1;
+        wb.in_w = Fin;
+        wb.in0 = x + rows_act * Fin;
+        wb.dy = dy + rows_act * Fout;
+        wb.mask = y_for_relu ? y_for_relu + rows_act * Fout : nullptr;
+        wb.n_out = Fout;
+        wb.partials = partB;
+        wb.partial_bytes = partB_bytes;
+        rc = launch_wgrad_partials(wb, has_bias, &nB, &m4B, st);
         if (rc) return rc;
     }
-    if (K == 1) {
-        cudaError_t e = cudaMemcpyAsync(dx, P, (size_t)plane * sizeof(float), cudaMemcpyDeviceToDevice, st);
-        if (e != cudaSuccess) return set_err(MVB_ECUDA, "cheb_bwd: memcpy: %s", cudaGetErrorString(e));
+    rc = launch_wgrad_finalize(partA, nA, m4A, partB, nB, m4B, Fin, K * Fin, Fout, dweight, dbias, st);
+    if (rc || !dx) return rc;
+
+    if (rows_act > 0) {
+        // P_k = dY W_k^T for all k in one pass (plane k of the workspace)
+        ContractArgs a;
+        fill_contract(a);
+        a.rows = rows_act;
+        a.in_planes = 1;
+        a.in_w = Fout;
+        a.in0 = dy;
+        a.mask = y_for_relu;
+        a.wmat = weight;          // [K*Fin, Fout] row-major == [Nn, M] -> transposed view
+        a.w_transposed = 1;
+        a.out_planes = K;
+        a.out_w = Fin;
+        a.out = P;
+        rc = launch_contract(a, st);
+        if (rc) return rc;
+        // reverse recurrence, in place on the P planes (G_k overwrites P_k):
+        //   G_{K-1} = P_{K-1};  G_k = P_k + 2 L^T G_{k+1} - G_{k+2}  (k >= 1);  dX = P_0 + L^T G_1 - G_2
+        for (int k = K - 2; k >= 0; --k) {
+            float *pk = P + (int64_t)k * plane;
+            const float *gk1 = P + (int64_t)(k + 1) * plane;
+            const float *gk2 = (k + 2 <= K - 1) ? P + (int64_t)(k + 2) * plane : nullptr;
+            float *dst = (k == 0) ? dx : pk;
+            rc = launch_spmm(n_active, rowptr_t, colidx_t, vals_t, gk1, dst, gk2, pk, k == 0 ? 1.f : 2.f, -1.f, ncols, st);
+            if (rc) return rc;
+        }
+        if (K == 1) {
+            cudaError_t e = cudaMemcpyAsync(dx, P, (size_t)plane * sizeof(float), cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) return set_err(MVB_ECUDA, "cheb_bwd: memcpy: %s", cudaGetErrorString(e));
+        }
+    }
+    if (rows_in > 0) {
+        // empty rows: dX = dY (sum_k c_k W_k)^T
+        ContractArgs a;
+        fill_contract(a);
+        a.rows = rows_in;
+        a.in_planes = 1;
+        a.in_w = Fout;
+        a.in0 = dy + rows_act * Fout;
+        a.mask = y_for_relu ? y_for_relu + rows_act * Fout : nullptr;
+        a.wmat = weight;
+        a.w_transposed = 1;
+        a.w_fold = K;
+        a.out_planes = 1;
+        a.out_w = Fin;
+        a.out = dx + rows_act * Fin;
+        rc = launch_contract(a, st);
+        if (rc) return rc;
     }
     return MVB_OK;
 }

@@ -72,10 +72,19 @@ contract_kernel(ContractArgs a, int M, int Nn, int M4, int N4, int LD, int R, in
     const int RG = R / TR;
     const int ni = tid % NT, rg = tid / NT;
 
+    // W tile; with w_fold = K > 1 the K weight blocks are folded with the Chebyshev values at 0,
+    // c_k = cos(k pi/2) = 1,0,-1,0,...: rows of the operator without entries see sum_k c_k W_k
+    const int nfold = a.w_fold > 1 ? a.w_fold : 1;
     for (int i = tid; i < M4 * N4; i += nthreads) {
         const int m = i / N4, n = i - m * N4;
         float v = 0.f;
-        if (m < M && n < Nn) v = a.w_transposed ? __ldg(a.wmat + (int64_t)n * M + m) : __ldg(a.wmat + (int64_t)m * Nn + n);
+        if (m < M && n < Nn) {
+            for (int k = 0; k < nfold; k += 2) {
+                const float wv = a.w_transposed ? __ldg(a.wmat + ((int64_t)k * Nn + n) * M + m)
+                                                : __ldg(a.wmat + ((int64_t)k * M + m) * Nn + n);
+                v += (k & 2) ? -wv : wv;
+            }
+        }
         Ws[i] = v;
     }
     if (M4 > M) {
@@ -179,6 +188,10 @@ static int launch_contract_t(const ContractArgs &a, int M, int Nn, int M4, int N
 
 int launch_contract(const ContractArgs &a, cudaStream_t st) {
     if (a.rows == 0) return MVB_OK;
+    {   // tensor-core (tcgen05, 3xTF32) path for the 16/32-wide planes; FFMA below for everything else
+        const int rc = launch_contract_tc(a, st);
+        if (rc != 0) return rc < 0 ? rc : MVB_OK;
+    }
     const int M = a.in_planes * a.in_w, Nn = a.out_planes * a.out_w;
     MVB_REQUIRE(M > 0 && Nn > 0, "contract: empty shape");
     const int M4 = round4(M), N4 = round4(Nn), LD = pad_ld(M4), NT = N4 / 4;
@@ -290,17 +303,45 @@ wgrad_kernel(WgradArgs a, int M, int has_bias, int M4, int N4, int LDT, int R, i
     }
 }
 
-__global__ void wgrad_finalize_kernel(const float *__restrict__ partials, int nparts, int M,
-                                      int n_out, int M4, int N4, float *dweight, float *dbias) {
+// Ordered final reduction of the per-CTA partials.  Thread (tx, ty) of a 32 x 8 block sums
+// partials ty, ty+8, ... of output element blockIdx.x*32 + tx (coalesced over tx); the 8 partial
+// sums are then added in fixed order -> bit-reproducible.  Optional second partial set B holds
+// S = x^T dY over the operator's EMPTY rows ([Fin+1, n_out], single plane): there T_k = c_k x, so
+// dW_k += c_k S with c_k = cos(k pi/2)  (models/cheb_VAE.py:288 quirk path).
+__global__ void __launch_bounds__(256)
+wgrad_finalize_kernel(const float *__restrict__ partA, int nA, int M4A, const float *__restrict__ partB,
+                      int nB, int M4B, int fin, int M, int n_out, int N4, float *dweight,
+                      float *dbias) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
     const int total = (M + (dbias ? 1 : 0)) * n_out;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int i = blockIdx.x * 32 + tx;
+    float s = 0.f;
+    if (i < total) {
         const int m = i / n_out, n = i - m * n_out;
-        float s = 0.f;
-        for (int p = 0; p < nparts; ++p) s += partials[(size_t)p * M4 * N4 + m * N4 + n];
+        for (int p = ty; p < nA; p += 8) s += partA[(size_t)p * M4A * N4 + m * N4 + n];
+        if (nB > 0) {
+            const int k = m / fin;
+            const int mb = (m < M) ? (m - k * fin) : fin;          // bias row of B sits at index fin
+            const float c = (m < M) ? ((k & 1) ? 0.f : ((k & 2) ? -1.f : 1.f)) : 1.f;
+            if (c != 0.f) {
+                float sb = 0.f;
+                for (int p = ty; p < nB; p += 8) sb += partB[(size_t)p * M4B * N4 + mb * N4 + n];
+                s += c * sb;
+            }
+        }
+    }
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && i < total) {
+        float t = red[0][tx];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) t += red[q][tx];
+        const int m = i / n_out, n = i - m * n_out;
         if (m < M)
-            dweight[(size_t)m * n_out + n] = s;
+            dweight[(size_t)m * n_out + n] = t;
         else
-            dbias[n] = s;
+            dbias[n] = t;
     }
 }
 
@@ -330,11 +371,19 @@ size_t wgrad_partial_bytes(int M, int n_out) {
     return (size_t)num_sms() * 2 * M4 * N4 * sizeof(float);
 }
 
-int launch_wgrad(const WgradArgs &a, cudaStream_t st) {
+// phase 1: per-CTA partials of [T_0|..|T_{P-1}|1]^T dY over a.rows rows; returns the number of
+// partial blocks written and their row count M4 through nparts / m4_out
+int launch_wgrad_partials(const WgradArgs &a, int has_bias, int *nparts, int *m4_out, cudaStream_t st) {
     const int M = a.in_planes * a.in_w;
-    const int has_bias = a.dbias != nullptr;
     int M4, N4, LDT, MT, NT, ngroups, R;
     wgrad_shape(M, a.n_out, has_bias, M4, N4, LDT, MT, NT, ngroups, R);
+    *m4_out = M4;
+    *nparts = 0;
+    if (a.rows <= 0) return MVB_OK;
+    {
+        const int rc = launch_wgrad_tc(a, has_bias, M4, N4, nparts, st);
+        if (rc != 0) return rc < 0 ? rc : MVB_OK;
+    }
     const int G = MT * NT;
     MVB_REQUIRE(G <= 512, "wgrad: K*Fin x Fout = %d x %d too large for the register-tiled reduction", M, a.n_out);
     const int threads = G * ngroups;
@@ -350,13 +399,18 @@ int launch_wgrad(const WgradArgs &a, cudaStream_t st) {
     }
     const int in_vec = (a.in_w % 4 == 0) && aligned16(a.in0) && (a.in_planes == 1 || aligned16(a.in_rest));
     const int dy_vec = (a.n_out % 4 == 0) && aligned16(a.dy) && (!a.mask || aligned16(a.mask));
-    if (a.rows > 0) {
-        wgrad_kernel<<<grid, threads, smem, st>>>(a, M, has_bias, M4, N4, LDT, R, MT, NT, ngroups, in_vec, dy_vec);
-        int rc = check_launch("mvb wgrad");
-        if (rc) return rc;
-    }
-    const int total = (M + has_bias) * a.n_out;
-    wgrad_finalize_kernel<<<(total + 127) / 128, 128, 0, st>>>(a.partials, a.rows > 0 ? grid : 0, M, a.n_out, M4, N4, a.dweight, a.dbias);
+    wgrad_kernel<<<grid, threads, smem, st>>>(a, M, has_bias, M4, N4, LDT, R, MT, NT, ngroups, in_vec, dy_vec);
+    *nparts = grid;
+    return check_launch("mvb wgrad");
+}
+
+// phase 2: dweight [M, n_out] (M = K*fin), dbias [n_out] or null
+int launch_wgrad_finalize(const float *partA, int nA, int M4A, const float *partB, int nB, int M4B,
+                          int fin, int M, int n_out, float *dweight, float *dbias, cudaStream_t st) {
+    const int total = (M + (dbias ? 1 : 0)) * n_out;
+    const int N4 = round4(n_out);
+    wgrad_finalize_kernel<<<(total + 31) / 32, dim3(32, 8), 0, st>>>(partA, nA, M4A, partB, nB, M4B, fin, M, n_out,
+                                                                    N4, dweight, dbias);
     return check_launch("mvb wgrad finalize");
 }
 

@@ -50,6 +50,7 @@ struct ContractArgs {
     const float *mask;
     const float *wmat;
     int w_transposed;
+    int w_fold;           // > 1: fold that many weight blocks with c_k = cos(k pi/2) (empty-row closed form)
     const float *bias;
     int relu;
     int out_planes, out_w;
@@ -67,12 +68,16 @@ struct WgradArgs {
     const float *dy;
     const float *mask;
     int n_out;            // Fout
-    float *dweight;       // [in_planes*in_w, n_out]
-    float *dbias;         // [n_out] or nullptr
     float *partials;      // workspace
     size_t partial_bytes;
 };
 size_t wgrad_partial_bytes(int M, int n_out);
-int launch_wgrad(const WgradArgs &a, cudaStream_t st);
+int launch_wgrad_partials(const WgradArgs &a, int has_bias, int *nparts, int *m4_out, cudaStream_t st);
+int launch_wgrad_finalize(const float *partA, int nA, int M4A, const float *partB, int nB, int M4B,
+                          int fin, int M, int n_out, float *dweight, float *dbias, cudaStream_t st);
+
+// tcgen05 paths (mvb_tc.cu): return 1 = handled, 0 = shape unsupported (use FFMA), < 0 = error
+int launch_contract_tc(const ContractArgs &a, cudaStream_t st);
+int launch_wgrad_tc(const WgradArgs &a, int has_bias, int M4, int N4, int *nparts, cudaStream_t st);
 
 }  // namespace mvb

@@ -1,0 +1,566 @@
+// tcgen05 (5th-gen tensor core) versions of the two dense contractions of the Chebyshev convolution.
+//
+//   tc_rowgemm_kernel : out[row, :] = act( A[row, :] . Bm + bias ),  A = K planes of width Fin
+//                       (forward, nn/conv.py:559-575) or one plane dY of width Fout (backward
+//                       P_k = dY W_k^T); 128 rows per tile = the M of one UMMA, N = Fout (or K*Fin),
+//                       accumulators in TMEM, read back with tcgen05.ld for the bias/ReLU epilogue.
+//   tc_wgrad_kernel   : dW[K*Fin, Fout] (+ db) = [T_0|..|T_{K-1}|1]^T dY : the feature index is the
+//                       M of the UMMA (MN-major A straight from the vertex-major tile), rows of the
+//                       activation are the K dimension, one TMEM accumulator per CTA over all its
+//                       tiles, per-CTA partials + the ordered finalize kernel (deterministic).
+//
+// Precision: kind::tf32 alone would break the 1e-4 parity gate (10-bit mantissa), so both kernels
+// run the error-compensated 3xTF32 scheme: every fp32 operand is split while it is staged into
+// shared memory, hi = x & 0xffffe000 (exactly representable in tf32), lo = x - hi (exact in fp32),
+// and D += A_hi B_hi + A_lo B_hi + A_hi B_lo  (dropped term ~2^-22).  Tensor throughput is >20x what
+// these HBM-bound contractions need, so the 3x MMA count is free.
+//
+// Operands are staged global -> registers -> shared (the split needs the register pass, so TMA
+// would not remove it) directly into the canonical SWIZZLE_64B / SWIZZLE_128B layouts the UMMA
+// shared-memory descriptors expect: a tile row is 64 B (Fin = 16) or 128 B (Fin = 32) and its
+// 16-byte chunk index is XORed with address bits [7,9) / [7,10), which also makes the staging
+// stores bank-conflict free.
+#include "mvb_internal.cuh"
+
+namespace mvb {
+
+static int g_tc_enabled = 1;
+void set_tc_enabled(int v) { g_tc_enabled = v; }
+int tc_enabled() { return g_tc_enabled; }
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t ncols) {  // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 16 consecutive 32-bit columns: thread i of the warp gets TMEM lane (base_lane + i)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout, sm_100 "version 1")
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
+//   [46,48) version = 1 | [61,64) layout type (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout_type << 61;
+    return d;
+}
+// instruction descriptor for kind::tf32, fp32 accumulate (cute::UMMA::InstrDescriptor):
+//   [4,6) c_format = 1 (F32) | [7,10) a_format = 2 (TF32) | [10,13) b_format = 2 | [15] a_major | [16] b_major
+//   [17,23) N >> 3 | [24,29) M >> 4        (major: 0 = K-major, 1 = MN-major)
+__device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    lo = x - hi;
+}
+__device__ __forceinline__ void split4(const float4 &v, float4 &hi, float4 &lo) {
+    split_tf32(v.x, hi.x, lo.x);
+    split_tf32(v.y, hi.y, lo.y);
+    split_tf32(v.z, hi.z, lo.z);
+    split_tf32(v.w, hi.w, lo.w);
+}
+// byte offset of 16-byte chunk q of row r inside a swizzled tile whose rows are row_bytes (64 / 128) long
+__device__ __forceinline__ uint32_t swz_off(int r, int q, int row_bytes) {
+    const int x = (row_bytes == 128) ? (r & 7) : ((r >> 1) & 3);
+    return (uint32_t)(r * row_bytes + ((q ^ x) << 4));
+}
+
+// stage `nr` rows of one [rows x w] fp32 plane (w = 16 or 32) as hi/lo swizzled tiles of R rows;
+// rows >= nr are zero-filled; optional ReLU mask (value kept where mask > 0)
+template <int NLOAD>
+__device__ __forceinline__ void stage_plane_split(const float *__restrict__ src, const float *__restrict__ msk,
+                                                  int nr, int R, int w, char *hi, char *lo, int tid, int nthreads) {
+    const int q4 = w >> 2;
+    const int row_bytes = w * 4;
+    const int total = R * q4;
+    const float4 *s4 = reinterpret_cast<const float4 *>(src);
+    const float4 *m4 = reinterpret_cast<const float4 *>(msk);
+    for (int base = 0; base < total; base += nthreads * NLOAD) {
+        float4 v[NLOAD];
+#pragma unroll
+        for (int j = 0; j < NLOAD; ++j) {
+            const int i = base + j * nthreads + tid;
+            const int r = i / q4;
+            v[j] = (i < total && r < nr) ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (msk) {
+#pragma unroll
+            for (int j = 0; j < NLOAD; ++j) {
+                const int i = base + j * nthreads + tid;
+                const int r = i / q4;
+                if (i < total && r < nr) {
+                    const float4 mk = __ldg(m4 + i);
+                    v[j].x = mk.x > 0.f ? v[j].x : 0.f;
+                    v[j].y = mk.y > 0.f ? v[j].y : 0.f;
+                    v[j].z = mk.z > 0.f ? v[j].z : 0.f;
+                    v[j].w = mk.w > 0.f ? v[j].w : 0.f;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NLOAD; ++j) {
+            const int i = base + j * nthreads + tid;
+            if (i < total) {
+                const int r = i / q4, q = i - r * q4;
+                float4 h, l;
+                split4(v[j], h, l);
+                const uint32_t off = swz_off(r, q, row_bytes);
+                *reinterpret_cast<float4 *>(hi + off) = h;
+                *reinterpret_cast<float4 *>(lo + off) = l;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// row GEMM:  out = act(A . Bm + bias)
+// ---------------------------------------------------------------------------------------------
+struct TcRowArgs {
+    int64_t rows;
+    int in_planes, in_w;          // in_w = 16 or 32
+    const float *in0, *in_rest, *mask;
+    const float *wmat;
+    int w_transposed, w_fold;
+    int nn_true, nn16;            // real and padded (multiple of 16) output width
+    const float *bias;
+    int relu;
+    int out_w;                    // width of one output plane (nn_true = out_planes * out_w)
+    float *out;
+    int tmem_cols;
+};
+
+__global__ void __launch_bounds__(128)
+tc_rowgemm_kernel(TcRowArgs a) {
+    extern __shared__ __align__(1024) char smem_raw[];
+    char *smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int w = a.in_w, row_bytes = w * 4;
+    const int R = 128;
+    const int a_plane = R * row_bytes;               // bytes of one A plane tile (8 or 16 KB)
+    const int b_plane = a.nn16 * row_bytes;          // bytes of one B plane tile
+    char *Ahi = smem;
+    char *Alo = Ahi + a.in_planes * a_plane;
+    char *Bhi = Alo + a.in_planes * a_plane;
+    char *Blo = Bhi + a.in_planes * b_plane;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(Blo + a.in_planes * b_plane);
+    uint32_t *slot = reinterpret_cast<uint32_t *>(bar + 1);
+
+    if (warp == 0) tmem_alloc(slot, (uint32_t)a.tmem_cols);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    // B operand: Bt[n][kd] (n = output column, kd = p*w + i), K-major, swizzled like A; hi/lo split.
+    {
+        const int Kd = a.in_planes * w;
+        const int nfold = a.w_fold > 1 ? a.w_fold : 1;
+        for (int i = tid; i < a.nn16 * Kd; i += blockDim.x) {
+            const int n = i / Kd, kd = i - n * Kd;
+            float v = 0.f;
+            if (n < a.nn_true) {
+                for (int k = 0; k < nfold; k += 2) {
+                    const float wv = a.w_transposed ? __ldg(a.wmat + ((int64_t)k * a.nn_true + n) * Kd + kd)
+                                                    : __ldg(a.wmat + ((int64_t)k * Kd + kd) * a.nn_true + n);
+                    v += (k & 2) ? -wv : wv;
+                }
+            }
+            float h, l;
+            split_tf32(v, h, l);
+            const int p = kd / w, c = kd - p * w;
+            const uint32_t off = (uint32_t)(p * b_plane) + swz_off(n, c >> 2, row_bytes) + (uint32_t)((c & 3) << 2);
+            *reinterpret_cast<float *>(Bhi + off) = h;
+            *reinterpret_cast<float *>(Blo + off) = l;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *slot;
+    const uint32_t idesc = make_idesc(128, a.nn16, 0, 0);
+    const uint32_t layout_type = (row_bytes == 128) ? 2u : 4u;
+    const uint32_t sbo = 8u * row_bytes;
+    const int kslices = w / 8;
+    const int row = warp * 32 + lane;                 // D row (TMEM lane) this thread reads back
+    uint32_t phase = 0;
+
+    const int64_t ntiles = (a.rows + R - 1) / R;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t row0 = t * R;
+        const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
+        for (int p = 0; p < a.in_planes; ++p) {
+            const float *src = (p == 0 ? a.in0 : a.in_rest + (int64_t)(p - 1) * a.rows * w) + row0 * w;
+            const float *msk = (p == 0 && a.mask) ? a.mask + row0 * w : nullptr;
+            stage_plane_split<4>(src, msk, nr, R, w, Ahi + p * a_plane, Alo + p * a_plane, tid, blockDim.x);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            uint32_t acc = 0;
+            for (int p = 0; p < a.in_planes; ++p) {
+                for (int j = 0; j < kslices; ++j) {
+                    const uint64_t ah = make_desc(smem_u32(Ahi + p * a_plane) + j * 32, 16, sbo, layout_type);
+                    const uint64_t al = make_desc(smem_u32(Alo + p * a_plane) + j * 32, 16, sbo, layout_type);
+                    const uint64_t bh = make_desc(smem_u32(Bhi + p * b_plane) + j * 32, 16, sbo, layout_type);
+                    const uint64_t bl = make_desc(smem_u32(Blo + p * b_plane) + j * 32, 16, sbo, layout_type);
+                    umma_tf32(tmem_base, al, bh, idesc, acc);     // small terms first
+                    umma_tf32(tmem_base, ah, bl, idesc, 1);
+                    umma_tf32(tmem_base, ah, bh, idesc, 1);
+                    acc = 1;
+                }
+            }
+            umma_commit(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        // epilogue: TMEM -> registers -> bias / ReLU -> global (thread = row, 16 columns per pass)
+        for (int n0 = 0; n0 < a.nn16; n0 += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, v);
+            if (row < nr && n0 < a.nn_true) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (a.bias && n0 + j < a.nn_true) v[j] += __ldg(a.bias + n0 + j);
+                    if (a.relu) v[j] = v[j] > 0.f ? v[j] : 0.f;
+                }
+                const int64_t grow = row0 + row;
+                if (a.nn_true - n0 >= 16 && (a.out_w & 15) == 0) {
+                    const int p = n0 / a.out_w, jj = n0 - p * a.out_w;
+                    float4 *dst = reinterpret_cast<float4 *>(a.out + ((int64_t)p * a.rows + grow) * a.out_w + jj);
+                    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    dst[2] = make_float4(v[8], v[9], v[10], v[11]);
+                    dst[3] = make_float4(v[12], v[13], v[14], v[15]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = n0 + j;
+                        if (n < a.nn_true) {
+                            const int p = n / a.out_w, jj = n - p * a.out_w;
+                            a.out[((int64_t)p * a.rows + grow) * a.out_w + jj] = v[j];
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();   // order this tile's TMEM reads before the barrier that precedes the next MMA
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+}
+
+static int pow2_cols(int n) {
+    int c = 32;
+    while (c < n) c <<= 1;
+    return c;
+}
+
+// returns 1 if the tensor-core path took the call, 0 if the shape is not supported (caller falls
+// back to the FFMA kernel), < 0 on error
+int launch_contract_tc(const ContractArgs &a, cudaStream_t st) {
+    if (!g_tc_enabled) return 0;
+    const int w = a.in_w;
+    if (w != 16 && w != 32) return 0;
+    const int nn_true = a.out_planes * a.out_w;
+    const int nn16 = (nn_true + 15) & ~15;
+    if (nn16 > 256 || a.rows < 128) return 0;
+    if (!aligned16(a.in0) || (a.in_planes > 1 && !aligned16(a.in_rest)) || (a.mask && !aligned16(a.mask)) || !aligned16(a.out)) return 0;
+    const size_t smem = 1024 + (size_t)a.in_planes * (2 * 128 * w * 4 + 2 * nn16 * w * 4) + 64;
+    if (smem > 200 * 1024) return 0;
+    TcRowArgs t;
+    t.rows = a.rows;
+    t.in_planes = a.in_planes;
+    t.in_w = w;
+    t.in0 = a.in0;
+    t.in_rest = a.in_rest;
+    t.mask = a.mask;
+    t.wmat = a.wmat;
+    t.w_transposed = a.w_transposed;
+    t.w_fold = a.w_fold;
+    t.nn_true = nn_true;
+    t.nn16 = nn16;
+    t.bias = a.bias;
+    t.relu = a.relu;
+    t.out_w = a.out_w;
+    t.out = a.out;
+    t.tmem_cols = pow2_cols(nn16);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_rowgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return set_err(MVB_ECUDA, "tc_rowgemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int64_t ntiles = (a.rows + 127) / 128;
+    // CTAs per SM: shared memory and TMEM (512 columns) permitting
+    int per_sm = (int)((220 * 1024) / smem);
+    if (per_sm > 512 / t.tmem_cols) per_sm = 512 / t.tmem_cols;
+    if (per_sm > 8) per_sm = 8;
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)num_sms() * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    tc_rowgemm_kernel<<<(unsigned)grid, 128, smem, st>>>(t);
+    int rc = check_launch("mvb tc_rowgemm");
+    return rc ? rc : 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight gradient on tensor cores
+// ---------------------------------------------------------------------------------------------
+// Both operands are consumed MN-major (the contiguous index of the staged tile - the feature - is
+// the M / N of the MMA, the activation row is K).  For 32-bit operands the only MN-major shared
+// memory layout UMMA accepts is SWIZZLE_128B_BASE32B (layout type 1): rows of 128 bytes = 32
+// features, K atoms of 4 rows (stride byte offset = 512), MN blocks of 32 features at the leading
+// byte offset, and a 32-byte-granular swizzle (cute Swizzle<2,5,2> on the byte address): the
+// 32-byte unit index (address bits [5,7)) ^= row & 3 (address bits [7,9)).
+struct TcWgradArgs {
+    int64_t rows;
+    int in_planes;                 // K (<= 7), planes of width 16
+    const float *in0, *in_rest;
+    const float *dy, *mask;
+    int n_out;                     // Fout: 16 or 32
+    int has_bias;
+    int M4, N4;                    // partial block layout [M4][N4] expected by the finalize kernel
+    float *partials;
+    int tmem_cols;
+};
+
+// stage nr rows of a [rows x w] plane (w = 16 / 32 floats) into 128-byte-row BASE32B tiles (hi, lo),
+// the plane occupying 16-byte chunks [chunk0, chunk0 + w/4) of each logical row; rows >= nr zero-filled.
+// physical offset of logical chunk c of row r: r*128 + (((c >> 1) ^ (r & 3)) << 5) + ((c & 1) << 4)
+__device__ __forceinline__ void stage_plane_b32(const float *__restrict__ src, const float *__restrict__ msk,
+                                                int nr, int R, int w, int chunk0, char *hi, char *lo, int tid,
+                                                int nthreads) {
+    const int q4 = w >> 2;
+    const int total = R * q4;
+    const float4 *s4 = reinterpret_cast<const float4 *>(src);
+    const float4 *m4 = reinterpret_cast<const float4 *>(msk);
+    for (int base = 0; base < total; base += 2 * nthreads) {
+        float4 v[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int i = base + j * nthreads + tid;
+            const int r = i / q4;
+            v[j] = (i < total && r < nr) ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (msk && i < total && r < nr) {
+                const float4 mk = __ldg(m4 + i);
+                v[j].x = mk.x > 0.f ? v[j].x : 0.f;
+                v[j].y = mk.y > 0.f ? v[j].y : 0.f;
+                v[j].z = mk.z > 0.f ? v[j].z : 0.f;
+                v[j].w = mk.w > 0.f ? v[j].w : 0.f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int i = base + j * nthreads + tid;
+            if (i < total) {
+                const int r = i / q4, q = i - r * q4;
+                const int c = chunk0 + q;
+                float4 h, l;
+                split4(v[j], h, l);
+                const uint32_t off = (uint32_t)(r * 128 + (((c >> 1) ^ (r & 3)) << 5) + ((c & 1) << 4));
+                *reinterpret_cast<float4 *>(hi + off) = h;
+                *reinterpret_cast<float4 *>(lo + off) = l;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+tc_wgrad_kernel(TcWgradArgs a) {
+    extern __shared__ __align__(1024) char smem_raw[];
+    char *smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int R = 64;                                  // activation rows (= UMMA K extent) per tile
+    const int blk = R * 128;                           // one 32-feature block of the T tile: 8 KB
+    char *Thi = smem;                                  // 4 blocks: plane pairs (0,1) (2,3) (4,5) (6,7)
+    char *Tlo = Thi + 4 * blk;
+    char *Dhi = Tlo + 4 * blk;                         // dY tile, rows of 128 B (first 64 B used when Fout = 16)
+    char *Dlo = Dhi + blk;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(Dlo + blk);
+    uint32_t *slot = reinterpret_cast<uint32_t *>(bar + 1);
+
+    if (warp == 0) tmem_alloc(slot, (uint32_t)a.tmem_cols);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    // zero everything once (planes beyond K, the unused half of 64-byte dY rows), then the ones column:
+    // feature 0 of plane K (M index K*16), whose product with dY is the bias gradient
+    for (int i = tid; i < (8 * blk + 2 * blk) / 16; i += blockDim.x)
+        reinterpret_cast<float4 *>(Thi)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    if (a.has_bias) {
+        const int p = a.in_planes, c = (p & 1) * 4;     // logical chunk c of the row, word 0
+        for (int r = tid; r < R; r += blockDim.x)
+            *reinterpret_cast<float *>(Thi + (p >> 1) * blk + r * 128 + (((c >> 1) ^ (r & 3)) << 5) + ((c & 1) << 4)) = 1.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *slot;
+    const uint32_t idesc = make_idesc(128, a.n_out, 1, 1);
+    uint32_t acc = 0;
+
+    const int64_t ntiles = (a.rows + R - 1) / R;
+    uint32_t phase = 0;
+    bool pending = false;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t row0 = t * R;
+        const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
+        if (pending) {   // the previous tile's MMAs must have finished reading shared memory
+            mbar_wait(bar, phase);
+            phase ^= 1;
+        }
+        for (int p = 0; p < a.in_planes; ++p) {
+            const float *src = (p == 0 ? a.in0 : a.in_rest + (int64_t)(p - 1) * a.rows * 16) + row0 * 16;
+            stage_plane_b32(src, nullptr, nr, R, 16, (p & 1) * 4, Thi + (p >> 1) * blk, Tlo + (p >> 1) * blk, tid, blockDim.x);
+        }
+        stage_plane_b32(a.dy + row0 * a.n_out, a.mask ? a.mask + row0 * a.n_out : nullptr, nr, R, a.n_out, 0, Dhi, Dlo,
+                        tid, blockDim.x);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            for (int ks = 0; ks < R / 8; ++ks) {          // 8 activation rows per MMA = two 4-row K atoms
+                const uint64_t ah = make_desc(smem_u32(Thi) + ks * 1024, blk, 512, 1u);
+                const uint64_t al = make_desc(smem_u32(Tlo) + ks * 1024, blk, 512, 1u);
+                const uint64_t bh = make_desc(smem_u32(Dhi) + ks * 1024, blk, 512, 1u);
+                const uint64_t bl = make_desc(smem_u32(Dlo) + ks * 1024, blk, 512, 1u);
+                umma_tf32(tmem_base, al, bh, idesc, acc);
+                umma_tf32(tmem_base, ah, bl, idesc, 1);
+                umma_tf32(tmem_base, ah, bh, idesc, 1);
+                acc = 1;
+            }
+            umma_commit(bar);
+        }
+        pending = true;
+    }
+    if (pending) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
+    }
+    tc_fence_after();
+    // D[m = feature (or bias row)][n = fo] -> per-CTA partial block [M4][N4]
+    const int m = warp * 32 + lane;
+    float *part = a.partials + (size_t)blockIdx.x * a.M4 * a.N4;
+    for (int n0 = 0; n0 < a.n_out; n0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, v);
+        if (m < a.M4) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (n0 + j < a.N4) part[m * a.N4 + n0 + j] = pending ? v[j] : 0.f;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+}
+
+// returns 1 if taken, 0 if unsupported, < 0 on error.  Partial layout matches the FFMA wgrad kernel.
+int launch_wgrad_tc(const WgradArgs &a, int has_bias, int M4, int N4, int *nparts, cudaStream_t st) {
+    if (!g_tc_enabled) return 0;
+    if (a.in_w != 16 || a.in_planes + (has_bias ? 1 : 0) > 8 || a.rows < 256) return 0;
+    if (a.n_out != 16 && a.n_out != 32) return 0;
+    if (!aligned16(a.in0) || (a.in_planes > 1 && !aligned16(a.in_rest)) || !aligned16(a.dy) || (a.mask && !aligned16(a.mask))) return 0;
+    if (M4 > 128) return 0;
+    TcWgradArgs t;
+    t.rows = a.rows;
+    t.in_planes = a.in_planes;
+    t.in0 = a.in0;
+    t.in_rest = a.in_rest;
+    t.dy = a.dy;
+    t.mask = a.mask;
+    t.n_out = a.n_out;
+    t.has_bias = has_bias;
+    t.M4 = M4;
+    t.N4 = N4;
+    t.partials = a.partials;
+    t.tmem_cols = 32;
+    const size_t smem = 1024 + 10 * 64 * 128 + 64;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return set_err(MVB_ECUDA, "tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int64_t ntiles = (a.rows + 63) / 64;
+    int64_t grid = (int64_t)num_sms() * 2;
+    if (grid > ntiles) grid = ntiles;
+    if ((size_t)grid * M4 * N4 * sizeof(float) > a.partial_bytes) return set_err(MVB_EWORKSPACE, "tc_wgrad: workspace too small");
+    tc_wgrad_kernel<<<(unsigned)grid, 128, smem, st>>>(t);
+    int rc = check_launch("mvb tc_wgrad");
+    if (rc) return rc;
+    *nparts = (int)grid;
+    return 1;
+}
+
+}  // namespace mvb
+
+extern "C" int mvb_set_tensor_cores(int enable) {
+    const int old = mvb::tc_enabled();
+    mvb::set_tc_enabled(enable ? 1 : 0);
+    return old;
+}

@@ -49,10 +49,11 @@ class _ChebConvFn(torch.autograd.Function):
         x_vm = x_vm.contiguous()
         w = weight.contiguous()
         bb = None if bias is None else bias.contiguous()
-        basis = torch.empty((max(k - 1, 0), n, b, fin), device=x_vm.device, dtype=torch.float32)
+        na = op.n_active
+        basis = torch.empty((max(k - 1, 0), na, b, fin), device=x_vm.device, dtype=torch.float32)
         y = torch.empty((n, b, fout), device=x_vm.device, dtype=torch.float32)
-        check(lib.mvb_cheb_fwd(n, b, fin, fout, k, ptr(op.rowptr), ptr(op.colidx), ptr(op.vals), ptr(x_vm), ptr(w),
-                               ptr(bb), 1 if relu else 0, ptr(basis) if k > 1 else None, ptr(y), stream_ptr()),
+        check(lib.mvb_cheb_fwd(n, b, fin, fout, k, na, ptr(op.rowptr), ptr(op.colidx), ptr(op.vals), ptr(x_vm), ptr(w),
+                               ptr(bb), 1 if relu else 0, ptr(basis) if basis.numel() else None, ptr(y), stream_ptr()),
               "mvb_cheb_fwd")
         ctx.op, ctx.relu, ctx.has_bias = op, relu, bias is not None
         ctx.save_for_backward(x_vm, basis, w, y if relu else None)
@@ -69,10 +70,11 @@ class _ChebConvFn(torch.autograd.Function):
         dx = torch.empty_like(x_vm) if need_dx else None
         dw = torch.empty_like(w)
         db = torch.empty(fout, device=w.device, dtype=torch.float32) if ctx.has_bias else None
-        ws_bytes = lib.mvb_cheb_bwd_workspace_bytes(n, b, fin, fout, k, 1 if need_dx else 0)
+        na = op.n_active
+        ws_bytes = lib.mvb_cheb_bwd_workspace_bytes(n, b, fin, fout, k, na, 1 if need_dx else 0)
         ws = torch.empty(ws_bytes, device=w.device, dtype=torch.uint8)
-        check(lib.mvb_cheb_bwd(n, b, fin, fout, k, ptr(op.rowptr_t), ptr(op.colidx_t), ptr(op.vals_t), ptr(x_vm),
-                               ptr(basis) if k > 1 else None, ptr(w), ptr(y) if ctx.relu else None, ptr(dy), ptr(dx),
+        check(lib.mvb_cheb_bwd(n, b, fin, fout, k, na, ptr(op.rowptr_t), ptr(op.colidx_t), ptr(op.vals_t), ptr(x_vm),
+                               ptr(basis) if basis.numel() else None, ptr(w), ptr(y) if ctx.relu else None, ptr(dy), ptr(dx),
                                ptr(dw), ptr(db), ptr(ws), ws_bytes, stream_ptr()), "mvb_cheb_bwd")
         return dx, dw, db, None, None
 

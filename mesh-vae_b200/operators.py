@@ -46,6 +46,11 @@ class MeshOperator:
         self.rowptr_t, self.colidx_t, self.vals_t = up(rpt), up(cit), up(vt)
         # one nonzero per row with value 1 (the D matrices, mesh_operations.py:72-85): pure row selection
         self.is_selection = bool(self.nnz == n_rows and np.all(np.diff(rp) == 1) and np.all(v == 1.0))
+        # square operators: rows >= n_active are empty and no entry references a column >= n_active
+        # (the coarse operator applied to a finer tensor, models/cheb_VAE.py:288) -> closed-form rows
+        self.n_active = self.n_rows
+        if n_rows == n_cols:
+            self.n_active = int(max(rows.max(), cols.max())) + 1 if self.nnz else 0
 
     def csr_bytes(self) -> int:
         return (self.n_rows + 1) * 4 + self.nnz * 8
