@@ -20,6 +20,7 @@
 // shared-memory descriptors expect: a tile row is 64 B (Fin = 16) or 128 B (Fin = 32) and its
 // 16-byte chunk index is XORed with address bits [7,9) / [7,10), which also makes the staging
 // stores bank-conflict free.
+#include <stdlib.h>
 #include "mvb_internal.cuh"
 
 namespace mvb {
@@ -124,59 +125,12 @@ __device__ __forceinline__ uint32_t swz_off(int r, int q, int row_bytes) {
     return (uint32_t)(r * row_bytes + ((q ^ x) << 4));
 }
 
-// stage `nr` rows of one [rows x w] fp32 plane (w = 16 or 32) as hi/lo swizzled tiles of R rows;
-// rows >= nr are zero-filled; optional ReLU mask (value kept where mask > 0)
-template <int NLOAD>
-__device__ __forceinline__ void stage_plane_split(const float *__restrict__ src, const float *__restrict__ msk,
-                                                  int nr, int R, int w, char *hi, char *lo, int tid, int nthreads) {
-    const int q4 = w >> 2;
-    const int row_bytes = w * 4;
-    const int total = R * q4;
-    const float4 *s4 = reinterpret_cast<const float4 *>(src);
-    const float4 *m4 = reinterpret_cast<const float4 *>(msk);
-    for (int base = 0; base < total; base += nthreads * NLOAD) {
-        float4 v[NLOAD];
-#pragma unroll
-        for (int j = 0; j < NLOAD; ++j) {
-            const int i = base + j * nthreads + tid;
-            const int r = i / q4;
-            v[j] = (i < total && r < nr) ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (msk) {
-#pragma unroll
-            for (int j = 0; j < NLOAD; ++j) {
-                const int i = base + j * nthreads + tid;
-                const int r = i / q4;
-                if (i < total && r < nr) {
-                    const float4 mk = __ldg(m4 + i);
-                    v[j].x = mk.x > 0.f ? v[j].x : 0.f;
-                    v[j].y = mk.y > 0.f ? v[j].y : 0.f;
-                    v[j].z = mk.z > 0.f ? v[j].z : 0.f;
-                    v[j].w = mk.w > 0.f ? v[j].w : 0.f;
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < NLOAD; ++j) {
-            const int i = base + j * nthreads + tid;
-            if (i < total) {
-                const int r = i / q4, q = i - r * q4;
-                float4 h, l;
-                split4(v[j], h, l);
-                const uint32_t off = swz_off(r, q, row_bytes);
-                *reinterpret_cast<float4 *>(hi + off) = h;
-                *reinterpret_cast<float4 *>(lo + off) = l;
-            }
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // row GEMM:  out = act(A . Bm + bias)
 // ---------------------------------------------------------------------------------------------
 struct TcRowArgs {
     int64_t rows;
-    int in_planes, in_w;          // in_w = 16 or 32
+    int in_planes, in_w;
     const float *in0, *in_rest, *mask;
     const float *wmat;
     int w_transposed, w_fold;
@@ -186,22 +140,129 @@ struct TcRowArgs {
     int out_w;                    // width of one output plane (nn_true = out_planes * out_w)
     float *out;
     int tmem_cols;
+    int tile_w;                   // floats per staged tile row (16 or 32)
+    int tile_planes;              // number of staged tiles (= in_planes when planar, 1 when packed)
 };
 
+// B operand: Bt[n][kd] (n = output column, kd = logical K index p*in_w + i), K-major, swizzled like A,
+// hi/lo split.  kd maps to (tile plane, column) = (kd / tile_w, kd % tile_w) - for the packed layout
+// there is a single tile plane.  Loads are issued four at a time (the weights are L2/L1 resident).
+__device__ __forceinline__ void stage_b_operand(const TcRowArgs &a, char *Bhi, char *Blo, int b_plane, int row_bytes,
+                                                int tid, int nthreads) {
+    const int Kd = a.in_planes * a.in_w;
+    const int nfold = a.w_fold > 1 ? a.w_fold : 1;
+    const int total = a.nn16 * Kd;
+    for (int base = 0; base < total; base += 4 * nthreads) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * nthreads + tid;
+            v[u] = 0.f;
+            if (i < total) {
+                const int n = i / Kd, kd = i - n * Kd;
+                if (n < a.nn_true) {
+                    for (int k = 0; k < nfold; k += 2) {
+                        const float wv = a.w_transposed ? __ldg(a.wmat + ((int64_t)k * a.nn_true + n) * Kd + kd)
+                                                        : __ldg(a.wmat + ((int64_t)k * Kd + kd) * a.nn_true + n);
+                        v[u] += (k & 2) ? -wv : wv;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * nthreads + tid;
+            if (i < total) {
+                const int n = i / Kd, kd = i - n * Kd;
+                float h, l;
+                split_tf32(v[u], h, l);
+                const int p = kd / a.tile_w, c = kd - p * a.tile_w;
+                const uint32_t off = (uint32_t)(p * b_plane) + swz_off(n, c >> 2, row_bytes) + (uint32_t)((c & 3) << 2);
+                *reinterpret_cast<float *>(Bhi + off) = h;
+                *reinterpret_cast<float *>(Blo + off) = l;
+            }
+        }
+    }
+}
+
+// all MMAs of one 128-row tile: for every tile plane and 8-wide K slice, the three 3xTF32 terms
+__device__ __forceinline__ void issue_row_mmas(uint32_t tmem_base, char *Ahi, char *Alo, char *Bhi, char *Blo,
+                                               int planes, int a_plane, int b_plane, int kslices, uint32_t sbo,
+                                               uint32_t layout_type, uint32_t idesc) {
+    uint32_t acc = 0;
+    for (int p = 0; p < planes; ++p) {
+        for (int j = 0; j < kslices; ++j) {
+            const uint64_t ah = make_desc(smem_u32(Ahi + p * a_plane) + j * 32, 16, sbo, layout_type);
+            const uint64_t al = make_desc(smem_u32(Alo + p * a_plane) + j * 32, 16, sbo, layout_type);
+            const uint64_t bh = make_desc(smem_u32(Bhi + p * b_plane) + j * 32, 16, sbo, layout_type);
+            const uint64_t bl = make_desc(smem_u32(Blo + p * b_plane) + j * 32, 16, sbo, layout_type);
+            umma_tf32(tmem_base, al, bh, idesc, acc);     // small terms first
+            umma_tf32(tmem_base, ah, bl, idesc, 1);
+            umma_tf32(tmem_base, ah, bh, idesc, 1);
+            acc = 1;
+        }
+    }
+}
+
+// epilogue of one tile: TMEM -> registers -> bias / ReLU -> global (thread = row, 16 columns per pass)
+__device__ __forceinline__ void row_epilogue(const TcRowArgs &a, uint32_t tmem_base, int warp, int row, int nr,
+                                             int64_t row0) {
+    for (int n0 = 0; n0 < a.nn16; n0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, v);
+        if (row < nr && n0 < a.nn_true) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (a.bias && n0 + j < a.nn_true) v[j] += __ldg(a.bias + n0 + j);
+                if (a.relu) v[j] = v[j] > 0.f ? v[j] : 0.f;
+            }
+            const int64_t grow = row0 + row;
+            if (a.nn_true - n0 >= 16 && (a.out_w & 15) == 0) {
+                const int p = n0 / a.out_w, jj = n0 - p * a.out_w;
+                float4 *dst = reinterpret_cast<float4 *>(a.out + ((int64_t)p * a.rows + grow) * a.out_w + jj);
+                dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                dst[2] = make_float4(v[8], v[9], v[10], v[11]);
+                dst[3] = make_float4(v[12], v[13], v[14], v[15]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = n0 + j;
+                    if (n < a.nn_true) {
+                        const int p = n / a.out_w, jj = n - p * a.out_w;
+                        a.out[((int64_t)p * a.rows + grow) * a.out_w + jj] = v[j];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// W = 16 / 32: planar layout, one swizzled tile per input plane, the next tile's rows are prefetched
+//              into registers while the current tile's MMAs and epilogue run (single shared stage,
+//              two CTAs per SM overlap the rest);
+// W = 0      : packed layout for narrow planes (Fin = 3, Fout = 3 ...): the K*Fin <= 32 logical
+//              columns of a row are packed into one tile row, staged with scalar accesses.
+template <int W, int NP>
 __global__ void __launch_bounds__(128)
 tc_rowgemm_kernel(TcRowArgs a) {
     extern __shared__ __align__(1024) char smem_raw[];
     char *smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr bool PACKED = (W == 0);
+    constexpr int Q4 = PACKED ? 1 : W / 4;
+    constexpr int NPL = PACKED ? 1 : NP;
+    constexpr int NV = NPL * Q4;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int w = a.in_w, row_bytes = w * 4;
+    const int wt = PACKED ? a.tile_w : W;
+    const int row_bytes = wt * 4;
     const int R = 128;
-    const int a_plane = R * row_bytes;               // bytes of one A plane tile (8 or 16 KB)
-    const int b_plane = a.nn16 * row_bytes;          // bytes of one B plane tile
+    const int a_plane = R * row_bytes;
+    const int b_plane = a.nn16 * row_bytes;
     char *Ahi = smem;
-    char *Alo = Ahi + a.in_planes * a_plane;
-    char *Bhi = Alo + a.in_planes * a_plane;
-    char *Blo = Bhi + a.in_planes * b_plane;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(Blo + a.in_planes * b_plane);
+    char *Alo = Ahi + NPL * a_plane;
+    char *Bhi = Alo + NPL * a_plane;
+    char *Blo = Bhi + NPL * b_plane;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(Blo + NPL * b_plane);
     uint32_t *slot = reinterpret_cast<uint32_t *>(bar + 1);
 
     if (warp == 0) tmem_alloc(slot, (uint32_t)a.tmem_cols);
@@ -209,28 +270,12 @@ tc_rowgemm_kernel(TcRowArgs a) {
         mbar_init(bar, 1);
         fence_barrier_init();
     }
-    // B operand: Bt[n][kd] (n = output column, kd = p*w + i), K-major, swizzled like A; hi/lo split.
-    {
-        const int Kd = a.in_planes * w;
-        const int nfold = a.w_fold > 1 ? a.w_fold : 1;
-        for (int i = tid; i < a.nn16 * Kd; i += blockDim.x) {
-            const int n = i / Kd, kd = i - n * Kd;
-            float v = 0.f;
-            if (n < a.nn_true) {
-                for (int k = 0; k < nfold; k += 2) {
-                    const float wv = a.w_transposed ? __ldg(a.wmat + ((int64_t)k * a.nn_true + n) * Kd + kd)
-                                                    : __ldg(a.wmat + ((int64_t)k * Kd + kd) * a.nn_true + n);
-                    v += (k & 2) ? -wv : wv;
-                }
-            }
-            float h, l;
-            split_tf32(v, h, l);
-            const int p = kd / w, c = kd - p * w;
-            const uint32_t off = (uint32_t)(p * b_plane) + swz_off(n, c >> 2, row_bytes) + (uint32_t)((c & 3) << 2);
-            *reinterpret_cast<float *>(Bhi + off) = h;
-            *reinterpret_cast<float *>(Blo + off) = l;
-        }
+    if (PACKED) {   // padding columns of the packed tiles must be finite zeros in A and B
+        for (int i = tid; i < (2 * a_plane + 2 * b_plane) / 16; i += blockDim.x)
+            reinterpret_cast<float4 *>(Ahi)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
     }
+    stage_b_operand(a, Bhi, Blo, b_plane, row_bytes, tid, blockDim.x);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -238,72 +283,116 @@ tc_rowgemm_kernel(TcRowArgs a) {
     const uint32_t idesc = make_idesc(128, a.nn16, 0, 0);
     const uint32_t layout_type = (row_bytes == 128) ? 2u : 4u;
     const uint32_t sbo = 8u * row_bytes;
-    const int kslices = w / 8;
+    const int kslices = PACKED ? (a.in_planes * a.in_w + 7) / 8 : W / 8;
     const int row = warp * 32 + lane;                 // D row (TMEM lane) this thread reads back
     uint32_t phase = 0;
-
     const int64_t ntiles = (a.rows + R - 1) / R;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+
+    float4 pre[NV];
+    float4 prem[Q4];
+    // global -> registers for the tile starting at row0 (planar layout)
+    auto prefetch = [&](int64_t row0) {
+        const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
+#pragma unroll
+        for (int p = 0; p < NPL; ++p) {
+            const float4 *s4 = reinterpret_cast<const float4 *>((p == 0 ? a.in0 : a.in_rest + (int64_t)(p - 1) * a.rows * wt) + row0 * wt);
+#pragma unroll
+            for (int j = 0; j < Q4; ++j) {
+                const int i = j * 128 + tid;
+                pre[p * Q4 + j] = (i / Q4 < nr) ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        if (a.mask) {
+            const float4 *m4 = reinterpret_cast<const float4 *>(a.mask + row0 * wt);
+#pragma unroll
+            for (int j = 0; j < Q4; ++j) {
+                const int i = j * 128 + tid;
+                prem[j] = (i / Q4 < nr) ? __ldg(m4 + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+            }
+        }
+    };
+    // registers -> hi/lo swizzled shared tiles
+    auto commit = [&]() {
+#pragma unroll
+        for (int p = 0; p < NPL; ++p) {
+#pragma unroll
+            for (int j = 0; j < Q4; ++j) {
+                const int i = j * 128 + tid;
+                const int r = i / Q4, q = i - r * Q4;
+                float4 v = pre[p * Q4 + j];
+                if (p == 0 && a.mask) {
+                    v.x = prem[j].x > 0.f ? v.x : 0.f;
+                    v.y = prem[j].y > 0.f ? v.y : 0.f;
+                    v.z = prem[j].z > 0.f ? v.z : 0.f;
+                    v.w = prem[j].w > 0.f ? v.w : 0.f;
+                }
+                float4 h, l;
+                split4(v, h, l);
+                const uint32_t off = (uint32_t)(p * a_plane) + swz_off(r, q, row_bytes);
+                *reinterpret_cast<float4 *>(Ahi + off) = h;
+                *reinterpret_cast<float4 *>(Alo + off) = l;
+            }
+        }
+    };
+    // packed layout: scalar staging straight to shared memory; the (plane, row, feature) index space
+    // of the tile is flattened so that every thread has 8 independent coalesced loads in flight
+    auto stage_packed = [&](int64_t row0, int nr) {
+        const int per_plane = R * a.in_w;
+        const int total = a.in_planes * per_plane;
+        for (int base = 0; base < total; base += 8 * 128) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = base + u * 128 + tid;
+                v[u] = 0.f;
+                if (i < total) {
+                    const int p = i / per_plane, e = i - p * per_plane;
+                    if (e < nr * a.in_w) {
+                        const float *src = (p == 0 ? a.in0 : a.in_rest + (int64_t)(p - 1) * a.rows * a.in_w) + row0 * a.in_w;
+                        v[u] = __ldg(src + e);
+                        if (p == 0 && a.mask) v[u] = __ldg(a.mask + row0 * a.in_w + e) > 0.f ? v[u] : 0.f;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = base + u * 128 + tid;
+                if (i < total) {
+                    const int p = i / per_plane, e = i - p * per_plane;
+                    const int r = e / a.in_w, f = e - r * a.in_w;
+                    float h, l;
+                    split_tf32(v[u], h, l);
+                    const int col = p * a.in_w + f;
+                    const uint32_t off = swz_off(r, col >> 2, row_bytes) + (uint32_t)((col & 3) << 2);
+                    *reinterpret_cast<float *>(Ahi + off) = h;
+                    *reinterpret_cast<float *>(Alo + off) = l;
+                }
+            }
+        }
+    };
+
+    int64_t t = blockIdx.x;
+    if (!PACKED && t < ntiles) prefetch(t * R);
+    for (; t < ntiles; t += gridDim.x) {
         const int64_t row0 = t * R;
         const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
-        for (int p = 0; p < a.in_planes; ++p) {
-            const float *src = (p == 0 ? a.in0 : a.in_rest + (int64_t)(p - 1) * a.rows * w) + row0 * w;
-            const float *msk = (p == 0 && a.mask) ? a.mask + row0 * w : nullptr;
-            stage_plane_split<4>(src, msk, nr, R, w, Ahi + p * a_plane, Alo + p * a_plane, tid, blockDim.x);
-        }
+        if (PACKED)
+            stage_packed(row0, nr);
+        else
+            commit();
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            uint32_t acc = 0;
-            for (int p = 0; p < a.in_planes; ++p) {
-                for (int j = 0; j < kslices; ++j) {
-                    const uint64_t ah = make_desc(smem_u32(Ahi + p * a_plane) + j * 32, 16, sbo, layout_type);
-                    const uint64_t al = make_desc(smem_u32(Alo + p * a_plane) + j * 32, 16, sbo, layout_type);
-                    const uint64_t bh = make_desc(smem_u32(Bhi + p * b_plane) + j * 32, 16, sbo, layout_type);
-                    const uint64_t bl = make_desc(smem_u32(Blo + p * b_plane) + j * 32, 16, sbo, layout_type);
-                    umma_tf32(tmem_base, al, bh, idesc, acc);     // small terms first
-                    umma_tf32(tmem_base, ah, bl, idesc, 1);
-                    umma_tf32(tmem_base, ah, bh, idesc, 1);
-                    acc = 1;
-                }
-            }
+            issue_row_mmas(tmem_base, Ahi, Alo, Bhi, Blo, NPL, a_plane, b_plane, kslices, sbo, layout_type, idesc);
             umma_commit(bar);
         }
+        if (!PACKED && t + gridDim.x < ntiles) prefetch((t + gridDim.x) * R);   // in flight during MMA + epilogue
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
-        // epilogue: TMEM -> registers -> bias / ReLU -> global (thread = row, 16 columns per pass)
-        for (int n0 = 0; n0 < a.nn16; n0 += 16) {
-            float v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, v);
-            if (row < nr && n0 < a.nn_true) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    if (a.bias && n0 + j < a.nn_true) v[j] += __ldg(a.bias + n0 + j);
-                    if (a.relu) v[j] = v[j] > 0.f ? v[j] : 0.f;
-                }
-                const int64_t grow = row0 + row;
-                if (a.nn_true - n0 >= 16 && (a.out_w & 15) == 0) {
-                    const int p = n0 / a.out_w, jj = n0 - p * a.out_w;
-                    float4 *dst = reinterpret_cast<float4 *>(a.out + ((int64_t)p * a.rows + grow) * a.out_w + jj);
-                    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-                    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-                    dst[2] = make_float4(v[8], v[9], v[10], v[11]);
-                    dst[3] = make_float4(v[12], v[13], v[14], v[15]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int n = n0 + j;
-                        if (n < a.nn_true) {
-                            const int p = n / a.out_w, jj = n - p * a.out_w;
-                            a.out[((int64_t)p * a.rows + grow) * a.out_w + jj] = v[j];
-                        }
-                    }
-                }
-            }
-        }
+        row_epilogue(a, tmem_base, warp, row, nr, row0);
         tc_fence_before();   // order this tile's TMEM reads before the barrier that precedes the next MMA
     }
     __syncthreads();
@@ -316,18 +405,36 @@ static int pow2_cols(int n) {
     return c;
 }
 
+template <int W, int NP>
+static int launch_rowgemm_t(const TcRowArgs &t, unsigned grid, size_t smem, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_rowgemm_kernel<W, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return set_err(MVB_ECUDA, "tc_rowgemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    tc_rowgemm_kernel<W, NP><<<grid, 128, smem, st>>>(t);
+    return check_launch("mvb tc_rowgemm");
+}
+
 // returns 1 if the tensor-core path took the call, 0 if the shape is not supported (caller falls
 // back to the FFMA kernel), < 0 on error
 int launch_contract_tc(const ContractArgs &a, cudaStream_t st) {
     if (!g_tc_enabled) return 0;
     const int w = a.in_w;
-    if (w != 16 && w != 32) return 0;
+    const int Kd = a.in_planes * w;
     const int nn_true = a.out_planes * a.out_w;
     const int nn16 = (nn_true + 15) & ~15;
     if (nn16 > 256 || a.rows < 128) return 0;
-    if (!aligned16(a.in0) || (a.in_planes > 1 && !aligned16(a.in_rest)) || (a.mask && !aligned16(a.mask)) || !aligned16(a.out)) return 0;
-    const size_t smem = 1024 + (size_t)a.in_planes * (2 * 128 * w * 4 + 2 * nn16 * w * 4) + 64;
-    if (smem > 200 * 1024) return 0;
+    const bool planar = (w == 16 && a.in_planes <= 6) || (w == 32 && a.in_planes <= 3);
+    const bool vec_ok = aligned16(a.in0) && (a.in_planes == 1 || aligned16(a.in_rest)) && (!a.mask || aligned16(a.mask));
+    // the scalar-staged packed layout (narrow planes, Fin = 3 / Fout = 3) is functional but its index
+    // arithmetic makes it slower than the FFMA kernel: opt-in only (MVB_TC_PACKED=1) until those layers
+    // are padded to 4-wide planes
+    static const bool allow_packed = getenv("MVB_TC_PACKED") != nullptr;
+    const bool packed = allow_packed && !(planar && vec_ok) && Kd <= 32;
+    if (!(planar && vec_ok) && !packed) return 0;
+    if (!aligned16(a.out)) return 0;
     TcRowArgs t;
     t.rows = a.rows;
     t.in_planes = a.in_planes;
@@ -345,22 +452,37 @@ int launch_contract_tc(const ContractArgs &a, cudaStream_t st) {
     t.out_w = a.out_w;
     t.out = a.out;
     t.tmem_cols = pow2_cols(nn16);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_rowgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return set_err(MVB_ECUDA, "tc_rowgemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set = true;
-    }
+    t.tile_w = packed ? (Kd <= 16 ? 16 : 32) : w;
+    t.tile_planes = packed ? 1 : a.in_planes;
+    const size_t smem = 1024 + (size_t)t.tile_planes * (2 * 128 * t.tile_w * 4 + 2 * nn16 * t.tile_w * 4) + 64;
+    if (smem > 200 * 1024) return 0;
     const int64_t ntiles = (a.rows + 127) / 128;
     // CTAs per SM: shared memory and TMEM (512 columns) permitting
     int per_sm = (int)((220 * 1024) / smem);
     if (per_sm > 512 / t.tmem_cols) per_sm = 512 / t.tmem_cols;
-    if (per_sm > 8) per_sm = 8;
+    if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)num_sms() * per_sm;
     if (grid > ntiles) grid = ntiles;
-    tc_rowgemm_kernel<<<(unsigned)grid, 128, smem, st>>>(t);
-    int rc = check_launch("mvb tc_rowgemm");
+    int rc;
+    if (packed) {
+        rc = launch_rowgemm_t<0, 1>(t, (unsigned)grid, smem, st);
+    } else if (w == 16) {
+        switch (a.in_planes) {
+            case 1: rc = launch_rowgemm_t<16, 1>(t, (unsigned)grid, smem, st); break;
+            case 2: rc = launch_rowgemm_t<16, 2>(t, (unsigned)grid, smem, st); break;
+            case 3: rc = launch_rowgemm_t<16, 3>(t, (unsigned)grid, smem, st); break;
+            case 4: rc = launch_rowgemm_t<16, 4>(t, (unsigned)grid, smem, st); break;
+            case 5: rc = launch_rowgemm_t<16, 5>(t, (unsigned)grid, smem, st); break;
+            default: rc = launch_rowgemm_t<16, 6>(t, (unsigned)grid, smem, st); break;
+        }
+    } else {
+        switch (a.in_planes) {
+            case 1: rc = launch_rowgemm_t<32, 1>(t, (unsigned)grid, smem, st); break;
+            case 2: rc = launch_rowgemm_t<32, 2>(t, (unsigned)grid, smem, st); break;
+            default: rc = launch_rowgemm_t<32, 3>(t, (unsigned)grid, smem, st); break;
+        }
+    }
     return rc ? rc : 1;
 }
 
@@ -373,69 +495,39 @@ int launch_contract_tc(const ContractArgs &a, cudaStream_t st) {
 // features, K atoms of 4 rows (stride byte offset = 512), MN blocks of 32 features at the leading
 // byte offset, and a 32-byte-granular swizzle (cute Swizzle<2,5,2> on the byte address): the
 // 32-byte unit index (address bits [5,7)) ^= row & 3 (address bits [7,9)).
+// Logical feature column of plane p, feature f is p*in_w + f (= the dW row index k*Fin + fi); the
+// "ones" column that yields the bias gradient sits at column K*Fin.
 struct TcWgradArgs {
     int64_t rows;
-    int in_planes;                 // K (<= 7), planes of width 16
+    int in_planes, in_w;
     const float *in0, *in_rest;
     const float *dy, *mask;
-    int n_out;                     // Fout: 16 or 32
+    int n_out, n16;                // Fout and its padding to the MMA N (16 or 32)
     int has_bias;
     int M4, N4;                    // partial block layout [M4][N4] expected by the finalize kernel
     float *partials;
     int tmem_cols;
 };
 
-// stage nr rows of a [rows x w] plane (w = 16 / 32 floats) into 128-byte-row BASE32B tiles (hi, lo),
-// the plane occupying 16-byte chunks [chunk0, chunk0 + w/4) of each logical row; rows >= nr zero-filled.
-// physical offset of logical chunk c of row r: r*128 + (((c >> 1) ^ (r & 3)) << 5) + ((c & 1) << 4)
-__device__ __forceinline__ void stage_plane_b32(const float *__restrict__ src, const float *__restrict__ msk,
-                                                int nr, int R, int w, int chunk0, char *hi, char *lo, int tid,
-                                                int nthreads) {
-    const int q4 = w >> 2;
-    const int total = R * q4;
-    const float4 *s4 = reinterpret_cast<const float4 *>(src);
-    const float4 *m4 = reinterpret_cast<const float4 *>(msk);
-    for (int base = 0; base < total; base += 2 * nthreads) {
-        float4 v[2];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int i = base + j * nthreads + tid;
-            const int r = i / q4;
-            v[j] = (i < total && r < nr) ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (msk && i < total && r < nr) {
-                const float4 mk = __ldg(m4 + i);
-                v[j].x = mk.x > 0.f ? v[j].x : 0.f;
-                v[j].y = mk.y > 0.f ? v[j].y : 0.f;
-                v[j].z = mk.z > 0.f ? v[j].z : 0.f;
-                v[j].w = mk.w > 0.f ? v[j].w : 0.f;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int i = base + j * nthreads + tid;
-            if (i < total) {
-                const int r = i / q4, q = i - r * q4;
-                const int c = chunk0 + q;
-                float4 h, l;
-                split4(v[j], h, l);
-                const uint32_t off = (uint32_t)(r * 128 + (((c >> 1) ^ (r & 3)) << 5) + ((c & 1) << 4));
-                *reinterpret_cast<float4 *>(hi + off) = h;
-                *reinterpret_cast<float4 *>(lo + off) = l;
-            }
-        }
-    }
+// byte offset of logical (row r, feature column col) in a BASE32B tile made of 32-column blocks of blk bytes
+__device__ __forceinline__ uint32_t b32_off(int r, int col, int blk) {
+    const int b = col >> 5, c = (col & 31) >> 2;
+    return (uint32_t)(b * blk + r * 128 + (((c >> 1) ^ (r & 3)) << 5) + ((c & 1) << 4) + ((col & 3) << 2));
 }
 
+template <int NP16>   // > 0: in_w == 16, Fout in {16,32}, vector staging with register prefetch; 0: generic scalar staging
 __global__ void __launch_bounds__(128)
 tc_wgrad_kernel(TcWgradArgs a) {
     extern __shared__ __align__(1024) char smem_raw[];
     char *smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr bool FAST = NP16 > 0;
+    constexpr int NPV = FAST ? NP16 : 1;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int R = 64;                                  // activation rows (= UMMA K extent) per tile
     const int blk = R * 128;                           // one 32-feature block of the T tile: 8 KB
-    char *Thi = smem;                                  // 4 blocks: plane pairs (0,1) (2,3) (4,5) (6,7)
+    char *Thi = smem;                                  // 4 blocks = 128 feature columns
     char *Tlo = Thi + 4 * blk;
-    char *Dhi = Tlo + 4 * blk;                         // dY tile, rows of 128 B (first 64 B used when Fout = 16)
+    char *Dhi = Tlo + 4 * blk;                         // dY tile, rows of 128 B
     char *Dlo = Dhi + blk;
     uint64_t *bar = reinterpret_cast<uint64_t *>(Dlo + blk);
     uint32_t *slot = reinterpret_cast<uint32_t *>(bar + 1);
@@ -445,39 +537,140 @@ tc_wgrad_kernel(TcWgradArgs a) {
         mbar_init(bar, 1);
         fence_barrier_init();
     }
-    // zero everything once (planes beyond K, the unused half of 64-byte dY rows), then the ones column:
-    // feature 0 of plane K (M index K*16), whose product with dY is the bias gradient
-    for (int i = tid; i < (8 * blk + 2 * blk) / 16; i += blockDim.x)
+    // zero everything once (unused feature columns, padding of dY rows), then the ones column
+    for (int i = tid; i < (10 * blk) / 16; i += blockDim.x)
         reinterpret_cast<float4 *>(Thi)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     if (a.has_bias) {
-        const int p = a.in_planes, c = (p & 1) * 4;     // logical chunk c of the row, word 0
-        for (int r = tid; r < R; r += blockDim.x)
-            *reinterpret_cast<float *>(Thi + (p >> 1) * blk + r * 128 + (((c >> 1) ^ (r & 3)) << 5) + ((c & 1) << 4)) = 1.f;
+        const int col = a.in_planes * a.in_w;
+        for (int r = tid; r < R; r += blockDim.x) *reinterpret_cast<float *>(Thi + b32_off(r, col, blk)) = 1.f;
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *slot;
-    const uint32_t idesc = make_idesc(128, a.n_out, 1, 1);
-    uint32_t acc = 0;
-
+    const uint32_t idesc = make_idesc(128, a.n16, 1, 1);
     const int64_t ntiles = (a.rows + R - 1) / R;
-    uint32_t phase = 0;
+    const int dq4 = a.n_out >> 2;                      // float4 chunks per dY row (FAST only)
+
+    float4 pre[2 * NPV];
+    float4 pred[4], prem[4];
+    auto prefetch = [&](int64_t row0) {
+        const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
+#pragma unroll
+        for (int p = 0; p < NPV; ++p) {
+            const float4 *s4 = reinterpret_cast<const float4 *>((p == 0 ? a.in0 : a.in_rest + (int64_t)(p - 1) * a.rows * 16) + row0 * 16);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int i = j * 128 + tid;
+                pre[p * 2 + j] = ((i >> 2) < nr) ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        const float4 *d4 = reinterpret_cast<const float4 *>(a.dy + row0 * a.n_out);
+        const float4 *m4 = reinterpret_cast<const float4 *>(a.mask ? a.mask + row0 * a.n_out : nullptr);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = j * 128 + tid;
+            const bool ok = i < R * dq4 && (i / dq4) < nr;
+            pred[j] = ok ? __ldg(d4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.mask) prem[j] = ok ? __ldg(m4 + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+    };
+    auto commit = [&]() {
+#pragma unroll
+        for (int p = 0; p < NPV; ++p) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int i = j * 128 + tid;
+                const int r = i >> 2, q = i & 3;
+                float4 h, l;
+                split4(pre[p * 2 + j], h, l);
+                const uint32_t off = b32_off(r, p * 16 + q * 4, blk);
+                *reinterpret_cast<float4 *>(Thi + off) = h;
+                *reinterpret_cast<float4 *>(Tlo + off) = l;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = j * 128 + tid;
+            if (i < R * dq4) {
+                const int r = i / dq4, q = i - r * dq4;
+                float4 v = pred[j];
+                if (a.mask) {
+                    v.x = prem[j].x > 0.f ? v.x : 0.f;
+                    v.y = prem[j].y > 0.f ? v.y : 0.f;
+                    v.z = prem[j].z > 0.f ? v.z : 0.f;
+                    v.w = prem[j].w > 0.f ? v.w : 0.f;
+                }
+                float4 h, l;
+                split4(v, h, l);
+                const uint32_t off = b32_off(r, q * 4, blk);
+                *reinterpret_cast<float4 *>(Dhi + off) = h;
+                *reinterpret_cast<float4 *>(Dlo + off) = l;
+            }
+        }
+    };
+    // generic staging (narrow planes such as Fin = 3, or Fout = 3): flattened index space, 8 independent
+    // coalesced scalar loads in flight per thread
+    auto stage_generic = [&](int64_t row0, int nr) {
+        const int per_plane = R * a.in_w;
+        const int t_total = a.in_planes * per_plane;
+        const int total = t_total + R * a.n_out;          // T planes, then the dY tile
+        for (int base = 0; base < total; base += 8 * 128) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = base + u * 128 + tid;
+                v[u] = 0.f;
+                if (i < t_total) {
+                    const int p = i / per_plane, e = i - p * per_plane;
+                    if (e < nr * a.in_w)
+                        v[u] = __ldg((p == 0 ? a.in0 : a.in_rest + (int64_t)(p - 1) * a.rows * a.in_w) + row0 * a.in_w + e);
+                } else if (i < total) {
+                    const int e = i - t_total;
+                    if (e < nr * a.n_out) {
+                        v[u] = __ldg(a.dy + row0 * a.n_out + e);
+                        if (a.mask) v[u] = __ldg(a.mask + row0 * a.n_out + e) > 0.f ? v[u] : 0.f;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = base + u * 128 + tid;
+                float h, l;
+                split_tf32(v[u], h, l);
+                if (i < t_total) {
+                    const int p = i / per_plane, e = i - p * per_plane;
+                    const int r = e / a.in_w, f = e - r * a.in_w;
+                    const uint32_t off = b32_off(r, p * a.in_w + f, blk);
+                    *reinterpret_cast<float *>(Thi + off) = h;
+                    *reinterpret_cast<float *>(Tlo + off) = l;
+                } else if (i < total) {
+                    const int e = i - t_total;
+                    const int r = e / a.n_out, f = e - r * a.n_out;
+                    const uint32_t off = b32_off(r, f, blk);
+                    *reinterpret_cast<float *>(Dhi + off) = h;
+                    *reinterpret_cast<float *>(Dlo + off) = l;
+                }
+            }
+        }
+    };
+
+    uint32_t acc = 0, phase = 0;
     bool pending = false;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    int64_t t = blockIdx.x;
+    if (FAST && t < ntiles) prefetch(t * R);
+    for (; t < ntiles; t += gridDim.x) {
         const int64_t row0 = t * R;
         const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
         if (pending) {   // the previous tile's MMAs must have finished reading shared memory
             mbar_wait(bar, phase);
             phase ^= 1;
         }
-        for (int p = 0; p < a.in_planes; ++p) {
-            const float *src = (p == 0 ? a.in0 : a.in_rest + (int64_t)(p - 1) * a.rows * 16) + row0 * 16;
-            stage_plane_b32(src, nullptr, nr, R, 16, (p & 1) * 4, Thi + (p >> 1) * blk, Tlo + (p >> 1) * blk, tid, blockDim.x);
-        }
-        stage_plane_b32(a.dy + row0 * a.n_out, a.mask ? a.mask + row0 * a.n_out : nullptr, nr, R, a.n_out, 0, Dhi, Dlo,
-                        tid, blockDim.x);
+        if (FAST)
+            commit();
+        else
+            stage_generic(row0, nr);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -496,6 +689,7 @@ tc_wgrad_kernel(TcWgradArgs a) {
             umma_commit(bar);
         }
         pending = true;
+        if (FAST && t + gridDim.x < ntiles) prefetch((t + gridDim.x) * R);   // overlaps this tile's MMAs
     }
     if (pending) {
         mbar_wait(bar, phase);
@@ -505,7 +699,7 @@ tc_wgrad_kernel(TcWgradArgs a) {
     // D[m = feature (or bias row)][n = fo] -> per-CTA partial block [M4][N4]
     const int m = warp * 32 + lane;
     float *part = a.partials + (size_t)blockIdx.x * a.M4 * a.N4;
-    for (int n0 = 0; n0 < a.n_out; n0 += 16) {
+    for (int n0 = 0; n0 < a.n16; n0 += 16) {
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, v);
         if (m < a.M4) {
@@ -519,39 +713,60 @@ tc_wgrad_kernel(TcWgradArgs a) {
     if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
 }
 
+template <int NP16>
+static int launch_wgrad_t(const TcWgradArgs &t, unsigned grid, size_t smem, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<NP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return set_err(MVB_ECUDA, "tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    tc_wgrad_kernel<NP16><<<grid, 128, smem, st>>>(t);
+    return check_launch("mvb tc_wgrad");
+}
+
 // returns 1 if taken, 0 if unsupported, < 0 on error.  Partial layout matches the FFMA wgrad kernel.
 int launch_wgrad_tc(const WgradArgs &a, int has_bias, int M4, int N4, int *nparts, cudaStream_t st) {
     if (!g_tc_enabled) return 0;
-    if (a.in_w != 16 || a.in_planes + (has_bias ? 1 : 0) > 8 || a.rows < 256) return 0;
-    if (a.n_out != 16 && a.n_out != 32) return 0;
-    if (!aligned16(a.in0) || (a.in_planes > 1 && !aligned16(a.in_rest)) || !aligned16(a.dy) || (a.mask && !aligned16(a.mask))) return 0;
-    if (M4 > 128) return 0;
+    const int M = a.in_planes * a.in_w;
+    if (M + (has_bias ? 1 : 0) > 128 || M4 > 128 || a.n_out > 32 || a.rows < 256) return 0;
+    const bool fast = a.in_w == 16 && a.in_planes <= 6 && (a.n_out == 16 || a.n_out == 32) && aligned16(a.in0) &&
+                      (a.in_planes == 1 || aligned16(a.in_rest)) && aligned16(a.dy) && (!a.mask || aligned16(a.mask));
+    static const bool allow_generic = getenv("MVB_TC_PACKED") != nullptr;
+    if (!fast && !allow_generic) return 0;
     TcWgradArgs t;
     t.rows = a.rows;
     t.in_planes = a.in_planes;
+    t.in_w = a.in_w;
     t.in0 = a.in0;
     t.in_rest = a.in_rest;
     t.dy = a.dy;
     t.mask = a.mask;
     t.n_out = a.n_out;
+    t.n16 = (a.n_out + 15) & ~15;
     t.has_bias = has_bias;
     t.M4 = M4;
     t.N4 = N4;
     t.partials = a.partials;
     t.tmem_cols = 32;
     const size_t smem = 1024 + 10 * 64 * 128 + 64;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return set_err(MVB_ECUDA, "tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set = true;
-    }
     const int64_t ntiles = (a.rows + 63) / 64;
     int64_t grid = (int64_t)num_sms() * 2;
     if (grid > ntiles) grid = ntiles;
     if ((size_t)grid * M4 * N4 * sizeof(float) > a.partial_bytes) return set_err(MVB_EWORKSPACE, "tc_wgrad: workspace too small");
-    tc_wgrad_kernel<<<(unsigned)grid, 128, smem, st>>>(t);
-    int rc = check_launch("mvb tc_wgrad");
+    int rc;
+    if (!fast) {
+        rc = launch_wgrad_t<0>(t, (unsigned)grid, smem, st);
+    } else {
+        switch (a.in_planes) {
+            case 1: rc = launch_wgrad_t<1>(t, (unsigned)grid, smem, st); break;
+            case 2: rc = launch_wgrad_t<2>(t, (unsigned)grid, smem, st); break;
+            case 3: rc = launch_wgrad_t<3>(t, (unsigned)grid, smem, st); break;
+            case 4: rc = launch_wgrad_t<4>(t, (unsigned)grid, smem, st); break;
+            case 5: rc = launch_wgrad_t<5>(t, (unsigned)grid, smem, st); break;
+            default: rc = launch_wgrad_t<6>(t, (unsigned)grid, smem, st); break;
+        }
+    }
     if (rc) return rc;
     *nparts = (int)grid;
     return 1;

@@ -1,0 +1,47 @@
+"""Data-parallel plumbing (new - the reference is single-device, main.py:194-195): batch sharding
+and the ONE flat-gradient all-reduce per step.  Device-agnostic on purpose so the N>1 path is
+covered by world_size-2 `gloo` tests on CPU; on B200s the backend is NCCL over NVLink/NVSwitch.
+
+Semantics: every rank holds a contiguous slice of the global batch; the loss is the mean over the
+batch (models/cheb_VAE.py:342), so the gradient of the global-batch mean loss is the average of
+the per-rank gradients when the slices are equal."""
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
+    """[lo, hi) of the contiguous slice of the global batch owned by `rank`; the batch must divide
+    evenly (unequal slices would bias the mean of per-rank means)."""
+    if global_batch % world != 0:
+        raise ValueError(f"global batch {global_batch} is not divisible by world size {world}")
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
+def live_parameters(params: Sequence[torch.nn.Parameter]) -> List[torch.nn.Parameter]:
+    """parameters that received a gradient (dec_lin_1 of cheb_VAE never does, quirk 7; torch's Adam
+    skips such parameters, and so does the flat exchange buffer)"""
+    return [p for p in params if p.grad is not None]
+
+
+def pack_grads(params: Sequence[torch.nn.Parameter], out: torch.Tensor) -> torch.Tensor:
+    torch.cat([p.grad.reshape(-1) for p in params], out=out)
+    return out
+
+
+def unpack_grads(flat: torch.Tensor, params: Sequence[torch.nn.Parameter]) -> None:
+    off = 0
+    for p in params:
+        n = p.numel()
+        p.grad.copy_(flat[off:off + n].view_as(p))
+        off += n
+
+
+def allreduce_sum_(flat: torch.Tensor, group=None) -> torch.Tensor:
+    """in-place SUM all-reduce of the flat gradient buffer; the 1/world scaling is applied by the
+    consumer (folded into mvb_adam_step on the GPU)"""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return flat

@@ -14,7 +14,7 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
-from . import _lib
+from . import _lib, dp
 from ._lib import lib, check, ptr, stream_ptr
 
 
@@ -41,7 +41,7 @@ class FlatAdam:
 
     def pack_grads(self):
         """one concatenation of the per-parameter gradients into the flat exchange buffer"""
-        torch.cat([p.grad.reshape(-1) for p in self.params], out=self.flat_g)
+        dp.pack_grads(self.params, self.flat_g)
 
     def step(self, grad_scale: float = 1.0):
         check(lib.mvb_adam_step(self.n, ptr(self.flat_p), ptr(self.flat_g), ptr(self.m), ptr(self.v),
@@ -69,7 +69,7 @@ class TrainEngine:
         net.zero_grad(set_to_none=True)
         loss, *_ = net(self.x, self.x_gt, self.y_hot, m_type="train", eps=self.eps)
         loss.backward()
-        live = [p for p in net.parameters() if p.grad is not None]
+        live = dp.live_parameters(list(net.parameters()))
         net.zero_grad(set_to_none=True)
         self.opt = FlatAdam(live, lr=lr, weight_decay=weight_decay)
         self.loss = torch.zeros((), device=self.dev, dtype=torch.float64)
@@ -132,7 +132,7 @@ class TrainEngine:
         else:
             self._fwd_bwd()
         if self.distributed:
-            dist.all_reduce(self.opt.flat_g, op=dist.ReduceOp.SUM)
+            dp.allreduce_sum_(self.opt.flat_g)
         if self.use_graph:
             self.g_opt.replay()
         else:

@@ -1,0 +1,76 @@
+"""N>1 host logic on CPU: world_size-2 gloo.  A sharded step (each rank its slice, flat gradient
+all-reduce, 1/world scaling) must reproduce the single-process global-batch gradient."""
+import os
+import socket
+import sys
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests.helpers import ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _toy():
+    torch.manual_seed(3)
+    return torch.nn.Sequential(torch.nn.Linear(12, 9), torch.nn.ReLU(), torch.nn.Linear(9, 4))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from meshvae_b200 import dp
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(8, 12, generator=g)
+    y = torch.randn(8, 4, generator=g)
+    lo, hi = dp.shard_bounds(8, rank, world)
+    net = _toy()
+    loss = ((net(x[lo:hi]) - y[lo:hi]) ** 2).sum(-1).mean()          # mean over the LOCAL slice
+    loss.backward()
+    live = dp.live_parameters(list(net.parameters()))
+    flat = torch.empty(sum(p.numel() for p in live))
+    dp.pack_grads(live, flat)
+    dp.allreduce_sum_(flat)
+    flat.mul_(1.0 / world)
+    dp.unpack_grads(flat, live)
+    if rank == 0:
+        q.put([p.grad.clone() for p in net.parameters()])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_step_equals_global_batch_step():
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    grads = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(8, 12, generator=g)
+    y = torch.randn(8, 4, generator=g)
+    net = _toy()
+    ((net(x) - y) ** 2).sum(-1).mean().backward()
+    for a, p in zip(grads, net.parameters()):
+        assert torch.allclose(a, p.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_shard_bounds():
+    from meshvae_b200 import dp
+    assert [dp.shard_bounds(512, r, 8) for r in range(8)] == [(64 * r, 64 * (r + 1)) for r in range(8)]
+    with pytest.raises(ValueError):
+        dp.shard_bounds(10, 0, 4)
