@@ -51,6 +51,9 @@ int64_t mvb_launch_count(void);
 /* enable (default) / disable the tcgen05 3xTF32 tensor-core kernels for the dense contractions;
  * disabled, the strict-fp32 FFMA kernels run everywhere.  Returns the previous setting. */
 int mvb_set_tensor_cores(int enable);
+/* enable / disable (default) the experimental shared-memory banded SpMM variant (A/B testing;
+ * results are bit-identical either way: same per-row summation order) */
+int mvb_set_spmm_band(int enable);
 
 /* ---- operator hand-off: COO -> CSR (HOST function) ---------------------------------------
  * Replaces the implicit operator format of the reference: model.py:24-32 `scipy_to_torch_sparse`
