@@ -54,6 +54,9 @@ int mvb_set_tensor_cores(int enable);
 /* enable / disable (default) the experimental shared-memory banded SpMM variant (A/B testing;
  * results are bit-identical either way: same per-row summation order) */
 int mvb_set_spmm_band(int enable);
+/* enable (default) / disable the fused multi-step recurrence kernels used when a level fits shared
+ * memory (bit-identical to the step-by-step SpMM launches) */
+int mvb_set_fused_recurrence(int enable);
 
 /* ---- operator hand-off: COO -> CSR (HOST function) ---------------------------------------
  * Replaces the implicit operator format of the reference: model.py:24-32 `scipy_to_torch_sparse`
@@ -98,8 +101,10 @@ int mvb_pool_bwd(int n_in_rows, const int32_t *rowptr_t, const int32_t *colidx_t
  * the recurrence - the reference's output layer applies the 20-vertex operator to the
  * 4998-vertex mesh (models/cheb_VAE.py:288) and is 99.6 % such rows.
  * basis [(K-1), n_active, B, Fin] receives T_1..T_{K-1} of the active prefix (saved for the
- * backward pass; may be NULL when K == 1 or n_active == 0). */
-int mvb_cheb_fwd(int N, int B, int Fin, int Fout, int K, int n_active, const int32_t *rowptr,
+ * backward pass; may be NULL when K == 1 or n_active == 0).
+ * nnz: number of CSR entries (rowptr[N]), or -1 if unknown; lets the fused coarse-level
+ * recurrence kernel copy the operator into shared memory. */
+int mvb_cheb_fwd(int N, int B, int Fin, int Fout, int K, int n_active, int nnz, const int32_t *rowptr,
                  const int32_t *colidx, const float *vals, const float *x, const float *weight,
                  const float *bias, int relu, float *basis, float *y, void *stream);
 
@@ -113,7 +118,7 @@ int mvb_cheb_fwd(int N, int B, int Fin, int Fout, int K, int n_active, const int
  * reduction, no atomics).  workspace: mvb_cheb_bwd_workspace_bytes(...) bytes, 16-byte aligned. */
 size_t mvb_cheb_bwd_workspace_bytes(int N, int B, int Fin, int Fout, int K, int n_active,
                                     int need_dx);
-int mvb_cheb_bwd(int N, int B, int Fin, int Fout, int K, int n_active, const int32_t *rowptr_t,
+int mvb_cheb_bwd(int N, int B, int Fin, int Fout, int K, int n_active, int nnz, const int32_t *rowptr_t,
                  const int32_t *colidx_t, const float *vals_t, const float *x, const float *basis,
                  const float *weight, const float *y_for_relu, const float *dy, float *dx,
                  float *dweight, float *dbias, void *workspace, size_t workspace_bytes,

@@ -39,13 +39,14 @@ SIGNATURES = {
     "mvb_launch_count": (c_int64, []),
     "mvb_set_tensor_cores": (c_int, [c_int]),
     "mvb_set_spmm_band": (c_int, [c_int]),
+    "mvb_set_fused_recurrence": (c_int, [c_int]),
     "mvb_csr_from_coo_host": (c_int, [c_int64, c_int64, c_int64, _vp, _vp, _vp, c_int, _vp, _vp, _vp]),
     "mvb_spmm": (c_int, [c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_float, c_float, c_int64, _vp]),
     "mvb_pool_fwd": (c_int, [c_int, _vp, _vp, _vp, _vp, _vp, c_int64, _vp]),
     "mvb_pool_bwd": (c_int, [c_int, _vp, _vp, _vp, _vp, _vp, c_int64, _vp]),
-    "mvb_cheb_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp, c_int, _vp, _vp, _vp]),
+    "mvb_cheb_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp, c_int, _vp, _vp, _vp]),
     "mvb_cheb_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
-    "mvb_cheb_bwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+    "mvb_cheb_bwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                              _vp, c_size_t, _vp]),
     "mvb_vae_reparam_fwd": (c_int, [c_int64, _vp, _vp, _vp, _vp, _vp]),
     "mvb_vae_reparam_bwd": (c_int, [c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -124,7 +124,7 @@ static void fill_contract(ContractArgs &a) {
     memset(&a, 0, sizeof(a));
 }
 
-extern "C" int mvb_cheb_fwd(int N, int B, int Fin, int Fout, int K, int n_active,
+extern "C" int mvb_cheb_fwd(int N, int B, int Fin, int Fout, int K, int n_active, int nnz,
                             const int32_t *rowptr, const int32_t *colidx, const float *vals,
                             const float *x, const float *weight, const float *bias, int relu,
                             float *basis, float *y, void *stream) {
@@ -137,12 +137,15 @@ extern "C" int mvb_cheb_fwd(int N, int B, int Fin, int Fout, int K, int n_active
     int rc;
     if (n_active > 0) {
         // recurrence: T_1 = L x ; T_k = 2 L T_{k-1} - T_{k-2}     (nn/conv.py:564, 568-569)
-        for (int k = 1; k < K; ++k) {
+        // one fused launch when the level fits shared memory, else one SpMM launch per step
+        rc = (K > 1) ? launch_cheb_recur_fwd(n_active, nnz, K, rowptr, colidx, vals, x, basis, ncols, st) : 1;
+        if (rc < 0) return rc;
+        for (int k = 1; k < K && rc == 0; ++k) {
             float *tk = basis + (int64_t)(k - 1) * plane;
             const float *tkm1 = (k == 1) ? x : basis + (int64_t)(k - 2) * plane;
             const float *tkm2 = (k == 1) ? nullptr : (k == 2 ? x : basis + (int64_t)(k - 3) * plane);
-            rc = launch_spmm(n_active, rowptr, colidx, vals, tkm1, tk, tkm2, nullptr, k == 1 ? 1.f : 2.f, -1.f, ncols, st);
-            if (rc) return rc;
+            int rc2 = launch_spmm(n_active, rowptr, colidx, vals, tkm1, tk, tkm2, nullptr, k == 1 ? 1.f : 2.f, -1.f, ncols, st);
+            if (rc2) return rc2;
         }
         ContractArgs a;
         fill_contract(a);
@@ -190,7 +193,7 @@ extern "C" size_t mvb_cheb_bwd_workspace_bytes(int N, int B, int Fin, int Fout, 
     return bytes;
 }
 
-extern "C" int mvb_cheb_bwd(int N, int B, int Fin, int Fout, int K, int n_active,
+extern "C" int mvb_cheb_bwd(int N, int B, int Fin, int Fout, int K, int n_active, int nnz,
                             const int32_t *rowptr_t, const int32_t *colidx_t, const float *vals_t,
                             const float *x, const float *basis, const float *weight,
                             const float *y_for_relu, const float *dy, float *dx, float *dweight,
@@ -268,7 +271,9 @@ extern "C" int mvb_cheb_bwd(int N, int B, int Fin, int Fout, int K, int n_active
         if (rc) return rc;
         // reverse recurrence, in place on the P planes (G_k overwrites P_k):
         //   G_{K-1} = P_{K-1};  G_k = P_k + 2 L^T G_{k+1} - G_{k+2}  (k >= 1);  dX = P_0 + L^T G_1 - G_2
-        for (int k = K - 2; k >= 0; --k) {
+        int fused = (K > 1) ? launch_cheb_recur_bwd(n_active, nnz, K, rowptr_t, colidx_t, vals_t, P, dx, ncols, st) : 0;
+        if (fused < 0) return fused;
+        for (int k = K - 2; k >= 0 && fused == 0; --k) {
             float *pk = P + (int64_t)k * plane;
             const float *gk1 = P + (int64_t)(k + 1) * plane;
             const float *gk2 = (k + 2 <= K - 1) ? P + (int64_t)(k + 2) * plane : nullptr;

@@ -38,6 +38,12 @@ int launch_spmm(int n_rows, const int32_t *rowptr, const int32_t *colidx, const 
                 const float *x, float *y, const float *z, const float *w, float alpha, float beta,
                 int64_t ncols, cudaStream_t st);
 
+// fused multi-step recurrences for N that fits shared memory: 1 = handled, 0 = use the step kernels
+int launch_cheb_recur_fwd(int N, int nnz, int K, const int32_t *rowptr, const int32_t *colidx, const float *vals,
+                          const float *x, float *basis, int64_t ncols, cudaStream_t st);
+int launch_cheb_recur_bwd(int N, int nnz, int K, const int32_t *rowptr_t, const int32_t *colidx_t, const float *vals_t,
+                          const float *P, float *dx, int64_t ncols, cudaStream_t st);
+
 // Generic small-matrix contraction over the rows of vertex-major activations:
 //   out[p_out][row][j] = act( sum_{p_in,i} in[p_in][row][i] * Wm[p_in*in_w + i][p_out*out_w + j] + bias )
 // in plane 0 = in0, planes 1.. = in_rest + (p-1)*rows*in_w.  Wm is [M, Nn] row-major in global

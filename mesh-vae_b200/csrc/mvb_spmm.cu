@@ -203,6 +203,230 @@ spmm_band_kernel(int n_rows, const int32_t *__restrict__ rowptr, const int32_t *
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused Chebyshev recurrence for the coarse levels.  The recurrence couples all vertices but is
+// independent per (mesh, feature) column, so a CTA that owns a slab of CS4 column quads for ALL N
+// vertices can run every step k = 1..K-1 out of shared memory (two N x slab buffers, T_k written
+// in place over T_{k-2}) with a block barrier between steps instead of a kernel launch: one launch
+// per layer instead of K-1, x read once, each T_k written once.  N <= ~3000 fits (levels 1-4 of the
+// template: 1250 / 313 / 79 / 20 vertices).  The reverse recurrence of the backward pass
+// (G_k = P_k + 2 L^T G_{k+1} - G_{k+2}) is fused the same way.  Summation order per row is the CSR
+// order, as in the step-by-step kernels: results are bit-identical to them.
+// ---------------------------------------------------------------------------------------------
+template <int CS4>
+__device__ __forceinline__ float4 row_gather(const float4 *__restrict__ src, const int32_t *colidx,
+                                             const float *vals, int s, int e, int cl) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int j = s;
+    for (; j + 2 <= e; j += 2) {
+        const int ca = colidx[j], cb = colidx[j + 1];
+        const float va = vals[j], vb = vals[j + 1];
+        const float4 xa = src[ca * CS4 + cl];
+        const float4 xb = src[cb * CS4 + cl];
+        fma4(acc, va, xa);
+        fma4(acc, vb, xb);
+    }
+    if (j < e) fma4(acc, vals[j], src[colidx[j] * CS4 + cl]);
+    return acc;
+}
+
+// copy the CSR of the level into shared memory (after the two activation buffers) when it fits:
+// the per-row pointer chase rowptr -> colidx/vals -> gather then never leaves the SM
+__device__ __forceinline__ void stage_csr(int N, int nnz_smem, const int32_t *__restrict__ rowptr,
+                                          const int32_t *__restrict__ colidx, const float *__restrict__ vals,
+                                          void *dst, const int32_t *&rp, const int32_t *&ci, const float *&va) {
+    if (nnz_smem < 0) {        // does not fit: keep reading the L2-resident arrays
+        rp = rowptr;
+        ci = colidx;
+        va = vals;
+        return;
+    }
+    int32_t *srp = reinterpret_cast<int32_t *>(dst);
+    int32_t *sci = srp + ((N + 1 + 3) & ~3);
+    float *sva = reinterpret_cast<float *>(sci + ((nnz_smem + 3) & ~3));
+    for (int i = threadIdx.x; i <= N; i += blockDim.x) srp[i] = __ldg(rowptr + i);
+    for (int i = threadIdx.x; i < nnz_smem; i += blockDim.x) {
+        sci[i] = __ldg(colidx + i);
+        sva[i] = __ldg(vals + i);
+    }
+    rp = srp;
+    ci = sci;
+    va = sva;
+}
+
+template <int CS4>
+__global__ void __launch_bounds__(512)
+cheb_recur_fwd_kernel(int N, int K, const int32_t *__restrict__ g_rowptr, const int32_t *__restrict__ g_colidx,
+                      const float *__restrict__ g_vals, const float4 *__restrict__ x, float4 *__restrict__ basis,
+                      int nc4, int nnz_smem) {
+    extern __shared__ float4 sbuf[];
+    float4 *cur = sbuf;                  // T_{k-1}
+    float4 *old = sbuf + (size_t)N * CS4;  // T_{k-2}, overwritten by T_k
+    const int32_t *rowptr, *colidx;
+    const float *vals;
+    stage_csr(N, nnz_smem, g_rowptr, g_colidx, g_vals, sbuf + (size_t)2 * N * CS4, rowptr, colidx, vals);
+    const int tid = threadIdx.x;
+    const int cl = tid % CS4, rl = tid / CS4;
+    const int RPP = blockDim.x / CS4;
+    const int c = blockIdx.x * CS4 + cl;
+    const bool col_ok = c < nc4;
+    const int64_t plane = (int64_t)N * nc4;
+    for (int r = rl; r < N; r += RPP) cur[r * CS4 + cl] = col_ok ? __ldg(x + (int64_t)r * nc4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    for (int k = 1; k < K; ++k) {
+        float4 *outp = basis + (int64_t)(k - 1) * plane;
+        for (int r = rl; r < N; r += RPP) {
+            const int s = rowptr[r], e = rowptr[r + 1];
+            const float4 acc = row_gather<CS4>(cur, colidx, vals, s, e, cl);
+            float4 o;
+            if (k == 1) {
+                o = make_float4(1.f * acc.x, 1.f * acc.y, 1.f * acc.z, 1.f * acc.w);
+            } else {
+                const float4 zz = old[r * CS4 + cl];
+                o.x = fmaf(-1.f, zz.x, 2.f * acc.x);
+                o.y = fmaf(-1.f, zz.y, 2.f * acc.y);
+                o.z = fmaf(-1.f, zz.z, 2.f * acc.z);
+                o.w = fmaf(-1.f, zz.w, 2.f * acc.w);
+            }
+            old[r * CS4 + cl] = o;
+            if (col_ok) outp[(int64_t)r * nc4 + c] = o;
+        }
+        __syncthreads();
+        float4 *t = cur;
+        cur = old;
+        old = t;
+    }
+}
+
+// P: K planes [N, nc4] (P_k = dY W_k^T); dx = P_0 + L^T G_1 - G_2 with G_{K-1} = P_{K-1},
+// G_k = P_k + 2 L^T G_{k+1} - G_{k+2}.  CSR arguments are L^T.  Requires K >= 2.
+template <int CS4>
+__global__ void __launch_bounds__(512)
+cheb_recur_bwd_kernel(int N, int K, const int32_t *__restrict__ g_rowptr, const int32_t *__restrict__ g_colidx,
+                      const float *__restrict__ g_vals, const float4 *__restrict__ P, float4 *__restrict__ dx,
+                      int nc4, int nnz_smem) {
+    extern __shared__ float4 sbuf[];
+    float4 *g1 = sbuf;                   // G_{k+1}
+    float4 *g2 = sbuf + (size_t)N * CS4;   // G_{k+2}, overwritten by G_k
+    const int32_t *rowptr, *colidx;
+    const float *vals;
+    stage_csr(N, nnz_smem, g_rowptr, g_colidx, g_vals, sbuf + (size_t)2 * N * CS4, rowptr, colidx, vals);
+    const int tid = threadIdx.x;
+    const int cl = tid % CS4, rl = tid / CS4;
+    const int RPP = blockDim.x / CS4;
+    const int c = blockIdx.x * CS4 + cl;
+    const bool col_ok = c < nc4;
+    const int64_t plane = (int64_t)N * nc4;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = rl; r < N; r += RPP) g1[r * CS4 + cl] = col_ok ? __ldg(P + (int64_t)(K - 1) * plane + (int64_t)r * nc4 + c) : zero;
+    __syncthreads();
+    for (int k = K - 2; k >= 0; --k) {
+        const float4 *pk = P + (int64_t)k * plane;
+        const bool has_g2 = (k + 2 <= K - 1);
+        const float alpha = (k == 0) ? 1.f : 2.f;
+        for (int r = rl; r < N; r += RPP) {
+            const float4 pv = col_ok ? __ldg(pk + (int64_t)r * nc4 + c) : zero;     // issued before the gathers
+            const int s = rowptr[r], e = rowptr[r + 1];
+            const float4 acc = row_gather<CS4>(g1, colidx, vals, s, e, cl);
+            float4 o = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
+            if (has_g2) {
+                const float4 zz = g2[r * CS4 + cl];
+                o.x = fmaf(-1.f, zz.x, o.x);
+                o.y = fmaf(-1.f, zz.y, o.y);
+                o.z = fmaf(-1.f, zz.z, o.z);
+                o.w = fmaf(-1.f, zz.w, o.w);
+            }
+            o.x += pv.x;
+            o.y += pv.y;
+            o.z += pv.z;
+            o.w += pv.w;
+            if (k == 0) {
+                if (col_ok) dx[(int64_t)r * nc4 + c] = o;
+            } else {
+                g2[r * CS4 + cl] = o;
+            }
+        }
+        __syncthreads();
+        float4 *t = g1;
+        g1 = g2;
+        g2 = t;
+    }
+}
+
+static int g_recur_fused = 1;
+void set_recur_fused(int v) { g_recur_fused = v; }
+
+static bool recur_shape(int N, int nnz, int64_t ncols, const void *a, const void *b, int *cs4, size_t *smem, int *nnz_smem) {
+    if (!g_recur_fused || N < 1 || ncols % 4 != 0 || !aligned16(a) || !aligned16(b)) return false;
+    const int nc4 = (int)(ncols / 4);
+    int c = 2;                                   // 32-byte rows: whole sectors, >= 2 CTAs per SM at level 1
+    if (nc4 % 2 != 0) c = 1;
+    size_t bytes = (size_t)2 * N * c * sizeof(float4);
+    if (bytes > 200 * 1024 && c == 2) {
+        c = 1;
+        bytes = (size_t)2 * N * c * sizeof(float4);
+    }
+    if (bytes > 110 * 1024) return false;        // level 0 (4998 vertices) stays on the step-by-step kernels
+    *cs4 = c;
+    *nnz_smem = -1;
+    if (nnz >= 0) {
+        const size_t csr = ((size_t)((N + 1 + 3) & ~3) + 2 * (size_t)((nnz + 3) & ~3)) * 4;
+        if (bytes + csr <= 200 * 1024) {
+            bytes += csr;
+            *nnz_smem = nnz;
+        }
+    }
+    *smem = bytes;
+    return true;
+}
+
+// returns 1 = handled, 0 = shape not supported (caller runs the step-by-step SpMM), < 0 = error
+int launch_cheb_recur_fwd(int N, int nnz, int K, const int32_t *rowptr, const int32_t *colidx, const float *vals,
+                          const float *x, float *basis, int64_t ncols, cudaStream_t st) {
+    int cs4, nnz_smem;
+    size_t smem;
+    if (K < 2 || !recur_shape(N, nnz, ncols, x, basis, &cs4, &smem, &nnz_smem)) return 0;
+    const int nc4 = (int)(ncols / 4);
+    const int grid = (nc4 + cs4 - 1) / cs4;
+    static bool attr1 = false, attr2 = false;
+    cudaError_t e = cudaSuccess;
+    if (cs4 == 2) {
+        if (!attr2) { e = cudaFuncSetAttribute(cheb_recur_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr2 = true; }
+        if (e == cudaSuccess)
+            cheb_recur_fwd_kernel<2><<<grid, 512, smem, st>>>(N, K, rowptr, colidx, vals, (const float4 *)x, (float4 *)basis, nc4, nnz_smem);
+    } else {
+        if (!attr1) { e = cudaFuncSetAttribute(cheb_recur_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr1 = true; }
+        if (e == cudaSuccess)
+            cheb_recur_fwd_kernel<1><<<grid, 512, smem, st>>>(N, K, rowptr, colidx, vals, (const float4 *)x, (float4 *)basis, nc4, nnz_smem);
+    }
+    if (e != cudaSuccess) return set_err(MVB_ECUDA, "cheb_recur_fwd: %s", cudaGetErrorString(e));
+    int rc = check_launch("mvb cheb_recur_fwd");
+    return rc ? rc : 1;
+}
+
+int launch_cheb_recur_bwd(int N, int nnz, int K, const int32_t *rowptr_t, const int32_t *colidx_t, const float *vals_t,
+                          const float *P, float *dx, int64_t ncols, cudaStream_t st) {
+    int cs4, nnz_smem;
+    size_t smem;
+    if (K < 2 || !recur_shape(N, nnz, ncols, P, dx, &cs4, &smem, &nnz_smem)) return 0;
+    const int nc4 = (int)(ncols / 4);
+    const int grid = (nc4 + cs4 - 1) / cs4;
+    static bool attr1 = false, attr2 = false;
+    cudaError_t e = cudaSuccess;
+    if (cs4 == 2) {
+        if (!attr2) { e = cudaFuncSetAttribute(cheb_recur_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr2 = true; }
+        if (e == cudaSuccess)
+            cheb_recur_bwd_kernel<2><<<grid, 512, smem, st>>>(N, K, rowptr_t, colidx_t, vals_t, (const float4 *)P, (float4 *)dx, nc4, nnz_smem);
+    } else {
+        if (!attr1) { e = cudaFuncSetAttribute(cheb_recur_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr1 = true; }
+        if (e == cudaSuccess)
+            cheb_recur_bwd_kernel<1><<<grid, 512, smem, st>>>(N, K, rowptr_t, colidx_t, vals_t, (const float4 *)P, (float4 *)dx, nc4, nnz_smem);
+    }
+    if (e != cudaSuccess) return set_err(MVB_ECUDA, "cheb_recur_bwd: %s", cudaGetErrorString(e));
+    int rc = check_launch("mvb cheb_recur_bwd");
+    return rc ? rc : 1;
+}
+
 static int g_spmm_band = 0;   // experimental: measured SLOWER than the plain kernel (latency-bound phases), see profiles/README.md
 void set_spmm_band(int v) { g_spmm_band = v; }
 
@@ -267,6 +491,11 @@ int launch_spmm(int n_rows, const int32_t *rowptr, const int32_t *colidx, const 
 }
 
 }  // namespace mvb
+
+extern "C" int mvb_set_fused_recurrence(int enable) {
+    mvb::set_recur_fused(enable ? 1 : 0);
+    return 0;
+}
 
 extern "C" int mvb_set_spmm_band(int enable) {
     mvb::set_spmm_band(enable ? 1 : 0);

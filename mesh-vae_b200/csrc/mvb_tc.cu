@@ -249,11 +249,13 @@ tc_rowgemm_kernel(TcRowArgs a) {
     extern __shared__ __align__(1024) char smem_raw[];
     char *smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr bool PACKED = (W == 0);
+    constexpr bool ONE_TILE = (W == 4);              // 4-wide planes: all NP planes share one tile row
     constexpr int Q4 = PACKED ? 1 : W / 4;
-    constexpr int NPL = PACKED ? 1 : NP;
-    constexpr int NV = NPL * Q4;
+    constexpr int NPR = PACKED ? 1 : NP;             // planes prefetched into registers
+    constexpr int NPL = (PACKED || ONE_TILE) ? 1 : NP;   // staged tiles
+    constexpr int NV = NPR * Q4;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wt = PACKED ? a.tile_w : W;
+    const int wt = (PACKED || ONE_TILE) ? a.tile_w : W;
     const int row_bytes = wt * 4;
     const int R = 128;
     const int a_plane = R * row_bytes;
@@ -270,7 +272,7 @@ tc_rowgemm_kernel(TcRowArgs a) {
         mbar_init(bar, 1);
         fence_barrier_init();
     }
-    if (PACKED) {   // padding columns of the packed tiles must be finite zeros in A and B
+    if (PACKED || ONE_TILE) {   // padding columns of the packed tiles must be finite zeros in A and B
         for (int i = tid; i < (2 * a_plane + 2 * b_plane) / 16; i += blockDim.x)
             reinterpret_cast<float4 *>(Ahi)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
@@ -283,7 +285,7 @@ tc_rowgemm_kernel(TcRowArgs a) {
     const uint32_t idesc = make_idesc(128, a.nn16, 0, 0);
     const uint32_t layout_type = (row_bytes == 128) ? 2u : 4u;
     const uint32_t sbo = 8u * row_bytes;
-    const int kslices = PACKED ? (a.in_planes * a.in_w + 7) / 8 : W / 8;
+    const int kslices = (PACKED || ONE_TILE) ? (a.in_planes * a.in_w + 7) / 8 : W / 8;
     const int row = warp * 32 + lane;                 // D row (TMEM lane) this thread reads back
     uint32_t phase = 0;
     const int64_t ntiles = (a.rows + R - 1) / R;
@@ -294,8 +296,8 @@ tc_rowgemm_kernel(TcRowArgs a) {
     auto prefetch = [&](int64_t row0) {
         const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
 #pragma unroll
-        for (int p = 0; p < NPL; ++p) {
-            const float4 *s4 = reinterpret_cast<const float4 *>((p == 0 ? a.in0 : a.in_rest + (int64_t)(p - 1) * a.rows * wt) + row0 * wt);
+        for (int p = 0; p < NPR; ++p) {
+            const float4 *s4 = reinterpret_cast<const float4 *>((p == 0 ? a.in0 : a.in_rest + (int64_t)(p - 1) * a.rows * (Q4 * 4)) + row0 * (Q4 * 4));
 #pragma unroll
             for (int j = 0; j < Q4; ++j) {
                 const int i = j * 128 + tid;
@@ -303,7 +305,7 @@ tc_rowgemm_kernel(TcRowArgs a) {
             }
         }
         if (a.mask) {
-            const float4 *m4 = reinterpret_cast<const float4 *>(a.mask + row0 * wt);
+            const float4 *m4 = reinterpret_cast<const float4 *>(a.mask + row0 * (Q4 * 4));
 #pragma unroll
             for (int j = 0; j < Q4; ++j) {
                 const int i = j * 128 + tid;
@@ -314,7 +316,7 @@ tc_rowgemm_kernel(TcRowArgs a) {
     // registers -> hi/lo swizzled shared tiles
     auto commit = [&]() {
 #pragma unroll
-        for (int p = 0; p < NPL; ++p) {
+        for (int p = 0; p < NPR; ++p) {
 #pragma unroll
             for (int j = 0; j < Q4; ++j) {
                 const int i = j * 128 + tid;
@@ -328,7 +330,8 @@ tc_rowgemm_kernel(TcRowArgs a) {
                 }
                 float4 h, l;
                 split4(v, h, l);
-                const uint32_t off = (uint32_t)(p * a_plane) + swz_off(r, q, row_bytes);
+                const uint32_t off = ONE_TILE ? swz_off(r, p * Q4 + q, row_bytes)
+                                              : (uint32_t)(p * a_plane) + swz_off(r, q, row_bytes);
                 *reinterpret_cast<float4 *>(Ahi + off) = h;
                 *reinterpret_cast<float4 *>(Alo + off) = l;
             }
@@ -426,7 +429,7 @@ int launch_contract_tc(const ContractArgs &a, cudaStream_t st) {
     const int nn_true = a.out_planes * a.out_w;
     const int nn16 = (nn_true + 15) & ~15;
     if (nn16 > 256 || a.rows < 128) return 0;
-    const bool planar = (w == 16 && a.in_planes <= 6) || (w == 32 && a.in_planes <= 3);
+    const bool planar = (w == 16 && a.in_planes <= 6) || (w == 32 && a.in_planes <= 3) || (w == 4 && a.in_planes <= 8);
     const bool vec_ok = aligned16(a.in0) && (a.in_planes == 1 || aligned16(a.in_rest)) && (!a.mask || aligned16(a.mask));
     // the scalar-staged packed layout (narrow planes, Fin = 3 / Fout = 3) is functional but its index
     // arithmetic makes it slower than the FFMA kernel: opt-in only (MVB_TC_PACKED=1) until those layers
@@ -452,8 +455,8 @@ int launch_contract_tc(const ContractArgs &a, cudaStream_t st) {
     t.out_w = a.out_w;
     t.out = a.out;
     t.tmem_cols = pow2_cols(nn16);
-    t.tile_w = packed ? (Kd <= 16 ? 16 : 32) : w;
-    t.tile_planes = packed ? 1 : a.in_planes;
+    t.tile_w = (packed || w == 4) ? (Kd <= 16 ? 16 : 32) : w;
+    t.tile_planes = (packed || w == 4) ? 1 : a.in_planes;
     const size_t smem = 1024 + (size_t)t.tile_planes * (2 * 128 * t.tile_w * 4 + 2 * nn16 * t.tile_w * 4) + 64;
     if (smem > 200 * 1024) return 0;
     const int64_t ntiles = (a.rows + 127) / 128;
@@ -467,6 +470,17 @@ int launch_contract_tc(const ContractArgs &a, cudaStream_t st) {
     int rc;
     if (packed) {
         rc = launch_rowgemm_t<0, 1>(t, (unsigned)grid, smem, st);
+    } else if (w == 4) {
+        switch (a.in_planes) {
+            case 1: rc = launch_rowgemm_t<4, 1>(t, (unsigned)grid, smem, st); break;
+            case 2: rc = launch_rowgemm_t<4, 2>(t, (unsigned)grid, smem, st); break;
+            case 3: rc = launch_rowgemm_t<4, 3>(t, (unsigned)grid, smem, st); break;
+            case 4: rc = launch_rowgemm_t<4, 4>(t, (unsigned)grid, smem, st); break;
+            case 5: rc = launch_rowgemm_t<4, 5>(t, (unsigned)grid, smem, st); break;
+            case 6: rc = launch_rowgemm_t<4, 6>(t, (unsigned)grid, smem, st); break;
+            case 7: rc = launch_rowgemm_t<4, 7>(t, (unsigned)grid, smem, st); break;
+            default: rc = launch_rowgemm_t<4, 8>(t, (unsigned)grid, smem, st); break;
+        }
     } else if (w == 16) {
         switch (a.in_planes) {
             case 1: rc = launch_rowgemm_t<16, 1>(t, (unsigned)grid, smem, st); break;
@@ -515,13 +529,17 @@ __device__ __forceinline__ uint32_t b32_off(int r, int col, int blk) {
     return (uint32_t)(b * blk + r * 128 + (((c >> 1) ^ (r & 3)) << 5) + ((c & 1) << 4) + ((col & 3) << 2));
 }
 
-template <int NP16>   // > 0: in_w == 16, Fout in {16,32}, vector staging with register prefetch; 0: generic scalar staging
+// NPF > 0: planes of width 4*Q4 floats (4 or 16), Fout % 4 == 0: vector staging with register prefetch;
+// NPF == 0: generic scalar staging
+template <int NPF, int Q4>
 __global__ void __launch_bounds__(128)
 tc_wgrad_kernel(TcWgradArgs a) {
     extern __shared__ __align__(1024) char smem_raw[];
     char *smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    constexpr bool FAST = NP16 > 0;
-    constexpr int NPV = FAST ? NP16 : 1;
+    constexpr bool FAST = NPF > 0;
+    constexpr int NPV = FAST ? NPF : 1;
+    constexpr int W = 4 * Q4;                          // plane width (FAST only)
+    constexpr int LPT = (64 * Q4 + 127) / 128;         // float4 loads per thread per plane per 64-row tile
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int R = 64;                                  // activation rows (= UMMA K extent) per tile
     const int blk = R * 128;                           // one 32-feature block of the T tile: 8 KB
@@ -553,17 +571,17 @@ tc_wgrad_kernel(TcWgradArgs a) {
     const int64_t ntiles = (a.rows + R - 1) / R;
     const int dq4 = a.n_out >> 2;                      // float4 chunks per dY row (FAST only)
 
-    float4 pre[2 * NPV];
+    float4 pre[LPT * NPV];
     float4 pred[4], prem[4];
     auto prefetch = [&](int64_t row0) {
         const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
 #pragma unroll
         for (int p = 0; p < NPV; ++p) {
-            const float4 *s4 = reinterpret_cast<const float4 *>((p == 0 ? a.in0 : a.in_rest + (int64_t)(p - 1) * a.rows * 16) + row0 * 16);
+            const float4 *s4 = reinterpret_cast<const float4 *>((p == 0 ? a.in0 : a.in_rest + (int64_t)(p - 1) * a.rows * W) + row0 * W);
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < LPT; ++j) {
                 const int i = j * 128 + tid;
-                pre[p * 2 + j] = ((i >> 2) < nr) ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                pre[p * LPT + j] = (i < 64 * Q4 && (i / Q4) < nr) ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         const float4 *d4 = reinterpret_cast<const float4 *>(a.dy + row0 * a.n_out);
@@ -580,14 +598,16 @@ tc_wgrad_kernel(TcWgradArgs a) {
 #pragma unroll
         for (int p = 0; p < NPV; ++p) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < LPT; ++j) {
                 const int i = j * 128 + tid;
-                const int r = i >> 2, q = i & 3;
-                float4 h, l;
-                split4(pre[p * 2 + j], h, l);
-                const uint32_t off = b32_off(r, p * 16 + q * 4, blk);
-                *reinterpret_cast<float4 *>(Thi + off) = h;
-                *reinterpret_cast<float4 *>(Tlo + off) = l;
+                if (i < 64 * Q4) {
+                    const int r = i / Q4, q = i - r * Q4;
+                    float4 h, l;
+                    split4(pre[p * LPT + j], h, l);
+                    const uint32_t off = b32_off(r, p * W + q * 4, blk);
+                    *reinterpret_cast<float4 *>(Thi + off) = h;
+                    *reinterpret_cast<float4 *>(Tlo + off) = l;
+                }
             }
         }
 #pragma unroll
@@ -713,15 +733,15 @@ tc_wgrad_kernel(TcWgradArgs a) {
     if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
 }
 
-template <int NP16>
+template <int NPF, int Q4>
 static int launch_wgrad_t(const TcWgradArgs &t, unsigned grid, size_t smem, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<NP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<NPF, Q4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return set_err(MVB_ECUDA, "tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    tc_wgrad_kernel<NP16><<<grid, 128, smem, st>>>(t);
+    tc_wgrad_kernel<NPF, Q4><<<grid, 128, smem, st>>>(t);
     return check_launch("mvb tc_wgrad");
 }
 
@@ -730,7 +750,7 @@ int launch_wgrad_tc(const WgradArgs &a, int has_bias, int M4, int N4, int *npart
     if (!g_tc_enabled) return 0;
     const int M = a.in_planes * a.in_w;
     if (M + (has_bias ? 1 : 0) > 128 || M4 > 128 || a.n_out > 32 || a.rows < 256) return 0;
-    const bool fast = a.in_w == 16 && a.in_planes <= 6 && (a.n_out == 16 || a.n_out == 32) && aligned16(a.in0) &&
+    const bool fast = ((a.in_w == 16 && a.in_planes <= 6) || (a.in_w == 4 && a.in_planes <= 8)) && (a.n_out % 4 == 0) && aligned16(a.in0) &&
                       (a.in_planes == 1 || aligned16(a.in_rest)) && aligned16(a.dy) && (!a.mask || aligned16(a.mask));
     static const bool allow_generic = getenv("MVB_TC_PACKED") != nullptr;
     if (!fast && !allow_generic) return 0;
@@ -756,15 +776,26 @@ int launch_wgrad_tc(const WgradArgs &a, int has_bias, int M4, int N4, int *npart
     if ((size_t)grid * M4 * N4 * sizeof(float) > a.partial_bytes) return set_err(MVB_EWORKSPACE, "tc_wgrad: workspace too small");
     int rc;
     if (!fast) {
-        rc = launch_wgrad_t<0>(t, (unsigned)grid, smem, st);
+        rc = launch_wgrad_t<0, 1>(t, (unsigned)grid, smem, st);
+    } else if (a.in_w == 16) {
+        switch (a.in_planes) {
+            case 1: rc = launch_wgrad_t<1, 4>(t, (unsigned)grid, smem, st); break;
+            case 2: rc = launch_wgrad_t<2, 4>(t, (unsigned)grid, smem, st); break;
+            case 3: rc = launch_wgrad_t<3, 4>(t, (unsigned)grid, smem, st); break;
+            case 4: rc = launch_wgrad_t<4, 4>(t, (unsigned)grid, smem, st); break;
+            case 5: rc = launch_wgrad_t<5, 4>(t, (unsigned)grid, smem, st); break;
+            default: rc = launch_wgrad_t<6, 4>(t, (unsigned)grid, smem, st); break;
+        }
     } else {
         switch (a.in_planes) {
-            case 1: rc = launch_wgrad_t<1>(t, (unsigned)grid, smem, st); break;
-            case 2: rc = launch_wgrad_t<2>(t, (unsigned)grid, smem, st); break;
-            case 3: rc = launch_wgrad_t<3>(t, (unsigned)grid, smem, st); break;
-            case 4: rc = launch_wgrad_t<4>(t, (unsigned)grid, smem, st); break;
-            case 5: rc = launch_wgrad_t<5>(t, (unsigned)grid, smem, st); break;
-            default: rc = launch_wgrad_t<6>(t, (unsigned)grid, smem, st); break;
+            case 1: rc = launch_wgrad_t<1, 1>(t, (unsigned)grid, smem, st); break;
+            case 2: rc = launch_wgrad_t<2, 1>(t, (unsigned)grid, smem, st); break;
+            case 3: rc = launch_wgrad_t<3, 1>(t, (unsigned)grid, smem, st); break;
+            case 4: rc = launch_wgrad_t<4, 1>(t, (unsigned)grid, smem, st); break;
+            case 5: rc = launch_wgrad_t<5, 1>(t, (unsigned)grid, smem, st); break;
+            case 6: rc = launch_wgrad_t<6, 1>(t, (unsigned)grid, smem, st); break;
+            case 7: rc = launch_wgrad_t<7, 1>(t, (unsigned)grid, smem, st); break;
+            default: rc = launch_wgrad_t<8, 1>(t, (unsigned)grid, smem, st); break;
         }
     }
     if (rc) return rc;

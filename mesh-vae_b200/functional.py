@@ -52,7 +52,7 @@ class _ChebConvFn(torch.autograd.Function):
         na = op.n_active
         basis = torch.empty((max(k - 1, 0), na, b, fin), device=x_vm.device, dtype=torch.float32)
         y = torch.empty((n, b, fout), device=x_vm.device, dtype=torch.float32)
-        check(lib.mvb_cheb_fwd(n, b, fin, fout, k, na, ptr(op.rowptr), ptr(op.colidx), ptr(op.vals), ptr(x_vm), ptr(w),
+        check(lib.mvb_cheb_fwd(n, b, fin, fout, k, na, op.nnz, ptr(op.rowptr), ptr(op.colidx), ptr(op.vals), ptr(x_vm), ptr(w),
                                ptr(bb), 1 if relu else 0, ptr(basis) if basis.numel() else None, ptr(y), stream_ptr()),
               "mvb_cheb_fwd")
         ctx.op, ctx.relu, ctx.has_bias = op, relu, bias is not None
@@ -73,16 +73,32 @@ class _ChebConvFn(torch.autograd.Function):
         na = op.n_active
         ws_bytes = lib.mvb_cheb_bwd_workspace_bytes(n, b, fin, fout, k, na, 1 if need_dx else 0)
         ws = torch.empty(ws_bytes, device=w.device, dtype=torch.uint8)
-        check(lib.mvb_cheb_bwd(n, b, fin, fout, k, na, ptr(op.rowptr_t), ptr(op.colidx_t), ptr(op.vals_t), ptr(x_vm),
+        check(lib.mvb_cheb_bwd(n, b, fin, fout, k, na, op.nnz, ptr(op.rowptr_t), ptr(op.colidx_t), ptr(op.vals_t), ptr(x_vm),
                                ptr(basis) if basis.numel() else None, ptr(w), ptr(y) if ctx.relu else None, ptr(dy), ptr(dx),
                                ptr(dw), ptr(db), ptr(ws), ws_bytes, stream_ptr()), "mvb_cheb_bwd")
         return dx, dw, db, None, None
 
 
 def cheb_conv(x_vm: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], op: MeshOperator,
-              relu: bool = False) -> torch.Tensor:
-    """x_vm [N,B,Fin] -> [N,B,Fout] (vertex-major in, vertex-major out)."""
-    return _ChebConvFn.apply(x_vm, weight, bias, op, relu)
+              relu: bool = False, pad_to_quads: bool = True) -> torch.Tensor:
+    """x_vm [N,B,Fin] -> [N,B,Fout] (vertex-major in, vertex-major out).
+
+    Feature widths that are not a multiple of 4 (the 3-channel mesh coordinates at the encoder
+    input and the decoder output) are zero-padded to the next multiple of 4 around the kernel call,
+    so that every plane is made of whole 16-byte quads: the SpMM takes its vector path and the
+    contractions run on the tcgen05 kernels instead of the scalar FFMA fallback.  Zero features /
+    zero weight columns do not change any result; the padding ops are differentiable torch glue
+    (autograd slices the padded weight gradient back)."""
+    fin, fout = x_vm.shape[2], weight.shape[2]
+    pin, pout = (-fin) % 4, (-fout) % 4
+    if not pad_to_quads or (pin == 0 and pout == 0):
+        return _ChebConvFn.apply(x_vm, weight, bias, op, relu)
+    if pin:
+        x_vm = torch.nn.functional.pad(x_vm, (0, pin))
+    w = torch.nn.functional.pad(weight, (0, pout, 0, pin))
+    b = bias if (bias is None or pout == 0) else torch.nn.functional.pad(bias, (0, pout))
+    y = _ChebConvFn.apply(x_vm, w, b, op, relu)
+    return y[..., :fout] if pout else y
 
 
 class _PoolFn(torch.autograd.Function):

@@ -25,7 +25,7 @@ for tc in (0, 1):
         dx = torch.zeros_like(x); dw = torch.zeros_like(w); db = torch.zeros(Fout, device=dev)
         nb = lib.mvb_cheb_bwd_workspace_bytes(N, B, Fin, Fout, K, N, 1)
         ws = torch.zeros(nb, device=dev, dtype=torch.uint8)
-        L.check(lib.mvb_cheb_bwd(N, B, Fin, Fout, K, N, L.ptr(rowptr), L.ptr(colidx), L.ptr(vals), L.ptr(x), L.ptr(basis),
+        L.check(lib.mvb_cheb_bwd(N, B, Fin, Fout, K, N, 0, L.ptr(rowptr), L.ptr(colidx), L.ptr(vals), L.ptr(x), L.ptr(basis),
                                  L.ptr(w), None, L.ptr(dy), L.ptr(dx), L.ptr(dw), L.ptr(db), L.ptr(ws), nb, L.stream_ptr()))
         torch.cuda.synchronize()
         e = (dx.double() - ref_dx).abs()

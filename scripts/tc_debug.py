@@ -18,7 +18,7 @@ for tc in (0, 1):
     db = torch.full((Fout,), -7.0, device=dev)
     nb = lib.mvb_cheb_bwd_workspace_bytes(N, B, Fin, Fout, K, N, 0)
     ws = torch.zeros(nb, device=dev, dtype=torch.uint8)
-    L.check(lib.mvb_cheb_bwd(N, B, Fin, Fout, K, N, None, None, None, L.ptr(x), None, L.ptr(w), None, L.ptr(dy), None,
+    L.check(lib.mvb_cheb_bwd(N, B, Fin, Fout, K, N, 0, None, None, None, L.ptr(x), None, L.ptr(w), None, L.ptr(dy), None,
                              L.ptr(dw), L.ptr(db), L.ptr(ws), nb, L.stream_ptr()))
     torch.cuda.synchronize()
     print("tc", tc, "db", db.cpu())
