@@ -57,6 +57,10 @@ int mvb_set_spmm_band(int enable);
 /* enable (default) / disable the fused multi-step recurrence kernels used when a level fits shared
  * memory (bit-identical to the step-by-step SpMM launches) */
 int mvb_set_fused_recurrence(int enable);
+/* enable (default) / disable running the weight-gradient branch of mvb_cheb_bwd on an internal
+ * side stream, forked from and joined back into `stream` with events (capturable: the two
+ * branches become parallel branches of a CUDA graph).  Returns the previous setting. */
+int mvb_set_overlap(int enable);
 
 /* ---- operator hand-off: COO -> CSR (HOST function) ---------------------------------------
  * Replaces the implicit operator format of the reference: model.py:24-32 `scipy_to_torch_sparse`

@@ -46,6 +46,8 @@ extern "C" const char *mvb_last_error(void) { return err_buf(); }
 namespace mvb { long long launch_count(); }
 extern "C" int64_t mvb_launch_count(void) { return (int64_t)mvb::launch_count(); }
 
+extern "C" int mvb_set_overlap(int enable);
+
 extern "C" int mvb_device_cc(void) {
     int dev = 0, major = 0, minor = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -186,6 +188,30 @@ extern "C" int mvb_cheb_fwd(int N, int B, int Fin, int Fout, int K, int n_active
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// per-host-thread side stream + fork/join events for intra-call concurrency
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    bool ok = false;
+};
+static int g_overlap = 1;
+static SideStream *side_stream() {
+    static thread_local SideStream s;
+    static thread_local bool tried = false;
+    if (!tried) {
+        tried = true;
+        // creation is not a stream operation: legal while another stream is capturing only in relaxed
+        // mode, so it is done during the (uncaptured) warm-up calls; if it fails we simply do not fork
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess)
+            s.ok = true;
+        else
+            cudaGetLastError();
+    }
+    return s.ok ? &s : nullptr;
+}
+
 extern "C" size_t mvb_cheb_bwd_workspace_bytes(int N, int B, int Fin, int Fout, int K, int n_active, int need_dx) {
     size_t bytes = align_up(wgrad_partial_bytes(K * Fin, Fout), 256);
     if (n_active < N) bytes += align_up(wgrad_partial_bytes(Fin, Fout), 256);
@@ -219,6 +245,33 @@ extern "C" int mvb_cheb_bwd(int N, int B, int Fin, int Fout, int K, int n_active
     const int has_bias = dbias != nullptr;
     int rc, nA = 0, m4A = 0, nB = 0, m4B = 0;
 
+    // The weight-gradient branch (partials + ordered finalize) and the input-gradient branch
+    // (P_k, reverse recurrence) are independent: fork the former onto a side stream so that the two
+    // overlap (and become parallel branches of a captured CUDA graph), join before returning.
+    cudaStream_t wst = st;
+    SideStream *side = nullptr;
+    if (dx && g_overlap) {
+        side = side_stream();
+        if (side) {
+            if (cudaEventRecord(side->fork, st) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork, 0) != cudaSuccess) {
+                cudaGetLastError();
+                side = nullptr;
+            } else {
+                wst = side->stream;
+            }
+        }
+    }
+    struct Join {   // the side stream must rejoin on every exit path (a captured graph must not end forked)
+        SideStream *s;
+        cudaStream_t main;
+        ~Join() {
+            if (s) {
+                cudaEventRecord(s->join, s->stream);
+                cudaStreamWaitEvent(main, s->join, 0);
+            }
+        }
+    } join_guard{side, st};
+
     // dW_k = T_k^T dY, db = 1^T dY over the active prefix ...
     WgradArgs wa;
     memset(&wa, 0, sizeof(wa));
@@ -232,7 +285,7 @@ extern "C" int mvb_cheb_bwd(int N, int B, int Fin, int Fout, int K, int n_active
     wa.n_out = Fout;
     wa.partials = partA;
     wa.partial_bytes = partA_bytes;
-    rc = launch_wgrad_partials(wa, has_bias, &nA, &m4A, st);
+    rc = launch_wgrad_partials(wa, has_bias, &nA, &m4A, wst);
     if (rc) return rc;
     // ... plus S = x^T dY over the empty rows (dW_k += c_k S)
     if (rows_in > 0) {
@@ -247,10 +300,10 @@ extern "C" int mvb_cheb_bwd(int N, int B, int Fin, int Fout, int K, int n_active
         wb.n_out = Fout;
         wb.partials = partB;
         wb.partial_bytes = partB_bytes;
-        rc = launch_wgrad_partials(wb, has_bias, &nB, &m4B, st);
+        rc = launch_wgrad_partials(wb, has_bias, &nB, &m4B, wst);
         if (rc) return rc;
     }
-    rc = launch_wgrad_finalize(partA, nA, m4A, partB, nB, m4B, Fin, K * Fin, Fout, dweight, dbias, st);
+    rc = launch_wgrad_finalize(partA, nA, m4A, partB, nB, m4B, Fin, K * Fin, Fout, dweight, dbias, wst);
     if (rc || !dx) return rc;
 
     if (rows_act > 0) {
@@ -305,4 +358,10 @@ extern "C" int mvb_cheb_bwd(int N, int B, int Fin, int Fout, int K, int n_active
         if (rc) return rc;
     }
     return MVB_OK;
+}
+
+extern "C" int mvb_set_overlap(int enable) {
+    const int old = g_overlap;
+    g_overlap = enable ? 1 : 0;
+    return old;
 }
