@@ -186,7 +186,7 @@ def spmm_roofline(mvb, A, nn_, batch, dev, peaks, reps=30):
         flush.fill_(float(i))
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record(st)
-        L.check(L.lib.mvb_spmm(n, L.ptr(op.rowptr), L.ptr(op.colidx), L.ptr(op.vals), L.ptr(x), L.ptr(y), L.ptr(z),
+        L.check(L.lib.mvb_spmm(n, n, L.ptr(op.rowptr), L.ptr(op.colidx), L.ptr(op.vals), L.ptr(x), L.ptr(y), L.ptr(z),
                                None, 2.0, -1.0, batch * f, L.stream_ptr()))
         e.record(st)
         e.synchronize()

@@ -78,19 +78,19 @@ int mvb_csr_from_coo_host(int64_t n_out_rows, int64_t n_out_cols, int64_t nnz,
 /* ---- A1: sparse propagate  (nn/conv.py:242-331 MessagePassing.propagate = index_select
  *          :199-200, message :579-581, scatter-add :363-364) -------------------------------
  * y[r, :] = alpha * sum_{j in row r} vals[j] * x[colidx[j], :]  +  beta * z[r, :]  +  w[r, :]
- * x: [n_src_rows, ncols], y/z/w: [n_rows, ncols]; z and w may be NULL; y may alias z or w
+ * x: [n_src_rows, ncols] (every colidx < n_src_rows), y/z/w: [n_rows, ncols]; z and w may be NULL; y may alias z or w
  * (each row only reads its own z/w row) but must not alias x.  The 16-byte vector path is used
  * when ncols % 4 == 0 and all pointers are 16-byte aligned, else a scalar path. */
-int mvb_spmm(int n_rows, const int32_t *rowptr, const int32_t *colidx, const float *vals,
+int mvb_spmm(int n_rows, int n_src_rows, const int32_t *rowptr, const int32_t *colidx, const float *vals,
              const float *x, float *y, const float *z, const float *w, float alpha, float beta,
              int64_t ncols, void *stream);
 
 /* ---- A5/A6: mesh pooling  (nn/pool.py:13-23 SurfacePool.forward; models/cheb_cls.py:22-27 Pool)
  * forward : y[M, B*F] = P x[N, B*F]      with CSR(P)   (n_out_rows = M)
  * backward: dx[N, B*F] = P^T dy[M, B*F]  with CSR(P^T) (n_out_rows = N)  - no atomics. */
-int mvb_pool_fwd(int n_out_rows, const int32_t *rowptr, const int32_t *colidx, const float *vals,
+int mvb_pool_fwd(int n_out_rows, int n_in_rows, const int32_t *rowptr, const int32_t *colidx, const float *vals,
                  const float *x, float *y, int64_t ncols, void *stream);
-int mvb_pool_bwd(int n_in_rows, const int32_t *rowptr_t, const int32_t *colidx_t,
+int mvb_pool_bwd(int n_in_rows, int n_out_rows, const int32_t *rowptr_t, const int32_t *colidx_t,
                  const float *vals_t, const float *dy, float *dx, int64_t ncols, void *stream);
 
 /* ---- A3: Chebyshev convolution forward  (nn/conv.py:557-577 ChebConv_batch.forward; the PyG

@@ -42,9 +42,9 @@ SIGNATURES = {
     "mvb_set_fused_recurrence": (c_int, [c_int]),
     "mvb_set_overlap": (c_int, [c_int]),
     "mvb_csr_from_coo_host": (c_int, [c_int64, c_int64, c_int64, _vp, _vp, _vp, c_int, _vp, _vp, _vp]),
-    "mvb_spmm": (c_int, [c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_float, c_float, c_int64, _vp]),
-    "mvb_pool_fwd": (c_int, [c_int, _vp, _vp, _vp, _vp, _vp, c_int64, _vp]),
-    "mvb_pool_bwd": (c_int, [c_int, _vp, _vp, _vp, _vp, _vp, c_int64, _vp]),
+    "mvb_spmm": (c_int, [c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_float, c_float, c_int64, _vp]),
+    "mvb_pool_fwd": (c_int, [c_int, c_int, _vp, _vp, _vp, _vp, _vp, c_int64, _vp]),
+    "mvb_pool_bwd": (c_int, [c_int, c_int, _vp, _vp, _vp, _vp, _vp, c_int64, _vp]),
     "mvb_cheb_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp, c_int, _vp, _vp, _vp]),
     "mvb_cheb_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "mvb_cheb_bwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

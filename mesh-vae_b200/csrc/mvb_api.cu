@@ -92,25 +92,25 @@ extern "C" int mvb_csr_from_coo_host(int64_t n_out_rows, int64_t n_out_cols, int
 // ---------------------------------------------------------------------------------------------
 // SpMM / pooling
 // ---------------------------------------------------------------------------------------------
-extern "C" int mvb_spmm(int n_rows, const int32_t *rowptr, const int32_t *colidx, const float *vals,
+extern "C" int mvb_spmm(int n_rows, int n_src_rows, const int32_t *rowptr, const int32_t *colidx, const float *vals,
                         const float *x, float *y, const float *z, const float *w, float alpha,
                         float beta, int64_t ncols, void *stream) {
     MVB_REQUIRE(n_rows >= 0 && ncols >= 0, "spmm: negative size");
     MVB_REQUIRE(rowptr && x && y, "spmm: null pointer");
     MVB_REQUIRE(x != y, "spmm: y must not alias x");
-    return launch_spmm(n_rows, rowptr, colidx, vals, x, y, z, w, alpha, beta, ncols, (cudaStream_t)stream);
+    return launch_spmm(n_rows, n_src_rows, rowptr, colidx, vals, x, y, z, w, alpha, beta, ncols, (cudaStream_t)stream);
 }
 
-extern "C" int mvb_pool_fwd(int n_out_rows, const int32_t *rowptr, const int32_t *colidx,
+extern "C" int mvb_pool_fwd(int n_out_rows, int n_in_rows, const int32_t *rowptr, const int32_t *colidx,
                             const float *vals, const float *x, float *y, int64_t ncols, void *stream) {
     MVB_REQUIRE(n_out_rows >= 0 && ncols >= 0 && rowptr && x && y, "pool_fwd: bad arguments");
-    return launch_spmm(n_out_rows, rowptr, colidx, vals, x, y, nullptr, nullptr, 1.f, 0.f, ncols, (cudaStream_t)stream);
+    return launch_spmm(n_out_rows, n_in_rows, rowptr, colidx, vals, x, y, nullptr, nullptr, 1.f, 0.f, ncols, (cudaStream_t)stream);
 }
 
-extern "C" int mvb_pool_bwd(int n_in_rows, const int32_t *rowptr_t, const int32_t *colidx_t,
+extern "C" int mvb_pool_bwd(int n_in_rows, int n_out_rows, const int32_t *rowptr_t, const int32_t *colidx_t,
                             const float *vals_t, const float *dy, float *dx, int64_t ncols, void *stream) {
     MVB_REQUIRE(n_in_rows >= 0 && ncols >= 0 && rowptr_t && dy && dx, "pool_bwd: bad arguments");
-    return launch_spmm(n_in_rows, rowptr_t, colidx_t, vals_t, dy, dx, nullptr, nullptr, 1.f, 0.f, ncols, (cudaStream_t)stream);
+    return launch_spmm(n_in_rows, n_out_rows, rowptr_t, colidx_t, vals_t, dy, dx, nullptr, nullptr, 1.f, 0.f, ncols, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -146,7 +146,7 @@ extern "C" int mvb_cheb_fwd(int N, int B, int Fin, int Fout, int K, int n_active
             float *tk = basis + (int64_t)(k - 1) * plane;
             const float *tkm1 = (k == 1) ? x : basis + (int64_t)(k - 2) * plane;
             const float *tkm2 = (k == 1) ? nullptr : (k == 2 ? x : basis + (int64_t)(k - 3) * plane);
-            int rc2 = launch_spmm(n_active, rowptr, colidx, vals, tkm1, tk, tkm2, nullptr, k == 1 ? 1.f : 2.f, -1.f, ncols, st);
+            int rc2 = launch_spmm(n_active, n_active, rowptr, colidx, vals, tkm1, tk, tkm2, nullptr, k == 1 ? 1.f : 2.f, -1.f, ncols, st);
             if (rc2) return rc2;
         }
         ContractArgs a;
@@ -331,7 +331,7 @@ extern "C" int mvb_cheb_bwd(int N, int B, int Fin, int Fout, int K, int n_active
             const float *gk1 = P + (int64_t)(k + 1) * plane;
             const float *gk2 = (k + 2 <= K - 1) ? P + (int64_t)(k + 2) * plane : nullptr;
             float *dst = (k == 0) ? dx : pk;
-            rc = launch_spmm(n_active, rowptr_t, colidx_t, vals_t, gk1, dst, gk2, pk, k == 0 ? 1.f : 2.f, -1.f, ncols, st);
+            rc = launch_spmm(n_active, n_active, rowptr_t, colidx_t, vals_t, gk1, dst, gk2, pk, k == 0 ? 1.f : 2.f, -1.f, ncols, st);
             if (rc) return rc;
         }
         if (K == 1) {

@@ -34,7 +34,7 @@ inline int check_launch(const char *what) {
 int num_sms();  // cached multiprocessor count of the current device (148 on B200)
 
 // ---- launchers implemented in the .cu files ------------------------------------------------
-int launch_spmm(int n_rows, const int32_t *rowptr, const int32_t *colidx, const float *vals,
+int launch_spmm(int n_rows, int n_src_rows, const int32_t *rowptr, const int32_t *colidx, const float *vals,
                 const float *x, float *y, const float *z, const float *w, float alpha, float beta,
                 int64_t ncols, cudaStream_t st);
 

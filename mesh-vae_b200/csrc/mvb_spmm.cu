@@ -22,17 +22,24 @@ __device__ __forceinline__ void fma4(float4 &acc, float v, const float4 &x) {
     acc.w = fmaf(v, x.w, acc.w);
 }
 
-template <bool HAS_Z, bool HAS_W>
+// 2-D thread mapping: threadIdx.x walks the column quads of a row (coalesced), threadIdx.y the rows
+// of the block - no integer division anywhere; IdxT = uint32_t whenever the tensors have fewer than
+// 2^31 quads (always, in practice), so that address arithmetic is a single 32-bit multiply-add.
+// (The first version computed row = idx / nc4 in 64-bit arithmetic per thread: ncu showed 226
+// instructions per thread and an issue-bound kernel - see profiles/README.md.)
+template <bool HAS_Z, bool HAS_W, typename IdxT>
 __global__ void __launch_bounds__(256)
 spmm_v4_kernel(int n_rows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
                const float *__restrict__ vals, const float4 *__restrict__ x, float4 *y,
                const float4 *z, const float4 *w, float alpha, float beta, int nc4) {
-    const int64_t total = (int64_t)n_rows * nc4;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int r = (int)(idx / nc4);
-        const int c = (int)(idx - (int64_t)r * nc4);
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nc4) return;
+    for (int r = blockIdx.y * blockDim.y + threadIdx.y; r < n_rows; r += gridDim.y * blockDim.y) {
         const int s = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
+        const IdxT idx = (IdxT)r * (IdxT)nc4 + (IdxT)c;
+        float4 zz = make_float4(0.f, 0.f, 0.f, 0.f), ww = zz;
+        if (HAS_Z) zz = z[idx];                      // independent of the gathers: issue first
+        if (HAS_W) ww = w[idx];
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         int j = s;
         // 4 independent gathers in flight per thread (mean degree is 6)
@@ -41,10 +48,10 @@ spmm_v4_kernel(int n_rows, const int32_t *__restrict__ rowptr, const int32_t *__
             const int c2 = __ldg(colidx + j + 2), c3 = __ldg(colidx + j + 3);
             const float v0 = __ldg(vals + j), v1 = __ldg(vals + j + 1);
             const float v2 = __ldg(vals + j + 2), v3 = __ldg(vals + j + 3);
-            const float4 x0 = ldg4(x + (int64_t)c0 * nc4 + c);
-            const float4 x1 = ldg4(x + (int64_t)c1 * nc4 + c);
-            const float4 x2 = ldg4(x + (int64_t)c2 * nc4 + c);
-            const float4 x3 = ldg4(x + (int64_t)c3 * nc4 + c);
+            const float4 x0 = ldg4(x + ((IdxT)c0 * (IdxT)nc4 + (IdxT)c));
+            const float4 x1 = ldg4(x + ((IdxT)c1 * (IdxT)nc4 + (IdxT)c));
+            const float4 x2 = ldg4(x + ((IdxT)c2 * (IdxT)nc4 + (IdxT)c));
+            const float4 x3 = ldg4(x + ((IdxT)c3 * (IdxT)nc4 + (IdxT)c));
             fma4(acc, v0, x0);
             fma4(acc, v1, x1);
             fma4(acc, v2, x2);
@@ -53,18 +60,16 @@ spmm_v4_kernel(int n_rows, const int32_t *__restrict__ rowptr, const int32_t *__
         for (; j < e; ++j) {
             const int c0 = __ldg(colidx + j);
             const float v0 = __ldg(vals + j);
-            fma4(acc, v0, ldg4(x + (int64_t)c0 * nc4 + c));
+            fma4(acc, v0, ldg4(x + ((IdxT)c0 * (IdxT)nc4 + (IdxT)c)));
         }
         float4 o = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
         if (HAS_Z) {
-            const float4 zz = z[idx];
             o.x = fmaf(beta, zz.x, o.x);
             o.y = fmaf(beta, zz.y, o.y);
             o.z = fmaf(beta, zz.z, o.z);
             o.w = fmaf(beta, zz.w, o.w);
         }
         if (HAS_W) {
-            const float4 ww = w[idx];
             o.x += ww.x;
             o.y += ww.y;
             o.z += ww.z;
@@ -446,7 +451,7 @@ static int launch_band_t(int n_rows, const int32_t *rowptr, const int32_t *colid
     return check_launch("mvb_spmm band");
 }
 
-int launch_spmm(int n_rows, const int32_t *rowptr, const int32_t *colidx, const float *vals,
+int launch_spmm(int n_rows, int n_src_rows, const int32_t *rowptr, const int32_t *colidx, const float *vals,
                 const float *x, float *y, const float *z, const float *w, float alpha, float beta,
                 int64_t ncols, cudaStream_t st) {
     if (n_rows == 0 || ncols == 0) return MVB_OK;
@@ -472,16 +477,33 @@ int launch_spmm(int n_rows, const int32_t *rowptr, const int32_t *colidx, const 
             if (CB == 8) return launch_band_t<8>(n_rows, rowptr, colidx, vals, x4, y4, z4, w4, alpha, beta, nc4, R, wmax, st);
             return launch_band_t<4>(n_rows, rowptr, colidx, vals, x4, y4, z4, w4, alpha, beta, nc4, R, wmax, st);
         }
-        int64_t blocks = ((int64_t)n_rows * nc4 + threads - 1) / threads;
-        if (blocks > max_blocks) blocks = max_blocks;
+        // block = TX column quads x (256 / TX) rows, TX = smallest power of two covering min(nc4, 256)
+        int tx = 8;
+        while (tx < nc4 && tx < 256) tx <<= 1;
+        const dim3 block(tx, 256 / tx);
+        int64_t gy = ((int64_t)n_rows + block.y - 1) / block.y;
+        const int64_t gx = (nc4 + tx - 1) / tx;
+        if (gy * gx > max_blocks) gy = (max_blocks + gx - 1) / gx;
+        if (gy > 65535) gy = 65535;
+        const dim3 grid((unsigned)gx, (unsigned)gy);
+        const int64_t max_rows = n_rows > n_src_rows ? n_rows : n_src_rows;
+        const bool idx32 = max_rows * nc4 < (1LL << 31);
+#define MVB_SPMM_LAUNCH(HZ, HW)                                                                                         \
+    do {                                                                                                                \
+        if (idx32)                                                                                                      \
+            spmm_v4_kernel<HZ, HW, uint32_t><<<grid, block, 0, st>>>(n_rows, rowptr, colidx, vals, x4, y4, z4, w4, alpha, beta, nc4); \
+        else                                                                                                            \
+            spmm_v4_kernel<HZ, HW, int64_t><<<grid, block, 0, st>>>(n_rows, rowptr, colidx, vals, x4, y4, z4, w4, alpha, beta, nc4);  \
+    } while (0)
         if (z && w)
-            spmm_v4_kernel<true, true><<<(unsigned)blocks, threads, 0, st>>>(n_rows, rowptr, colidx, vals, x4, y4, z4, w4, alpha, beta, nc4);
+            MVB_SPMM_LAUNCH(true, true);
         else if (z)
-            spmm_v4_kernel<true, false><<<(unsigned)blocks, threads, 0, st>>>(n_rows, rowptr, colidx, vals, x4, y4, z4, w4, alpha, beta, nc4);
+            MVB_SPMM_LAUNCH(true, false);
         else if (w)
-            spmm_v4_kernel<false, true><<<(unsigned)blocks, threads, 0, st>>>(n_rows, rowptr, colidx, vals, x4, y4, z4, w4, alpha, beta, nc4);
+            MVB_SPMM_LAUNCH(false, true);
         else
-            spmm_v4_kernel<false, false><<<(unsigned)blocks, threads, 0, st>>>(n_rows, rowptr, colidx, vals, x4, y4, z4, w4, alpha, beta, nc4);
+            MVB_SPMM_LAUNCH(false, false);
+#undef MVB_SPMM_LAUNCH
     } else {
         int64_t blocks = ((int64_t)n_rows * ncols + threads - 1) / threads;
         if (blocks > max_blocks) blocks = max_blocks;

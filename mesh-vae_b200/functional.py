@@ -112,7 +112,7 @@ class _PoolFn(torch.autograd.Function):
             raise _lib.MvbError(f"pool: operator has {op.n_cols} columns, tensor has {n} vertices")
         x_vm = x_vm.contiguous()
         y = torch.empty((op.n_rows, b, f), device=x_vm.device, dtype=torch.float32)
-        check(lib.mvb_pool_fwd(op.n_rows, ptr(op.rowptr), ptr(op.colidx), ptr(op.vals), ptr(x_vm), ptr(y), b * f,
+        check(lib.mvb_pool_fwd(op.n_rows, op.n_cols, ptr(op.rowptr), ptr(op.colidx), ptr(op.vals), ptr(x_vm), ptr(y), b * f,
                                stream_ptr()), "mvb_pool_fwd")
         ctx.op = op
         return y
@@ -123,7 +123,7 @@ class _PoolFn(torch.autograd.Function):
         dy = dy.contiguous()
         _, b, f = dy.shape
         dx = torch.empty((op.n_cols, b, f), device=dy.device, dtype=torch.float32)
-        check(lib.mvb_pool_bwd(op.n_cols, ptr(op.rowptr_t), ptr(op.colidx_t), ptr(op.vals_t), ptr(dy), ptr(dx), b * f,
+        check(lib.mvb_pool_bwd(op.n_cols, op.n_rows, ptr(op.rowptr_t), ptr(op.colidx_t), ptr(op.vals_t), ptr(dy), ptr(dx), b * f,
                                stream_ptr()), "mvb_pool_bwd")
         return dx, None
 

@@ -23,7 +23,7 @@ for lvl, B, F in [(0, 64, 16), (0, 64, 3), (0, 256, 16), (1, 64, 16), (2, 64, 16
             flush.fill_(float(i))
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            L.check(L.lib.mvb_spmm(n, L.ptr(op.rowptr), L.ptr(op.colidx), L.ptr(op.vals), L.ptr(x), L.ptr(y), L.ptr(z), None, 2.0, -1.0, B * F, L.stream_ptr()))
+            L.check(L.lib.mvb_spmm(n, n, L.ptr(op.rowptr), L.ptr(op.colidx), L.ptr(op.vals), L.ptr(x), L.ptr(y), L.ptr(z), None, 2.0, -1.0, B * F, L.stream_ptr()))
             e.record(); e.synchronize()
             if i >= 3: ms.append(s.elapsed_time(e))
         outs[band] = y.clone()
