@@ -57,6 +57,9 @@ int mvb_set_spmm_band(int enable);
 /* enable (default) / disable the fused multi-step recurrence kernels used when a level fits shared
  * memory (bit-identical to the step-by-step SpMM launches) */
 int mvb_set_fused_recurrence(int enable);
+/* tuning hook: force the SpMM block shape (tx column quads per block row, chunk = consecutive rows
+ * walked by one block); 0, 0 restores the automatic choice */
+int mvb_set_spmm_shape(int tx, int chunk);
 /* enable (default) / disable running the weight-gradient branch of mvb_cheb_bwd on an internal
  * side stream, forked from and joined back into `stream` with events (capturable: the two
  * branches become parallel branches of a CUDA graph).  Returns the previous setting. */

@@ -39,6 +39,7 @@ SIGNATURES = {
     "mvb_launch_count": (c_int64, []),
     "mvb_set_tensor_cores": (c_int, [c_int]),
     "mvb_set_spmm_band": (c_int, [c_int]),
+    "mvb_set_spmm_shape": (c_int, [c_int, c_int]),
     "mvb_set_fused_recurrence": (c_int, [c_int]),
     "mvb_set_overlap": (c_int, [c_int]),
     "mvb_csr_from_coo_host": (c_int, [c_int64, c_int64, c_int64, _vp, _vp, _vp, c_int, _vp, _vp, _vp]),

@@ -31,10 +31,15 @@ template <bool HAS_Z, bool HAS_W, typename IdxT>
 __global__ void __launch_bounds__(256)
 spmm_v4_kernel(int n_rows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
                const float *__restrict__ vals, const float4 *__restrict__ x, float4 *y,
-               const float4 *z, const float4 *w, float alpha, float beta, int nc4) {
+               const float4 *z, const float4 *w, float alpha, float beta, int nc4, int chunk) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nc4) return;
-    for (int r = blockIdx.y * blockDim.y + threadIdx.y; r < n_rows; r += gridDim.y * blockDim.y) {
+    // a block walks `chunk` CONSECUTIVE rows of its column slab (blockDim.y rows at a time): the mesh
+    // operators are banded, so the x rows gathered by one row group are gathered again by the next
+    // ones and stay in L1 - the slab is narrow enough (blockDim.x * 16 bytes per row) for the sliding
+    // window of every resident block to fit
+    const int r_end = min(n_rows, (int)(blockIdx.y + 1) * chunk);
+    for (int r = blockIdx.y * chunk + threadIdx.y; r < r_end; r += blockDim.y) {
         const int s = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
         const IdxT idx = (IdxT)r * (IdxT)nc4 + (IdxT)c;
         float4 zz = make_float4(0.f, 0.f, 0.f, 0.f), ww = zz;
@@ -432,6 +437,8 @@ int launch_cheb_recur_bwd(int N, int nnz, int K, const int32_t *rowptr_t, const 
     return rc ? rc : 1;
 }
 
+static int g_spmm_tx = 0, g_spmm_chunk = 0;      // 0 = automatic; set through mvb_set_spmm_shape for tuning runs
+void set_spmm_shape(int tx, int chunk) { g_spmm_tx = tx; g_spmm_chunk = chunk; }
 static int g_spmm_band = 0;   // experimental: measured SLOWER than the plain kernel (latency-bound phases), see profiles/README.md
 void set_spmm_band(int v) { g_spmm_band = v; }
 
@@ -477,23 +484,32 @@ int launch_spmm(int n_rows, int n_src_rows, const int32_t *rowptr, const int32_t
             if (CB == 8) return launch_band_t<8>(n_rows, rowptr, colidx, vals, x4, y4, z4, w4, alpha, beta, nc4, R, wmax, st);
             return launch_band_t<4>(n_rows, rowptr, colidx, vals, x4, y4, z4, w4, alpha, beta, nc4, R, wmax, st);
         }
-        // block = TX column quads x (256 / TX) rows, TX = smallest power of two covering min(nc4, 256)
-        int tx = 8;
-        while (tx < nc4 && tx < 256) tx <<= 1;
+        // block = TX column quads x (256 / TX) rows; every block walks `chunk` consecutive rows
+        // measured sweep (scripts/spmm_tune.py, profiles/README.md): 256..512-byte slabs and 32-row
+        // chunks beat one-row-per-block by 1.1x (B = 64) to 1.6x (B = 256): L2->SM traffic, not HBM,
+        // bounds this kernel, and the narrow slab lets L1 serve repeated neighbour rows
+        int tx = g_spmm_tx, chunk = g_spmm_chunk;
+        if (tx <= 0) {
+            tx = (nc4 >= 512) ? 32 : 16;
+            while (tx > nc4 && tx > 1) tx >>= 1;
+        }
+        if (tx > 256) tx = 256;
         const dim3 block(tx, 256 / tx);
-        int64_t gy = ((int64_t)n_rows + block.y - 1) / block.y;
+        if (chunk <= 0) chunk = 32;
+        if (chunk < (int)block.y) chunk = block.y;
+        chunk = (chunk + block.y - 1) / block.y * block.y;
+        const int64_t gy = ((int64_t)n_rows + chunk - 1) / chunk;
         const int64_t gx = (nc4 + tx - 1) / tx;
-        if (gy * gx > max_blocks) gy = (max_blocks + gx - 1) / gx;
-        if (gy > 65535) gy = 65535;
+        if (gy > 65535) return set_err(MVB_EINVAL, "spmm: too many row chunks");
         const dim3 grid((unsigned)gx, (unsigned)gy);
         const int64_t max_rows = n_rows > n_src_rows ? n_rows : n_src_rows;
         const bool idx32 = max_rows * nc4 < (1LL << 31);
 #define MVB_SPMM_LAUNCH(HZ, HW)                                                                                         \
     do {                                                                                                                \
         if (idx32)                                                                                                      \
-            spmm_v4_kernel<HZ, HW, uint32_t><<<grid, block, 0, st>>>(n_rows, rowptr, colidx, vals, x4, y4, z4, w4, alpha, beta, nc4); \
+            spmm_v4_kernel<HZ, HW, uint32_t><<<grid, block, 0, st>>>(n_rows, rowptr, colidx, vals, x4, y4, z4, w4, alpha, beta, nc4, chunk); \
         else                                                                                                            \
-            spmm_v4_kernel<HZ, HW, int64_t><<<grid, block, 0, st>>>(n_rows, rowptr, colidx, vals, x4, y4, z4, w4, alpha, beta, nc4);  \
+            spmm_v4_kernel<HZ, HW, int64_t><<<grid, block, 0, st>>>(n_rows, rowptr, colidx, vals, x4, y4, z4, w4, alpha, beta, nc4, chunk);  \
     } while (0)
         if (z && w)
             MVB_SPMM_LAUNCH(true, true);
@@ -516,6 +532,11 @@ int launch_spmm(int n_rows, int n_src_rows, const int32_t *rowptr, const int32_t
 
 extern "C" int mvb_set_fused_recurrence(int enable) {
     mvb::set_recur_fused(enable ? 1 : 0);
+    return 0;
+}
+
+extern "C" int mvb_set_spmm_shape(int tx, int chunk) {
+    mvb::set_spmm_shape(tx, chunk);
     return 0;
 }
 
