@@ -37,25 +37,51 @@ __device__ __forceinline__ void stage_planes(float *Ts, int LD, int64_t rows, in
             const int n4 = nr * q4;
             const float4 *s4 = reinterpret_cast<const float4 *>(src);
             const float4 *m4 = reinterpret_cast<const float4 *>(msk);
-            for (int i = tid; i < n4; i += nthreads) {
-                const int r = i / q4, q = i - r * q4;
-                float4 v = __ldg(s4 + i);
-                if (msk) {
-                    const float4 mk = __ldg(m4 + i);
-                    v.x = mk.x > 0.f ? v.x : 0.f;
-                    v.y = mk.y > 0.f ? v.y : 0.f;
-                    v.z = mk.z > 0.f ? v.z : 0.f;
-                    v.w = mk.w > 0.f ? v.w : 0.f;
+            for (int base = 0; base < n4; base += 4 * nthreads) {      // 4 independent loads in flight
+                float4 v[4], mk[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + u * nthreads + tid;
+                    if (i < n4) {
+                        v[u] = __ldg(s4 + i);
+                        if (msk) mk[u] = __ldg(m4 + i);
+                    }
                 }
-                *reinterpret_cast<float4 *>(Ts + r * LD + p * in_w + 4 * q) = v;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + u * nthreads + tid;
+                    if (i < n4) {
+                        const int r = i / q4, q = i - r * q4;
+                        if (msk) {
+                            v[u].x = mk[u].x > 0.f ? v[u].x : 0.f;
+                            v[u].y = mk[u].y > 0.f ? v[u].y : 0.f;
+                            v[u].z = mk[u].z > 0.f ? v[u].z : 0.f;
+                            v[u].w = mk[u].w > 0.f ? v[u].w : 0.f;
+                        }
+                        *reinterpret_cast<float4 *>(Ts + r * LD + p * in_w + 4 * q) = v[u];
+                    }
+                }
             }
         } else {
             const int n = nr * in_w;
-            for (int i = tid; i < n; i += nthreads) {
-                const int r = i / in_w, q = i - r * in_w;
-                float v = __ldg(src + i);
-                if (msk) v = __ldg(msk + i) > 0.f ? v : 0.f;
-                Ts[r * LD + p * in_w + q] = v;
+            for (int base = 0; base < n; base += 4 * nthreads) {
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + u * nthreads + tid;
+                    if (i < n) {
+                        v[u] = __ldg(src + i);
+                        if (msk) v[u] = __ldg(msk + i) > 0.f ? v[u] : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = base + u * nthreads + tid;
+                    if (i < n) {
+                        const int r = i / in_w, q = i - r * in_w;
+                        Ts[r * LD + p * in_w + q] = v[u];
+                    }
+                }
             }
         }
     }
@@ -75,17 +101,28 @@ contract_kernel(ContractArgs a, int M, int Nn, int M4, int N4, int LD, int R, in
     // W tile; with w_fold = K > 1 the K weight blocks are folded with the Chebyshev values at 0,
     // c_k = cos(k pi/2) = 1,0,-1,0,...: rows of the operator without entries see sum_k c_k W_k
     const int nfold = a.w_fold > 1 ? a.w_fold : 1;
-    for (int i = tid; i < M4 * N4; i += nthreads) {
-        const int m = i / N4, n = i - m * N4;
-        float v = 0.f;
-        if (m < M && n < Nn) {
-            for (int k = 0; k < nfold; k += 2) {
-                const float wv = a.w_transposed ? __ldg(a.wmat + ((int64_t)k * Nn + n) * M + m)
-                                                : __ldg(a.wmat + ((int64_t)k * M + m) * Nn + n);
-                v += (k & 2) ? -wv : wv;
+    for (int base = 0; base < M4 * N4; base += 4 * nthreads) {          // 4 independent loads in flight
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * nthreads + tid;
+            v[u] = 0.f;
+            if (i < M4 * N4) {
+                const int m = i / N4, n = i - m * N4;
+                if (m < M && n < Nn) {
+                    for (int k = 0; k < nfold; k += 2) {
+                        const float wv = a.w_transposed ? __ldg(a.wmat + ((int64_t)k * Nn + n) * M + m)
+                                                        : __ldg(a.wmat + ((int64_t)k * M + m) * Nn + n);
+                        v[u] += (k & 2) ? -wv : wv;
+                    }
+                }
             }
         }
-        Ws[i] = v;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * nthreads + tid;
+            if (i < M4 * N4) Ws[i] = v[u];
+        }
     }
     if (M4 > M) {
         const int padw = M4 - M;

@@ -33,6 +33,29 @@ inline int check_launch(const char *what) {
 
 int num_sms();  // cached multiprocessor count of the current device (148 on B200)
 
+#ifdef __CUDACC__
+// global -> shared copy with U independent loads in flight per thread.  A plain
+// `for (i = tid; i < n; i += nthreads) dst[i] = src[i];` serialises on the load->store dependency
+// (one global-memory latency per iteration); small launch-latency-bound kernels spent most of their
+// time in such loops (profiles/README.md, B = 4 launch list).
+template <int U, typename T>
+__device__ __forceinline__ void g2s_copy(T *dst, const T *__restrict__ src, int n, int tid, int nthreads) {
+    for (int base = 0; base < n; base += U * nthreads) {
+        T v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + u * nthreads + tid;
+            if (i < n) v[u] = __ldg(src + i);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = base + u * nthreads + tid;
+            if (i < n) dst[i] = v[u];
+        }
+    }
+}
+#endif
+
 // ---- launchers implemented in the .cu files ------------------------------------------------
 int launch_spmm(int n_rows, int n_src_rows, const int32_t *rowptr, const int32_t *colidx, const float *vals,
                 const float *x, float *y, const float *z, const float *w, float alpha, float beta,

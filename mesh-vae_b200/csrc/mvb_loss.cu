@@ -33,13 +33,43 @@ vae_rec_partial_kernel(int B, int N, int C, int VCH, int BCH, const float *__res
     const int nv = min(VCH, N - v0), nb = min(BCH, B - b0);
     const int rw = nb * C;  // contiguous run per vertex in recon
     const int xw = nv * C;  // contiguous run per mesh in x_gt
-    for (int i = tid; i < nv * rw; i += nthreads) {
-        const int v = i / rw, rem = i - v * rw;
-        Rs[v * (BCH * C) + rem] = __ldg(recon + ((int64_t)(v0 + v) * B + b0) * C + rem);
+    for (int base = 0; base < nv * rw; base += 4 * nthreads) {       // 4 independent loads in flight
+        float t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * nthreads + tid;
+            if (i < nv * rw) {
+                const int v = i / rw, rem = i - v * rw;
+                t[u] = __ldg(recon + ((int64_t)(v0 + v) * B + b0) * C + rem);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * nthreads + tid;
+            if (i < nv * rw) {
+                const int v = i / rw, rem = i - v * rw;
+                Rs[v * (BCH * C) + rem] = t[u];
+            }
+        }
     }
-    for (int i = tid; i < nb * xw; i += nthreads) {
-        const int b = i / xw, rem = i - b * xw;
-        Xs[b * (VCH * C) + rem] = xgt[((int64_t)(b0 + b) * N + v0) * C + rem];
+    for (int base = 0; base < nb * xw; base += 4 * nthreads) {
+        XT t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * nthreads + tid;
+            if (i < nb * xw) {
+                const int b = i / xw, rem = i - b * xw;
+                t[u] = xgt[((int64_t)(b0 + b) * N + v0) * C + rem];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * nthreads + tid;
+            if (i < nb * xw) {
+                const int b = i / xw, rem = i - b * xw;
+                Xs[b * (VCH * C) + rem] = t[u];
+            }
+        }
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
@@ -80,7 +110,15 @@ vae_loss_finalize_kernel(int B, int Z, int ncls, int nchunks, const double *__re
     int lcnt = 0;
     for (int b = tid; b < B; b += blockDim.x) {
         double r = 0.0;
-        for (int ch = 0; ch < nchunks; ++ch) r += partial[(int64_t)ch * B + b];
+        int ch = 0;
+        for (; ch + 8 <= nchunks; ch += 8) {                 // 8 loads in flight, summation order unchanged
+            double t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = partial[(int64_t)(ch + u) * B + b];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) r += t[u];
+        }
+        for (; ch < nchunks; ++ch) r += partial[(int64_t)ch * B + b];
         rec[b] = r;
         float k = 0.f;
         for (int j = 0; j < Z; ++j) {

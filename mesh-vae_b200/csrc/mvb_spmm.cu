@@ -254,11 +254,9 @@ __device__ __forceinline__ void stage_csr(int N, int nnz_smem, const int32_t *__
     int32_t *srp = reinterpret_cast<int32_t *>(dst);
     int32_t *sci = srp + ((N + 1 + 3) & ~3);
     float *sva = reinterpret_cast<float *>(sci + ((nnz_smem + 3) & ~3));
-    for (int i = threadIdx.x; i <= N; i += blockDim.x) srp[i] = __ldg(rowptr + i);
-    for (int i = threadIdx.x; i < nnz_smem; i += blockDim.x) {
-        sci[i] = __ldg(colidx + i);
-        sva[i] = __ldg(vals + i);
-    }
+    g2s_copy<4>(srp, rowptr, N + 1, threadIdx.x, blockDim.x);
+    g2s_copy<8>(sci, colidx, nnz_smem, threadIdx.x, blockDim.x);
+    g2s_copy<8>(sva, vals, nnz_smem, threadIdx.x, blockDim.x);
     rp = srp;
     ci = sci;
     va = sva;
@@ -281,7 +279,19 @@ cheb_recur_fwd_kernel(int N, int K, const int32_t *__restrict__ g_rowptr, const 
     const int c = blockIdx.x * CS4 + cl;
     const bool col_ok = c < nc4;
     const int64_t plane = (int64_t)N * nc4;
-    for (int r = rl; r < N; r += RPP) cur[r * CS4 + cl] = col_ok ? __ldg(x + (int64_t)r * nc4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = rl; r < N; r += 8 * RPP) {        // 8 independent row loads in flight per thread
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int rr = r + u * RPP;
+            v[u] = (col_ok && rr < N) ? __ldg(x + (int64_t)rr * nc4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int rr = r + u * RPP;
+            if (rr < N) cur[rr * CS4 + cl] = v[u];
+        }
+    }
     __syncthreads();
     for (int k = 1; k < K; ++k) {
         float4 *outp = basis + (int64_t)(k - 1) * plane;
@@ -328,14 +338,44 @@ cheb_recur_bwd_kernel(int N, int K, const int32_t *__restrict__ g_rowptr, const 
     const bool col_ok = c < nc4;
     const int64_t plane = (int64_t)N * nc4;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = rl; r < N; r += RPP) g1[r * CS4 + cl] = col_ok ? __ldg(P + (int64_t)(K - 1) * plane + (int64_t)r * nc4 + c) : zero;
+    {
+        const float4 *pl = P + (int64_t)(K - 1) * plane;
+        for (int r = rl; r < N; r += 8 * RPP) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int rr = r + u * RPP;
+                v[u] = (col_ok && rr < N) ? __ldg(pl + (int64_t)rr * nc4 + c) : zero;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int rr = r + u * RPP;
+                if (rr < N) g1[rr * CS4 + cl] = v[u];
+            }
+        }
+    }
     __syncthreads();
     for (int k = K - 2; k >= 0; --k) {
         const float4 *pk = P + (int64_t)k * plane;
         const bool has_g2 = (k + 2 <= K - 1);
         const float alpha = (k == 0) ? 1.f : 2.f;
-        for (int r = rl; r < N; r += RPP) {
-            const float4 pv = col_ok ? __ldg(pk + (int64_t)r * nc4 + c) : zero;     // issued before the gathers
+        float4 pvr[8];                                   // P_k of this thread's first 8 rows: all loads in flight at once
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int rr = rl + u * RPP;
+            pvr[u] = (col_ok && rr < N) ? __ldg(pk + (int64_t)rr * nc4 + c) : zero;
+        }
+        int it = 0;
+        for (int r = rl; r < N; r += RPP, ++it) {
+            float4 pv;
+            if (it < 8) {
+                pv = zero;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (u == it) pv = pvr[u];
+            } else {
+                pv = col_ok ? __ldg(pk + (int64_t)r * nc4 + c) : zero;
+            }
             const int s = rowptr[r], e = rowptr[r + 1];
             const float4 acc = row_gather<CS4>(g1, colidx, vals, s, e, cl);
             float4 o = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
