@@ -60,6 +60,9 @@ int mvb_set_fused_recurrence(int enable);
 /* tuning hook: force the SpMM block shape (tx column quads per block row, chunk = consecutive rows
  * walked by one block); 0, 0 restores the automatic choice */
 int mvb_set_spmm_shape(int tx, int chunk);
+/* tuning hook: SpMM block size, 0 = automatic, 1/2/3 = force 256/512/1024 threads.  Results are
+ * bit-identical for every shape (same per-row summation order). */
+int mvb_set_spmm_mode(int mode);
 /* enable (default) / disable running the weight-gradient branch of mvb_cheb_bwd on an internal
  * side stream, forked from and joined back into `stream` with events (capturable: the two
  * branches become parallel branches of a CUDA graph).  Returns the previous setting. */
@@ -186,6 +189,52 @@ int mvb_gaussian_nll_bwd(int64_t n, const float *mu, const void *x, int x_is_f64
 int mvb_adam_step(int64_t n, float *p, const float *g, float *m, float *v, int64_t *step, float lr,
                   float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                   void *stream);
+
+/* ---- next row f2: the dense bottleneck between the two mesh pyramids ------------------------
+ * (models/cheb_VAE.py:149-168 layer definitions; :270-272 enc_lin; :253-258 classifier; :206-221
+ *  z heads + reparameterisation; :276-281 dec_lin / dec_lin_2 - torch.nn.Linear + F.relu +
+ *  nn.Dropout in the reference, ~60 ATen/cuBLAS launches per training step.)
+ *
+ * mvb_linear_fwd:  y = dropout_p(relu?(x W^T + bias)),  x logical [M,K], W [N,K] row-major
+ *   (torch.nn.Linear.weight), bias [N] or NULL, y logical [M,N].
+ *   x_vm_f / y_vm_f: 0 = the matrix is row-major; F > 0 = it is a VERTEX-MAJOR activation
+ *   [K/F, M, F] (resp. [N/F, M, F]) - what x.reshape(B, -1) / x.reshape(B, -1, F) of the reference
+ *   (models/cheb_VAE.py:270, :281) mean for the [vertices, B, F] buffers of the mesh kernels, so no
+ *   transpose copy is made on either side of the bottleneck.
+ *   Dropout (p_drop in [0,1), 0 = off / eval mode): inverted dropout with a Philox4x32-10 mask
+ *   keyed by (seed, offset, m*N + n), offset = offset_host + (offset_dev ? *offset_dev : 0); the
+ *   device term lets a captured CUDA graph draw a fresh mask on every replay.
+ * mvb_linear_bwd:  gp = gy * [y > 0]/(1 - p_drop) (relu != 0: y is the forward OUTPUT, a clamped
+ *   or dropped unit has y == 0) or gp = gy (relu == 0; p_drop must be 0);
+ *   dW [N,K] = gp^T x, db [N] = column sums of gp (may be NULL), dx = gp W in the layout of x (may
+ *   be NULL).  y and gy share the layout y_vm_f.  All three are OVERWRITTEN; fixed summation
+ *   order, no atomics. */
+int mvb_linear_fwd(int M, int K, int N, const float *x, int x_vm_f, const float *W, const float *bias,
+                   int relu, float p_drop, uint64_t seed, const int64_t *offset_dev, int64_t offset_host,
+                   float *y, int y_vm_f, void *stream);
+int mvb_linear_bwd(int M, int K, int N, const float *x, int x_vm_f, const float *W, const float *y,
+                   const float *gy, int y_vm_f, int relu, float p_drop, float *dx, float *dW, float *db,
+                   void *stream);
+/* mvb_vae_heads_fwd: the three heads on h [B,H] (the encoder code after enc_lin):
+ *   y_hat [B,C]  = softmax(dropout_p(h) Wc^T + bc)                  models/cheb_VAE.py:253-258
+ *   mu, logvar [B,Z] = cat(y, h) Wm^T + bm, cat(y, h) Wv^T + bv     :206-212  (Wm, Wv: [Z, C+H])
+ *   z [B,Z]      = mu + eps * exp(logvar/2), or mu when eps == NULL  :215-221, :309-319
+ *   zcat [B,C+Z] = cat(y, z)                                         :223
+ *   y_onehot [B,C] int64 (main.py:71).  The classifier's dropout is the SECOND mask on h (quirk 8).
+ * mvb_vae_heads_bwd: from the upstream gradients of the five outputs (any may be NULL = zero) to
+ *   g_h [B,H] and the six parameter gradients (OVERWRITTEN); same (p_drop, seed, offset) as the
+ *   forward call so that the mask is regenerated, not stored. */
+int mvb_vae_heads_fwd(int B, int H, int Z, int C, const float *h, const int64_t *y_onehot, const float *eps,
+                      const float *Wc, const float *bc, const float *Wm, const float *bm, const float *Wv,
+                      const float *bv, float p_drop, uint64_t seed, const int64_t *offset_dev,
+                      int64_t offset_host, float *y_hat, float *mu, float *logvar, float *z, float *zcat,
+                      void *stream);
+int mvb_vae_heads_bwd(int B, int H, int Z, int C, const float *h, const int64_t *y_onehot, const float *eps,
+                      const float *Wc, const float *Wm, const float *Wv, const float *y_hat,
+                      const float *logvar, float p_drop, uint64_t seed, const int64_t *offset_dev,
+                      int64_t offset_host, const float *g_yhat, const float *g_mu, const float *g_logvar,
+                      const float *g_z, const float *g_zcat, float *g_h, float *dWc, float *dbc, float *dWm,
+                      float *dbm, float *dWv, float *dbv, void *stream);
 
 #ifdef __cplusplus
 }

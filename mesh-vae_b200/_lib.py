@@ -5,7 +5,7 @@ import raises.  Every compute call goes through `check()`, which raises MvbError
 library's own message on a non-zero return code."""
 import ctypes
 import os
-from ctypes import c_int, c_int64, c_float, c_void_p, c_size_t, c_char_p
+from ctypes import c_int, c_int64, c_uint64, c_float, c_void_p, c_size_t, c_char_p
 
 from . import build as _build
 
@@ -40,6 +40,7 @@ SIGNATURES = {
     "mvb_set_tensor_cores": (c_int, [c_int]),
     "mvb_set_spmm_band": (c_int, [c_int]),
     "mvb_set_spmm_shape": (c_int, [c_int, c_int]),
+    "mvb_set_spmm_mode": (c_int, [c_int]),
     "mvb_set_fused_recurrence": (c_int, [c_int]),
     "mvb_set_overlap": (c_int, [c_int]),
     "mvb_csr_from_coo_host": (c_int, [c_int64, c_int64, c_int64, _vp, _vp, _vp, c_int, _vp, _vp, _vp]),
@@ -60,6 +61,12 @@ SIGNATURES = {
     "mvb_kld_bwd": (c_int, [c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvb_gaussian_nll_fwd": (c_int, [c_int64, _vp, _vp, c_int, c_float, _vp, _vp]),
     "mvb_gaussian_nll_bwd": (c_int, [c_int64, _vp, _vp, c_int, c_float, _vp, _vp, _vp]),
+    "mvb_linear_fwd": (c_int, [c_int, c_int, c_int, _vp, c_int, _vp, _vp, c_int, c_float, c_uint64, _vp, c_int64, _vp, c_int, _vp]),
+    "mvb_linear_bwd": (c_int, [c_int, c_int, c_int, _vp, c_int, _vp, _vp, _vp, c_int, c_int, c_float, _vp, _vp, _vp, _vp]),
+    "mvb_vae_heads_fwd": (c_int, [c_int, c_int, c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_float, c_uint64, _vp,
+                                  c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mvb_vae_heads_bwd": (c_int, [c_int, c_int, c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_float, c_uint64, _vp,
+                                  c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvb_adam_step": (c_int, [c_int64, _vp, _vp, _vp, _vp, _vp, c_float, c_float, c_float, c_float, c_float, c_float,
                               _vp]),
 }

@@ -64,6 +64,9 @@ class cheb_VAE(nn.Module):
         self.type = model
         self.noise = "cpu"
         self.log_sigma = Fn.LOG_SIGMA_DEFAULT
+        # fused dense bottleneck (row f2): one launch per Linear(+ReLU+dropout), one for the three heads
+        self.fused_dense = True
+        self.dropout_stream = Fn.DropoutStream()
 
     def reset_parameters(self):
         nn.init.normal_(self.enc_lin.weight, 0, 0.1)
@@ -82,16 +85,30 @@ class cheb_VAE(nn.Module):
         for i in range(self.n_layers):
             x = self._act(self.cheb[i], self.cheb[i](x, self.A_edge_index[i], self.A_norm[i]))
             x = self.pool(x, self.downsample_matrices[i])
+        if self.fused_dense and x.is_cuda:
+            # x.reshape(B, 640) of models/cheb_VAE.py:270 is read straight from the vertex-major buffer
+            return Fn.linear(Fn.to_vertex_major(x), self.enc_lin.weight, self.enc_lin.bias, relu=True, p=self._p(),
+                             rng=self.dropout_stream.site(0), x_vm=True)
         x = x.reshape(x.shape[0], self.enc_lin.in_features)
         return self.dropout(F.relu(self.enc_lin(x)))
+
+    def _p(self) -> float:
+        return float(self.dropout.p) if self.training else 0.0
 
     def classifier(self, x):
         return F.softmax(self.classifier_layer(self.dropout(x)), dim=1)
 
     def decoder(self, z):
-        x = self.dropout(F.relu(self.dec_lin(z)))
-        x = self.dropout(F.relu(self.dec_lin_2(x)))
-        x = x.reshape(x.shape[0], -1, self.filters[-1])
+        if self.fused_dense and z.is_cuda:
+            x = Fn.linear(z, self.dec_lin.weight, self.dec_lin.bias, relu=True, p=self._p(), rng=self.dropout_stream.site(2))
+            # x.reshape(B, -1, 32) of models/cheb_VAE.py:281 is written straight in the vertex-major layout
+            x = Fn.linear(x, self.dec_lin_2.weight, self.dec_lin_2.bias, relu=True, p=self._p(),
+                          rng=self.dropout_stream.site(3), y_vm_f=self.filters[-1])
+            x = Fn.from_vertex_major(x)
+        else:
+            x = self.dropout(F.relu(self.dec_lin(z)))
+            x = self.dropout(F.relu(self.dec_lin_2(x)))
+            x = x.reshape(x.shape[0], -1, self.filters[-1])
         for i in range(self.n_layers):
             lvl = self.n_layers - i - 1
             x = self.pool(x, self.upsample_matrices[lvl])
@@ -103,12 +120,14 @@ class cheb_VAE(nn.Module):
         x = self.decoder(torch.cat([y, z], -1))
         return x.reshape(z.shape[0], -1, self.filters[0])
 
+    def _draw_eps(self, shape, like):
+        if self.noise == "device":
+            return torch.randn(shape, device=like.device, dtype=like.dtype)
+        return torch.normal(mean=0, std=1, size=tuple(shape)).to(like.device)      # CPU generator, models/cheb_VAE.py:316
+
     def reparameterize(self, mu, logvar, eps: Optional[torch.Tensor] = None):
         if eps is None:
-            if self.noise == "device":
-                eps = torch.randn(mu.shape, device=mu.device, dtype=mu.dtype)
-            else:
-                eps = torch.normal(mean=0, std=1, size=tuple(mu.shape)).to(mu.device)
+            eps = self._draw_eps(mu.shape, mu)
         return Fn.reparameterize(mu, logvar, eps)
 
     def loss_function(self, x, recon_x, z, mu_z, logvar_z, y, y_hat):
@@ -122,12 +141,20 @@ class cheb_VAE(nn.Module):
         else:
             x, batch_size = data.x, data.num_graphs
         x = x.reshape(batch_size, -1, self.filters[0])
+        self.dropout_stream.advance()
         h = self.encoder(x)
-        y_hat = self.classifier(h)
-        h = torch.cat([y, h], -1)
-        x_mean, x_var = self.z_mean(h), self.z_log_var(h)
-        z_ = self.reparameterize(x_mean, x_var, eps) if m_type == "train" else x_mean
-        z = torch.cat([y, z_], -1)
+        if self.fused_dense and h.is_cuda:
+            if m_type == "train" and eps is None:
+                eps = self._draw_eps((batch_size, self.z), h)
+            y_hat, x_mean, x_var, z_, z = Fn.vae_heads(h, y, eps if m_type == "train" else None, self.classifier_layer,
+                                                       self.z_mean, self.z_log_var, p=self._p(),
+                                                       rng=self.dropout_stream.site(1))
+        else:
+            y_hat = self.classifier(h)
+            h = torch.cat([y, h], -1)
+            x_mean, x_var = self.z_mean(h), self.z_log_var(h)
+            z_ = self.reparameterize(x_mean, x_var, eps) if m_type == "train" else x_mean
+            z = torch.cat([y, z_], -1)
         recon = self.decoder(z).reshape(batch_size, -1, self.filters[0])
         loss, correct, kld, rec_loss = self.loss_function(x_gt, recon, z, x_mean, x_var, y, y_hat)
         return loss, correct, recon, [kld, rec_loss, z_], y_hat

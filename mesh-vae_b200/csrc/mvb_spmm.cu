@@ -28,7 +28,7 @@ __device__ __forceinline__ void fma4(float4 &acc, float v, const float4 &x) {
 // (The first version computed row = idx / nc4 in 64-bit arithmetic per thread: ncu showed 226
 // instructions per thread and an issue-bound kernel - see profiles/README.md.)
 template <bool HAS_Z, bool HAS_W, typename IdxT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 spmm_v4_kernel(int n_rows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
                const float *__restrict__ vals, const float4 *__restrict__ x, float4 *y,
                const float4 *z, const float4 *w, float alpha, float beta, int nc4, int chunk) {
@@ -43,8 +43,8 @@ spmm_v4_kernel(int n_rows, const int32_t *__restrict__ rowptr, const int32_t *__
         const int s = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
         const IdxT idx = (IdxT)r * (IdxT)nc4 + (IdxT)c;
         float4 zz = make_float4(0.f, 0.f, 0.f, 0.f), ww = zz;
-        if (HAS_Z) zz = z[idx];                      // independent of the gathers: issue first
-        if (HAS_W) ww = w[idx];
+        if (HAS_Z) zz = __ldcs(z + idx);             // independent of the gathers: issue first; streaming (read once)
+        if (HAS_W) ww = __ldcs(w + idx);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         int j = s;
         // 4 independent gathers in flight per thread (mean degree is 6)
@@ -479,6 +479,8 @@ int launch_cheb_recur_bwd(int N, int nnz, int K, const int32_t *rowptr_t, const 
 
 static int g_spmm_tx = 0, g_spmm_chunk = 0;      // 0 = automatic; set through mvb_set_spmm_shape for tuning runs
 void set_spmm_shape(int tx, int chunk) { g_spmm_tx = tx; g_spmm_chunk = chunk; }
+static int g_spmm_mode = 0;   // 0 = automatic block size, 1/2/3 = force 256/512/1024-thread blocks (tuning runs)
+void set_spmm_mode(int v) { g_spmm_mode = v; }
 static int g_spmm_band = 0;   // experimental: measured SLOWER than the plain kernel (latency-bound phases), see profiles/README.md
 void set_spmm_band(int v) { g_spmm_band = v; }
 
@@ -529,12 +531,20 @@ int launch_spmm(int n_rows, int n_src_rows, const int32_t *rowptr, const int32_t
         // chunks beat one-row-per-block by 1.1x (B = 64) to 1.6x (B = 256): L2->SM traffic, not HBM,
         // bounds this kernel, and the narrow slab lets L1 serve repeated neighbour rows
         int tx = g_spmm_tx, chunk = g_spmm_chunk;
+        int nthreads = (g_spmm_mode == 2) ? 512 : (g_spmm_mode == 3 ? 1024 : 256);
+        if (g_spmm_mode == 0 && tx <= 0 && chunk <= 0 && nc4 >= 128 && nc4 < 512 && n_rows >= 2048) {
+            // mid-size planes (the level-0 steps at 64 meshes per GPU): 32 x 32-thread blocks, 64-row
+            // chunks: 18.7 us vs 20.7 us for the 256-thread shape (scripts/spmm_ab.py, profiles/README.md)
+            nthreads = 1024;
+            tx = 32;
+            chunk = 64;
+        }
         if (tx <= 0) {
             tx = (nc4 >= 512) ? 32 : 16;
             while (tx > nc4 && tx > 1) tx >>= 1;
         }
         if (tx > 256) tx = 256;
-        const dim3 block(tx, 256 / tx);
+        const dim3 block(tx, nthreads / tx);
         if (chunk <= 0) chunk = 32;
         if (chunk < (int)block.y) chunk = block.y;
         chunk = (chunk + block.y - 1) / block.y * block.y;
@@ -577,6 +587,11 @@ extern "C" int mvb_set_fused_recurrence(int enable) {
 
 extern "C" int mvb_set_spmm_shape(int tx, int chunk) {
     mvb::set_spmm_shape(tx, chunk);
+    return 0;
+}
+
+extern "C" int mvb_set_spmm_mode(int mode) {
+    mvb::set_spmm_mode(mode);
     return 0;
 }
 

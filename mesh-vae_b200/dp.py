@@ -26,17 +26,28 @@ def live_parameters(params: Sequence[torch.nn.Parameter]) -> List[torch.nn.Param
     return [p for p in params if p.grad is not None]
 
 
-def pack_grads(params: Sequence[torch.nn.Parameter], out: torch.Tensor) -> torch.Tensor:
-    torch.cat([p.grad.reshape(-1) for p in params], out=out)
-    return out
-
-
-def unpack_grads(flat: torch.Tensor, params: Sequence[torch.nn.Parameter]) -> None:
-    off = 0
+def flat_layout(params: Sequence[torch.Tensor], align: int = 32) -> Tuple[List[int], int]:
+    """offsets (in elements, each a multiple of `align`) of the parameters in a flat buffer and the
+    buffer length; 32 fp32 = 128 bytes, so every view keeps the kernels' 16-byte vector paths"""
+    offsets, off = [], 0
     for p in params:
-        n = p.numel()
-        p.grad.copy_(flat[off:off + n].view_as(p))
-        off += n
+        offsets.append(off)
+        off += (p.numel() + align - 1) // align * align
+    return offsets, off
+
+
+def flat_views(flat: torch.Tensor, params: Sequence[torch.Tensor], offsets: Sequence[int]) -> List[torch.Tensor]:
+    return [flat[o:o + p.numel()].view_as(p) for p, o in zip(params, offsets)]
+
+
+def pack_grads(params: Sequence[torch.nn.Parameter], views: Sequence[torch.Tensor]) -> None:
+    """copy every parameter's gradient into its (aligned) view of the flat exchange buffer - one
+    multi-tensor launch"""
+    torch._foreach_copy_(list(views), [p.grad for p in params])
+
+
+def unpack_grads(views: Sequence[torch.Tensor], params: Sequence[torch.nn.Parameter]) -> None:
+    torch._foreach_copy_([p.grad for p in params], list(views))
 
 
 def allreduce_sum_(flat: torch.Tensor, group=None) -> torch.Tensor:

@@ -22,26 +22,29 @@ class FlatAdam:
     """Adam(lr, betas, eps, weight_decay) with torch.optim.Adam's arithmetic (main.py:251) as one
     fused kernel over a flat parameter buffer; parameters are re-pointed to views of that buffer."""
 
+    ALIGN = 32          # elements: every parameter starts on a 128-byte boundary of the flat buffers, so that
+                        # the kernels' 16-byte vector / cp.async paths apply to parameter and gradient views
+
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         self.params = [p for p in params]
         dev = self.params[0].device
-        self.n = sum(p.numel() for p in self.params)
-        self.flat_p = torch.empty(self.n, device=dev, dtype=torch.float32)
-        off = 0
-        for p in self.params:
+        self.offsets, self.n = dp.flat_layout(self.params, self.ALIGN)
+        # padding elements stay exactly zero: p = g = 0 => m = v = 0 and the update is 0
+        self.flat_p = torch.zeros(self.n, device=dev, dtype=torch.float32)
+        for p, o in zip(self.params, self.offsets):
             k = p.numel()
-            self.flat_p[off:off + k].copy_(p.detach().reshape(-1))
-            p.data = self.flat_p[off:off + k].view_as(p)
-            off += k
+            self.flat_p[o:o + k].copy_(p.detach().reshape(-1))
+            p.data = self.flat_p[o:o + k].view_as(p)
         self.flat_g = torch.zeros(self.n, device=dev, dtype=torch.float32)
+        self.grad_views = dp.flat_views(self.flat_g, self.params, self.offsets)
         self.m = torch.zeros_like(self.flat_p)
         self.v = torch.zeros_like(self.flat_p)
         self.step_count = torch.zeros((), device=dev, dtype=torch.int64)
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
 
     def pack_grads(self):
-        """one concatenation of the per-parameter gradients into the flat exchange buffer"""
-        dp.pack_grads(self.params, self.flat_g)
+        """one multi-tensor copy of the per-parameter gradients into the flat exchange buffer"""
+        dp.pack_grads(self.params, self.grad_views)
 
     def step(self, grad_scale: float = 1.0):
         check(lib.mvb_adam_step(self.n, ptr(self.flat_p), ptr(self.flat_g), ptr(self.m), ptr(self.v),
@@ -72,6 +75,12 @@ class TrainEngine:
         live = dp.live_parameters(list(net.parameters()))
         net.zero_grad(set_to_none=True)
         self.opt = FlatAdam(live, lr=lr, weight_decay=weight_decay)
+        if hasattr(net, "dropout_stream"):
+            # fresh dropout masks on every graph replay: the fused dense kernels add Adam's device step
+            # counter to their Philox offset; per-rank streams
+            rank = dist.get_rank() if self.world > 1 else 0
+            net.dropout_stream.offset_dev = self.opt.step_count
+            net.dropout_stream.seed = (net.dropout_stream.seed + 7919 * rank) & 0xFFFFFFFFFFFFFFFF
         self.loss = torch.zeros((), device=self.dev, dtype=torch.float64)
         self.stats = torch.zeros(3, device=self.dev, dtype=torch.float64)   # kld mean, rec mean, correct
         self.use_graph = use_graph

@@ -270,3 +270,140 @@ class _GaussianNllFn(torch.autograd.Function):
 
 def gaussian_nll(mu, x, log_sigma: float):
     return _GaussianNllFn.apply(mu, x, log_sigma)
+
+
+# ---------------------------------------------------------------------------------------------
+# dense bottleneck: fused Linear(+ReLU+dropout) and the three VAE heads
+# ---------------------------------------------------------------------------------------------
+class DropoutStream:
+    """Counter-based dropout stream shared by the fused dense kernels: a mask is a pure function of
+    (seed + site, offset, element), offset = host counter + *device counter.  The backward pass
+    regenerates the mask from the same triple; a captured CUDA graph gets fresh masks on every replay
+    through the device counter (the engine points it at Adam's device step counter)."""
+
+    def __init__(self, seed: int = 0x5EED):
+        self.seed = int(seed)
+        self.offset_host = 0
+        self.offset_dev: Optional[torch.Tensor] = None     # int64 scalar on the device, or None
+
+    def advance(self):
+        self.offset_host += 1
+
+    def site(self, site_id: int):
+        return ((self.seed + 0x9E3779B97F4A7C15 * (site_id + 1)) & 0xFFFFFFFFFFFFFFFF, self.offset_dev, self.offset_host)
+
+
+_NO_RNG = (0, None, 0)
+
+
+class _LinearFn(torch.autograd.Function):
+    """mvb_linear_fwd / mvb_linear_bwd: y = dropout(relu(x W^T + b)) (torch.nn.Linear + F.relu +
+    nn.Dropout, models/cheb_VAE.py:270-272, 276-281).  x is [M,K] row-major, or - x_vm - a
+    vertex-major activation [V,M,F] standing for x.reshape(M, V*F); likewise the output."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu: bool, p: float, rng, x_vm: bool, y_vm_f: int):
+        _req_cuda(x, "linear x")
+        _req_cuda(weight, "linear weight")
+        x = x.contiguous()
+        w = weight.contiguous()
+        n, k = w.shape
+        if x_vm:
+            v, m, f = x.shape
+            if v * f != k:
+                raise _lib.MvbError(f"linear: vertex-major input {tuple(x.shape)} does not flatten to {k} features")
+            x_vm_f = f
+        else:
+            m = x.shape[0]
+            if x.dim() != 2 or x.shape[1] != k:
+                raise _lib.MvbError(f"linear: input {tuple(x.shape)} does not match weight {tuple(w.shape)}")
+            x_vm_f = 0
+        if y_vm_f:
+            if n % y_vm_f:
+                raise _lib.MvbError(f"linear: {n} outputs do not split into vertices of {y_vm_f} features")
+            y = torch.empty((n // y_vm_f, m, y_vm_f), device=x.device, dtype=torch.float32)
+        else:
+            y = torch.empty((m, n), device=x.device, dtype=torch.float32)
+        bb = None if bias is None else bias.contiguous()
+        seed, off_dev, off_host = rng if p > 0 else _NO_RNG
+        check(lib.mvb_linear_fwd(m, k, n, ptr(x), x_vm_f, ptr(w), ptr(bb), 1 if relu else 0, float(p), seed, ptr(off_dev),
+                                 off_host, ptr(y), y_vm_f, stream_ptr()), "mvb_linear_fwd")
+        ctx.dims = (m, k, n, x_vm_f, y_vm_f, relu, float(p))
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, w, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        m, k, n, x_vm_f, y_vm_f, relu, p = ctx.dims
+        gy = gy.contiguous()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w)
+        db = torch.empty(n, device=w.device, dtype=torch.float32) if ctx.has_bias else None
+        check(lib.mvb_linear_bwd(m, k, n, ptr(x), x_vm_f, ptr(w), ptr(y), ptr(gy), y_vm_f, 1 if relu else 0, p, ptr(dx), ptr(dw),
+                                 ptr(db), stream_ptr()), "mvb_linear_bwd")
+        return dx, dw, db, None, None, None, None, None
+
+
+def linear(x, weight, bias=None, relu: bool = False, p: float = 0.0, rng=_NO_RNG, x_vm: bool = False, y_vm_f: int = 0):
+    """Fused dense layer.  `p > 0` needs `relu=True` (the backward recovers the dropout mask from y == 0)."""
+    if p > 0 and not relu:
+        raise _lib.MvbError("linear: dropout without ReLU is not supported by the fused kernel")
+    return _LinearFn.apply(x, weight, bias, relu, float(p), rng, x_vm, int(y_vm_f))
+
+
+class _VaeHeadsFn(torch.autograd.Function):
+    """mvb_vae_heads_fwd / _bwd: classifier + softmax, z_mean, z_log_var on cat(y, h), the
+    reparameterisation and cat(y, z) (models/cheb_VAE.py:206-223, 253-258, 309-319)."""
+
+    @staticmethod
+    def forward(ctx, h, y_onehot, eps, wc, bc, wm, bm, wv, bv, p: float, rng):
+        _req_cuda(h, "vae_heads h")
+        h = h.contiguous()
+        b, hd = h.shape
+        c, z = wc.shape[0], wm.shape[0]
+        if wc.shape[1] != hd or wm.shape[1] != c + hd or tuple(wv.shape) != tuple(wm.shape):
+            raise _lib.MvbError("vae_heads: weight shapes do not match h / the one-hot width")
+        y_onehot = y_onehot.to(torch.int64).contiguous()
+        if tuple(y_onehot.shape) != (b, c):
+            raise _lib.MvbError(f"vae_heads: y is {tuple(y_onehot.shape)}, expected {(b, c)}")
+        eps_c = None if eps is None else eps.contiguous()
+        wc, bc, wm, bm, wv, bv = (t.contiguous() for t in (wc, bc, wm, bm, wv, bv))
+        dev = h.device
+        y_hat = torch.empty((b, c), device=dev, dtype=torch.float32)
+        mu = torch.empty((b, z), device=dev, dtype=torch.float32)
+        logvar = torch.empty_like(mu)
+        zz = torch.empty_like(mu)
+        zcat = torch.empty((b, c + z), device=dev, dtype=torch.float32)
+        seed, off_dev, off_host = rng if p > 0 else _NO_RNG
+        check(lib.mvb_vae_heads_fwd(b, hd, z, c, ptr(h), ptr(y_onehot), ptr(eps_c), ptr(wc), ptr(bc), ptr(wm), ptr(bm), ptr(wv),
+                                    ptr(bv), float(p), seed, ptr(off_dev), off_host, ptr(y_hat), ptr(mu), ptr(logvar), ptr(zz),
+                                    ptr(zcat), stream_ptr()), "mvb_vae_heads_fwd")
+        ctx.save_for_backward(h, y_onehot, eps_c, wc, wm, wv, y_hat, logvar)
+        ctx.cfg = (b, hd, z, c, float(p), seed, off_dev, off_host)
+        return y_hat, mu, logvar, zz, zcat
+
+    @staticmethod
+    def backward(ctx, g_yhat, g_mu, g_logvar, g_z, g_zcat):
+        h, y_onehot, eps, wc, wm, wv, y_hat, logvar = ctx.saved_tensors
+        b, hd, z, c, p, seed, off_dev, off_host = ctx.cfg
+        gs = [None if g is None else g.contiguous() for g in (g_yhat, g_mu, g_logvar, g_z, g_zcat)]
+        dev = h.device
+        g_h = torch.empty_like(h)
+        dwc, dwm, dwv = torch.empty_like(wc), torch.empty_like(wm), torch.empty_like(wv)
+        dbc = torch.empty(c, device=dev, dtype=torch.float32)
+        dbm = torch.empty(z, device=dev, dtype=torch.float32)
+        dbv = torch.empty(z, device=dev, dtype=torch.float32)
+        check(lib.mvb_vae_heads_bwd(b, hd, z, c, ptr(h), ptr(y_onehot), ptr(eps), ptr(wc), ptr(wm), ptr(wv), ptr(y_hat),
+                                    ptr(logvar), p, seed, ptr(off_dev), off_host, ptr(gs[0]), ptr(gs[1]), ptr(gs[2]), ptr(gs[3]),
+                                    ptr(gs[4]), ptr(g_h), ptr(dwc), ptr(dbc), ptr(dwm), ptr(dbm), ptr(dwv), ptr(dbv),
+                                    stream_ptr()), "mvb_vae_heads_bwd")
+        return g_h, None, None, dwc, dbc, dwm, dbm, dwv, dbv, None, None
+
+
+def vae_heads(h, y_onehot, eps, classifier, z_mean, z_log_var, p: float = 0.0, rng=_NO_RNG):
+    """-> (y_hat, mu, logvar, z, cat(y, z)); `classifier`, `z_mean`, `z_log_var` are the model's
+    nn.Linear modules (their Parameters receive the gradients); eps=None means z = mu (test mode)."""
+    return _VaeHeadsFn.apply(h, y_onehot, eps, classifier.weight, classifier.bias, z_mean.weight, z_mean.bias,
+                             z_log_var.weight, z_log_var.bias, float(p), rng)

@@ -38,11 +38,14 @@ def _worker(rank, world, port, q):
     loss = ((net(x[lo:hi]) - y[lo:hi]) ** 2).sum(-1).mean()          # mean over the LOCAL slice
     loss.backward()
     live = dp.live_parameters(list(net.parameters()))
-    flat = torch.empty(sum(p.numel() for p in live))
-    dp.pack_grads(live, flat)
+    offsets, n = dp.flat_layout(live)
+    assert all(o % 32 == 0 for o in offsets)
+    flat = torch.zeros(n)
+    views = dp.flat_views(flat, live, offsets)
+    dp.pack_grads(live, views)
     dp.allreduce_sum_(flat)
     flat.mul_(1.0 / world)
-    dp.unpack_grads(flat, live)
+    dp.unpack_grads(views, live)
     if rank == 0:
         q.put([p.grad.clone() for p in net.parameters()])
     dist.barrier()
