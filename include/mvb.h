@@ -190,6 +190,36 @@ int mvb_adam_step(int64_t n, float *p, const float *g, float *m, float *v, int64
                   float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                   void *stream);
 
+/* ---- A12 fused: one whole encoder / decoder layer of a COARSE level per launch ---------------
+ * (models/cheb_VAE.py:264-265  x = relu(cheb[i](x, L)); x = pool(x, D)   and
+ *  models/cheb_VAE.py:284-285  x = pool(x, U); x = relu(cheb_dec[i](x, L)) ).
+ * One thread block per mesh keeps the layer in shared memory: optional up-sampling prologue
+ * T_0 = U x, the recurrence, the contraction with bias / ReLU, and an optional row-selection
+ * epilogue (only the rows that D keeps are contracted and written).
+ *   x [n_in,B,Fin] (n_in == N unless U [N x n_in] is given), y [n_out,B,Fout] (n_out == N unless
+ *   sel[n_out] is given: output row r is conv row sel[r] - D is such a selection,
+ *   mesh_operations.py:72-85: one 1.0 per row).
+ * mvb_cheb_layer_supported: 1 when the level fits (Fin, Fout multiples of 4 and powers of two up to
+ *   64, per-mesh planes + operators within 200 KB of shared memory), else 0 - the caller then uses
+ *   mvb_pool_* + mvb_cheb_*.
+ * Backward: nothing but x and y is kept from the forward pass (the basis is recomputed in shared
+ *   memory).  dweight / dbias OVERWRITTEN; dx [n_in,B,Fin] may be NULL.  L^T / U^T as in
+ *   mvb_cheb_bwd / mvb_pool_bwd.  workspace: mvb_cheb_layer_bwd_workspace_bytes (per-mesh partials,
+ *   summed in mesh order by a second kernel: deterministic). */
+int mvb_cheb_layer_supported(int N, int B, int Fin, int Fout, int K, int L_nnz, int n_in, int U_nnz, int n_out);
+int mvb_cheb_layer_fwd(int N, int B, int Fin, int Fout, int K, const int32_t *L_rowptr, const int32_t *L_colidx,
+                       const float *L_vals, int L_nnz, int n_in, const int32_t *U_rowptr, const int32_t *U_colidx,
+                       const float *U_vals, int U_nnz, int n_out, const int32_t *sel, const float *x,
+                       const float *weight, const float *bias, int relu, float *y, void *stream);
+size_t mvb_cheb_layer_bwd_workspace_bytes(int B, int Fin, int Fout, int K);
+int mvb_cheb_layer_bwd(int N, int B, int Fin, int Fout, int K, const int32_t *L_rowptr, const int32_t *L_colidx,
+                       const float *L_vals, const int32_t *Lt_rowptr, const int32_t *Lt_colidx, const float *Lt_vals,
+                       int L_nnz, int n_in, const int32_t *U_rowptr, const int32_t *U_colidx, const float *U_vals,
+                       const int32_t *Ut_rowptr, const int32_t *Ut_colidx, const float *Ut_vals, int U_nnz, int n_out,
+                       const int32_t *sel, const float *x, const float *weight, const float *y_for_relu,
+                       const float *dy, float *dx, float *dweight, float *dbias, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
 /* ---- next row f2: the dense bottleneck between the two mesh pyramids ------------------------
  * (models/cheb_VAE.py:149-168 layer definitions; :270-272 enc_lin; :253-258 classifier; :206-221
  *  z heads + reparameterisation; :276-281 dec_lin / dec_lin_2 - torch.nn.Linear + F.relu +

@@ -66,6 +66,9 @@ class cheb_VAE(nn.Module):
         self.log_sigma = Fn.LOG_SIGMA_DEFAULT
         # fused dense bottleneck (row f2): one launch per Linear(+ReLU+dropout), one for the three heads
         self.fused_dense = True
+        # coarse levels: pool + conv + ReLU (+ pool) as one mesh-resident kernel (Fn.cheb_layer)
+        self.fused_layers = True
+        self.A_num_nodes = tuple(int(n) for n in num_nodes)
         self.dropout_stream = Fn.DropoutStream()
 
     def reset_parameters(self):
@@ -80,11 +83,29 @@ class cheb_VAE(nn.Module):
         """F.relu of models/cheb_VAE.py:264,285 - already applied inside the conv epilogue when fused"""
         return y if conv.fuse_relu else F.relu(y)
 
+    def _layer(self, x, conv, lvl, up=None, down=None):
+        """one step of the encoder loop (conv, relu, pool(D): models/cheb_VAE.py:264-265) or of the decoder
+        loop (pool(U), conv, relu: :284-285); coarse levels run as ONE mesh-resident kernel per direction"""
+        if self.fused_layers and x.is_cuda and conv.fuse_relu:
+            l_op = operators.from_edges(self.A_edge_index[lvl], self.A_norm[lvl], self.A_num_nodes[lvl], x.device)
+            u_op = None if up is None else operators.from_sparse(up, x.device)
+            d_op = None if down is None else operators.from_sparse(down, x.device)
+            fin, fout = conv.weight.shape[1], conv.weight.shape[2]
+            if fin % 4 == 0 and fout % 4 == 0 and Fn.cheb_layer_supported(l_op.n_rows, x.shape[0], fin, fout, conv.weight.shape[0],
+                                                                           l_op, u_op, d_op):
+                y = Fn.cheb_layer(Fn.to_vertex_major(x), conv.weight, conv.bias, l_op, u_op, d_op, relu=True)
+                return Fn.from_vertex_major(y)
+        if up is not None:
+            x = self.pool(x, up)
+        x = self._act(conv, conv(x, self.A_edge_index[lvl], self.A_norm[lvl]))
+        if down is not None:
+            x = self.pool(x, down)
+        return x
+
     # ---- sub-networks (logical [B, N, F] tensors; physically vertex-major views) -----------------
     def encoder(self, x):
         for i in range(self.n_layers):
-            x = self._act(self.cheb[i], self.cheb[i](x, self.A_edge_index[i], self.A_norm[i]))
-            x = self.pool(x, self.downsample_matrices[i])
+            x = self._layer(x, self.cheb[i], i, down=self.downsample_matrices[i])
         if self.fused_dense and x.is_cuda:
             # x.reshape(B, 640) of models/cheb_VAE.py:270 is read straight from the vertex-major buffer
             return Fn.linear(Fn.to_vertex_major(x), self.enc_lin.weight, self.enc_lin.bias, relu=True, p=self._p(),
@@ -111,8 +132,7 @@ class cheb_VAE(nn.Module):
             x = x.reshape(x.shape[0], -1, self.filters[-1])
         for i in range(self.n_layers):
             lvl = self.n_layers - i - 1
-            x = self.pool(x, self.upsample_matrices[lvl])
-            x = self._act(self.cheb_dec[i], self.cheb_dec[i](x, self.A_edge_index[lvl], self.A_norm[lvl]))
+            x = self._layer(x, self.cheb_dec[i], lvl, up=self.upsample_matrices[lvl])
         # quirk 1: the output conv runs the COARSEST operator on the finest mesh (models/cheb_VAE.py:288)
         return self.cheb_dec[-1](x, self.A_edge_index[-1], self.A_norm[-1])
 

@@ -47,20 +47,9 @@ __device__ __forceinline__ float gp_value(float gy, float yv, int relu, float sc
     return relu ? (yv > 0.f ? gy * scale : 0.f) : gy * scale;
 }
 
-// cp.async (global -> shared without a register round trip): every copy of a tile is in flight at
-// once, so staging costs ONE exposed memory latency instead of one per batch of register loads - the
-// first version of these kernels (register staging, 3 integer divisions per element) spent 80 us in
-// enc_lin's forward, 95 % of it address arithmetic and serialised latencies (profiles/README.md).
-template <int VEC>
-__device__ __forceinline__ void cp_async(float *smem_dst, const float *gsrc, bool valid) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    const int sz = valid ? 4 * VEC : 0;                 // src-size 0: the destination is zero-filled
-    if (VEC == 4)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
-    else
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
+// Staging uses cp.async (mvb_internal.cuh): the first version of these kernels (register staging, 3
+// integer divisions per element) spent 80 us in enc_lin's forward, 95 % of it address arithmetic and
+// serialised latencies (profiles/README.md).
 
 // A logical [R, C] matrix in global memory: element (r, c) at base + r*rs + (c / f)*cso + c % f.
 // Row-major [R, C]: rs = C, f = INT_MAX.  Vertex-major [C/f, R, f]: rs = f, cso = R*f.

@@ -54,6 +54,25 @@ __device__ __forceinline__ void g2s_copy(T *dst, const T *__restrict__ src, int 
         }
     }
 }
+
+// cp.async (global -> shared without a register round trip): every copy of a tile is in flight at
+// once, so staging costs ONE exposed memory latency instead of one per batch of register loads.
+// VEC = 4: 16-byte copies (both addresses 16-byte aligned); VEC = 1: 4-byte copies.  !valid: the
+// destination is zero-filled (src-size 0) and the source is not dereferenced.
+template <int VEC>
+__device__ __forceinline__ void cp_async(void *smem_dst, const void *gsrc, bool valid = true) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 4 * VEC : 0;
+    if (VEC == 4)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
+// n 4-byte words global -> shared (any alignment)
+__device__ __forceinline__ void cp_async_words(void *dst, const void *src, int n, int tid, int nthreads) {
+    for (int i = tid; i < n; i += nthreads) cp_async<1>(reinterpret_cast<char *>(dst) + 4 * i, reinterpret_cast<const char *>(src) + 4 * i);
+}
 #endif
 
 // ---- launchers implemented in the .cu files ------------------------------------------------

@@ -407,3 +407,89 @@ def vae_heads(h, y_onehot, eps, classifier, z_mean, z_log_var, p: float = 0.0, r
     nn.Linear modules (their Parameters receive the gradients); eps=None means z = mu (test mode)."""
     return _VaeHeadsFn.apply(h, y_onehot, eps, classifier.weight, classifier.bias, z_mean.weight, z_mean.bias,
                              z_log_var.weight, z_log_var.bias, float(p), rng)
+
+
+# ---------------------------------------------------------------------------------------------
+# mesh-resident fused layers for the coarse levels (models/cheb_VAE.py:264-265, 284-285)
+# ---------------------------------------------------------------------------------------------
+def cheb_layer_supported(n: int, b: int, fin: int, fout: int, k: int, l_op: MeshOperator, u_op: Optional[MeshOperator],
+                         d_op: Optional[MeshOperator]) -> bool:
+    if l_op.n_active != n or l_op.n_rows != n:
+        return False
+    if d_op is not None and not d_op.is_selection:
+        return False
+    n_in = u_op.n_cols if u_op is not None else n
+    n_out = d_op.n_rows if d_op is not None else n
+    return bool(lib.mvb_cheb_layer_supported(n, b, fin, fout, k, l_op.nnz, n_in, u_op.nnz if u_op is not None else 0, n_out))
+
+
+class _ChebLayerFn(torch.autograd.Function):
+    """mvb_cheb_layer_fwd / _bwd: [pool(U)] -> ChebConv -> ReLU -> [pool(D)] for one coarse level, one
+    launch per direction.  Saves only its input and output (the basis is recomputed in shared memory)."""
+
+    @staticmethod
+    def forward(ctx, x_vm, weight, bias, l_op: MeshOperator, u_op, d_op, relu: bool):
+        _req_cuda(x_vm, "cheb_layer x")
+        _req_cuda(weight, "cheb_layer weight")
+        x_vm = x_vm.contiguous()
+        w = weight.contiguous()
+        n_in, b, fin = x_vm.shape
+        k, fin_w, fout = w.shape
+        n = l_op.n_rows
+        if fin_w != fin:
+            raise _lib.MvbError(f"cheb_layer: x has {fin} features, weight expects {fin_w}")
+        if (u_op.n_cols if u_op is not None else n) != n_in:
+            raise _lib.MvbError(f"cheb_layer: x has {n_in} vertices, the layer expects {u_op.n_cols if u_op is not None else n}")
+        n_out = d_op.n_rows if d_op is not None else n
+        bb = None if bias is None else bias.contiguous()
+        y = torch.empty((n_out, b, fout), device=x_vm.device, dtype=torch.float32)
+        u = u_op
+        check(lib.mvb_cheb_layer_fwd(n, b, fin, fout, k, ptr(l_op.rowptr), ptr(l_op.colidx), ptr(l_op.vals), l_op.nnz, n_in,
+                                     ptr(u.rowptr) if u else None, ptr(u.colidx) if u else None, ptr(u.vals) if u else None,
+                                     u.nnz if u else 0, n_out, ptr(d_op.colidx) if d_op is not None else None, ptr(x_vm), ptr(w),
+                                     ptr(bb), 1 if relu else 0, ptr(y), stream_ptr()), "mvb_cheb_layer_fwd")
+        ctx.ops = (l_op, u_op, d_op)
+        ctx.relu, ctx.has_bias = relu, bias is not None
+        ctx.save_for_backward(x_vm, w, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_vm, w, y = ctx.saved_tensors
+        l_op, u, d_op = ctx.ops
+        n_in, b, fin = x_vm.shape
+        k, _, fout = w.shape
+        n = l_op.n_rows
+        n_out = d_op.n_rows if d_op is not None else n
+        dy = dy.contiguous()
+        dx = torch.empty_like(x_vm) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w)
+        db = torch.empty(fout, device=w.device, dtype=torch.float32) if ctx.has_bias else None
+        ws_bytes = lib.mvb_cheb_layer_bwd_workspace_bytes(b, fin, fout, k)
+        ws = torch.empty(ws_bytes, device=w.device, dtype=torch.uint8)
+        check(lib.mvb_cheb_layer_bwd(n, b, fin, fout, k, ptr(l_op.rowptr), ptr(l_op.colidx), ptr(l_op.vals), ptr(l_op.rowptr_t),
+                                     ptr(l_op.colidx_t), ptr(l_op.vals_t), l_op.nnz, n_in,
+                                     ptr(u.rowptr) if u else None, ptr(u.colidx) if u else None, ptr(u.vals) if u else None,
+                                     ptr(u.rowptr_t) if u else None, ptr(u.colidx_t) if u else None, ptr(u.vals_t) if u else None,
+                                     u.nnz if u else 0, n_out, ptr(d_op.colidx) if d_op is not None else None, ptr(x_vm), ptr(w),
+                                     ptr(y) if ctx.relu else None, ptr(dy), ptr(dx), ptr(dw), ptr(db), ptr(ws), ws_bytes,
+                                     stream_ptr()), "mvb_cheb_layer_bwd")
+        return dx, dw, db, None, None, None, None
+
+
+def cheb_layer(x_vm, weight, bias, l_op: MeshOperator, u_op: Optional[MeshOperator] = None,
+               d_op: Optional[MeshOperator] = None, relu: bool = True):
+    """[U prologue] -> Chebyshev conv (+bias, ReLU) -> [D row selection] on vertex-major tensors: the fused
+    one-launch kernel when the level fits shared memory (cheb_layer_supported), else the composition of
+    pool / cheb_conv / pool."""
+    n = l_op.n_rows
+    b, fin = x_vm.shape[1], x_vm.shape[2]
+    k, _, fout = weight.shape
+    if x_vm.is_cuda and cheb_layer_supported(n, b, fin, fout, k, l_op, u_op, d_op):
+        return _ChebLayerFn.apply(x_vm, weight, bias, l_op, u_op, d_op, relu)
+    if u_op is not None:
+        x_vm = pool(x_vm, u_op)
+    y = cheb_conv(x_vm, weight, bias, l_op, relu)
+    if d_op is not None:
+        y = pool(y, d_op)
+    return y

@@ -1,0 +1,116 @@
+"""GPU parity of the mesh-resident fused coarse-level layers (mvb_cheb_layer_fwd/bwd through the C
+ABI; models/cheb_VAE.py:264-265, 284-285) against (1) the CPU oracle's SurfacePool / ChebConv_batch
+composition on the same seeded inputs and (2) the step-by-step CUDA path (pool + cheb_conv + pool).
+fp32 tolerance 1e-4 relative (max|a-b| / max|b| per tensor); measured <= 3e-6."""
+import pytest
+import torch
+
+from tests.helpers import OPERATORS_NPZ, rel_err
+from oracle import mesh_vae_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def mvb():
+    import meshvae_b200
+    return meshvae_b200
+
+
+@pytest.fixture(scope="module")
+def ops():
+    return O.load_operators(OPERATORS_NPZ)
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+# (kind, level of the conv, batch, Fin, Fout, relu, bias)
+CASES = [("enc", 2, 64, 16, 16, True, True), ("enc", 3, 64, 16, 32, True, True), ("dec", 3, 64, 32, 32, True, True),
+         ("dec", 2, 64, 32, 16, True, True), ("plain", 2, 5, 16, 16, False, True), ("plain", 3, 1, 32, 8, True, False),
+         ("enc", 2, 3, 8, 16, True, True), ("dec", 2, 100, 16, 32, False, True), ("plain", 4, 7, 32, 32, True, True)]
+
+
+@pytest.mark.parametrize("kind,lvl,b,fin,fout,relu,bias", CASES)
+def test_fused_layer_matches_oracle_and_stepwise(mvb, ops, kind, lvl, b, fin, fout, relu, bias):
+    A, D, U, nn_ = ops
+    Fn = mvb.functional
+    n = nn_[lvl]
+    K = 6
+    ei, norm = O.cheb_norm(A[lvl]._indices(), n)
+    up = U[lvl] if kind == "dec" else None            # U[lvl]: level lvl+1 -> lvl
+    down = D[lvl] if kind == "enc" else None          # D[lvl]: level lvl -> lvl+1
+    n_in = up.shape[1] if up is not None else n
+    x = _rand(b, n_in, fin, seed=1)
+    w = _rand(K, fin, fout, seed=2, scale=0.1)
+    bs = _rand(fout, seed=3, scale=0.1) if bias else None
+    # ---- oracle (CPU): the reference's module composition ----
+    xr, wr = x.clone().requires_grad_(), w.clone().requires_grad_()
+    br = bs.clone().requires_grad_() if bias else None
+    h = O.surface_pool(xr, up._indices(), up._values(), up.shape) if up is not None else xr
+    h = O.cheb_conv_batch(h, ei, norm, wr, br)
+    h = torch.relu(h) if relu else h
+    yr = O.surface_pool(h, down._indices(), down._values(), down.shape) if down is not None else h
+    gy = _rand(*yr.shape, seed=4)
+    yr.backward(gy)
+    # ---- fused kernel ----
+    dev = torch.device("cuda:0")
+    l_op = mvb.operators.from_edges(ei.to(dev), norm.to(dev), n, dev)
+    u_op = None if up is None else mvb.operators.from_sparse(up.to(dev), dev)
+    d_op = None if down is None else mvb.operators.from_sparse(down.to(dev), dev)
+    assert Fn.cheb_layer_supported(n, b, fin, fout, K, l_op, u_op, d_op)
+    xg = Fn.to_vertex_major(x.to(dev)).clone().requires_grad_()
+    wg = w.to(dev).requires_grad_()
+    bg = bs.to(dev).requires_grad_() if bias else None
+    c0 = mvb._lib.lib.mvb_launch_count()
+    yg = Fn.cheb_layer(xg, wg, bg, l_op, u_op, d_op, relu=relu)
+    assert mvb._lib.lib.mvb_launch_count() - c0 == 1, "the fused layer must be ONE launch"
+    yg.backward(Fn.to_vertex_major(gy.to(dev)).contiguous())
+    assert rel_err(Fn.from_vertex_major(yg), yr) < TOL
+    assert rel_err(Fn.from_vertex_major(xg.grad), xr.grad) < TOL
+    assert rel_err(wg.grad, wr.grad) < TOL
+    if bias:
+        assert rel_err(bg.grad, br.grad) < TOL
+    # ---- step-by-step CUDA path on the same inputs ----
+    xs = xg.detach().clone().requires_grad_()
+    ws = wg.detach().clone().requires_grad_()
+    bsg = bg.detach().clone().requires_grad_() if bias else None
+    h = Fn.pool(xs, u_op) if u_op is not None else xs
+    h = Fn.cheb_conv(h, ws, bsg, l_op, relu)
+    ys = Fn.pool(h, d_op) if d_op is not None else h
+    ys.backward(Fn.to_vertex_major(gy.to(dev)).contiguous())
+    assert rel_err(yg, ys) < TOL and rel_err(xg.grad, xs.grad) < TOL and rel_err(wg.grad, ws.grad) < TOL
+
+
+def test_fused_layer_is_deterministic_and_needs_no_input_grad(mvb, ops):
+    A, D, U, nn_ = ops
+    Fn = mvb.functional
+    dev = torch.device("cuda:0")
+    n = nn_[2]
+    ei, norm = O.cheb_norm(A[2]._indices(), n)
+    l_op = mvb.operators.from_edges(ei.to(dev), norm.to(dev), n, dev)
+    d_op = mvb.operators.from_sparse(D[2].to(dev), dev)
+    x = _rand(n, 64, 16, seed=5).to(dev)                     # no grad: dx is skipped
+    w = _rand(6, 16, 16, seed=6, scale=0.1).to(dev).requires_grad_()
+    outs = []
+    for _ in range(2):
+        w.grad = None
+        y = Fn.cheb_layer(x, w, None, l_op, None, d_op, relu=True)
+        y.square().sum().backward()
+        outs.append((y.detach().clone(), w.grad.clone()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_unsupported_levels_fall_back(mvb, ops):
+    A, D, U, nn_ = ops
+    Fn = mvb.functional
+    dev = torch.device("cuda:0")
+    ei, norm = O.cheb_norm(A[0]._indices(), nn_[0])
+    l_op = mvb.operators.from_edges(ei.to(dev), norm.to(dev), nn_[0], dev)
+    assert not Fn.cheb_layer_supported(nn_[0], 4, 16, 16, 6, l_op, None, None)      # level 0 does not fit shared memory
+    x = _rand(nn_[0], 2, 16, seed=7).to(dev)
+    w = _rand(6, 16, 16, seed=8, scale=0.1).to(dev)
+    y = Fn.cheb_layer(x, w, None, l_op, None, None, relu=True)                       # composition path
+    assert torch.equal(y, Fn.cheb_conv(x, w, None, l_op, True))
