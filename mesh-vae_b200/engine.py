@@ -81,8 +81,21 @@ class TrainEngine:
             rank = dist.get_rank() if self.world > 1 else 0
             net.dropout_stream.offset_dev = self.opt.step_count
             net.dropout_stream.seed = (net.dropout_stream.seed + 7919 * rank) & 0xFFFFFFFFFFFFFFFF
+        # Gradient sinks: the backward kernels write dW / db straight into the parameter's view of the flat
+        # exchange buffer (no per-parameter allocation, no pack copy).  A second probe step finds the few
+        # parameters whose gradient still arrives through torch autograd (the 3-channel convolutions, whose
+        # weights pass through the differentiable zero-padding of functional.cheb_conv): those are copied.
+        for p, v in zip(self.opt.params, self.opt.grad_views):
+            p._mvb_grad_sink = v
+        net.zero_grad(set_to_none=True)
+        loss, *_ = net(self.x, self.x_gt, self.y_hot, m_type="train", eps=self.eps)
+        loss.backward()
+        self.loose = [(p, v) for p, v in zip(self.opt.params, self.opt.grad_views) if p.grad is not None]
+        for p, v in zip(self.opt.params, self.opt.grad_views):
+            if p.grad is None:
+                p.grad = v                      # the sink IS the gradient
         self.loss = torch.zeros((), device=self.dev, dtype=torch.float64)
-        self.stats = torch.zeros(3, device=self.dev, dtype=torch.float64)   # kld mean, rec mean, correct
+        self.kld = self.rec = self.correct = None
         self.use_graph = use_graph
         self.g_fb = self.g_opt = None
         self.launches_per_step = None
@@ -90,15 +103,21 @@ class TrainEngine:
 
     # ---- device work of one step -------------------------------------------------------------
     def _fwd_bwd(self):
-        self.net.zero_grad(set_to_none=True)
+        for p, _ in self.loose:
+            p.grad = None
         loss, correct, recon, (kld, rec, z_), y_hat = self.net(self.x, self.x_gt, self.y_hot, m_type="train",
                                                                 eps=self.eps)
         loss.backward()
-        self.opt.pack_grads()
+        if self.loose:
+            torch._foreach_copy_([v for _, v in self.loose], [p.grad for p, _ in self.loose])
         self.loss.copy_(loss.detach())
-        self.stats[0] = kld.mean()
-        self.stats[1] = rec.mean()
-        self.stats[2] = correct
+        # per-batch statistics of main.py:83-85: the tensors stay device-resident (static addresses under
+        # graph replay); stats() reduces them on demand instead of inside every step
+        self.kld, self.rec, self.correct = kld, rec, correct
+
+    def stats(self):
+        """(mean kld, mean rec_loss, correct) of the last step - main.py:83-85 reads these per batch"""
+        return float(self.kld.mean()), float(self.rec.mean()), int(self.correct)
 
     def _optim(self):
         self.opt.step(1.0 / self.world)

@@ -21,6 +21,21 @@ def _req_cuda(t: torch.Tensor, name: str, dtype=torch.float32):
         raise _lib.MvbError(f"{name}: expected {dtype}, got {t.dtype}")
 
 
+def _sink(t):
+    """Gradient sink of a Parameter: a contiguous view (of the engine's flat gradient buffer) that the
+    backward kernels write straight into; the Function then returns None for that input, so autograd
+    neither allocates nor copies (engine.TrainEngine installs the sinks; absent = ordinary autograd)."""
+    return None if t is None else getattr(t, "_mvb_grad_sink", None)
+
+
+def _grad_out(sink, like):
+    return sink if sink is not None else torch.empty_like(like)
+
+
+def _ret(sink, g):
+    return None if sink is not None else g
+
+
 def to_vertex_major(x: torch.Tensor) -> torch.Tensor:
     """logical [B, N, F] (any strides) -> physical [N, B, F] contiguous; free when x is already a
     permuted view of a vertex-major buffer (which is what every module of this package returns)."""
@@ -56,6 +71,7 @@ class _ChebConvFn(torch.autograd.Function):
                                ptr(bb), 1 if relu else 0, ptr(basis) if basis.numel() else None, ptr(y), stream_ptr()),
               "mvb_cheb_fwd")
         ctx.op, ctx.relu, ctx.has_bias = op, relu, bias is not None
+        ctx.sinks = (_sink(weight), _sink(bias))
         ctx.save_for_backward(x_vm, basis, w, y if relu else None)
         return y
 
@@ -68,15 +84,16 @@ class _ChebConvFn(torch.autograd.Function):
         dy = dy.contiguous()
         need_dx = ctx.needs_input_grad[0]
         dx = torch.empty_like(x_vm) if need_dx else None
-        dw = torch.empty_like(w)
-        db = torch.empty(fout, device=w.device, dtype=torch.float32) if ctx.has_bias else None
+        sw, sb = ctx.sinks
+        dw = _grad_out(sw, w)
+        db = (sb if sb is not None else torch.empty(fout, device=w.device, dtype=torch.float32)) if ctx.has_bias else None
         na = op.n_active
         ws_bytes = lib.mvb_cheb_bwd_workspace_bytes(n, b, fin, fout, k, na, 1 if need_dx else 0)
         ws = torch.empty(ws_bytes, device=w.device, dtype=torch.uint8)
         check(lib.mvb_cheb_bwd(n, b, fin, fout, k, na, op.nnz, ptr(op.rowptr_t), ptr(op.colidx_t), ptr(op.vals_t), ptr(x_vm),
                                ptr(basis) if basis.numel() else None, ptr(w), ptr(y) if ctx.relu else None, ptr(dy), ptr(dx),
                                ptr(dw), ptr(db), ptr(ws), ws_bytes, stream_ptr()), "mvb_cheb_bwd")
-        return dx, dw, db, None, None
+        return dx, _ret(sw, dw), _ret(sb, db), None, None
 
 
 def cheb_conv(x_vm: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], op: MeshOperator,
@@ -192,6 +209,7 @@ class _VaeLossFn(torch.autograd.Function):
                                    ptr(dnll), ptr(ws), ws_bytes, stream_ptr()), "mvb_vae_loss_fwd")
         ctx.save_for_backward(dnll, mu, logvar, y_hat, y)
         ctx.dims = (b, n, c, z, ncls)
+        ctx.set_materialize_grads(False)          # no zero tensors for the undefined grads of kld / rec / correct
         if not f64:                     # all-fp32 call (inference.py:87): the reference returns fp32
             loss, rec = loss.float(), rec.float()
         ctx.mark_non_differentiable(kld, rec, correct)
@@ -330,6 +348,7 @@ class _LinearFn(torch.autograd.Function):
                                  off_host, ptr(y), y_vm_f, stream_ptr()), "mvb_linear_fwd")
         ctx.dims = (m, k, n, x_vm_f, y_vm_f, relu, float(p))
         ctx.has_bias = bias is not None
+        ctx.sinks = (_sink(weight), _sink(bias))
         ctx.save_for_backward(x, w, y if relu else None)
         return y
 
@@ -339,11 +358,12 @@ class _LinearFn(torch.autograd.Function):
         m, k, n, x_vm_f, y_vm_f, relu, p = ctx.dims
         gy = gy.contiguous()
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        dw = torch.empty_like(w)
-        db = torch.empty(n, device=w.device, dtype=torch.float32) if ctx.has_bias else None
+        sw, sb = ctx.sinks
+        dw = _grad_out(sw, w)
+        db = (sb if sb is not None else torch.empty(n, device=w.device, dtype=torch.float32)) if ctx.has_bias else None
         check(lib.mvb_linear_bwd(m, k, n, ptr(x), x_vm_f, ptr(w), ptr(y), ptr(gy), y_vm_f, 1 if relu else 0, p, ptr(dx), ptr(dw),
                                  ptr(db), stream_ptr()), "mvb_linear_bwd")
-        return dx, dw, db, None, None, None, None, None
+        return dx, _ret(sw, dw), _ret(sb, db), None, None, None, None, None
 
 
 def linear(x, weight, bias=None, relu: bool = False, p: float = 0.0, rng=_NO_RNG, x_vm: bool = False, y_vm_f: int = 0):
@@ -369,6 +389,7 @@ class _VaeHeadsFn(torch.autograd.Function):
         if tuple(y_onehot.shape) != (b, c):
             raise _lib.MvbError(f"vae_heads: y is {tuple(y_onehot.shape)}, expected {(b, c)}")
         eps_c = None if eps is None else eps.contiguous()
+        ctx_params = (wc, bc, wm, bm, wv, bv)
         wc, bc, wm, bm, wv, bv = (t.contiguous() for t in (wc, bc, wm, bm, wv, bv))
         dev = h.device
         y_hat = torch.empty((b, c), device=dev, dtype=torch.float32)
@@ -382,6 +403,7 @@ class _VaeHeadsFn(torch.autograd.Function):
                                     ptr(zcat), stream_ptr()), "mvb_vae_heads_fwd")
         ctx.save_for_backward(h, y_onehot, eps_c, wc, wm, wv, y_hat, logvar)
         ctx.cfg = (b, hd, z, c, float(p), seed, off_dev, off_host)
+        ctx.sinks = tuple(_sink(t) for t in (ctx_params[0], ctx_params[1], ctx_params[2], ctx_params[3], ctx_params[4], ctx_params[5]))
         return y_hat, mu, logvar, zz, zcat
 
     @staticmethod
@@ -391,15 +413,17 @@ class _VaeHeadsFn(torch.autograd.Function):
         gs = [None if g is None else g.contiguous() for g in (g_yhat, g_mu, g_logvar, g_z, g_zcat)]
         dev = h.device
         g_h = torch.empty_like(h)
-        dwc, dwm, dwv = torch.empty_like(wc), torch.empty_like(wm), torch.empty_like(wv)
-        dbc = torch.empty(c, device=dev, dtype=torch.float32)
-        dbm = torch.empty(z, device=dev, dtype=torch.float32)
-        dbv = torch.empty(z, device=dev, dtype=torch.float32)
+        sk = ctx.sinks
+        dwc, dwm, dwv = _grad_out(sk[0], wc), _grad_out(sk[2], wm), _grad_out(sk[4], wv)
+        dbc = sk[1] if sk[1] is not None else torch.empty(c, device=dev, dtype=torch.float32)
+        dbm = sk[3] if sk[3] is not None else torch.empty(z, device=dev, dtype=torch.float32)
+        dbv = sk[5] if sk[5] is not None else torch.empty(z, device=dev, dtype=torch.float32)
         check(lib.mvb_vae_heads_bwd(b, hd, z, c, ptr(h), ptr(y_onehot), ptr(eps), ptr(wc), ptr(wm), ptr(wv), ptr(y_hat),
                                     ptr(logvar), p, seed, ptr(off_dev), off_host, ptr(gs[0]), ptr(gs[1]), ptr(gs[2]), ptr(gs[3]),
                                     ptr(gs[4]), ptr(g_h), ptr(dwc), ptr(dbc), ptr(dwm), ptr(dbm), ptr(dwv), ptr(dbv),
                                     stream_ptr()), "mvb_vae_heads_bwd")
-        return g_h, None, None, dwc, dbc, dwm, dbm, dwv, dbv, None, None
+        return (g_h, None, None, _ret(sk[0], dwc), _ret(sk[1], dbc), _ret(sk[2], dwm), _ret(sk[3], dbm), _ret(sk[4], dwv),
+                _ret(sk[5], dbv), None, None)
 
 
 def vae_heads(h, y_onehot, eps, classifier, z_mean, z_log_var, p: float = 0.0, rng=_NO_RNG):
@@ -450,6 +474,7 @@ class _ChebLayerFn(torch.autograd.Function):
                                      ptr(bb), 1 if relu else 0, ptr(y), stream_ptr()), "mvb_cheb_layer_fwd")
         ctx.ops = (l_op, u_op, d_op)
         ctx.relu, ctx.has_bias = relu, bias is not None
+        ctx.sinks = (_sink(weight), _sink(bias))
         ctx.save_for_backward(x_vm, w, y if relu else None)
         return y
 
@@ -463,8 +488,9 @@ class _ChebLayerFn(torch.autograd.Function):
         n_out = d_op.n_rows if d_op is not None else n
         dy = dy.contiguous()
         dx = torch.empty_like(x_vm) if ctx.needs_input_grad[0] else None
-        dw = torch.empty_like(w)
-        db = torch.empty(fout, device=w.device, dtype=torch.float32) if ctx.has_bias else None
+        sw, sb = ctx.sinks
+        dw = _grad_out(sw, w)
+        db = (sb if sb is not None else torch.empty(fout, device=w.device, dtype=torch.float32)) if ctx.has_bias else None
         ws_bytes = lib.mvb_cheb_layer_bwd_workspace_bytes(b, fin, fout, k)
         ws = torch.empty(ws_bytes, device=w.device, dtype=torch.uint8)
         check(lib.mvb_cheb_layer_bwd(n, b, fin, fout, k, ptr(l_op.rowptr), ptr(l_op.colidx), ptr(l_op.vals), ptr(l_op.rowptr_t),
@@ -474,7 +500,7 @@ class _ChebLayerFn(torch.autograd.Function):
                                      u.nnz if u else 0, n_out, ptr(d_op.colidx) if d_op is not None else None, ptr(x_vm), ptr(w),
                                      ptr(y) if ctx.relu else None, ptr(dy), ptr(dx), ptr(dw), ptr(db), ptr(ws), ws_bytes,
                                      stream_ptr()), "mvb_cheb_layer_bwd")
-        return dx, dw, db, None, None, None, None
+        return dx, _ret(sw, dw), _ret(sb, db), None, None, None, None
 
 
 def cheb_layer(x_vm, weight, bias, l_op: MeshOperator, u_op: Optional[MeshOperator] = None,

@@ -1,0 +1,104 @@
+"""Training-loop parity on the GPU (-m gpu): TrainEngine (CUDA graphs, gradient sinks into the flat
+buffer, fused Adam) against the CPU oracle model trained with torch.optim.Adam - the body of
+main.py:67-85 - on the same weights, batches and reparameterisation noise.
+north_star gate: loss curves within 1 % over 100 steps; asserted here at 1e-3 relative per step
+(dropout off so that both sides are deterministic; measured ~1e-5)."""
+import copy
+
+import pytest
+import torch
+
+from tests.helpers import OPERATORS_NPZ, seeded_state_dict, seeded_batch, rel_err
+from oracle import mesh_vae_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _models(mvb, dropout):
+    A, D, U, nn_ = O.load_operators(OPERATORS_NPZ)
+    cfg = copy.deepcopy(O.DEFAULT_CONFIG)
+    cfg["dropout"] = dropout
+    ref = O.OracleChebVAE(3, cfg, D, U, A, nn_)
+    ref.load_state_dict(seeded_state_dict(ref, 11))
+    dev = torch.device("cuda:0")
+    net = mvb.cheb_VAE(3, copy.deepcopy(cfg), [d.to(dev) for d in D], [u.to(dev) for u in U], [a.to(dev) for a in A], nn_)
+    net.load_state_dict(seeded_state_dict(net, 11))
+    return ref, net.to(dev), nn_
+
+
+def test_loss_curve_matches_oracle_100_steps():
+    import meshvae_b200 as mvb
+    from meshvae_b200.engine import TrainEngine
+    B, steps = 4, 100
+    ref, net, nn_ = _models(mvb, 0.0)
+    ref.train()
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3, weight_decay=5e-4)          # main.py:251
+    eng = TrainEngine(net, B, lr=1e-3, weight_decay=5e-4, x_gt_dtype=torch.float64, use_graph=True)
+    eng.capture(warmup=2)
+    batches = [seeded_batch(B, nn_[0], 100 + i) for i in range(4)]                # 4 batches, cycled (epochs)
+    worst = 0.0
+    for s in range(steps):
+        x, y, eps = batches[s % len(batches)]
+        opt.zero_grad()
+        lo, *_ = ref(x, x.double(), torch.nn.functional.one_hot(y, 2), m_type="train", eps=eps)
+        lo.backward()
+        lg = eng.step(x.pin_memory(), x.double().pin_memory(), y.pin_memory(), eps_host=eps.pin_memory())
+        if s == 0:
+            # the flat exchange buffer holds exactly the oracle's gradients (sinks + the copied 3-channel convs)
+            views = dict(zip([id(p) for p in eng.opt.params], eng.opt.grad_views))
+            for (name, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+                if q.grad is None:
+                    assert id(p) not in views, name
+                else:
+                    assert rel_err(views[id(p)], q.grad) < 1e-4, name
+        opt.step()
+        rel = abs(lg - float(lo.detach())) / abs(float(lo.detach()))
+        worst = max(worst, rel)
+        assert rel < 1e-3, f"step {s}: engine loss {lg} vs oracle {float(lo.detach())}"
+    # The trained parameters: Adam normalises the step, so elements whose gradient is at rounding-noise
+    # level drift by up to lr per step on either side.  Two runs of the CPU oracle itself whose gradients
+    # differ by 1e-5 relative (the parity tolerance) end 100 steps 1-8 % apart per tensor (L2) with a loss
+    # deviation of 6e-5 - measured with the reference arithmetic; the bound below is that envelope.
+    po = dict(ref.named_parameters())
+    for name, p in net.named_parameters():
+        if name.startswith("dec_lin_1"):
+            continue                                    # dead parameter (quirk 7): untouched on both sides
+        a, r = p.detach().cpu().double(), po[name].detach().double()
+        d = float((a - r).norm() / r.norm())
+        assert d < 0.2, (name, d)
+    kld, rec, correct = eng.stats()
+    assert kld >= 0 and rec > 0 and 0 <= correct <= B
+    print(f"worst relative loss deviation over {steps} steps: {worst:.2e}")
+
+
+def test_graph_and_eager_engines_are_bit_identical():
+    import meshvae_b200 as mvb
+    from meshvae_b200.engine import TrainEngine
+    B = 3
+    losses = []
+    for use_graph in (True, False):
+        _, net, nn_ = _models(mvb, 0.0)
+        eng = TrainEngine(net, B, use_graph=use_graph)
+        eng.capture(warmup=1)
+        out = []
+        for s in range(5):
+            x, y, eps = seeded_batch(B, nn_[0], 300 + s)
+            out.append(eng.step(x, x.double(), y, eps_host=eps))
+        losses.append(out)
+    assert losses[0] == losses[1]
+
+
+def test_dropout_training_runs_and_decreases_loss():
+    """dropout 0.2 as in files/default.cfg: masks change from replay to replay (device offset = Adam step
+    counter) and the loss still goes down on a fixed batch."""
+    import meshvae_b200 as mvb
+    from meshvae_b200.engine import TrainEngine
+    B = 8
+    _, net, nn_ = _models(mvb, 0.2)
+    eng = TrainEngine(net, B, lr=1e-3, weight_decay=5e-4)
+    eng.capture(warmup=2)
+    x, y, eps = seeded_batch(B, nn_[0], 77)
+    ls = [eng.step(x, x.double(), y, eps_host=eps) for _ in range(60)]
+    assert all(l == l for l in ls)                      # finite
+    assert len(set(ls[:10])) == 10                      # fresh masks / updates every replay
+    assert sum(ls[-10:]) / 10 < sum(ls[:10]) / 10
