@@ -55,7 +55,8 @@ int mvb_set_tensor_cores(int enable);
  * results are bit-identical either way: same per-row summation order) */
 int mvb_set_spmm_band(int enable);
 /* enable (default) / disable the fused multi-step recurrence kernels used when a level fits shared
- * memory (bit-identical to the step-by-step SpMM launches) */
+ * memory (bit-identical to the step-by-step SpMM launches); a value >= 64 enables them with that
+ * many threads per block (tuning hook; default 1024) */
 int mvb_set_fused_recurrence(int enable);
 /* tuning hook: force the SpMM block shape (tx column quads per block row, chunk = consecutive rows
  * walked by one block); 0, 0 restores the automatic choice */
@@ -119,13 +120,22 @@ int mvb_cheb_fwd(int N, int B, int Fin, int Fout, int K, int n_active, int nnz, 
                  const float *bias, int relu, float *basis, float *y, void *stream);
 
 /* ---- A13: Chebyshev convolution backward (autograd of nn/conv.py:557-577) ------------------
- * dW_k = sum_{v,b} T_k^T dY ; db = sum dY ; G_{K-1} = dY W_{K-1}^T ;
- * G_k = dY W_k^T + 2 L^T G_{k+1} - G_{k+2} ; dX = dY W_0^T + L^T G_1 - G_2.
+ * Two algebraically equal forms (L acts on vertices, W on features, so they commute):
+ *   basis form  : dW_k = T_k^T G ; G_{K-1} = G W_{K-1}^T ; G_k = G W_k^T + 2 L^T G_{k+1} - G_{k+2} ;
+ *                 dX = G W_0^T + L^T G_1 - G_2          (what autograd does to the reference code;
+ *                 needs the forward basis T_1..T_{K-1});
+ *   adjoint form: S_0 = G, S_1 = L^T G, S_k = 2 L^T S_{k-1} - S_{k-2} ; dW_k = x^T S_k ;
+ *                 dX = sum_k S_k W_k^T                  (the forward kernels run on G; `basis` unused).
+ * G = dY, masked by y_for_relu > 0 when the forward ran with relu != 0 (pass the forward output).
+ * mvb_cheb_bwd_uses_basis(Fin, Fout, need_dx) tells which form mvb_cheb_bwd takes (1 = basis form:
+ * the caller must keep `basis` from the forward call; 0 = adjoint form: `basis` may be NULL and the
+ * forward planes need not be kept).  The adjoint form is chosen when dx is wanted and
+ * Fout <= 1.2 Fin (less plane traffic, no reverse recurrence).
  * CSR arguments are L^T (for the symmetric L_hat of nn/conv.py:541-555 this equals L).
- * y_for_relu: the forward output when the forward ran with relu != 0 (dY is masked by y > 0),
- * else NULL.  dx may be NULL (first encoder layer: the input needs no gradient), dbias may be
- * NULL.  dweight [K,Fin,Fout] and dbias [Fout] are OVERWRITTEN (deterministic two-pass
- * reduction, no atomics).  workspace: mvb_cheb_bwd_workspace_bytes(...) bytes, 16-byte aligned. */
+ * dx may be NULL (first encoder layer: the input needs no gradient), dbias may be NULL.
+ * dweight [K,Fin,Fout] and dbias [Fout] are OVERWRITTEN (deterministic ordered reductions, no
+ * atomics).  workspace: mvb_cheb_bwd_workspace_bytes(...) bytes, 16-byte aligned. */
+int mvb_cheb_bwd_uses_basis(int Fin, int Fout, int need_dx);
 size_t mvb_cheb_bwd_workspace_bytes(int N, int B, int Fin, int Fout, int K, int n_active,
                                     int need_dx);
 int mvb_cheb_bwd(int N, int B, int Fin, int Fout, int K, int n_active, int nnz, const int32_t *rowptr_t,

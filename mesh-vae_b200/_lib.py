@@ -48,6 +48,7 @@ SIGNATURES = {
     "mvb_pool_fwd": (c_int, [c_int, c_int, _vp, _vp, _vp, _vp, _vp, c_int64, _vp]),
     "mvb_pool_bwd": (c_int, [c_int, c_int, _vp, _vp, _vp, _vp, _vp, c_int64, _vp]),
     "mvb_cheb_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp, c_int, _vp, _vp, _vp]),
+    "mvb_cheb_bwd_uses_basis": (c_int, [c_int, c_int, c_int]),
     "mvb_cheb_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     "mvb_cheb_bwd": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                              _vp, c_size_t, _vp]),

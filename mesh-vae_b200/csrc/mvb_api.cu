@@ -212,12 +212,59 @@ static SideStream *side_stream() {
     return s.ok ? &s : nullptr;
 }
 
+// Two algebraically equal forms of the backward pass (L acts on vertices, W on features: they commute):
+//   basis form  : dW_k = T_k(L x)^T G,  dX = sum_k T_k(L^T) (G W_k^T)      - needs the forward basis T_k,
+//                 K planes P_k = G W_k^T and a reverse recurrence on Fin-wide planes;
+//   adjoint form: S_k = T_k(L^T) G,  dW_k = x^T S_k,  dX = sum_k S_k W_k^T - the FORWARD kernels run on G
+//                 (recurrence on Fout-wide planes, one contraction), nothing saved by the forward pass.
+// Plane traffic is ~(32 Fin + 2 Fout) vs ~(27 Fout + 2 Fin) plane-widths: the adjoint form is used when
+// the input gradient is wanted and Fout <= 1.2 Fin (every 16->16 layer of the reference model; the
+// first encoder layer, which needs no dX, keeps the basis form: its basis is only 3-4 columns wide).
+static bool adjoint_form(int Fin, int Fout, int need_dx) { return need_dx && 25 * Fout <= 30 * Fin && Fout % 4 == 0; }
+
+// fork the per-thread side stream from `st` (NULL when overlap is off or the fork fails)
+static SideStream *fork_side(cudaStream_t st) {
+    if (!g_overlap) return nullptr;
+    SideStream *side = side_stream();
+    if (!side) return nullptr;
+    if (cudaEventRecord(side->fork, st) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return side;
+}
+struct JoinGuard {   // the side stream must rejoin on every exit path (a captured graph must not end forked)
+    SideStream *s;
+    cudaStream_t main;
+    ~JoinGuard() {
+        if (s) {
+            cudaEventRecord(s->join, s->stream);
+            cudaStreamWaitEvent(main, s->join, 0);
+        }
+    }
+};
+
+extern "C" int mvb_cheb_bwd_uses_basis(int Fin, int Fout, int need_dx) { return adjoint_form(Fin, Fout, need_dx) ? 0 : 1; }
+
 extern "C" size_t mvb_cheb_bwd_workspace_bytes(int N, int B, int Fin, int Fout, int K, int n_active, int need_dx) {
+    if (adjoint_form(Fin, Fout, need_dx)) {
+        size_t bytes = align_up(wgrad_partial_bytes(K * Fout, Fin), 256);
+        if (n_active < N) bytes += align_up(wgrad_partial_bytes(Fin, Fout), 256);
+        bytes += align_up((size_t)mask_colsum_blocks((int64_t)N * B) * Fout * sizeof(float), 256);
+        bytes += align_up((size_t)N * B * Fout * sizeof(float), 256);                       // G
+        bytes += align_up((size_t)(K > 1 ? K - 1 : 0) * n_active * B * Fout * sizeof(float), 256);   // S_1..S_{K-1}
+        return bytes;
+    }
     size_t bytes = align_up(wgrad_partial_bytes(K * Fin, Fout), 256);
     if (n_active < N) bytes += align_up(wgrad_partial_bytes(Fin, Fout), 256);
     if (need_dx) bytes += align_up((size_t)K * n_active * B * Fin * sizeof(float), 256);
     return bytes;
 }
+
+static int cheb_bwd_adjoint(int N, int B, int Fin, int Fout, int K, int n_active, int nnz, const int32_t *rowptr_t,
+                            const int32_t *colidx_t, const float *vals_t, const float *x, const float *weight,
+                            const float *y_for_relu, const float *dy, float *dx, float *dweight, float *dbias, char *ws,
+                            cudaStream_t st);
 
 extern "C" int mvb_cheb_bwd(int N, int B, int Fin, int Fout, int K, int n_active, int nnz,
                             const int32_t *rowptr_t, const int32_t *colidx_t, const float *vals_t,
@@ -226,12 +273,19 @@ extern "C" int mvb_cheb_bwd(int N, int B, int Fin, int Fout, int K, int n_active
                             float *dbias, void *workspace, size_t workspace_bytes, void *stream) {
     MVB_REQUIRE(N > 0 && B > 0 && Fin > 0 && Fout > 0 && K > 0, "cheb_bwd: bad sizes");
     MVB_REQUIRE(n_active >= 0 && n_active <= N, "cheb_bwd: n_active=%d outside [0,%d]", n_active, N);
-    MVB_REQUIRE(x && weight && dy && dweight && workspace && (K == 1 || n_active == 0 || basis), "cheb_bwd: null pointer");
+    const bool adj = adjoint_form(Fin, Fout, dx != nullptr);
+    MVB_REQUIRE(x && weight && dy && dweight && workspace && (adj || K == 1 || n_active == 0 || basis), "cheb_bwd: null pointer");
     MVB_REQUIRE(!dx || K == 1 || n_active == 0 || rowptr_t, "cheb_bwd: dx requested without L^T");
     if (!aligned16(workspace)) return set_err(MVB_EALIGN, "cheb_bwd: workspace not 16-byte aligned");
     const size_t need = mvb_cheb_bwd_workspace_bytes(N, B, Fin, Fout, K, n_active, dx != nullptr);
     if (workspace_bytes < need) return set_err(MVB_EWORKSPACE, "cheb_bwd: workspace %zu < %zu", workspace_bytes, need);
     cudaStream_t st = (cudaStream_t)stream;
+    if (adj) {
+        if (!aligned16(dy) || (y_for_relu && !aligned16(y_for_relu)))
+            return set_err(MVB_EALIGN, "cheb_bwd: dy / y must be 16-byte aligned");
+        return cheb_bwd_adjoint(N, B, Fin, Fout, K, n_active, nnz, rowptr_t, colidx_t, vals_t, x, weight, y_for_relu, dy, dx,
+                                dweight, dbias, reinterpret_cast<char *>(workspace), st);
+    }
     const int64_t rows_act = (int64_t)n_active * B;
     const int64_t rows_in = (int64_t)(N - n_active) * B;
     const int64_t ncols = (int64_t)B * Fin;
@@ -249,28 +303,9 @@ extern "C" int mvb_cheb_bwd(int N, int B, int Fin, int Fout, int K, int n_active
     // (P_k, reverse recurrence) are independent: fork the former onto a side stream so that the two
     // overlap (and become parallel branches of a captured CUDA graph), join before returning.
     cudaStream_t wst = st;
-    SideStream *side = nullptr;
-    if (dx && g_overlap) {
-        side = side_stream();
-        if (side) {
-            if (cudaEventRecord(side->fork, st) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork, 0) != cudaSuccess) {
-                cudaGetLastError();
-                side = nullptr;
-            } else {
-                wst = side->stream;
-            }
-        }
-    }
-    struct Join {   // the side stream must rejoin on every exit path (a captured graph must not end forked)
-        SideStream *s;
-        cudaStream_t main;
-        ~Join() {
-            if (s) {
-                cudaEventRecord(s->join, s->stream);
-                cudaStreamWaitEvent(main, s->join, 0);
-            }
-        }
-    } join_guard{side, st};
+    SideStream *side = dx ? fork_side(st) : nullptr;
+    if (side) wst = side->stream;
+    JoinGuard join_guard{side, st};
 
     // dW_k = T_k^T dY, db = 1^T dY over the active prefix ...
     WgradArgs wa;
@@ -348,6 +383,110 @@ extern "C" int mvb_cheb_bwd(int N, int B, int Fin, int Fout, int K, int n_active
         a.in_w = Fout;
         a.in0 = dy + rows_act * Fout;
         a.mask = y_for_relu ? y_for_relu + rows_act * Fout : nullptr;
+        a.wmat = weight;
+        a.w_transposed = 1;
+        a.w_fold = K;
+        a.out_planes = 1;
+        a.out_w = Fin;
+        a.out = dx + rows_act * Fin;
+        rc = launch_contract(a, st);
+        if (rc) return rc;
+    }
+    return MVB_OK;
+}
+
+static int cheb_bwd_adjoint(int N, int B, int Fin, int Fout, int K, int n_active, int nnz, const int32_t *rowptr_t,
+                            const int32_t *colidx_t, const float *vals_t, const float *x, const float *weight,
+                            const float *y_for_relu, const float *dy, float *dx, float *dweight, float *dbias, char *ws,
+                            cudaStream_t st) {
+    const int64_t rows_act = (int64_t)n_active * B, rows_in = (int64_t)(N - n_active) * B, rows_all = (int64_t)N * B;
+    const int64_t ncols = (int64_t)B * Fout;
+    const int64_t plane = (int64_t)n_active * ncols;
+    const size_t partA_bytes = align_up(wgrad_partial_bytes(K * Fout, Fin), 256);
+    const size_t partB_bytes = (n_active < N) ? align_up(wgrad_partial_bytes(Fin, Fout), 256) : 0;
+    const size_t col_bytes = align_up((size_t)mask_colsum_blocks(rows_all) * Fout * sizeof(float), 256);
+    const size_t g_bytes = align_up((size_t)rows_all * Fout * sizeof(float), 256);
+    float *partA = reinterpret_cast<float *>(ws);
+    float *partB = reinterpret_cast<float *>(ws + partA_bytes);
+    float *colpart = reinterpret_cast<float *>(ws + partA_bytes + partB_bytes);
+    float *Gbuf = reinterpret_cast<float *>(ws + partA_bytes + partB_bytes + col_bytes);
+    float *S = reinterpret_cast<float *>(ws + partA_bytes + partB_bytes + col_bytes + g_bytes);
+    // G = dY * [y > 0] over ALL rows, db = column sums of G
+    const float *G = y_for_relu ? Gbuf : dy;
+    int rc = launch_mask_colsum(rows_all, Fout, dy, y_for_relu, y_for_relu ? Gbuf : nullptr, dbias, colpart, st);
+    if (rc) return rc;
+    // S_k = T_k(L^T) G on the active prefix: the forward recurrence kernels with CSR(L^T)
+    if (n_active > 0 && K > 1) {
+        rc = launch_cheb_recur_fwd(n_active, nnz, K, rowptr_t, colidx_t, vals_t, G, S, ncols, st);
+        if (rc < 0) return rc;
+        for (int k = 1; k < K && rc == 0; ++k) {
+            float *sk = S + (int64_t)(k - 1) * plane;
+            const float *skm1 = (k == 1) ? G : S + (int64_t)(k - 2) * plane;
+            const float *skm2 = (k == 1) ? nullptr : (k == 2 ? G : S + (int64_t)(k - 3) * plane);
+            int rc2 = launch_spmm(n_active, n_active, rowptr_t, colidx_t, vals_t, skm1, sk, skm2, nullptr, k == 1 ? 1.f : 2.f, -1.f, ncols, st);
+            if (rc2) return rc2;
+        }
+    }
+    // weight-gradient branch on the side stream, input-gradient contraction on the main stream
+    cudaStream_t wst = st;
+    SideStream *side = fork_side(st);
+    if (side) wst = side->stream;
+    JoinGuard join_guard{side, st};
+    int nA = 0, m4A = 0, nB = 0, m4B = 0;
+    if (rows_act > 0) {      // A = [S_0|..|S_{K-1}]^T x   ([K*Fout, Fin]; dW_k[i][o] = A[k*Fout + o][i])
+        WgradArgs wa;
+        memset(&wa, 0, sizeof(wa));
+        wa.rows = rows_act;
+        wa.in_planes = K;
+        wa.in_w = Fout;
+        wa.in0 = G;
+        wa.in_rest = S;
+        wa.dy = x;
+        wa.n_out = Fin;
+        wa.partials = partA;
+        wa.partial_bytes = partA_bytes;
+        rc = launch_wgrad_partials(wa, 0, &nA, &m4A, wst);
+        if (rc) return rc;
+    }
+    if (rows_in > 0) {       // empty rows of the operator: S = x^T G, dW_k += cos(k pi/2) S
+        WgradArgs wb;
+        memset(&wb, 0, sizeof(wb));
+        wb.rows = rows_in;
+        wb.in_planes = 1;
+        wb.in_w = Fin;
+        wb.in0 = x + rows_act * Fin;
+        wb.dy = G + rows_act * Fout;
+        wb.n_out = Fout;
+        wb.partials = partB;
+        wb.partial_bytes = partB_bytes;
+        rc = launch_wgrad_partials(wb, 0, &nB, &m4B, wst);
+        if (rc) return rc;
+    }
+    rc = launch_wgrad_finalize(partA, nA, m4A, partB, nB, m4B, Fin, K * Fin, Fout, dweight, nullptr, wst, 1);
+    if (rc) return rc;
+    if (rows_act > 0) {      // dX = sum_k S_k W_k^T
+        ContractArgs a;
+        fill_contract(a);
+        a.rows = rows_act;
+        a.in_planes = K;
+        a.in_w = Fout;
+        a.in0 = G;
+        a.in_rest = S;
+        a.wmat = weight;
+        a.w_transposed = 2;
+        a.out_planes = 1;
+        a.out_w = Fin;
+        a.out = dx;
+        rc = launch_contract(a, st);
+        if (rc) return rc;
+    }
+    if (rows_in > 0) {       // empty rows: dX = G (sum_k c_k W_k)^T
+        ContractArgs a;
+        fill_contract(a);
+        a.rows = rows_in;
+        a.in_planes = 1;
+        a.in_w = Fout;
+        a.in0 = G + rows_act * Fout;
         a.wmat = weight;
         a.w_transposed = 1;
         a.w_fold = K;

@@ -110,10 +110,15 @@ contract_kernel(ContractArgs a, int M, int Nn, int M4, int N4, int LD, int R, in
             if (i < M4 * N4) {
                 const int m = i / N4, n = i - m * N4;
                 if (m < M && n < Nn) {
-                    for (int k = 0; k < nfold; k += 2) {
-                        const float wv = a.w_transposed ? __ldg(a.wmat + ((int64_t)k * Nn + n) * M + m)
-                                                        : __ldg(a.wmat + ((int64_t)k * M + m) * Nn + n);
-                        v[u] += (k & 2) ? -wv : wv;
+                    if (a.w_transposed == 2) {      // per-plane transposed: W[k][n][o], m = k*in_w + o
+                        const int k = m / a.in_w, o = m - k * a.in_w;
+                        v[u] = __ldg(a.wmat + ((int64_t)k * Nn + n) * a.in_w + o);
+                    } else {
+                        for (int k = 0; k < nfold; k += 2) {
+                            const float wv = a.w_transposed ? __ldg(a.wmat + ((int64_t)k * Nn + n) * M + m)
+                                                            : __ldg(a.wmat + ((int64_t)k * M + m) * Nn + n);
+                            v[u] += (k & 2) ? -wv : wv;
+                        }
                     }
                 }
             }
@@ -345,9 +350,12 @@ wgrad_kernel(WgradArgs a, int M, int has_bias, int M4, int N4, int LDT, int R, i
 // sums are then added in fixed order -> bit-reproducible.  Optional second partial set B holds
 // S = x^T dY over the operator's EMPTY rows ([Fin+1, n_out], single plane): there T_k = c_k x, so
 // dW_k += c_k S with c_k = cos(k pi/2)  (models/cheb_VAE.py:288 quirk path).
+// a_tr != 0: partial set A comes from the adjoint-basis backward, [S_0|..|S_{K-1}]^T x, stored
+// [K*fout][N4A] with N4A = round4(fin): element (k*fin + i, o) of dW is A[(k*fout + o)][i]; the bias
+// gradient then comes from the column-sum kernel, not from a "ones" row of A.
 __global__ void __launch_bounds__(256)
 wgrad_finalize_kernel(const float *__restrict__ partA, int nA, int M4A, const float *__restrict__ partB,
-                      int nB, int M4B, int fin, int M, int n_out, int N4, float *dweight,
+                      int nB, int M4B, int fin, int M, int n_out, int N4, int a_tr, int N4A, float *dweight,
                       float *dbias) {
     __shared__ float red[8][33];
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -356,9 +364,16 @@ wgrad_finalize_kernel(const float *__restrict__ partA, int nA, int M4A, const fl
     float s = 0.f;
     if (i < total) {
         const int m = i / n_out, n = i - m * n_out;
-        for (int p = ty; p < nA; p += 8) s += partA[(size_t)p * M4A * N4 + m * N4 + n];
+        const int k = m / fin;
+        if (a_tr) {
+            if (m < M) {
+                const size_t off = (size_t)(k * n_out + n) * N4A + (m - k * fin);
+                for (int p = ty; p < nA; p += 8) s += partA[(size_t)p * M4A * N4A + off];
+            }
+        } else {
+            for (int p = ty; p < nA; p += 8) s += partA[(size_t)p * M4A * N4 + m * N4 + n];
+        }
         if (nB > 0) {
-            const int k = m / fin;
             const int mb = (m < M) ? (m - k * fin) : fin;          // bias row of B sits at index fin
             const float c = (m < M) ? ((k & 1) ? 0.f : ((k & 2) ? -1.f : 1.f)) : 1.f;
             if (c != 0.f) {
@@ -380,6 +395,77 @@ wgrad_finalize_kernel(const float *__restrict__ partA, int nA, int M4A, const fl
         else
             dbias[n] = t;
     }
+}
+
+// G = dY * [y > 0] (optional write) and per-block column sums of G (for db): rows x ncol, ncol % 4 == 0.
+// Block = 256 threads = (ncol/4 column quads) x row lanes, a fixed chunk of rows per block; the
+// per-block partial sums are added in block order by colsum_finalize_kernel: deterministic.
+__global__ void __launch_bounds__(256)
+mask_colsum_kernel(int64_t rows, int nq, const float4 *__restrict__ dy, const float4 *__restrict__ y,
+                   float4 *__restrict__ g, float4 *__restrict__ part, int64_t rows_per_block) {
+    __shared__ float4 red[256];
+    const int tid = threadIdx.x;
+    const int q = tid % nq, rl = tid / nq, nrl = 256 / nq;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rl < nrl)
+        for (int64_t r = r0 + rl; r < r1; r += nrl) {
+            float4 v = __ldg(dy + r * nq + q);
+            if (y) {
+                const float4 m = __ldg(y + r * nq + q);
+                v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+                if (g) g[r * nq + q] = v;
+            }
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+    red[tid] = s;
+    __syncthreads();
+    if (part && tid < nq) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int l = 0; l < nrl; ++l) {
+            const float4 v = red[l * nq + tid];
+            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        part[(int64_t)blockIdx.x * nq + tid] = t;
+    }
+}
+
+// db[c] = sum over the blocks' partials, one warp per column: lane l adds partials l, l+32, ... in
+// order, then a fixed shuffle tree - deterministic, and ~nblocks/32 dependent loads instead of nblocks
+__global__ void __launch_bounds__(256)
+colsum_finalize_kernel(int nblocks, int ncol, const float *__restrict__ part, float *__restrict__ db) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (c >= ncol) return;
+    float s = 0.f;
+    for (int b = lane; b < nblocks; b += 32) s += part[(int64_t)b * ncol + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) db[c] = s;
+}
+
+int mask_colsum_blocks(int64_t rows) {
+    int64_t nb = (rows + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 2;
+    if (nb > cap) nb = cap;
+    return (int)(nb < 1 ? 1 : nb);
+}
+
+// g (may be NULL when y is NULL: then G is dy itself), db (may be NULL), part: mask_colsum_blocks(rows)*ncol floats
+int launch_mask_colsum(int64_t rows, int ncol, const float *dy, const float *y, float *g, float *db, float *part,
+                       cudaStream_t st) {
+    if (rows <= 0) return MVB_OK;
+    if (!y && !db) return MVB_OK;
+    MVB_REQUIRE(ncol % 4 == 0 && ncol <= 1024 && aligned16(dy) && (!y || aligned16(y)) && (!g || aligned16(g)) && aligned16(part),
+                "mask_colsum: %d columns / alignment not supported", ncol);
+    const int nb = mask_colsum_blocks(rows);
+    const int64_t rpb = (rows + nb - 1) / nb;
+    mask_colsum_kernel<<<nb, 256, 0, st>>>(rows, ncol / 4, (const float4 *)dy, (const float4 *)y, (float4 *)g,
+                                           db ? (float4 *)part : nullptr, rpb);
+    int rc = check_launch("mvb mask_colsum");
+    if (rc || !db) return rc;
+    colsum_finalize_kernel<<<(ncol + 7) / 8, 256, 0, st>>>(nb, ncol, part, db);
+    return check_launch("mvb colsum finalize");
 }
 
 static void wgrad_shape(int M, int n_out, int has_bias, int &M4, int &N4, int &LDT, int &MT, int &NT,
@@ -441,13 +527,13 @@ int launch_wgrad_partials(const WgradArgs &a, int has_bias, int *nparts, int *m4
     return check_launch("mvb wgrad");
 }
 
-// phase 2: dweight [M, n_out] (M = K*fin), dbias [n_out] or null
+// phase 2: dweight [M, n_out] (M = K*fin), dbias [n_out] or null.  a_transposed: see the kernel.
 int launch_wgrad_finalize(const float *partA, int nA, int M4A, const float *partB, int nB, int M4B,
-                          int fin, int M, int n_out, float *dweight, float *dbias, cudaStream_t st) {
+                          int fin, int M, int n_out, float *dweight, float *dbias, cudaStream_t st, int a_transposed) {
     const int total = (M + (dbias ? 1 : 0)) * n_out;
     const int N4 = round4(n_out);
     wgrad_finalize_kernel<<<(total + 31) / 32, dim3(32, 8), 0, st>>>(partA, nA, M4A, partB, nB, M4B, fin, M, n_out,
-                                                                    N4, dweight, dbias);
+                                                                    N4, a_transposed, round4(fin), dweight, dbias);
     return check_launch("mvb wgrad finalize");
 }
 

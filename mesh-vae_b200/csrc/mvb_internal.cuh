@@ -89,7 +89,8 @@ int launch_cheb_recur_bwd(int N, int nnz, int K, const int32_t *rowptr_t, const 
 // Generic small-matrix contraction over the rows of vertex-major activations:
 //   out[p_out][row][j] = act( sum_{p_in,i} in[p_in][row][i] * Wm[p_in*in_w + i][p_out*out_w + j] + bias )
 // in plane 0 = in0, planes 1.. = in_rest + (p-1)*rows*in_w.  Wm is [M, Nn] row-major in global
-// memory, or [Nn, M] row-major when w_transposed.  mask (optional, same layout as plane 0 of the
+// memory, or [Nn, M] row-major when w_transposed == 1, or - w_transposed == 2 - the weight tensor
+// [in_planes][Nn][in_w] itself read as sum_k S_k W_k^T (the adjoint-basis backward).  mask (optional, same layout as plane 0 of the
 // input): input values of plane 0 are zeroed where mask <= 0 (fused ReLU backward).
 struct ContractArgs {
     int64_t rows;
@@ -122,7 +123,11 @@ struct WgradArgs {
 size_t wgrad_partial_bytes(int M, int n_out);
 int launch_wgrad_partials(const WgradArgs &a, int has_bias, int *nparts, int *m4_out, cudaStream_t st);
 int launch_wgrad_finalize(const float *partA, int nA, int M4A, const float *partB, int nB, int M4B,
-                          int fin, int M, int n_out, float *dweight, float *dbias, cudaStream_t st);
+                          int fin, int M, int n_out, float *dweight, float *dbias, cudaStream_t st, int a_transposed = 0);
+// G = dY * [y > 0] (g written only when y != NULL) and db = column sums of G (when db != NULL)
+int mask_colsum_blocks(int64_t rows);
+int launch_mask_colsum(int64_t rows, int ncol, const float *dy, const float *y, float *g, float *db, float *part,
+                       cudaStream_t st);
 
 // tcgen05 paths (mvb_tc.cu): return 1 = handled, 0 = shape unsupported (use FFMA), < 0 = error
 int launch_contract_tc(const ContractArgs &a, cudaStream_t st);

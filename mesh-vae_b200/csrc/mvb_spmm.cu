@@ -223,56 +223,67 @@ spmm_band_kernel(int n_rows, const int32_t *__restrict__ rowptr, const int32_t *
 // (G_k = P_k + 2 L^T G_{k+1} - G_{k+2}) is fused the same way.  Summation order per row is the CSR
 // order, as in the step-by-step kernels: results are bit-identical to them.
 // ---------------------------------------------------------------------------------------------
+// CSR entries as (column, value) pairs: one 8-byte shared (or global) load per neighbour instead of two
+// 4-byte ones - the recurrence kernels are bound by shared-memory wavefronts (16 different rows per warp
+// make every CSR read a 16-address access)
 template <int CS4>
-__device__ __forceinline__ float4 row_gather(const float4 *__restrict__ src, const int32_t *colidx,
-                                             const float *vals, int s, int e, int cl) {
+__device__ __forceinline__ float4 row_gather(const float4 *__restrict__ src, const int2 *ce, int s, int e, int cl) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int j = s;
     for (; j + 2 <= e; j += 2) {
-        const int ca = colidx[j], cb = colidx[j + 1];
-        const float va = vals[j], vb = vals[j + 1];
-        const float4 xa = src[ca * CS4 + cl];
-        const float4 xb = src[cb * CS4 + cl];
-        fma4(acc, va, xa);
-        fma4(acc, vb, xb);
+        const int2 ea = ce[j], eb = ce[j + 1];
+        const float4 xa = src[ea.x * CS4 + cl];
+        const float4 xb = src[eb.x * CS4 + cl];
+        fma4(acc, __int_as_float(ea.y), xa);
+        fma4(acc, __int_as_float(eb.y), xb);
     }
-    if (j < e) fma4(acc, vals[j], src[colidx[j] * CS4 + cl]);
+    if (j < e) {
+        const int2 ea = ce[j];
+        fma4(acc, __int_as_float(ea.y), src[ea.x * CS4 + cl]);
+    }
     return acc;
 }
 
-// copy the CSR of the level into shared memory (after the two activation buffers) when it fits:
-// the per-row pointer chase rowptr -> colidx/vals -> gather then never leaves the SM
-__device__ __forceinline__ void stage_csr(int N, int nnz_smem, const int32_t *__restrict__ rowptr,
+// copy the CSR of the level into shared memory (after the two activation buffers): row pointers and
+// packed (column, value) entries.  The launcher guarantees that it fits.
+__device__ __forceinline__ void stage_csr(int N, int nnz, const int32_t *__restrict__ rowptr,
                                           const int32_t *__restrict__ colidx, const float *__restrict__ vals,
-                                          void *dst, const int32_t *&rp, const int32_t *&ci, const float *&va) {
-    if (nnz_smem < 0) {        // does not fit: keep reading the L2-resident arrays
-        rp = rowptr;
-        ci = colidx;
-        va = vals;
-        return;
-    }
+                                          void *dst, const int32_t *&rp, const int2 *&ce) {
     int32_t *srp = reinterpret_cast<int32_t *>(dst);
-    int32_t *sci = srp + ((N + 1 + 3) & ~3);
-    float *sva = reinterpret_cast<float *>(sci + ((nnz_smem + 3) & ~3));
+    int2 *sce = reinterpret_cast<int2 *>(srp + ((N + 1 + 3) & ~3));
     g2s_copy<4>(srp, rowptr, N + 1, threadIdx.x, blockDim.x);
-    g2s_copy<8>(sci, colidx, nnz_smem, threadIdx.x, blockDim.x);
-    g2s_copy<8>(sva, vals, nnz_smem, threadIdx.x, blockDim.x);
+    for (int base = 0; base < nnz; base += 8 * blockDim.x) {
+        int c[8];
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = base + u * blockDim.x + threadIdx.x;
+            if (i < nnz) {
+                c[u] = __ldg(colidx + i);
+                v[u] = __ldg(vals + i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = base + u * blockDim.x + threadIdx.x;
+            if (i < nnz) sce[i] = make_int2(c[u], __float_as_int(v[u]));
+        }
+    }
     rp = srp;
-    ci = sci;
-    va = sva;
+    ce = sce;
 }
 
 template <int CS4>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 cheb_recur_fwd_kernel(int N, int K, const int32_t *__restrict__ g_rowptr, const int32_t *__restrict__ g_colidx,
                       const float *__restrict__ g_vals, const float4 *__restrict__ x, float4 *__restrict__ basis,
                       int nc4, int nnz_smem) {
     extern __shared__ float4 sbuf[];
     float4 *cur = sbuf;                  // T_{k-1}
     float4 *old = sbuf + (size_t)N * CS4;  // T_{k-2}, overwritten by T_k
-    const int32_t *rowptr, *colidx;
-    const float *vals;
-    stage_csr(N, nnz_smem, g_rowptr, g_colidx, g_vals, sbuf + (size_t)2 * N * CS4, rowptr, colidx, vals);
+    const int32_t *rowptr;
+    const int2 *ce;
+    stage_csr(N, nnz_smem, g_rowptr, g_colidx, g_vals, sbuf + (size_t)2 * N * CS4, rowptr, ce);
     const int tid = threadIdx.x;
     const int cl = tid % CS4, rl = tid / CS4;
     const int RPP = blockDim.x / CS4;
@@ -297,7 +308,7 @@ cheb_recur_fwd_kernel(int N, int K, const int32_t *__restrict__ g_rowptr, const 
         float4 *outp = basis + (int64_t)(k - 1) * plane;
         for (int r = rl; r < N; r += RPP) {
             const int s = rowptr[r], e = rowptr[r + 1];
-            const float4 acc = row_gather<CS4>(cur, colidx, vals, s, e, cl);
+            const float4 acc = row_gather<CS4>(cur, ce, s, e, cl);
             float4 o;
             if (k == 1) {
                 o = make_float4(1.f * acc.x, 1.f * acc.y, 1.f * acc.z, 1.f * acc.w);
@@ -321,16 +332,16 @@ cheb_recur_fwd_kernel(int N, int K, const int32_t *__restrict__ g_rowptr, const 
 // P: K planes [N, nc4] (P_k = dY W_k^T); dx = P_0 + L^T G_1 - G_2 with G_{K-1} = P_{K-1},
 // G_k = P_k + 2 L^T G_{k+1} - G_{k+2}.  CSR arguments are L^T.  Requires K >= 2.
 template <int CS4>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 cheb_recur_bwd_kernel(int N, int K, const int32_t *__restrict__ g_rowptr, const int32_t *__restrict__ g_colidx,
                       const float *__restrict__ g_vals, const float4 *__restrict__ P, float4 *__restrict__ dx,
                       int nc4, int nnz_smem) {
     extern __shared__ float4 sbuf[];
     float4 *g1 = sbuf;                   // G_{k+1}
     float4 *g2 = sbuf + (size_t)N * CS4;   // G_{k+2}, overwritten by G_k
-    const int32_t *rowptr, *colidx;
-    const float *vals;
-    stage_csr(N, nnz_smem, g_rowptr, g_colidx, g_vals, sbuf + (size_t)2 * N * CS4, rowptr, colidx, vals);
+    const int32_t *rowptr;
+    const int2 *ce;
+    stage_csr(N, nnz_smem, g_rowptr, g_colidx, g_vals, sbuf + (size_t)2 * N * CS4, rowptr, ce);
     const int tid = threadIdx.x;
     const int cl = tid % CS4, rl = tid / CS4;
     const int RPP = blockDim.x / CS4;
@@ -377,7 +388,7 @@ cheb_recur_bwd_kernel(int N, int K, const int32_t *__restrict__ g_rowptr, const 
                 pv = col_ok ? __ldg(pk + (int64_t)r * nc4 + c) : zero;
             }
             const int s = rowptr[r], e = rowptr[r + 1];
-            const float4 acc = row_gather<CS4>(g1, colidx, vals, s, e, cl);
+            const float4 acc = row_gather<CS4>(g1, ce, s, e, cl);
             float4 o = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
             if (has_g2) {
                 const float4 zz = g2[r * CS4 + cl];
@@ -403,8 +414,11 @@ cheb_recur_bwd_kernel(int N, int K, const int32_t *__restrict__ g_rowptr, const 
     }
 }
 
-static int g_recur_fused = 1;
-void set_recur_fused(int v) { g_recur_fused = v; }
+static int g_recur_fused = 1, g_recur_threads = 1024;
+void set_recur_fused(int v) {          // 0 = off, 1 = on, >= 64: on with that many threads per block (tuning runs)
+    g_recur_fused = v != 0;
+    if (v >= 64 && v <= 1024) g_recur_threads = v & ~31;
+}
 
 static bool recur_shape(int N, int nnz, int64_t ncols, const void *a, const void *b, int *cs4, size_t *smem, int *nnz_smem) {
     if (!g_recur_fused || N < 1 || ncols % 4 != 0 || !aligned16(a) || !aligned16(b)) return false;
@@ -417,15 +431,15 @@ static bool recur_shape(int N, int nnz, int64_t ncols, const void *a, const void
         bytes = (size_t)2 * N * c * sizeof(float4);
     }
     if (bytes > 110 * 1024) return false;        // level 0 (4998 vertices) stays on the step-by-step kernels
+    // one block per SM at most: beyond a single wave the L2-resident step-by-step launches win
+    // (scripts/recur_ab.py: level 1, 256 meshes: 136 us stepwise vs 167 us fused; 64 meshes: 67 vs 54)
+    if ((nc4 + c - 1) / c > num_sms()) return false;
     *cs4 = c;
-    *nnz_smem = -1;
-    if (nnz >= 0) {
-        const size_t csr = ((size_t)((N + 1 + 3) & ~3) + 2 * (size_t)((nnz + 3) & ~3)) * 4;
-        if (bytes + csr <= 200 * 1024) {
-            bytes += csr;
-            *nnz_smem = nnz;
-        }
-    }
+    if (nnz < 0) return false;                   // the operator is staged in shared memory: its size must be known
+    const size_t csr = ((size_t)((N + 1 + 3) & ~3) + 2 * (size_t)((nnz + 3) & ~3)) * 4;
+    if (bytes + csr > 200 * 1024) return false;
+    bytes += csr;
+    *nnz_smem = nnz;
     *smem = bytes;
     return true;
 }
@@ -443,11 +457,11 @@ int launch_cheb_recur_fwd(int N, int nnz, int K, const int32_t *rowptr, const in
     if (cs4 == 2) {
         if (!attr2) { e = cudaFuncSetAttribute(cheb_recur_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr2 = true; }
         if (e == cudaSuccess)
-            cheb_recur_fwd_kernel<2><<<grid, 512, smem, st>>>(N, K, rowptr, colidx, vals, (const float4 *)x, (float4 *)basis, nc4, nnz_smem);
+            cheb_recur_fwd_kernel<2><<<grid, g_recur_threads, smem, st>>>(N, K, rowptr, colidx, vals, (const float4 *)x, (float4 *)basis, nc4, nnz_smem);
     } else {
         if (!attr1) { e = cudaFuncSetAttribute(cheb_recur_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr1 = true; }
         if (e == cudaSuccess)
-            cheb_recur_fwd_kernel<1><<<grid, 512, smem, st>>>(N, K, rowptr, colidx, vals, (const float4 *)x, (float4 *)basis, nc4, nnz_smem);
+            cheb_recur_fwd_kernel<1><<<grid, g_recur_threads, smem, st>>>(N, K, rowptr, colidx, vals, (const float4 *)x, (float4 *)basis, nc4, nnz_smem);
     }
     if (e != cudaSuccess) return set_err(MVB_ECUDA, "cheb_recur_fwd: %s", cudaGetErrorString(e));
     int rc = check_launch("mvb cheb_recur_fwd");
@@ -466,11 +480,11 @@ int launch_cheb_recur_bwd(int N, int nnz, int K, const int32_t *rowptr_t, const 
     if (cs4 == 2) {
         if (!attr2) { e = cudaFuncSetAttribute(cheb_recur_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr2 = true; }
         if (e == cudaSuccess)
-            cheb_recur_bwd_kernel<2><<<grid, 512, smem, st>>>(N, K, rowptr_t, colidx_t, vals_t, (const float4 *)P, (float4 *)dx, nc4, nnz_smem);
+            cheb_recur_bwd_kernel<2><<<grid, g_recur_threads, smem, st>>>(N, K, rowptr_t, colidx_t, vals_t, (const float4 *)P, (float4 *)dx, nc4, nnz_smem);
     } else {
         if (!attr1) { e = cudaFuncSetAttribute(cheb_recur_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr1 = true; }
         if (e == cudaSuccess)
-            cheb_recur_bwd_kernel<1><<<grid, 512, smem, st>>>(N, K, rowptr_t, colidx_t, vals_t, (const float4 *)P, (float4 *)dx, nc4, nnz_smem);
+            cheb_recur_bwd_kernel<1><<<grid, g_recur_threads, smem, st>>>(N, K, rowptr_t, colidx_t, vals_t, (const float4 *)P, (float4 *)dx, nc4, nnz_smem);
     }
     if (e != cudaSuccess) return set_err(MVB_ECUDA, "cheb_recur_bwd: %s", cudaGetErrorString(e));
     int rc = check_launch("mvb cheb_recur_bwd");
@@ -581,7 +595,7 @@ int launch_spmm(int n_rows, int n_src_rows, const int32_t *rowptr, const int32_t
 }  // namespace mvb
 
 extern "C" int mvb_set_fused_recurrence(int enable) {
-    mvb::set_recur_fused(enable ? 1 : 0);
+    mvb::set_recur_fused(enable);
     return 0;
 }
 

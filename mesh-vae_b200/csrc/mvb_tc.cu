@@ -26,6 +26,8 @@
 namespace mvb {
 
 static int g_tc_enabled = 1;
+static int g_tc_pg6 = 2;           // planes staged at a time by the 6-plane forward contraction (tuning: 1, 2, 3, 6)
+void set_tc_pg6(int v) { if (v == 1 || v == 2 || v == 3 || v == 6) g_tc_pg6 = v; }
 void set_tc_enabled(int v) { g_tc_enabled = v; }
 int tc_enabled() { return g_tc_enabled; }
 
@@ -161,10 +163,15 @@ __device__ __forceinline__ void stage_b_operand(const TcRowArgs &a, char *Bhi, c
             if (i < total) {
                 const int n = i / Kd, kd = i - n * Kd;
                 if (n < a.nn_true) {
-                    for (int k = 0; k < nfold; k += 2) {
-                        const float wv = a.w_transposed ? __ldg(a.wmat + ((int64_t)k * a.nn_true + n) * Kd + kd)
-                                                        : __ldg(a.wmat + ((int64_t)k * Kd + kd) * a.nn_true + n);
-                        v[u] += (k & 2) ? -wv : wv;
+                    if (a.w_transposed == 2) {      // per-plane transposed: W[k][n][o], kd = k*in_w + o
+                        const int k = kd / a.in_w, o = kd - k * a.in_w;
+                        v[u] = __ldg(a.wmat + ((int64_t)k * a.nn_true + n) * a.in_w + o);
+                    } else {
+                        for (int k = 0; k < nfold; k += 2) {
+                            const float wv = a.w_transposed ? __ldg(a.wmat + ((int64_t)k * a.nn_true + n) * Kd + kd)
+                                                            : __ldg(a.wmat + ((int64_t)k * Kd + kd) * a.nn_true + n);
+                            v[u] += (k & 2) ? -wv : wv;
+                        }
                     }
                 }
             }
@@ -188,8 +195,7 @@ __device__ __forceinline__ void stage_b_operand(const TcRowArgs &a, char *Bhi, c
 // all MMAs of one 128-row tile: for every tile plane and 8-wide K slice, the three 3xTF32 terms
 __device__ __forceinline__ void issue_row_mmas(uint32_t tmem_base, char *Ahi, char *Alo, char *Bhi, char *Blo,
                                                int planes, int a_plane, int b_plane, int kslices, uint32_t sbo,
-                                               uint32_t layout_type, uint32_t idesc) {
-    uint32_t acc = 0;
+                                               uint32_t layout_type, uint32_t idesc, uint32_t acc) {
     for (int p = 0; p < planes; ++p) {
         for (int j = 0; j < kslices; ++j) {
             const uint64_t ah = make_desc(smem_u32(Ahi + p * a_plane) + j * 32, 16, sbo, layout_type);
@@ -238,12 +244,17 @@ __device__ __forceinline__ void row_epilogue(const TcRowArgs &a, uint32_t tmem_b
     }
 }
 
-// W = 16 / 32: planar layout, one swizzled tile per input plane, the next tile's rows are prefetched
-//              into registers while the current tile's MMAs and epilogue run (single shared stage,
-//              two CTAs per SM overlap the rest);
+// W = 16 / 32: planar layout, one swizzled tile per input plane, staged PG planes at a time ("plane
+//              groups": the accumulator stays in TMEM across the groups of a tile).  The next group's rows
+//              are prefetched into registers while the current group's MMAs run.  Small groups keep the
+//              shared-memory footprint low enough for 3-4 resident CTAs per SM, whose phases (global loads
+//              in flight / register->shared commit / MMA / epilogue) then overlap - with all 6 planes of
+//              the forward contraction staged at once only ONE 128-thread CTA fitted per SM and the
+//              kernel ran at 2.7 TB/s (profiles/README.md).
+// W = 4      : all NP planes share one tile row (PG = NP).
 // W = 0      : packed layout for narrow planes (Fin = 3, Fout = 3 ...): the K*Fin <= 32 logical
 //              columns of a row are packed into one tile row, staged with scalar accesses.
-template <int W, int NP>
+template <int W, int NP, int PG>
 __global__ void __launch_bounds__(128)
 tc_rowgemm_kernel(TcRowArgs a) {
     extern __shared__ __align__(1024) char smem_raw[];
@@ -251,8 +262,11 @@ tc_rowgemm_kernel(TcRowArgs a) {
     constexpr bool PACKED = (W == 0);
     constexpr bool ONE_TILE = (W == 4);              // 4-wide planes: all NP planes share one tile row
     constexpr int Q4 = PACKED ? 1 : W / 4;
-    constexpr int NPR = PACKED ? 1 : NP;             // planes prefetched into registers
-    constexpr int NPL = (PACKED || ONE_TILE) ? 1 : NP;   // staged tiles
+    constexpr int NPR = PACKED ? 1 : PG;             // planes prefetched into registers (one group)
+    constexpr int NPL = (PACKED || ONE_TILE) ? 1 : PG;   // staged A tiles
+    constexpr int NPB = (PACKED || ONE_TILE) ? 1 : NP;   // staged B tiles (all planes, once)
+    constexpr int NG = (PACKED || ONE_TILE) ? 1 : NP / PG;
+    static_assert(PACKED || ONE_TILE || NP % PG == 0, "plane groups must divide the plane count");
     constexpr int NV = NPR * Q4;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wt = (PACKED || ONE_TILE) ? a.tile_w : W;
@@ -263,8 +277,8 @@ tc_rowgemm_kernel(TcRowArgs a) {
     char *Ahi = smem;
     char *Alo = Ahi + NPL * a_plane;
     char *Bhi = Alo + NPL * a_plane;
-    char *Blo = Bhi + NPL * b_plane;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(Blo + NPL * b_plane);
+    char *Blo = Bhi + NPB * b_plane;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(Blo + NPB * b_plane);
     uint32_t *slot = reinterpret_cast<uint32_t *>(bar + 1);
 
     if (warp == 0) tmem_alloc(slot, (uint32_t)a.tmem_cols);
@@ -292,19 +306,20 @@ tc_rowgemm_kernel(TcRowArgs a) {
 
     float4 pre[NV];
     float4 prem[Q4];
-    // global -> registers for the tile starting at row0 (planar layout)
-    auto prefetch = [&](int64_t row0) {
+    // global -> registers for plane group g of the tile starting at row0 (planar layout)
+    auto prefetch = [&](int64_t row0, int g) {
         const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
 #pragma unroll
-        for (int p = 0; p < NPR; ++p) {
+        for (int pp = 0; pp < NPR; ++pp) {
+            const int p = g * NPR + pp;
             const float4 *s4 = reinterpret_cast<const float4 *>((p == 0 ? a.in0 : a.in_rest + (int64_t)(p - 1) * a.rows * (Q4 * 4)) + row0 * (Q4 * 4));
 #pragma unroll
             for (int j = 0; j < Q4; ++j) {
                 const int i = j * 128 + tid;
-                pre[p * Q4 + j] = (i / Q4 < nr) ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                pre[pp * Q4 + j] = (i / Q4 < nr) ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        if (a.mask) {
+        if (a.mask && g == 0) {
             const float4 *m4 = reinterpret_cast<const float4 *>(a.mask + row0 * (Q4 * 4));
 #pragma unroll
             for (int j = 0; j < Q4; ++j) {
@@ -314,7 +329,7 @@ tc_rowgemm_kernel(TcRowArgs a) {
         }
     };
     // registers -> hi/lo swizzled shared tiles
-    auto commit = [&]() {
+    auto commit = [&](int g) {
 #pragma unroll
         for (int p = 0; p < NPR; ++p) {
 #pragma unroll
@@ -322,7 +337,7 @@ tc_rowgemm_kernel(TcRowArgs a) {
                 const int i = j * 128 + tid;
                 const int r = i / Q4, q = i - r * Q4;
                 float4 v = pre[p * Q4 + j];
-                if (p == 0 && a.mask) {
+                if (p == 0 && g == 0 && a.mask) {
                     v.x = prem[j].x > 0.f ? v.x : 0.f;
                     v.y = prem[j].y > 0.f ? v.y : 0.f;
                     v.z = prem[j].z > 0.f ? v.z : 0.f;
@@ -375,26 +390,34 @@ tc_rowgemm_kernel(TcRowArgs a) {
     };
 
     int64_t t = blockIdx.x;
-    if (!PACKED && t < ntiles) prefetch(t * R);
+    if (!PACKED && t < ntiles) prefetch(t * R, 0);
     for (; t < ntiles; t += gridDim.x) {
         const int64_t row0 = t * R;
         const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
-        if (PACKED)
-            stage_packed(row0, nr);
-        else
-            commit();
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            if (PACKED)
+                stage_packed(row0, nr);
+            else
+                commit(g);
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                issue_row_mmas(tmem_base, Ahi, Alo, Bhi + g * NPL * b_plane, Blo + g * NPL * b_plane, NPL, a_plane, b_plane, kslices, sbo,
+                               layout_type, idesc, g > 0 ? 1u : 0u);
+                umma_commit(bar);
+            }
+            // the next group's rows are in flight during the MMAs (and, for the last group, the epilogue)
+            if (!PACKED) {
+                if (g + 1 < NG) prefetch(row0, g + 1);
+                else if (t + gridDim.x < ntiles) prefetch((t + gridDim.x) * R, 0);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1;
             tc_fence_after();
-            issue_row_mmas(tmem_base, Ahi, Alo, Bhi, Blo, NPL, a_plane, b_plane, kslices, sbo, layout_type, idesc);
-            umma_commit(bar);
         }
-        if (!PACKED && t + gridDim.x < ntiles) prefetch((t + gridDim.x) * R);   // in flight during MMA + epilogue
-        mbar_wait(bar, phase);
-        phase ^= 1;
-        tc_fence_after();
         row_epilogue(a, tmem_base, warp, row, nr, row0);
         tc_fence_before();   // order this tile's TMEM reads before the barrier that precedes the next MMA
     }
@@ -408,15 +431,15 @@ static int pow2_cols(int n) {
     return c;
 }
 
-template <int W, int NP>
+template <int W, int NP, int PG = NP>
 static int launch_rowgemm_t(const TcRowArgs &t, unsigned grid, size_t smem, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_rowgemm_kernel<W, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(tc_rowgemm_kernel<W, NP, PG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return set_err(MVB_ECUDA, "tc_rowgemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    tc_rowgemm_kernel<W, NP><<<grid, 128, smem, st>>>(t);
+    tc_rowgemm_kernel<W, NP, PG><<<grid, 128, smem, st>>>(t);
     return check_launch("mvb tc_rowgemm");
 }
 
@@ -457,7 +480,12 @@ int launch_contract_tc(const ContractArgs &a, cudaStream_t st) {
     t.tmem_cols = pow2_cols(nn16);
     t.tile_w = (packed || w == 4) ? (Kd <= 16 ? 16 : 32) : w;
     t.tile_planes = (packed || w == 4) ? 1 : a.in_planes;
-    const size_t smem = 1024 + (size_t)t.tile_planes * (2 * 128 * t.tile_w * 4 + 2 * nn16 * t.tile_w * 4) + 64;
+    // plane groups (A tiles staged at a time): 3 of 6 / 2 of 4 planes for 16-wide planes, 1 of 2-3 for 32-wide
+    int pg = t.tile_planes;
+    if (w == 16 && a.in_planes == 6) pg = g_tc_pg6;
+    else if (w == 16 && a.in_planes == 4) pg = 2;
+    else if (w == 32 && a.in_planes >= 2) pg = 1;
+    const size_t smem = 1024 + (size_t)pg * (2 * 128 * t.tile_w * 4) + (size_t)t.tile_planes * (2 * nn16 * t.tile_w * 4) + 64;
     if (smem > 200 * 1024) return 0;
     const int64_t ntiles = (a.rows + 127) / 128;
     // CTAs per SM: shared memory and TMEM (512 columns) permitting
@@ -486,15 +514,20 @@ int launch_contract_tc(const ContractArgs &a, cudaStream_t st) {
             case 1: rc = launch_rowgemm_t<16, 1>(t, (unsigned)grid, smem, st); break;
             case 2: rc = launch_rowgemm_t<16, 2>(t, (unsigned)grid, smem, st); break;
             case 3: rc = launch_rowgemm_t<16, 3>(t, (unsigned)grid, smem, st); break;
-            case 4: rc = launch_rowgemm_t<16, 4>(t, (unsigned)grid, smem, st); break;
+            case 4: rc = launch_rowgemm_t<16, 4, 2>(t, (unsigned)grid, smem, st); break;
             case 5: rc = launch_rowgemm_t<16, 5>(t, (unsigned)grid, smem, st); break;
-            default: rc = launch_rowgemm_t<16, 6>(t, (unsigned)grid, smem, st); break;
+            default:
+                if (pg == 6) rc = launch_rowgemm_t<16, 6, 6>(t, (unsigned)grid, smem, st);
+                else if (pg == 2) rc = launch_rowgemm_t<16, 6, 2>(t, (unsigned)grid, smem, st);
+                else if (pg == 1) rc = launch_rowgemm_t<16, 6, 1>(t, (unsigned)grid, smem, st);
+                else rc = launch_rowgemm_t<16, 6, 3>(t, (unsigned)grid, smem, st);
+                break;
         }
     } else {
         switch (a.in_planes) {
             case 1: rc = launch_rowgemm_t<32, 1>(t, (unsigned)grid, smem, st); break;
-            case 2: rc = launch_rowgemm_t<32, 2>(t, (unsigned)grid, smem, st); break;
-            default: rc = launch_rowgemm_t<32, 3>(t, (unsigned)grid, smem, st); break;
+            case 2: rc = launch_rowgemm_t<32, 2, 1>(t, (unsigned)grid, smem, st); break;
+            default: rc = launch_rowgemm_t<32, 3, 1>(t, (unsigned)grid, smem, st); break;
         }
     }
     return rc ? rc : 1;
@@ -808,5 +841,6 @@ int launch_wgrad_tc(const WgradArgs &a, int has_bias, int M4, int N4, int *npart
 extern "C" int mvb_set_tensor_cores(int enable) {
     const int old = mvb::tc_enabled();
     mvb::set_tc_enabled(enable ? 1 : 0);
+    if (enable >= 10) mvb::set_tc_pg6(enable - 10);      // tuning hook: 11 / 12 / 13 / 16 = plane-group size 1 / 2 / 3 / 6
     return old;
 }

@@ -72,7 +72,9 @@ class _ChebConvFn(torch.autograd.Function):
               "mvb_cheb_fwd")
         ctx.op, ctx.relu, ctx.has_bias = op, relu, bias is not None
         ctx.sinks = (_sink(weight), _sink(bias))
-        ctx.save_for_backward(x_vm, basis, w, y if relu else None)
+        # the adjoint-form backward recomputes its planes from dY: the forward basis is then a temporary
+        keep = bool(lib.mvb_cheb_bwd_uses_basis(fin, fout, 1 if ctx.needs_input_grad[0] else 0))
+        ctx.save_for_backward(x_vm, basis if keep else None, w, y if relu else None)
         return y
 
     @staticmethod
@@ -91,7 +93,8 @@ class _ChebConvFn(torch.autograd.Function):
         ws_bytes = lib.mvb_cheb_bwd_workspace_bytes(n, b, fin, fout, k, na, 1 if need_dx else 0)
         ws = torch.empty(ws_bytes, device=w.device, dtype=torch.uint8)
         check(lib.mvb_cheb_bwd(n, b, fin, fout, k, na, op.nnz, ptr(op.rowptr_t), ptr(op.colidx_t), ptr(op.vals_t), ptr(x_vm),
-                               ptr(basis) if basis.numel() else None, ptr(w), ptr(y) if ctx.relu else None, ptr(dy), ptr(dx),
+                               ptr(basis) if (basis is not None and basis.numel()) else None, ptr(w), ptr(y) if ctx.relu else None,
+                               ptr(dy), ptr(dx),
                                ptr(dw), ptr(db), ptr(ws), ws_bytes, stream_ptr()), "mvb_cheb_bwd")
         return dx, _ret(sw, dw), _ret(sb, db), None, None
 
