@@ -154,8 +154,10 @@ class cheb_VAE(nn.Module):
         loss, kld, rec, correct = Fn.vae_loss(Fn.to_vertex_major(recon_x), x, mu_z, logvar_z, y_hat, y, self.log_sigma)
         return loss, correct, kld, rec
 
-    def forward(self, data, x_gt, y, supervise=True, m_type="test", eps: Optional[torch.Tensor] = None):
-        self.supervise = supervise
+    def forward_recon(self, data, y, m_type="test", eps: Optional[torch.Tensor] = None):
+        """everything of forward() that does not need the ground truth: encoder, heads, decoder
+        (models/cheb_VAE.py:195-243).  -> (recon, z, x_mean, x_var, z_, y_hat).  The step engine runs this
+        part while the ground-truth batch is still on its way to the device."""
         if isinstance(data, torch.Tensor):
             x, batch_size = data, data.shape[0]
         else:
@@ -176,5 +178,10 @@ class cheb_VAE(nn.Module):
             z_ = self.reparameterize(x_mean, x_var, eps) if m_type == "train" else x_mean
             z = torch.cat([y, z_], -1)
         recon = self.decoder(z).reshape(batch_size, -1, self.filters[0])
+        return recon, z, x_mean, x_var, z_, y_hat
+
+    def forward(self, data, x_gt, y, supervise=True, m_type="test", eps: Optional[torch.Tensor] = None):
+        self.supervise = supervise
+        recon, z, x_mean, x_var, z_, y_hat = self.forward_recon(data, y, m_type, eps)
         loss, correct, kld, rec_loss = self.loss_function(x_gt, recon, z, x_mean, x_var, y, y_hat)
         return loss, correct, recon, [kld, rec_loss, z_], y_hat

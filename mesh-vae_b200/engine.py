@@ -97,16 +97,22 @@ class TrainEngine:
         self.loss = torch.zeros((), device=self.dev, dtype=torch.float64)
         self.kld = self.rec = self.correct = None
         self.use_graph = use_graph
-        self.g_fb = self.g_opt = None
+        self.g_fwd = self.g_fb = self.g_opt = None
         self.launches_per_step = None
-        self._pinned = None
+        self._copy_stream = self._gt_ready = None
+        self._fwd_out = None
 
     # ---- device work of one step -------------------------------------------------------------
-    def _fwd_bwd(self):
+    def _fwd(self):
+        """part A of the step: everything that does not need the ground-truth batch"""
         for p, _ in self.loose:
             p.grad = None
-        loss, correct, recon, (kld, rec, z_), y_hat = self.net(self.x, self.x_gt, self.y_hot, m_type="train",
-                                                                eps=self.eps)
+        self._fwd_out = self.net.forward_recon(self.x, self.y_hot, m_type="train", eps=self.eps)
+
+    def _loss_bwd(self):
+        """part B: loss (needs x_gt), backward, gradients of the few autograd-routed parameters"""
+        recon, z, mu, logvar, z_, y_hat = self._fwd_out
+        loss, correct, kld, rec = self.net.loss_function(self.x_gt, recon, z, mu, logvar, self.y_hot, y_hat)
         loss.backward()
         if self.loose:
             torch._foreach_copy_([v for _, v in self.loose], [p.grad for p, _ in self.loose])
@@ -114,6 +120,11 @@ class TrainEngine:
         # per-batch statistics of main.py:83-85: the tensors stay device-resident (static addresses under
         # graph replay); stats() reduces them on demand instead of inside every step
         self.kld, self.rec, self.correct = kld, rec, correct
+        self._fwd_out = None
+
+    def _fwd_bwd(self):
+        self._fwd()
+        self._loss_bwd()
 
     def stats(self):
         """(mean kld, mean rec_loss, correct) of the last step - main.py:83-85 reads these per batch"""
@@ -144,21 +155,34 @@ class TrainEngine:
             self.opt.step_count.copy_(state[3])
             return
         c0 = lib.mvb_launch_count()
+        # three graphs: A = forward without the ground truth, B = loss + backward, C = optimizer.  A | B
+        # lets step() overlap the H2D copy of the (fp64, 2/3 of the bytes) ground truth with the forward
+        # pass; B | C leaves room for the data-parallel all-reduce.
+        self.g_fwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fwd):
+            self._fwd()
         self.g_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_fb):
-            self._fwd_bwd()
+        with torch.cuda.graph(self.g_fb, pool=self.g_fwd.pool()):
+            self._loss_bwd()
         self.g_opt = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_opt, pool=self.g_fb.pool()):
+        with torch.cuda.graph(self.g_opt, pool=self.g_fwd.pool()):
             self._optim()
         self.launches_per_step = lib.mvb_launch_count() - c0
         torch.cuda.synchronize()
 
-    def device_step(self):
-        """one training step on inputs already resident in the static device buffers"""
+    def device_step(self, gt_ready: Optional[torch.cuda.Event] = None):
+        """one training step on inputs already resident in the static device buffers (gt_ready: event
+        after which the ground-truth buffer may be read)"""
+        if self.use_graph:
+            self.g_fwd.replay()
+        else:
+            self._fwd()
+        if gt_ready is not None:
+            torch.cuda.current_stream().wait_event(gt_ready)
         if self.use_graph:
             self.g_fb.replay()
         else:
-            self._fwd_bwd()
+            self._loss_bwd()
         if self.distributed:
             dp.allreduce_sum_(self.opt.flat_g)
         if self.use_graph:
@@ -170,15 +194,23 @@ class TrainEngine:
     def step(self, x_host: torch.Tensor, x_gt_host: torch.Tensor, y_host: torch.Tensor,
              eps_host: Optional[torch.Tensor] = None) -> float:
         """x_host [B,N,3] f32, x_gt_host [B,N,3] f64/f32, y_host [B] int64 labels (pinned host memory for
-        asynchronous copies).  Mirrors main.py:69-85: H2D, one-hot, step, loss read-back."""
+        asynchronous copies).  Mirrors main.py:69-85: H2D, one-hot, step, loss read-back.  The ground truth
+        travels on a second stream while the forward pass runs."""
+        main = torch.cuda.current_stream()
         self.x.copy_(x_host, non_blocking=True)
-        self.x_gt.copy_(x_gt_host, non_blocking=True)
         if eps_host is None:   # the reference draws the noise on the CPU generator (cheb_VAE.py:316)
             eps_host = torch.normal(mean=0, std=1, size=(self.batch, self.net.z))
         self.eps.copy_(eps_host, non_blocking=True)
         # one-hot on the host, then H2D, as main.py:71 does
         self.y_hot.copy_(torch.nn.functional.one_hot(y_host, self.net.num_class), non_blocking=True)
-        self.device_step()
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._gt_ready = torch.cuda.Event()
+        self._copy_stream.wait_stream(main)          # the previous step's loss kernel has read x_gt
+        with torch.cuda.stream(self._copy_stream):
+            self.x_gt.copy_(x_gt_host, non_blocking=True)
+            self._gt_ready.record(self._copy_stream)
+        self.device_step(self._gt_ready)
         return float(self.loss)          # D2H read of the step's loss (synchronises)
 
     def h2d_bytes(self) -> int:
