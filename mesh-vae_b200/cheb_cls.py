@@ -4,6 +4,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import functional as Fn
+from . import operators
 from .conv import ChebConv
 from .pool import Pool  # noqa: F401  (re-exported: the reference defines Pool in this module)
 
@@ -38,8 +40,17 @@ class cheb_GCN(nn.Module):
         b = x.shape[0]
         x = x.reshape(b, -1, self.filters[0])
         for i in range(self.n_layers):
-            x = self.cheb[i](x, self.A_edge_index[i])
-            if not self.cheb[i].fuse_relu:      # F.relu of cheb_cls.py:97, fused into the conv epilogue otherwise
+            conv = self.cheb[i]
+            if conv.fuse_relu and x.is_cuda:
+                # conv + relu + Pool(D) (cheb_cls.py:95-99) as one call: a single mesh-resident launch at the
+                # coarse levels, the pool / conv / pool composition elsewhere
+                op = conv.mesh_operator(self.A_edge_index[i], x.shape[1], x.device, x.dtype)
+                d_op = operators.from_sparse(self.downsample_matrices[i], x.device)
+                x = Fn.from_vertex_major(Fn.cheb_layer(Fn.to_vertex_major(x), conv.stacked_weight(), conv.bias, op, None, d_op,
+                                                       relu=True))
+                continue
+            x = conv(x, self.A_edge_index[i])
+            if not conv.fuse_relu:      # F.relu of cheb_cls.py:97, fused into the conv epilogue otherwise
                 x = F.relu(x)
             x = Pool(x, self.downsample_matrices[i])
         x = x.reshape(b, self.enc_lin.in_features)

@@ -99,17 +99,21 @@ class ChebConv(torch.nn.Module):
         squeeze = x.dim() == 2
         if squeeze:
             x = x.unsqueeze(0)
-        n = x.size(-2)
-        # L_hat = 2 L_sym / lambda_max - I = -D^-1/2 A D^-1/2; PyG's explicit +1/-1 diagonal cancels
+        op = self.mesh_operator(edge_index, x.size(-2), x.device, x.dtype)
+        y = Fn.from_vertex_major(Fn.cheb_conv(Fn.to_vertex_major(x), self.stacked_weight(), self.bias, op, self.fuse_relu))
+        return y.squeeze(0) if squeeze else y
+
+    def mesh_operator(self, edge_index, n, device, dtype=torch.float32):
+        """L_hat = 2 L_sym / lambda_max - I = -D^-1/2 A D^-1/2 (PyG's explicit +1/-1 diagonal cancels), cached"""
         key = ("pyg_norm", edge_index.data_ptr(), edge_index._version, int(edge_index.shape[1]), n)
         cached = _PYG_NORM.get(key)
         if cached is None:
-            cached = _PYG_NORM[key] = ChebConv_batch.norm(edge_index, n, None, x.dtype) + (edge_index,)
-        ei, norm = cached[0], cached[1]
-        op = operators.from_edges(ei, norm, n, x.device)
-        w = torch.stack([lin.weight.t() for lin in self.lins], dim=0)
-        y = Fn.from_vertex_major(Fn.cheb_conv(Fn.to_vertex_major(x), w, self.bias, op, self.fuse_relu))
-        return y.squeeze(0) if squeeze else y
+            cached = _PYG_NORM[key] = ChebConv_batch.norm(edge_index, n, None, dtype) + (edge_index,)
+        return operators.from_edges(cached[0], cached[1], n, device)
+
+    def stacked_weight(self):
+        """[K, Fin, Fout] with W_k = lins[k].weight^T (differentiable view of the K Linear weights)"""
+        return torch.stack([lin.weight.t() for lin in self.lins], dim=0)
 
     def __repr__(self):
         return "{}({}, {}, K={}, normalization={})".format(self.__class__.__name__, self.in_channels,
