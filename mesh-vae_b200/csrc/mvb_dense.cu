@@ -86,6 +86,13 @@ __device__ __forceinline__ void stage_async(float *dst, int ld, int tile_rows, i
                 cp_async<VEC>(dst + r * ld + c, ok ? v.base + (int64_t)(r0 + r) * v.rs + coff : v.base, ok);
             }
         }
+    } else if ((ncg & (ncg - 1)) == 0 && v.f == 0x7fffffff) {       // narrow row-major tile, power-of-two groups: no divisions
+        const int lg = 31 - __clz(ncg);
+        for (int i = tid; i < tile_rows * ncg; i += nthreads) {
+            const int r = i >> lg, c = (i & (ncg - 1)) * VEC;
+            const bool ok = r < valid_rows && c < valid_cols;
+            cp_async<VEC>(dst + r * ld + c, ok ? v.base + (int64_t)(r0 + r) * v.rs + c0 + c : v.base, ok);
+        }
     } else {
         for (int i = tid; i < tile_rows * ncg; i += nthreads) {
             const int r = i / ncg, c = (i - r * ncg) * VEC;
@@ -158,7 +165,7 @@ linear_fwd_kernel(int M, int K, int N, const float *__restrict__ x, int x_vmf, c
 // ---------------------------------------------------------------------------------------------
 constexpr int BW_TN = 64, BW_TK = 64, BW_LA = 68, BW_TMB = 32, BW_TKX = 16;
 
-template <int VEC>
+template <int VN, int VK>      // cp.async width of the N-indexed arrays (gy, y) and of the K-indexed ones (x, W)
 __global__ void __launch_bounds__(256)
 linear_bwd_kernel(int M, int K, int N, const float *__restrict__ x, int x_vmf, const float *__restrict__ W,
                   const float *__restrict__ y, const float *__restrict__ gy, int y_vmf, int relu, float scale,
@@ -185,13 +192,13 @@ linear_bwd_kernel(int M, int K, int N, const float *__restrict__ x, int x_vmf, c
         for (int m0 = 0; m0 < M; m0 += 64) {
             const int rows = min(64, M - m0);
             if (m0) __syncthreads();
-            stage_async<VEC>(gps, BW_LA, 64, rows, BW_TN, ncols, gv, m0, n0, tid, 256);
-            if (relu) stage_async<VEC>(ys, BW_LA, 64, rows, BW_TN, ncols, yv, m0, n0, tid, 256);
-            stage_async<VEC>(xs, BW_LA, 64, rows, BW_TK, kcols, xv, m0, k0, tid, 256);
+            stage_async<VN>(gps, BW_LA, 64, rows, BW_TN, ncols, gv, m0, n0, tid, 256);
+            if (relu) stage_async<VN>(ys, BW_LA, 64, rows, BW_TN, ncols, yv, m0, n0, tid, 256);
+            stage_async<VK>(xs, BW_LA, 64, rows, BW_TK, kcols, xv, m0, k0, tid, 256);
             cp_async_wait_all();
             __syncthreads();
             for (int i = tid; i < 64 * BW_TN; i += 256) {
-                const int r = i / BW_TN, c = i % BW_TN;
+                const int r = i / BW_TN, c = i % BW_TN;            // BW_TN is a compile-time power of two
                 gps[r * BW_LA + c] = gp_value(gps[r * BW_LA + c], relu ? ys[r * BW_LA + c] : 1.f, relu, scale);
             }
             __syncthreads();
@@ -239,15 +246,23 @@ linear_bwd_kernel(int M, int K, int N, const float *__restrict__ x, int x_vmf, c
         const int nc = min(nc_b, N - nc0);
         const int nc4 = (nc + 3) & ~3;
         if (nc0) __syncthreads();
-        stage_async<VEC>(gps, LG, BW_TMB, rows, nc4, nc, gv, m0, nc0, tid, 256);
-        if (relu) stage_async<VEC>(ys, LG, BW_TMB, rows, nc4, nc, yv, m0, nc0, tid, 256);
-        stage_async<VEC>(wt, BW_TKX, nc4, nc, BW_TKX, kcols, wv, nc0, k0, tid, 256);
+        stage_async<VN>(gps, LG, BW_TMB, rows, nc4, nc, gv, m0, nc0, tid, 256);
+        if (relu) stage_async<VN>(ys, LG, BW_TMB, rows, nc4, nc, yv, m0, nc0, tid, 256);
+        stage_async<VK>(wt, BW_TKX, nc4, nc, BW_TKX, kcols, wv, nc0, k0, tid, 256);
         cp_async_wait_all();
         __syncthreads();
-        for (int i = tid; i < BW_TMB * nc4; i += 256) {
-            const int r = i / nc4, c = i - r * nc4;
-            gps[r * LG + c] = gp_value(gps[r * LG + c], relu ? ys[r * LG + c] : 1.f, relu, scale);
-        }
+        for (int r = tid >> 5; r < BW_TMB; r += 8)                  // a warp per row: no divisions
+            for (int c = (tid & 31) * 4; c < nc4; c += 128) {
+                float4 g = *reinterpret_cast<float4 *>(gps + r * LG + c);
+                if (relu) {
+                    const float4 yy = *reinterpret_cast<const float4 *>(ys + r * LG + c);
+                    g.x = gp_value(g.x, yy.x, 1, scale); g.y = gp_value(g.y, yy.y, 1, scale);
+                    g.z = gp_value(g.z, yy.z, 1, scale); g.w = gp_value(g.w, yy.w, 1, scale);
+                } else {
+                    g.x *= scale; g.y *= scale; g.z *= scale; g.w *= scale;
+                }
+                *reinterpret_cast<float4 *>(gps + r * LG + c) = g;
+            }
         __syncthreads();
         const float4 *g4 = reinterpret_cast<const float4 *>(gps + m * LG);
         for (int q = 0; q < (nc4 >> 2); ++q) {
@@ -379,17 +394,42 @@ __device__ __forceinline__ float heads_small_grad(int o, int b, int Z, int C, co
     return g;
 }
 
+// The small per-mesh inputs of the heads' backward pass (upstream gradients, y_hat, logvar, eps) for rows
+// [rb0, rb0 + nr) staged in shared memory with cp.async, so that heads_small_grad reads shared memory
+// instead of chasing ~6 dependent global loads per element.
+struct SmallIn {
+    const float *y_hat, *logvar, *eps, *g_yhat, *g_mu, *g_logvar, *g_z, *g_zcat;
+};
+__device__ __forceinline__ const float *stage_small(float *&cursor, const float *src, int64_t first, int n, int tid, int nthreads) {
+    if (!src) return nullptr;
+    float *dst = cursor;
+    cursor += (n + 3) & ~3;
+    cp_async_words(dst, src + first, n, tid, nthreads);
+    return dst;
+}
+__device__ __forceinline__ SmallIn stage_small_inputs(float *buf, int rb0, int nr, int Z, int C, const SmallIn &g, int tid, int nthreads) {
+    SmallIn s;
+    float *cur = buf;
+    s.y_hat = stage_small(cur, g.y_hat, (int64_t)rb0 * C, nr * C, tid, nthreads);
+    s.logvar = stage_small(cur, g.logvar, (int64_t)rb0 * Z, nr * Z, tid, nthreads);
+    s.eps = stage_small(cur, g.eps, (int64_t)rb0 * Z, nr * Z, tid, nthreads);
+    s.g_yhat = stage_small(cur, g.g_yhat, (int64_t)rb0 * C, nr * C, tid, nthreads);
+    s.g_mu = stage_small(cur, g.g_mu, (int64_t)rb0 * Z, nr * Z, tid, nthreads);
+    s.g_logvar = stage_small(cur, g.g_logvar, (int64_t)rb0 * Z, nr * Z, tid, nthreads);
+    s.g_z = stage_small(cur, g.g_z, (int64_t)rb0 * Z, nr * Z, tid, nthreads);
+    s.g_zcat = stage_small(cur, g.g_zcat, (int64_t)rb0 * (C + Z), nr * (C + Z), tid, nthreads);
+    return s;
+}
+__host__ __device__ inline int small_in_words(int nr, int Z, int C) { return nr * (2 * C + 5 * Z + (C + Z)) + 32; }
+
 // blocks [0, nbg): g_h of HB_ROWS meshes each (weights staged once per block).  blocks [nbg, nbg + ntile):
 // a 32-column tile of the three weight gradients (column C + H is the bias), batch reduced in order.
-constexpr int HB_ROWS = 4, HB_MAXO = 12;     // HB_MAXO = ceil(HEADS_MAX_OUT / 8)
+constexpr int HB_ROWS = 2, HB_MAXO = 12;     // HB_MAXO = ceil(HEADS_MAX_OUT / 8)
 
 __global__ void __launch_bounds__(256)
 vae_heads_bwd_kernel(int B, int H, int Z, int C, const float *__restrict__ h, const int64_t *__restrict__ yoh,
-                     const float *__restrict__ eps, const float *__restrict__ Wc, const float *__restrict__ Wm,
-                     const float *__restrict__ Wv, const float *__restrict__ y_hat, const float *__restrict__ logvar,
-                     float p, uint64_t seed, const int64_t *off_dev, int64_t off_host,
-                     const float *__restrict__ g_yhat, const float *__restrict__ g_mu, const float *__restrict__ g_logvar,
-                     const float *__restrict__ g_z, const float *__restrict__ g_zcat, float *__restrict__ g_h,
+                     const float *__restrict__ Wc, const float *__restrict__ Wm, const float *__restrict__ Wv, SmallIn gin,
+                     float p, uint64_t seed, const int64_t *off_dev, int64_t off_host, float *__restrict__ g_h,
                      float *__restrict__ dWc, float *__restrict__ dbc, float *__restrict__ dWm, float *__restrict__ dbm,
                      float *__restrict__ dWv, float *__restrict__ dbv, int nbg) {
     extern __shared__ float4 dsm4[];
@@ -402,13 +442,17 @@ vae_heads_bwd_kernel(int B, int H, int Z, int C, const float *__restrict__ h, co
         const int ldw = C + H + 1;
         float *wsm = sm;                               // [nout][ldw]
         float *gs = sm + nout * ldw;                   // [HB_ROWS][nout]
-        stage_head_weights(wsm, ldw, H, Z, C, Wc, Wm, Wv, tid, blockDim.x);
+        float *small = gs + ((HB_ROWS * nout + 3) & ~3);
         const int b0 = blockIdx.x * HB_ROWS;
-        for (int i = tid; i < HB_ROWS * nout; i += blockDim.x) {
-            const int b = b0 + i / nout;
-            gs[i] = b < B ? heads_small_grad(i % nout, b, Z, C, y_hat, logvar, eps, g_yhat, g_mu, g_logvar, g_z, g_zcat) : 0.f;
-        }
+        const int nr = min(HB_ROWS, B - b0);
+        const SmallIn si = stage_small_inputs(small, b0, nr, Z, C, gin, tid, blockDim.x);
+        stage_head_weights(wsm, ldw, H, Z, C, Wc, Wm, Wv, tid, blockDim.x);
         cp_async_wait_all();
+        __syncthreads();
+        for (int i = tid; i < HB_ROWS * nout; i += blockDim.x) {
+            const int bl = i / nout;
+            gs[i] = bl < nr ? heads_small_grad(i % nout, bl, Z, C, si.y_hat, si.logvar, si.eps, si.g_yhat, si.g_mu, si.g_logvar, si.g_z, si.g_zcat) : 0.f;
+        }
         __syncthreads();
         for (int i = tid; i < HB_ROWS * H; i += blockDim.x) {
             const int bl = i / H, j = i - bl * H;
@@ -427,12 +471,10 @@ vae_heads_bwd_kernel(int B, int H, int Z, int C, const float *__restrict__ h, co
     float *gs = sm;                                    // [B][nout]
     float *ht = sm + B * nout;                         // [B][33]: columns j0..j0+31 of cat(y, h, 1)
     float *hdt = ht + B * 33;                          // same, with the classifier's dropout mask
+    float *small = hdt + ((B * 33 + 3) & ~3);
     const int j0 = ((int)blockIdx.x - nbg) * 32;
-    for (int i = tid; i < B * nout; i += blockDim.x) {
-        const int b = i / nout, o = i - b * nout;
-        gs[i] = heads_small_grad(o, b, Z, C, y_hat, logvar, eps, g_yhat, g_mu, g_logvar, g_z, g_zcat);
-    }
-    for (int i = tid; i < B * 32; i += blockDim.x) {
+    const SmallIn si = stage_small_inputs(small, 0, B, Z, C, gin, tid, blockDim.x);
+    for (int i = tid; i < B * 32; i += blockDim.x) {       // the h tile (plain loads, independent of the cp.async group)
         const int b = i >> 5, j = j0 + (i & 31);
         float in = 0.f, ind = 0.f;
         if (j == C + H) in = ind = 1.f;
@@ -443,6 +485,12 @@ vae_heads_bwd_kernel(int B, int H, int Z, int C, const float *__restrict__ h, co
         }
         ht[b * 33 + (i & 31)] = in;
         hdt[b * 33 + (i & 31)] = ind;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    for (int i = tid; i < B * nout; i += blockDim.x) {
+        const int b = i / nout, o = i - b * nout;
+        gs[i] = heads_small_grad(o, b, Z, C, si.y_hat, si.logvar, si.eps, si.g_yhat, si.g_mu, si.g_logvar, si.g_z, si.g_zcat);
     }
     __syncthreads();
     const int jl = tid & 31, og = tid >> 5;           // 8 output groups: o = og, og + 8, ...
@@ -531,16 +579,23 @@ extern "C" int mvb_linear_bwd(int M, int K, int N, const float *x, int x_vm_f, c
     const size_t smA = (size_t)3 * 64 * BW_LA * sizeof(float);
     const size_t smB = (size_t)(2 * BW_TMB * (nc_b + 4) + nc_b * BW_TKX) * sizeof(float);
     const size_t smem = nB ? (smA > smB ? smA : smB) : smA;
-    const bool vec = (K % 4 == 0) && (N % 4 == 0) && (x_vm_f == 0 || x_vm_f % 4 == 0) && (y_vm_f == 0 || y_vm_f % 4 == 0) &&
-                     al16(x) && al16(W) && al16(gy) && (!relu || al16(y));
-    static size_t granted4 = 48 * 1024, granted1 = 48 * 1024;
-    int rc = vec ? ensure_smem(linear_bwd_kernel<4>, smem, &granted4, "linear_bwd") : ensure_smem(linear_bwd_kernel<1>, smem, &granted1, "linear_bwd");
-    if (rc) return rc;
+    const bool vn = (N % 4 == 0) && (y_vm_f == 0 || y_vm_f % 4 == 0) && al16(gy) && (!relu || al16(y));
+    const bool vk = (K % 4 == 0) && (x_vm_f == 0 || x_vm_f % 4 == 0) && al16(x) && al16(W);
+    static size_t granted[4] = {48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024};
     const float scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
-    if (vec)
-        linear_bwd_kernel<4><<<nA + nB, 256, smem, (cudaStream_t)stream>>>(M, K, N, x, x_vm_f, W, y, gy, y_vm_f, relu, scale, dx, dW, db, nA, k_tiles, nc_b);
-    else
-        linear_bwd_kernel<1><<<nA + nB, 256, smem, (cudaStream_t)stream>>>(M, K, N, x, x_vm_f, W, y, gy, y_vm_f, relu, scale, dx, dW, db, nA, k_tiles, nc_b);
+    int rc;
+#define MVB_LBWD(VN_, VK_, SLOT)                                                                                             \
+    do {                                                                                                                     \
+        rc = ensure_smem(linear_bwd_kernel<VN_, VK_>, smem, &granted[SLOT], "linear_bwd");                                   \
+        if (rc) return rc;                                                                                                   \
+        linear_bwd_kernel<VN_, VK_><<<nA + nB, 256, smem, (cudaStream_t)stream>>>(M, K, N, x, x_vm_f, W, y, gy, y_vm_f, relu, \
+                                                                                  scale, dx, dW, db, nA, k_tiles, nc_b);     \
+    } while (0)
+    if (vn && vk) MVB_LBWD(4, 4, 0);
+    else if (vn) MVB_LBWD(4, 1, 1);
+    else if (vk) MVB_LBWD(1, 4, 2);
+    else MVB_LBWD(1, 1, 3);
+#undef MVB_LBWD
     return check_launch("mvb_linear_bwd");
 }
 
@@ -573,8 +628,8 @@ extern "C" int mvb_vae_heads_bwd(int B, int H, int Z, int C, const float *h, con
                     dbc && dWm && dbm && dWv && dbv, "vae_heads_bwd: bad arguments");
     MVB_REQUIRE(C + 2 * Z <= HEADS_MAX_OUT && C <= 32, "vae_heads_bwd: C=%d Z=%d too large", C, Z);
     const int nout = C + 2 * Z;
-    const size_t smA = (size_t)(nout * (C + H + 1) + HB_ROWS * nout) * sizeof(float);
-    const size_t smB = (size_t)(B * nout + 2 * B * 33) * sizeof(float);
+    const size_t smA = (size_t)(nout * (C + H + 1) + HB_ROWS * nout + 4 + small_in_words(HB_ROWS, Z, C)) * sizeof(float);
+    const size_t smB = (size_t)(B * nout + 2 * B * 33 + 4 + small_in_words(B, Z, C)) * sizeof(float);
     const size_t smem = smA > smB ? smA : smB;
     MVB_REQUIRE(smem <= 220 * 1024, "vae_heads_bwd: batch %d / H=%d too large for one pass", B, H);
     static size_t granted = 48 * 1024;
@@ -582,8 +637,11 @@ extern "C" int mvb_vae_heads_bwd(int B, int H, int Z, int C, const float *h, con
     if (rc) return rc;
     const int nbg = (B + HB_ROWS - 1) / HB_ROWS;
     const int ntile = (C + H + 1 + 31) / 32;
-    vae_heads_bwd_kernel<<<nbg + ntile, 256, smem, (cudaStream_t)stream>>>(B, H, Z, C, h, y_onehot, eps, Wc, Wm, Wv, y_hat, logvar,
-                                                                            p_drop, seed, offset_dev, offset_host, g_yhat, g_mu,
-                                                                            g_logvar, g_z, g_zcat, g_h, dWc, dbc, dWm, dbm, dWv, dbv, nbg);
+    SmallIn gin;
+    gin.y_hat = y_hat; gin.logvar = logvar; gin.eps = eps; gin.g_yhat = g_yhat; gin.g_mu = g_mu; gin.g_logvar = g_logvar;
+    gin.g_z = g_z; gin.g_zcat = g_zcat;
+    vae_heads_bwd_kernel<<<nbg + ntile, 256, smem, (cudaStream_t)stream>>>(B, H, Z, C, h, y_onehot, Wc, Wm, Wv, gin, p_drop, seed,
+                                                                            offset_dev, offset_host, g_h, dWc, dbc, dWm, dbm, dWv,
+                                                                            dbv, nbg);
     return check_launch("mvb_vae_heads_bwd");
 }

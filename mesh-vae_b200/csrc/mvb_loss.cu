@@ -33,43 +33,28 @@ vae_rec_partial_kernel(int B, int N, int C, int VCH, int BCH, const float *__res
     const int nv = min(VCH, N - v0), nb = min(BCH, B - b0);
     const int rw = nb * C;  // contiguous run per vertex in recon
     const int xw = nv * C;  // contiguous run per mesh in x_gt
-    for (int base = 0; base < nv * rw; base += 4 * nthreads) {       // 4 independent loads in flight
-        float t[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = base + u * nthreads + tid;
-            if (i < nv * rw) {
-                const int v = i / rw, rem = i - v * rw;
-                t[u] = __ldg(recon + ((int64_t)(v0 + v) * B + b0) * C + rem);
+    // both tiles through cp.async: every element of the block's two tiles is in flight at once (one exposed
+    // latency instead of one per batch of register loads); a warp walks one contiguous run at a time
+    {
+        const int warp_ = tid >> 5, lane_ = tid & 31, nwarps_ = nthreads >> 5;
+        for (int v = warp_; v < nv; v += nwarps_) {
+            const float *src = recon + ((int64_t)(v0 + v) * B + b0) * C;
+            float *dst = Rs + v * (BCH * C);
+            for (int e = lane_; e < rw; e += 32) cp_async<1>(dst + e, src + e);
+        }
+        for (int b = warp_; b < nb; b += nwarps_) {
+            const XT *src = xgt + ((int64_t)(b0 + b) * N + v0) * C;
+            XT *dst = Xs + b * (VCH * C);
+            for (int e = lane_; e < xw; e += 32) {
+                if (sizeof(XT) == 8) {
+                    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + e);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(src + e) : "memory");
+                } else {
+                    cp_async<1>(dst + e, src + e);
+                }
             }
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = base + u * nthreads + tid;
-            if (i < nv * rw) {
-                const int v = i / rw, rem = i - v * rw;
-                Rs[v * (BCH * C) + rem] = t[u];
-            }
-        }
-    }
-    for (int base = 0; base < nb * xw; base += 4 * nthreads) {
-        XT t[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = base + u * nthreads + tid;
-            if (i < nb * xw) {
-                const int b = i / xw, rem = i - b * xw;
-                t[u] = xgt[((int64_t)(b0 + b) * N + v0) * C + rem];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = base + u * nthreads + tid;
-            if (i < nb * xw) {
-                const int b = i / xw, rem = i - b * xw;
-                Xs[b * (VCH * C) + rem] = t[u];
-            }
-        }
+        cp_async_wait_all();
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
@@ -108,18 +93,19 @@ vae_loss_finalize_kernel(int B, int Z, int ncls, int nchunks, const double *__re
     const int tid = threadIdx.x;
     double lsum = 0.0;
     int lcnt = 0;
-    for (int b = tid; b < B; b += blockDim.x) {
+    // phase 1: a warp per mesh sums the vertex-chunk partials (lane-strided, fixed shuffle tree)
+    const int wid = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+    for (int b = wid; b < B; b += nw) {
         double r = 0.0;
-        int ch = 0;
-        for (; ch + 8 <= nchunks; ch += 8) {                 // 8 loads in flight, summation order unchanged
-            double t[8];
+        for (int ch = lane; ch < nchunks; ch += 32) r += partial[(int64_t)ch * B + b];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) t[u] = partial[(int64_t)(ch + u) * B + b];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) r += t[u];
-        }
-        for (; ch < nchunks; ++ch) r += partial[(int64_t)ch * B + b];
-        rec[b] = r;
+        for (int off = 16; off > 0; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
+        if (lane == 0) rec[b] = r;
+    }
+    __syncthreads();
+    // phase 2: a thread per mesh for the per-mesh terms
+    for (int b = tid; b < B; b += blockDim.x) {
+        const double r = rec[b];
         float k = 0.f;
         for (int j = 0; j < Z; ++j) {
             const float m = mu[b * Z + j], lv = logvar[b * Z + j];
