@@ -605,7 +605,7 @@ extern "C" int mvb_set_spmm_shape(int tx, int chunk) {
 }
 
 extern "C" int mvb_set_spmm_mode(int mode) {
-    mvb::set_spmm_mode(mode);
+    mvb::set_spmm_mode(mode & 15);
     return 0;
 }
 

@@ -1,0 +1,42 @@
+"""SpMM on the level-0 operator in the template's vertex order vs the patch order of operators.locality_order."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import meshvae_b200 as mvb
+import bench
+dev = torch.device("cuda:0")
+_, net, A, nn_ = bench.build_model(dev)
+L = mvb._lib
+n = nn_[0]
+ei, norm = mvb.ChebConv_batch.norm(A[0]._indices(), n)
+def timeit(op, B, F):
+    u = n * B * F * 4
+    nsets = max(3, int(4 * 126e6 / (3 * u)) + 1)
+    sets = [(torch.randn(n, B, F, device=dev), torch.randn(n, B, F, device=dev), torch.empty(n, B, F, device=dev)) for _ in range(nsets)]
+    def launch(x, z, y):
+        L.check(L.lib.mvb_spmm(n, n, L.ptr(op.rowptr), L.ptr(op.colidx), L.ptr(op.vals), L.ptr(x), L.ptr(y), L.ptr(z), None, 2.0, -1.0, B * F, L.stream_ptr()))
+    for t in sets: launch(*t)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(6):
+        for t in sets: launch(*t)
+    e.record(); e.synchronize()
+    ms = s.elapsed_time(e) / (6 * nsets)
+    return ms * 1e3, (3 * u + op.csr_bytes()) / ms / 1e6
+op0 = mvb.operators.from_edges(ei, norm, n, dev)
+for cluster in (0, 32, 64, 128):
+    if cluster == 0:
+        op = op0
+    else:
+        order = mvb.operators.locality_order(n, ei[1].cpu().numpy(), ei[0].cpu().numpy(), 20, cluster)
+        inv = torch.empty(n, dtype=torch.long); inv[torch.from_numpy(order)] = torch.arange(n)
+        ei_p = inv.to(ei.device)[ei]
+        op = mvb.operators.from_edges(ei_p.contiguous(), norm.clone(), n, dev)
+    for B, F in [(64, 16), (256, 16), (64, 4)]:
+        for shape in [(0, 0), (32, 64), (32, 128), (16, 64)]:
+            L.lib.mvb_set_spmm_mode(3 if shape != (0, 0) else 0); L.lib.mvb_set_spmm_shape(*shape)
+            us, gbs = timeit(op, B, F)
+            print(f"cluster {cluster:3d} B{B} F{F} shape {shape}: {us:6.1f} us {gbs:6.0f} GB/s ({gbs/6548.2:.2f})")
+L.lib.mvb_set_spmm_mode(0); L.lib.mvb_set_spmm_shape(0, 0)
