@@ -166,9 +166,12 @@ extern "C" int mvb_cheb_fwd(int N, int B, int Fin, int Fout, int K, int n_active
         if (rc) return rc;
     }
     if (n_active < N) {
+        const int64_t off = (int64_t)n_active * B;
+        rc = launch_fold_fwd((int64_t)(N - n_active) * B, K, Fin, Fout, x + off * Fin, weight, bias, relu, y + off * Fout, st);
+        if (rc < 0) return rc;
+        if (rc == 1) return MVB_OK;
         ContractArgs a;
         fill_contract(a);
-        const int64_t off = (int64_t)n_active * B;
         a.rows = (int64_t)(N - n_active) * B;
         a.in_planes = 1;
         a.in_w = Fin;
@@ -449,6 +452,10 @@ static int cheb_bwd_adjoint(int N, int B, int Fin, int Fout, int K, int n_active
         if (rc) return rc;
     }
     if (rows_in > 0) {       // empty rows of the operator: S = x^T G, dW_k += cos(k pi/2) S
+        rc = launch_fold_wgrad(rows_in, Fin, Fout, x + rows_act * Fin, G + rows_act * Fout, partB, partB_bytes, &nB, &m4B, wst);
+        if (rc < 0) return rc;
+    }
+    if (rows_in > 0 && nB == 0) {
         WgradArgs wb;
         memset(&wb, 0, sizeof(wb));
         wb.rows = rows_in;
@@ -481,6 +488,9 @@ static int cheb_bwd_adjoint(int N, int B, int Fin, int Fout, int K, int n_active
         if (rc) return rc;
     }
     if (rows_in > 0) {       // empty rows: dX = G (sum_k c_k W_k)^T
+        rc = launch_fold_dx(rows_in, K, Fin, Fout, G + rows_act * Fout, weight, dx + rows_act * Fin, st);
+        if (rc < 0) return rc;
+        if (rc == 1) return MVB_OK;
         ContractArgs a;
         fill_contract(a);
         a.rows = rows_in;

@@ -527,6 +527,165 @@ int launch_wgrad_partials(const WgradArgs &a, int has_bias, int *nparts, int *m4
     return check_launch("mvb wgrad");
 }
 
+// ---------------------------------------------------------------------------------------------
+// Closed-form rows (operator rows without entries: T_k = cos(k pi/2) x, api.cu) with narrow planes.
+// The reference's output layer (16 -> 3 features, 99.6 % of its rows closed-form, models/cheb_VAE.py:288)
+// is pure streaming: 80 bytes per row.  The 128-row tensor-core tiles spend their time in per-tile
+// set-up there (31-39 us for 25 MB, in-graph timeline); these three FFMA kernels are bandwidth-bound.
+//   Wf = sum_k cos(k pi/2) W_k  [Fin x Fout]  folded in shared memory at block start.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fold_weights(float *Wf, const float *__restrict__ w, int K, int Fin, int Fout, int tid, int nthreads) {
+    for (int i = tid; i < Fin * Fout; i += nthreads) {
+        float v = 0.f;
+        for (int k = 0; k < K; k += 2) {
+            const float wv = __ldg(w + (int64_t)k * Fin * Fout + i);
+            v += (k & 2) ? -wv : wv;
+        }
+        Wf[i] = v;
+    }
+}
+
+// out[row, :] = act(x[row, :] Wf + b);  thread = (row, output quad)
+__global__ void __launch_bounds__(256)
+fold_rows_fwd_kernel(int64_t rows, int K, int Fin, int Fout, const float *__restrict__ x, const float *__restrict__ w,
+                     const float *__restrict__ bias, int relu, float *__restrict__ out) {
+    extern __shared__ float4 smem4[];
+    float *Wf = reinterpret_cast<float *>(smem4);
+    fold_weights(Wf, w, K, Fin, Fout, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int oq = Fout >> 2, iq = Fin >> 2;
+    const int64_t total = rows * oq;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = t / oq;
+        const int q = (int)(t - row * oq);
+        const float4 *xr = reinterpret_cast<const float4 *>(x + row * Fin);
+        float4 acc = bias ? __ldg(reinterpret_cast<const float4 *>(bias) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i4 = 0; i4 < iq; ++i4) {
+            const float4 xv = __ldg(xr + i4);
+            const float4 w0 = *reinterpret_cast<const float4 *>(Wf + (4 * i4 + 0) * Fout + 4 * q);
+            const float4 w1 = *reinterpret_cast<const float4 *>(Wf + (4 * i4 + 1) * Fout + 4 * q);
+            const float4 w2 = *reinterpret_cast<const float4 *>(Wf + (4 * i4 + 2) * Fout + 4 * q);
+            const float4 w3 = *reinterpret_cast<const float4 *>(Wf + (4 * i4 + 3) * Fout + 4 * q);
+            acc.x = fmaf(xv.x, w0.x, fmaf(xv.y, w1.x, fmaf(xv.z, w2.x, fmaf(xv.w, w3.x, acc.x))));
+            acc.y = fmaf(xv.x, w0.y, fmaf(xv.y, w1.y, fmaf(xv.z, w2.y, fmaf(xv.w, w3.y, acc.y))));
+            acc.z = fmaf(xv.x, w0.z, fmaf(xv.y, w1.z, fmaf(xv.z, w2.z, fmaf(xv.w, w3.z, acc.z))));
+            acc.w = fmaf(xv.x, w0.w, fmaf(xv.y, w1.w, fmaf(xv.z, w2.w, fmaf(xv.w, w3.w, acc.w))));
+        }
+        if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+        reinterpret_cast<float4 *>(out + row * Fout)[q] = acc;
+    }
+}
+
+// dx[row, :] = g[row, :] Wf^T;  thread = (row, input quad)
+__global__ void __launch_bounds__(256)
+fold_rows_dx_kernel(int64_t rows, int K, int Fin, int Fout, const float *__restrict__ g, const float *__restrict__ w,
+                    float *__restrict__ dx) {
+    extern __shared__ float4 smem4[];
+    float *Wf = reinterpret_cast<float *>(smem4);
+    fold_weights(Wf, w, K, Fin, Fout, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int oq = Fout >> 2, iq = Fin >> 2;
+    const int64_t total = rows * iq;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = t / iq;
+        const int q = (int)(t - row * iq);
+        const float4 *gr = reinterpret_cast<const float4 *>(g + row * Fout);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int o4 = 0; o4 < oq; ++o4) {
+            const float4 gv = __ldg(gr + o4);
+            const float4 w0 = *reinterpret_cast<const float4 *>(Wf + (4 * q + 0) * Fout + 4 * o4);
+            const float4 w1 = *reinterpret_cast<const float4 *>(Wf + (4 * q + 1) * Fout + 4 * o4);
+            const float4 w2 = *reinterpret_cast<const float4 *>(Wf + (4 * q + 2) * Fout + 4 * o4);
+            const float4 w3 = *reinterpret_cast<const float4 *>(Wf + (4 * q + 3) * Fout + 4 * o4);
+            acc.x = fmaf(gv.x, w0.x, fmaf(gv.y, w0.y, fmaf(gv.z, w0.z, fmaf(gv.w, w0.w, acc.x))));
+            acc.y = fmaf(gv.x, w1.x, fmaf(gv.y, w1.y, fmaf(gv.z, w1.z, fmaf(gv.w, w1.w, acc.y))));
+            acc.z = fmaf(gv.x, w2.x, fmaf(gv.y, w2.y, fmaf(gv.z, w2.z, fmaf(gv.w, w2.w, acc.z))));
+            acc.w = fmaf(gv.x, w3.x, fmaf(gv.y, w3.y, fmaf(gv.z, w3.z, fmaf(gv.w, w3.w, acc.w))));
+        }
+        reinterpret_cast<float4 *>(dx + row * Fin)[q] = acc;
+    }
+}
+
+// S = x^T g over `rows` rows as per-block partials in the layout of the generic weight-gradient partials
+// ([M4][N4], M4 = round4(Fin), N4 = round4(Fout)); thread = (4x4 block of S, row lane), rows strided over
+// lanes and blocks in a fixed pattern, ordered reduction over the lanes: deterministic.
+__global__ void __launch_bounds__(256)
+fold_rows_wgrad_kernel(int64_t rows, int Fin, int Fout, const float *__restrict__ x, const float *__restrict__ g,
+                       float *__restrict__ partials) {
+    extern __shared__ float4 smem4[];
+    float *red = reinterpret_cast<float *>(smem4);     // [lanes][nblk * 16]
+    const int iq = Fin >> 2, oq = Fout >> 2, nblk = iq * oq;
+    const int lanes = blockDim.x / nblk;
+    const int blk = threadIdx.x % nblk, lane = threadIdx.x / nblk;
+    const int bi = blk % iq, bo = blk / iq;
+    float4 c0 = make_float4(0.f, 0.f, 0.f, 0.f), c1 = c0, c2 = c0, c3 = c0;
+    if (lane < lanes)
+        for (int64_t r = (int64_t)blockIdx.x * lanes + lane; r < rows; r += (int64_t)gridDim.x * lanes) {
+            const float4 xv = __ldg(reinterpret_cast<const float4 *>(x + r * Fin) + bi);
+            const float4 gv = __ldg(reinterpret_cast<const float4 *>(g + r * Fout) + bo);
+            c0.x = fmaf(xv.x, gv.x, c0.x); c0.y = fmaf(xv.x, gv.y, c0.y); c0.z = fmaf(xv.x, gv.z, c0.z); c0.w = fmaf(xv.x, gv.w, c0.w);
+            c1.x = fmaf(xv.y, gv.x, c1.x); c1.y = fmaf(xv.y, gv.y, c1.y); c1.z = fmaf(xv.y, gv.z, c1.z); c1.w = fmaf(xv.y, gv.w, c1.w);
+            c2.x = fmaf(xv.z, gv.x, c2.x); c2.y = fmaf(xv.z, gv.y, c2.y); c2.z = fmaf(xv.z, gv.z, c2.z); c2.w = fmaf(xv.z, gv.w, c2.w);
+            c3.x = fmaf(xv.w, gv.x, c3.x); c3.y = fmaf(xv.w, gv.y, c3.y); c3.z = fmaf(xv.w, gv.z, c3.z); c3.w = fmaf(xv.w, gv.w, c3.w);
+        }
+    if (lane < lanes) {
+        float *d = red + ((size_t)lane * nblk + blk) * 16;
+        *reinterpret_cast<float4 *>(d) = c0; *reinterpret_cast<float4 *>(d + 4) = c1;
+        *reinterpret_cast<float4 *>(d + 8) = c2; *reinterpret_cast<float4 *>(d + 12) = c3;
+    }
+    __syncthreads();
+    float *part = partials + (size_t)blockIdx.x * Fin * Fout;       // M4 = Fin, N4 = Fout (both multiples of 4)
+    for (int e = threadIdx.x; e < nblk * 16; e += blockDim.x) {
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += red[(size_t)l * nblk * 16 + e];
+        const int bk = e >> 4, m = (e >> 2) & 3, c = e & 3;
+        part[(4 * (bk % iq) + m) * Fout + 4 * (bk / iq) + c] = s;
+    }
+}
+
+static bool fold_ok(int K, int Fin, int Fout, const void *a, const void *b, const void *c) {
+    return K >= 1 && Fin % 4 == 0 && Fout % 4 == 0 && Fin <= 64 && Fout <= 64 && (Fin / 4) * (Fout / 4) <= 64 &&
+           (Fin <= 8 || Fout <= 8) && aligned16(a) && aligned16(b) && (!c || aligned16(c));
+}
+static int fold_grid(int64_t threads) {
+    int64_t g = (threads + 255) / 256;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    return (int)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+// 1 = handled, 0 = shape not covered (caller uses the generic kernels), < 0 = error
+int launch_fold_fwd(int64_t rows, int K, int Fin, int Fout, const float *x, const float *w, const float *bias, int relu,
+                    float *out, cudaStream_t st) {
+    if (!fold_ok(K, Fin, Fout, x, out, bias)) return 0;
+    fold_rows_fwd_kernel<<<fold_grid(rows * (Fout / 4)), 256, (size_t)Fin * Fout * 4, st>>>(rows, K, Fin, Fout, x, w, bias, relu, out);
+    const int rc = check_launch("mvb fold_rows_fwd");
+    return rc ? rc : 1;
+}
+int launch_fold_dx(int64_t rows, int K, int Fin, int Fout, const float *g, const float *w, float *dx, cudaStream_t st) {
+    if (!fold_ok(K, Fin, Fout, g, dx, nullptr)) return 0;
+    fold_rows_dx_kernel<<<fold_grid(rows * (Fin / 4)), 256, (size_t)Fin * Fout * 4, st>>>(rows, K, Fin, Fout, g, w, dx);
+    const int rc = check_launch("mvb fold_rows_dx");
+    return rc ? rc : 1;
+}
+// partials: at least wgrad_partial_bytes(Fin, Fout); *nparts blocks of [Fin][Fout] are written, *m4 = Fin
+int launch_fold_wgrad(int64_t rows, int Fin, int Fout, const float *x, const float *g, float *partials, size_t partial_bytes,
+                      int *nparts, int *m4, cudaStream_t st) {
+    if (!fold_ok(1, Fin, Fout, x, g, partials)) return 0;
+    const int nblk = (Fin / 4) * (Fout / 4);
+    const int lanes = 256 / nblk;
+    int64_t grid = (rows + (int64_t)lanes * 16 - 1) / ((int64_t)lanes * 16);      // >= 16 rows per lane
+    const int64_t cap = (int64_t)num_sms() * 2;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    if ((size_t)grid * Fin * Fout * sizeof(float) > partial_bytes) return 0;
+    fold_rows_wgrad_kernel<<<(unsigned)grid, 256, (size_t)lanes * nblk * 16 * 4, st>>>(rows, Fin, Fout, x, g, partials);
+    const int rc = check_launch("mvb fold_rows_wgrad");
+    if (rc) return rc;
+    *nparts = (int)grid;
+    *m4 = Fin;
+    return 1;
+}
+
 // phase 2: dweight [M, n_out] (M = K*fin), dbias [n_out] or null.  a_transposed: see the kernel.
 int launch_wgrad_finalize(const float *partA, int nA, int M4A, const float *partB, int nB, int M4B,
                           int fin, int M, int n_out, float *dweight, float *dbias, cudaStream_t st, int a_transposed) {

@@ -129,6 +129,13 @@ int mask_colsum_blocks(int64_t rows);
 int launch_mask_colsum(int64_t rows, int ncol, const float *dy, const float *y, float *g, float *db, float *part,
                        cudaStream_t st);
 
+// narrow closed-form rows (operator rows without entries): 1 = handled, 0 = shape not covered, < 0 = error
+int launch_fold_fwd(int64_t rows, int K, int Fin, int Fout, const float *x, const float *w, const float *bias, int relu,
+                    float *out, cudaStream_t st);
+int launch_fold_dx(int64_t rows, int K, int Fin, int Fout, const float *g, const float *w, float *dx, cudaStream_t st);
+int launch_fold_wgrad(int64_t rows, int Fin, int Fout, const float *x, const float *g, float *partials, size_t partial_bytes,
+                      int *nparts, int *m4, cudaStream_t st);
+
 // tcgen05 paths (mvb_tc.cu): return 1 = handled, 0 = shape unsupported (use FFMA), < 0 = error
 int launch_contract_tc(const ContractArgs &a, cudaStream_t st);
 int launch_wgrad_tc(const WgradArgs &a, int has_bias, int M4, int N4, int *nparts, cudaStream_t st);
