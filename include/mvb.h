@@ -69,6 +69,12 @@ int mvb_set_spmm_mode(int mode);
  * branches become parallel branches of a CUDA graph).  Returns the previous setting. */
 int mvb_set_overlap(int enable);
 
+/* step-engine plumbing: cudaStreamWaitEvent(stream, event, cudaEventWaitExternal).  Legal during stream
+ * capture (becomes an external event-wait node): each replay of the captured graph waits for the latest
+ * host-side record of `event` - how the one-graph training step waits for the ground-truth H2D copy that
+ * main.py:70 issues per batch while the forward pass is already running. */
+int mvb_stream_wait_external_event(void *stream, void *event);
+
 /* ---- operator hand-off: COO -> CSR (HOST function) ---------------------------------------
  * Replaces the implicit operator format of the reference: model.py:24-32 `scipy_to_torch_sparse`
  * (uncoalesced COO, int64 / f32), consumed via `_indices()/_values()` at nn/pool.py:19 and

@@ -43,6 +43,7 @@ SIGNATURES = {
     "mvb_set_spmm_mode": (c_int, [c_int]),
     "mvb_set_fused_recurrence": (c_int, [c_int]),
     "mvb_set_overlap": (c_int, [c_int]),
+    "mvb_stream_wait_external_event": (c_int, [_vp, _vp]),
     "mvb_csr_from_coo_host": (c_int, [c_int64, c_int64, c_int64, _vp, _vp, _vp, c_int, _vp, _vp, _vp]),
     "mvb_spmm": (c_int, [c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_float, c_float, c_int64, _vp]),
     "mvb_pool_fwd": (c_int, [c_int, c_int, _vp, _vp, _vp, _vp, _vp, c_int64, _vp]),

@@ -509,6 +509,19 @@ static int cheb_bwd_adjoint(int N, int B, int Fin, int Fout, int K, int n_active
     return MVB_OK;
 }
 
+// Make `stream` wait for the LATEST record of `event` at execution time.  With cudaEventWaitExternal the call is
+// legal while `stream` is being captured and becomes an external event-wait node: every replay of the graph then
+// waits for whatever the host recorded on the event last (the step engine's ground-truth H2D copy).
+extern "C" int mvb_stream_wait_external_event(void *stream, void *event) {
+    MVB_REQUIRE(event != nullptr, "stream_wait_external_event: null event");
+    cudaError_t e = cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, cudaEventWaitExternal);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(MVB_ECUDA, "stream_wait_external_event: %s", cudaGetErrorString(e));
+    }
+    return MVB_OK;
+}
+
 extern "C" int mvb_set_overlap(int enable) {
     const int old = g_overlap;
     g_overlap = enable ? 1 : 0;

@@ -97,7 +97,7 @@ class TrainEngine:
         self.loss = torch.zeros((), device=self.dev, dtype=torch.float64)
         self.kld = self.rec = self.correct = None
         self.use_graph = use_graph
-        self.g_fwd = self.g_fb = self.g_opt = None
+        self.g_fb = self.g_opt = None
         self.launches_per_step = None
         self._copy_stream = self._gt_ready = None
         self._fwd_out = None
@@ -155,38 +155,42 @@ class TrainEngine:
             self.opt.step_count.copy_(state[3])
             return
         c0 = lib.mvb_launch_count()
-        # three graphs: A = forward without the ground truth, B = loss + backward, C = optimizer.  A | B
-        # lets step() overlap the H2D copy of the (fp64, 2/3 of the bytes) ground truth with the forward
-        # pass; B | C leaves room for the data-parallel all-reduce.
-        self.g_fwd = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_fwd):
-            self._fwd()
+        # ONE graph on a single GPU: forward, an EXTERNAL event-wait node (the ground-truth H2D copy that
+        # step() issues on the copy stream - the fp64 ground truth is 2/3 of the H2D bytes and is only needed by
+        # the loss), loss + backward, Adam.  Data parallel: the optimizer is a second graph so that the NCCL
+        # all-reduce of the flat gradient buffer runs between the two.
+        self._copy_stream = torch.cuda.Stream()
+        self._gt_ready = torch.cuda.Event()
+        self._gt_ready.record(self._copy_stream)
+        torch.cuda.synchronize()
         self.g_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_fb, pool=self.g_fwd.pool()):
+        with torch.cuda.graph(self.g_fb):
+            self._fwd()
+            check(lib.mvb_stream_wait_external_event(stream_ptr(), self._gt_ready.cuda_event), "mvb_stream_wait_external_event")
             self._loss_bwd()
-        self.g_opt = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_opt, pool=self.g_fwd.pool()):
-            self._optim()
+            if not self.distributed:
+                self._optim()
+        if self.distributed:
+            self.g_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_opt, pool=self.g_fb.pool()):
+                self._optim()
         self.launches_per_step = lib.mvb_launch_count() - c0
         torch.cuda.synchronize()
 
-    def device_step(self, gt_ready: Optional[torch.cuda.Event] = None):
-        """one training step on inputs already resident in the static device buffers (gt_ready: event
-        after which the ground-truth buffer may be read)"""
-        if self.use_graph:
-            self.g_fwd.replay()
-        else:
-            self._fwd()
-        if gt_ready is not None:
-            torch.cuda.current_stream().wait_event(gt_ready)
+    def device_step(self):
+        """one training step on inputs already resident in the static device buffers"""
         if self.use_graph:
             self.g_fb.replay()
         else:
+            self._fwd()
+            if self._gt_ready is not None:
+                torch.cuda.current_stream().wait_event(self._gt_ready)
             self._loss_bwd()
         if self.distributed:
             dp.allreduce_sum_(self.opt.flat_g)
         if self.use_graph:
-            self.g_opt.replay()
+            if self.distributed:
+                self.g_opt.replay()
         else:
             self._optim()
 
@@ -210,7 +214,7 @@ class TrainEngine:
         with torch.cuda.stream(self._copy_stream):
             self.x_gt.copy_(x_gt_host, non_blocking=True)
             self._gt_ready.record(self._copy_stream)
-        self.device_step(self._gt_ready)
+        self.device_step()
         return float(self.loss)          # D2H read of the step's loss (synchronises)
 
     def h2d_bytes(self) -> int:
