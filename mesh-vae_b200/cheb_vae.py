@@ -165,7 +165,7 @@ class cheb_VAE(nn.Module):
         x = x.reshape(batch_size, -1, self.filters[0])
         self.dropout_stream.advance()
         h = self.encoder(x)
-        if self.fused_dense and h.is_cuda:
+        if self.fused_dense and h.is_cuda and batch_size <= Fn.VAE_HEADS_MAX_BATCH:
             if m_type == "train" and eps is None:
                 eps = self._draw_eps((batch_size, self.z), h)
             y_hat, x_mean, x_var, z_, z = Fn.vae_heads(h, y, eps if m_type == "train" else None, self.classifier_layer,

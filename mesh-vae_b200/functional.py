@@ -315,6 +315,7 @@ class DropoutStream:
 
 
 _NO_RNG = (0, None, 0)
+VAE_HEADS_MAX_BATCH = 256      # the one-launch heads backward keeps the whole batch's small gradients in shared memory
 
 
 class _LinearFn(torch.autograd.Function):
