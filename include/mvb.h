@@ -196,6 +196,18 @@ int mvb_gaussian_nll_fwd(int64_t n, const float *mu, const void *x, int x_is_f64
 int mvb_gaussian_nll_bwd(int64_t n, const float *mu, const void *x, int x_is_f64, float log_sigma,
                          const void *gout, float *d_mu, void *stream);
 
+/* ---- next row f3: per-batch reconstruction error  (main.py:88-93, :139-146; inference.py:100-127)
+ * recon_mesh = out * std + mean (fp32) ; recon_mesh = bmm(recon_mesh * s, R) + m (fp64) ;
+ * diff = sqrt(((recon_mesh - gt_mesh)^2).sum(-1)) ; mean_err[b] = diff.mean(-1), max_err[b] = diff.max(-1).
+ * recon [N,B,ld] fp32 vertex-major with ld >= 3 floats per (vertex, mesh) entry (the decoder output as
+ * the kernels produce it, padded to 4); mean/std [N,3] fp32 (norm.npz); s [B], R [B,3,3], m [B,3] fp64
+ * (Procrustes scale / rotation / translation, utils.py:58-156); gt [B,N,3] fp64 original meshes.
+ * The reference copies the [B,N,3] reconstruction to the host for this every batch. */
+size_t mvb_recon_error_workspace_bytes(int B, int N);
+int mvb_recon_error(int B, int N, int ld, const float *recon, const float *mean, const float *std, const double *s,
+                    const double *R, const double *m, const double *gt, double *mean_err, double *max_err,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- next row f2: fused Adam on a flat parameter buffer  (main.py:251 torch.optim.Adam(lr,
  *          weight_decay), L2-style decay; main.py:81 optimizer.step()) --------------------------
  * step: DEVICE int64 counter, incremented by one inside the call (graph-capturable, no host state).

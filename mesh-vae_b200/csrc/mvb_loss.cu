@@ -179,6 +179,64 @@ __global__ void vae_loss_bwd_small_kernel(int B, int Z, int ncls, const float *_
     }
 }
 
+// ---- next row f3: per-batch reconstruction error of the training / evaluation loops ---------------
+// main.py:88-93, :139-146, inference.py:100-127:  recon_mesh = out.cpu() * std + mean (fp32);
+// recon_mesh = bmm(recon_mesh * s, R) + m (fp64: s, R, m come from the Procrustes alignment as float64);
+// diff = sqrt(((recon_mesh - gt_mesh)**2).sum(-1)) -> .mean(-1), .max(-1) per mesh.
+// The reference moves the whole [B,N,3] reconstruction to the host for this every batch; here it is one
+// pass over the vertex-major reconstruction on the device, per-(vertex chunk, mesh) partial sums / maxima
+// and an ordered final reduction.
+__global__ void __launch_bounds__(256)
+recon_error_partial_kernel(int B, int N, int ld, const float *__restrict__ recon, const float *__restrict__ mean,
+                           const float *__restrict__ stdv, const double *__restrict__ sc, const double *__restrict__ R,
+                           const double *__restrict__ m, const double *__restrict__ gt, double *__restrict__ psum,
+                           double *__restrict__ pmax) {
+    __shared__ double s_sum[256], s_max[256];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int v = blockIdx.x * 256 + tid;
+    double err = 0.0;
+    if (v < N) {
+        const float *rp = recon + ((int64_t)v * B + b) * ld;
+        const double s = sc[b];
+        double p[3], q[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) p[c] = (double)__fadd_rn(__fmul_rn(rp[c], stdv[v * 3 + c]), mean[v * 3 + c]) * s;
+        const double *Rb = R + (int64_t)b * 9;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) q[j] = p[0] * Rb[j] + p[1] * Rb[3 + j] + p[2] * Rb[6 + j] + m[(int64_t)b * 3 + j];
+        const double *g = gt + ((int64_t)b * N + v) * 3;
+        const double d0 = q[0] - g[0], d1 = q[1] - g[1], d2 = q[2] - g[2];
+        err = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+    }
+    s_sum[tid] = err;
+    s_max[tid] = err;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (tid < off) {
+            s_sum[tid] += s_sum[tid + off];
+            s_max[tid] = fmax(s_max[tid], s_max[tid + off]);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        psum[(int64_t)blockIdx.x * B + b] = s_sum[0];
+        pmax[(int64_t)blockIdx.x * B + b] = s_max[0];
+    }
+}
+
+__global__ void recon_error_finalize_kernel(int B, int N, int nchunks, const double *__restrict__ psum,
+                                            const double *__restrict__ pmax, double *mean_err, double *max_err) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double s = 0.0, mx = 0.0;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        s += psum[(int64_t)ch * B + b];
+        mx = fmax(mx, pmax[(int64_t)ch * B + b]);
+    }
+    mean_err[b] = s / (double)N;
+    max_err[b] = mx;
+}
+
 // ---- reparameterisation ----------------------------------------------------------------------
 __global__ void reparam_fwd_kernel(int64_t n, const float *__restrict__ mu,
                                    const float *__restrict__ logvar, const float *__restrict__ eps,
@@ -372,4 +430,23 @@ extern "C" int mvb_gaussian_nll_bwd(int64_t n, const float *mu, const void *x, i
     else
         nll_bwd_kernel<float><<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(n, mu, (const float *)x, sigma, (const float *)gout, d_mu);
     return check_launch("mvb_gaussian_nll_bwd");
+}
+
+extern "C" size_t mvb_recon_error_workspace_bytes(int B, int N) { return (size_t)2 * ((N + 255) / 256) * B * sizeof(double); }
+
+extern "C" int mvb_recon_error(int B, int N, int ld, const float *recon, const float *mean, const float *std, const double *s,
+                               const double *R, const double *m, const double *gt, double *mean_err, double *max_err,
+                               void *workspace, size_t workspace_bytes, void *stream) {
+    MVB_REQUIRE(B > 0 && N > 0 && ld >= 3 && recon && mean && std && s && R && m && gt && mean_err && max_err && workspace,
+                "recon_error: bad arguments");
+    const int nch = (N + 255) / 256;
+    MVB_REQUIRE(workspace_bytes >= mvb_recon_error_workspace_bytes(B, N), "recon_error: workspace too small");
+    double *psum = reinterpret_cast<double *>(workspace);
+    double *pmax = psum + (size_t)nch * B;
+    cudaStream_t st = (cudaStream_t)stream;
+    mvb::recon_error_partial_kernel<<<dim3(nch, B), 256, 0, st>>>(B, N, ld, recon, mean, std, s, R, m, gt, psum, pmax);
+    int rc = mvb::check_launch("mvb_recon_error partial");
+    if (rc) return rc;
+    mvb::recon_error_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, N, nch, psum, pmax, mean_err, max_err);
+    return mvb::check_launch("mvb_recon_error finalize");
 }

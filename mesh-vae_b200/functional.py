@@ -523,3 +523,33 @@ def cheb_layer(x_vm, weight, bias, l_op: MeshOperator, u_op: Optional[MeshOperat
     if d_op is not None:
         y = pool(y, d_op)
     return y
+
+
+
+def recon_error(recon, mean, std, s, R, m, gt_mesh):
+    """Per-mesh reconstruction error of the train / evaluate / inference loops (main.py:88-93, :139-146;
+    inference.py:100-127) on the device: recon [B,N,3] (any strides - the model's output is a view of the
+    vertex-major decoder buffer and is read in place), mean/std [N,3] (norm.npz), s [B] / R [B,3,3] /
+    m [B,1,3] or [B,3] (Procrustes), gt_mesh [B,N,3].  -> (mean_err [B], max_err [B]) fp64 device tensors;
+    `mean_err.mean()` is main.py:93's `diff`."""
+    _req_cuda(recon, "recon_error recon")
+    b, n, c = recon.shape
+    if c != 3:
+        raise _lib.MvbError("recon_error: meshes have 3 coordinates")
+    rv = recon.permute(1, 0, 2)                      # [N,B,3] view
+    if rv.stride(2) == 1 and rv.stride(0) == b * rv.stride(1) and rv.stride(1) >= 3:
+        ld = rv.stride(1)                            # in place: entries of ld floats (3, or 4 for the padded decoder output)
+    else:
+        rv, ld = rv.contiguous(), 3
+    dev = recon.device
+    f32 = lambda t: torch.as_tensor(t).to(device=dev, dtype=torch.float32).contiguous()      # noqa: E731
+    f64 = lambda t: torch.as_tensor(t).to(device=dev, dtype=torch.float64).contiguous()      # noqa: E731
+    mean, std = f32(mean).reshape(n, 3), f32(std).reshape(n, 3)
+    s, R, m, gt = f64(s).reshape(b), f64(R).reshape(b, 3, 3), f64(m).reshape(b, 3), f64(gt_mesh).reshape(b, n, 3)
+    mean_err = torch.empty(b, device=dev, dtype=torch.float64)
+    max_err = torch.empty(b, device=dev, dtype=torch.float64)
+    ws_bytes = lib.mvb_recon_error_workspace_bytes(b, n)
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    check(lib.mvb_recon_error(b, n, ld, ptr(rv), ptr(mean), ptr(std), ptr(s), ptr(R), ptr(m), ptr(gt), ptr(mean_err),
+                              ptr(max_err), ptr(ws), ws_bytes, stream_ptr()), "mvb_recon_error")
+    return mean_err, max_err

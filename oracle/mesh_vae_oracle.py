@@ -340,6 +340,22 @@ class OracleChebGCN(torch.nn.Module):
 
 
 # --------------------------------------------------------------------------------------
+# f3  per-batch reconstruction error  (main.py:51-52, 88-93; inference.py:100-127)
+# --------------------------------------------------------------------------------------
+def recon_error(out: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, s: torch.Tensor, R: torch.Tensor,
+                m: torch.Tensor, gt_mesh) -> Tuple[np.ndarray, np.ndarray]:
+    """out [B,N,3] fp32; mean/std FloatTensor [N,3] (main.py:57-58); s [B,1], R [B,3,3], m [B,1,3] float64 as the
+    DataLoader collates them; gt_mesh [B,N,3] float64.  Returns (diff.mean(-1), diff.max(-1)) per mesh."""
+    recon_mesh = out.cpu() * std + mean                       # main.py:88 (fp32)
+    s = s.unsqueeze(1)                                        # main.py:89
+    recon_mesh = torch.bmm(recon_mesh * s, R) + m             # main.py:90 (promotes to fp64)
+    recon_mesh = recon_mesh.detach().cpu().numpy()
+    gt = np.asarray(gt_mesh)
+    diff = np.sqrt(((recon_mesh - gt) ** 2).sum(-1))          # main.py:51-52 euclidean_distances
+    return diff.mean(-1), diff.max(-1)                        # inference.py:126-127
+
+
+# --------------------------------------------------------------------------------------
 # fixtures
 # --------------------------------------------------------------------------------------
 DEFAULT_CONFIG = {            # files/default.cfg:8-9,17-21,26-33

@@ -147,3 +147,27 @@ def test_vae_heads_classifier_dropout(Fn):
     o = Fn.vae_heads(hg, y, None, *mods, p=p, rng=stream.site(1))
     o[0][:, 0].sum().backward()
     assert torch.isfinite(hg.grad).all() and torch.isfinite(mods[0].weight.grad).all()
+
+
+def test_recon_error_matches_reference_arithmetic():
+    """row f3: the per-batch error of main.py:88-93 / inference.py:100-127 on the device, read in place from the
+    (padded, vertex-major) decoder output, against the oracle's restatement (fp64: 1e-12 relative)."""
+    import meshvae_b200
+    from oracle import mesh_vae_oracle as O
+    Fn = meshvae_b200.functional
+    b, n = 5, 4998
+    g = torch.Generator().manual_seed(3)
+    buf = torch.randn(n, b, 4, generator=g)                           # decoder output buffer, 3 channels padded to 4
+    out = buf.permute(1, 0, 2)[..., :3]                               # the model's [B,N,3] view
+    mean, std = torch.randn(n, 3, generator=g), torch.rand(n, 3, generator=g) + 0.5
+    s = torch.rand(b, 1, generator=g, dtype=torch.float64) + 0.5
+    R = torch.linalg.qr(torch.randn(b, 3, 3, generator=g, dtype=torch.float64))[0]
+    m = torch.randn(b, 1, 3, generator=g, dtype=torch.float64)
+    gt = torch.randn(b, n, 3, generator=g, dtype=torch.float64) * 2
+    ref_mean, ref_max = O.recon_error(out, mean, std, s, R, m, gt.numpy())
+    buf_d = buf.cuda()
+    out_d = buf_d.permute(1, 0, 2)[..., :3]
+    got_mean, got_max = Fn.recon_error(out_d, mean, std, s, R, m, gt)
+    assert rel_err(got_mean, torch.from_numpy(ref_mean)) < 1e-12 and rel_err(got_max, torch.from_numpy(ref_max)) < 1e-12
+    got2, _ = Fn.recon_error(out_d.contiguous(), mean, std, s, R, m, gt)          # contiguous [B,N,3] input: copied path
+    assert torch.equal(got2, got_mean)
