@@ -28,6 +28,8 @@ namespace mvb {
 static int g_tc_enabled = 1;
 static int g_tc_pg6 = 2;           // planes staged at a time by the 6-plane forward contraction (tuning: 1, 2, 3, 6)
 void set_tc_pg6(int v) { if (v == 1 || v == 2 || v == 3 || v == 6) g_tc_pg6 = v; }
+static int g_tc_cap = 4;           // resident CTAs per SM the row-GEMM grid is sized for (tuning: 1..4)
+void set_tc_cap(int v) { if (v >= 1 && v <= 4) g_tc_cap = v; }
 void set_tc_enabled(int v) { g_tc_enabled = v; }
 int tc_enabled() { return g_tc_enabled; }
 
@@ -491,7 +493,7 @@ int launch_contract_tc(const ContractArgs &a, cudaStream_t st) {
     // CTAs per SM: shared memory and TMEM (512 columns) permitting
     int per_sm = (int)((220 * 1024) / smem);
     if (per_sm > 512 / t.tmem_cols) per_sm = 512 / t.tmem_cols;
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > g_tc_cap) per_sm = g_tc_cap;
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)num_sms() * per_sm;
     if (grid > ntiles) grid = ntiles;
@@ -841,6 +843,7 @@ int launch_wgrad_tc(const WgradArgs &a, int has_bias, int M4, int N4, int *npart
 extern "C" int mvb_set_tensor_cores(int enable) {
     const int old = mvb::tc_enabled();
     mvb::set_tc_enabled(enable ? 1 : 0);
-    if (enable >= 10) mvb::set_tc_pg6(enable - 10);      // tuning hook: 11 / 12 / 13 / 16 = plane-group size 1 / 2 / 3 / 6
+    if (enable >= 10 && enable < 20) mvb::set_tc_pg6(enable - 10);      // tuning hook: 11 / 12 / 13 / 16 = plane-group size 1 / 2 / 3 / 6
+    if (enable >= 20 && enable < 30) mvb::set_tc_cap(enable - 20);      // tuning hook: 21..24 = grid sized for 1..4 CTAs per SM
     return old;
 }

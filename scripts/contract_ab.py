@@ -10,7 +10,8 @@ dev = torch.device("cuda:0")
 _, net, A, nn_ = bench.build_model(dev)
 L = mvb._lib
 flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
-for lvl, B, F in [(0, 64, 16), (1, 64, 16), (0, 256, 16)]:
+L.lib.mvb_set_fused_recurrence(0)      # step-by-step recurrence: identical across variants, isolates the contraction
+for lvl, B, F in [(0, 64, 16), (1, 64, 16), (1, 256, 16)]:
     n = nn_[lvl]
     ei, norm = mvb.ChebConv_batch.norm(A[lvl]._indices(), n)
     op = mvb.operators.from_edges(ei, norm, n, dev)
@@ -18,8 +19,8 @@ for lvl, B, F in [(0, 64, 16), (1, 64, 16), (0, 256, 16)]:
     w = torch.randn(6, F, 16, device=dev) * 0.1
     bias = torch.randn(16, device=dev)
     ref = None
-    for pg in (6, 3, 2, 1):
-        L.lib.mvb_set_tensor_cores(10 + pg)
+    for pg, cap in ((6, 4), (2, 4), (2, 3), (2, 2), (2, 1), (3, 2), (3, 1)):
+        L.lib.mvb_set_tensor_cores(10 + pg); L.lib.mvb_set_tensor_cores(20 + cap)
         basis = torch.empty(5, n, B, F, device=dev); y = torch.empty(n, B, 16, device=dev)
         ms = {}
         for cold in (True, False):
@@ -33,5 +34,5 @@ for lvl, B, F in [(0, 64, 16), (1, 64, 16), (0, 256, 16)]:
                 if i >= 3: t.append(s.elapsed_time(e))
             ms[cold] = sum(t) / len(t) * 1e3
         if ref is None: ref = y.clone()
-        print(f"lvl{lvl} B{B} F{F} plane group {pg}: cheb_fwd cold {ms[True]:6.1f} us  warm {ms[False]:6.1f} us  max|dy| vs pg6 {float((y-ref).abs().max()):.2e}")
-L.lib.mvb_set_tensor_cores(12)
+        print(f"lvl{lvl} B{B} F{F} plane group {pg} cap {cap}: cheb_fwd cold {ms[True]:6.1f} us  warm {ms[False]:6.1f} us  max|dy| vs pg6 {float((y-ref).abs().max()):.2e}")
+L.lib.mvb_set_tensor_cores(12); L.lib.mvb_set_tensor_cores(24); L.lib.mvb_set_fused_recurrence(1)
