@@ -40,6 +40,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL announces its version there) are sent to
+# stderr by swapping the descriptors for the duration of the run; emit() writes to the real stdout
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm / cpu_baseline: the oracle port of the reference training step
 # ------------------------------------------------------------------------------------------------
@@ -88,7 +110,7 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -335,7 +357,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(eng.launches_per_step) * args.steps,
             "gpu_launches_per_step": int(eng.launches_per_step),
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -428,7 +450,7 @@ def run_secondary(args, local_rank):
             "data": "synthetic", "config": {"workload": work, "batch_per_gpu": B, "cuda_graph": True,
                                             "l2": "flushed between timed steps (256 MiB write, outside the event pairs)"},
             "gpu_launches_per_step": int(launches), "gpu_launches": int(launches) * args.steps}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -445,6 +467,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    guard_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -459,8 +482,6 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL writes its version / debug lines to stdout by default: keep stdout for the ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
         return run_ours(args, rank, world, local_rank)
