@@ -68,6 +68,8 @@ class cheb_VAE(nn.Module):
         self.fused_dense = True
         # coarse levels: pool + conv + ReLU (+ pool) as one mesh-resident kernel (Fn.cheb_layer)
         self.fused_layers = True
+        self.keep_encoder_conv_out = False
+        self.encoder_conv_out = None
         self.A_num_nodes = tuple(int(n) for n in num_nodes)
         self.dropout_stream = Fn.DropoutStream()
 
@@ -106,6 +108,10 @@ class cheb_VAE(nn.Module):
     def encoder(self, x):
         for i in range(self.n_layers):
             x = self._layer(x, self.cheb[i], i, down=self.downsample_matrices[i])
+        if self.keep_encoder_conv_out:
+            # one-shot hand-over to the step engine, which splits the backward pass (gradient buckets) at this
+            # tensor and clears the attribute at once - a lasting reference would keep the step's autograd graph alive
+            self.encoder_conv_out = x
         if self.fused_dense and x.is_cuda:
             # x.reshape(B, 640) of models/cheb_VAE.py:270 is read straight from the vertex-major buffer
             return Fn.linear(Fn.to_vertex_major(x), self.enc_lin.weight, self.enc_lin.bias, relu=True, p=self._p(),

@@ -74,7 +74,18 @@ class TrainEngine:
         loss.backward()
         live = dp.live_parameters(list(net.parameters()))
         net.zero_grad(set_to_none=True)
+        # Flat-buffer order = gradient buckets for data parallelism.  Bucket 2 (front of the buffer, ~30 KB): the
+        # encoder convolutions, whose gradients are the last ones of the backward pass, and the 3-channel
+        # convolutions, whose gradients arrive through autograd.  Bucket 1: everything else (99 % of the bytes),
+        # final once the backward pass reaches the encoder's last pooled output - its all-reduce runs on NCCL's
+        # stream while the encoder backward (a second graph) computes.
+        self._enc_ids = {id(p) for p in getattr(net, "cheb", torch.nn.ModuleList()).parameters()}
+        late = [p for p in live if id(p) in self._enc_ids or (p.dim() == 3 and (p.shape[1] % 4 or p.shape[2] % 4))]
+        late_ids = {id(p) for p in late}
+        live = late + [p for p in live if id(p) not in late_ids]
         self.opt = FlatAdam(live, lr=lr, weight_decay=weight_decay)
+        self.split = self.opt.offsets[len(late)] if (self.distributed and use_graph and hasattr(net, "keep_encoder_conv_out")
+                                                     and 0 < len(late) < len(live)) else 0
         if hasattr(net, "dropout_stream"):
             # fresh dropout masks on every graph replay: the fused dense kernels add Adam's device step
             # counter to their Philox offset; per-rank streams
@@ -97,7 +108,8 @@ class TrainEngine:
         self.loss = torch.zeros((), device=self.dev, dtype=torch.float64)
         self.kld = self.rec = self.correct = None
         self.use_graph = use_graph
-        self.g_fb = self.g_opt = None
+        self.g_fb = self.g_opt = self.g_enc = None
+        self._cut = self._cut_grad = None
         self.launches_per_step = None
         self._copy_stream = self._gt_ready = None
         self._fwd_out = None
@@ -107,20 +119,39 @@ class TrainEngine:
         """part A of the step: everything that does not need the ground-truth batch"""
         for p, _ in self.loose:
             p.grad = None
+        self.net.keep_encoder_conv_out = bool(self.split)
         self._fwd_out = self.net.forward_recon(self.x, self.y_hot, m_type="train", eps=self.eps)
+        if self.split:
+            self._cut, self.net.encoder_conv_out = self.net.encoder_conv_out, None
 
-    def _loss_bwd(self):
-        """part B: loss (needs x_gt), backward, gradients of the few autograd-routed parameters"""
-        recon, z, mu, logvar, z_, y_hat = self._fwd_out
-        loss, correct, kld, rec = self.net.loss_function(self.x_gt, recon, z, mu, logvar, self.y_hot, y_hat)
-        loss.backward()
-        if self.loose:
-            torch._foreach_copy_([v for _, v in self.loose], [p.grad for p, _ in self.loose])
-        self.loss.copy_(loss.detach())
-        # per-batch statistics of main.py:83-85: the tensors stay device-resident (static addresses under
-        # graph replay); stats() reduces them on demand instead of inside every step
-        self.kld, self.rec, self.correct = kld, rec, correct
-        self._fwd_out = None
+    def _loss_bwd(self, part: int = 0):
+        """part B: loss (needs x_gt), backward, gradients of the few autograd-routed parameters.
+        part 0 = all of it; part 1 = down to the encoder's last pooled output (every gradient of bucket 1 is then
+        final); part 2 = the encoder convolutions."""
+        if part in (0, 1):
+            recon, z, mu, logvar, z_, y_hat = self._fwd_out
+            loss, correct, kld, rec = self.net.loss_function(self.x_gt, recon, z, mu, logvar, self.y_hot, y_hat)
+            self.loss.copy_(loss.detach())
+            # per-batch statistics of main.py:83-85: the tensors stay device-resident (static addresses under
+            # graph replay); stats() reduces them on demand instead of inside every step
+            self.kld, self.rec, self.correct = kld, rec, correct
+            self._fwd_out = None
+        if part == 0:
+            loss.backward()
+            self._cut = None
+            sel = self.loose
+        elif part == 1:
+            sel = [(p, v) for p, v in self.loose if id(p) not in self._enc_ids]
+            grads = torch.autograd.grad(loss, [self._cut] + [p for p, _ in sel])
+            self._cut_grad = grads[0]
+            for (p, _), g in zip(sel, grads[1:]):
+                p.grad = g
+        else:
+            sel = [(p, v) for p, v in self.loose if id(p) in self._enc_ids]
+            torch.autograd.backward([self._cut], [self._cut_grad])
+            self._cut = self._cut_grad = None
+        if sel:       # autograd-routed gradients into their views (all of them live in bucket 2)
+            torch._foreach_copy_([v for _, v in sel], [p.grad for p, _ in sel])
 
     def _fwd_bwd(self):
         self._fwd()
@@ -163,16 +194,23 @@ class TrainEngine:
         self._gt_ready = torch.cuda.Event()
         self._gt_ready.record(self._copy_stream)
         torch.cuda.synchronize()
+        # all captures on ONE stream: autograd replays a node's backward on the stream of its forward, so the
+        # encoder backward (its own graph when the gradient buckets are split) must be captured on that stream
+        cap = torch.cuda.Stream()
         self.g_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_fb):
+        with torch.cuda.graph(self.g_fb, stream=cap):
             self._fwd()
             check(lib.mvb_stream_wait_external_event(stream_ptr(), self._gt_ready.cuda_event), "mvb_stream_wait_external_event")
-            self._loss_bwd()
+            self._loss_bwd(1 if self.split else 0)
             if not self.distributed:
                 self._optim()
         if self.distributed:
+            if self.split:
+                self.g_enc = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.g_enc, pool=self.g_fb.pool(), stream=cap):
+                    self._loss_bwd(2)
             self.g_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_opt, pool=self.g_fb.pool()):
+            with torch.cuda.graph(self.g_opt, pool=self.g_fb.pool(), stream=cap):
                 self._optim()
         self.launches_per_step = lib.mvb_launch_count() - c0
         torch.cuda.synchronize()
@@ -187,7 +225,15 @@ class TrainEngine:
                 torch.cuda.current_stream().wait_event(self._gt_ready)
             self._loss_bwd()
         if self.distributed:
-            dp.allreduce_sum_(self.opt.flat_g)
+            if self.use_graph and self.split:
+                # bucket 1 is reduced on NCCL's stream while graph g_enc computes the encoder backward
+                w1 = dist.all_reduce(self.opt.flat_g[self.split:], op=dist.ReduceOp.SUM, async_op=True)
+                self.g_enc.replay()
+                w2 = dist.all_reduce(self.opt.flat_g[:self.split], op=dist.ReduceOp.SUM, async_op=True)
+                w1.wait()
+                w2.wait()
+            else:
+                dp.allreduce_sum_(self.opt.flat_g)
         if self.use_graph:
             if self.distributed:
                 self.g_opt.replay()
