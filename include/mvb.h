@@ -51,9 +51,10 @@ int64_t mvb_launch_count(void);
 /* enable (default) / disable the tcgen05 3xTF32 tensor-core kernels for the dense contractions;
  * disabled, the strict-fp32 FFMA kernels run everywhere.  Returns the previous setting. */
 int mvb_set_tensor_cores(int enable);
-/* enable / disable (default) the experimental shared-memory banded SpMM variant (A/B testing;
- * results are bit-identical either way: same per-row summation order) */
-int mvb_set_spmm_band(int enable);
+/* tuning hook for the tcgen05 row GEMM: planes of the 6-plane contraction staged at a time (1, 2, 3 or 6;
+ * default 2) and resident CTAs per SM its grid is sized for (1..4; default 4); 0 leaves a value unchanged.
+ * Results are bit-identical for every setting. */
+int mvb_set_tc_tuning(int plane_group, int ctas_per_sm);
 /* enable (default) / disable the fused multi-step recurrence kernels used when a level fits shared
  * memory (bit-identical to the step-by-step SpMM launches); a value >= 64 enables them with that
  * many threads per block (tuning hook; default 1024) */

@@ -8,7 +8,6 @@
 // B*F columns of a row first, so every neighbour gather is a run of fully coalesced 512-byte
 // warp requests.  Nothing is materialised per edge (the reference materialises [E,B,F]).
 // Roofline: HBM/L2 bandwidth; algorithmic bytes = (2 or 3)*N*ncols*4 + CSR.
-#include <limits.h>
 #include "mvb_internal.cuh"
 
 namespace mvb {
@@ -101,114 +100,6 @@ spmm_scalar_kernel(int n_rows, const int32_t *__restrict__ rowptr,
         float o = alpha * acc;
         if (z) o = fmaf(beta, z[idx], o);
         if (w) o += w[idx];
-        y[idx] = o;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Banded variant.  The mesh operators are banded in the template's vertex order (|row - col| <= 141
-// of 4998 at level 0, <= 179 of 1250 at level 1): all neighbours of a band of R consecutive rows
-// live in a window of R + 2*bandwidth rows.  A CTA owns (band of R rows) x (slab of CB column
-// quads = CB*16 bytes per row), finds its window [lo, hi] from the CSR itself (block min/max over
-// the band's column indices - no host-side hint), stages the window of x once in shared memory
-// with coalesced loads and serves all ~6 gathers per output from there: L2->SM traffic per step
-// drops from ~(6+2)u to ~(window/R + 2)u.  Any CSR is still handled: a band whose window does not
-// fit falls back to global gathers inside the same kernel (CTA-uniform branch).
-// ---------------------------------------------------------------------------------------------
-template <int CB>
-__global__ void __launch_bounds__(256)
-spmm_band_kernel(int n_rows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
-                 const float *__restrict__ vals, const float4 *__restrict__ x, float4 *y, const float4 *z,
-                 const float4 *w, float alpha, float beta, int nc4, int R, int wmax) {
-    extern __shared__ float4 xs[];                 // [wmax][CB]
-    __shared__ int s_lo, s_hi;
-    const int tid = threadIdx.x;
-    const int row0 = blockIdx.x * R;
-    const int nr = min(R, n_rows - row0);
-    const int c0 = blockIdx.y * CB;                // first column quad of the slab
-    const int cl = tid % CB;                       // column quad inside the slab
-    const int rl = tid / CB;                       // row lane
-    constexpr int RPP = 256 / CB;                  // rows per pass
-    const bool col_ok = (c0 + cl) < nc4;
-
-    // window of source rows referenced by this band
-    if (tid == 0) {
-        s_lo = INT_MAX;
-        s_hi = -1;
-    }
-    __syncthreads();
-    {
-        const int e0 = __ldg(rowptr + row0), e1 = __ldg(rowptr + row0 + nr);
-        int lo = INT_MAX, hi = -1;
-        for (int e = e0 + tid; e < e1; e += 256) {
-            const int c = __ldg(colidx + e);
-            lo = min(lo, c);
-            hi = max(hi, c);
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off));
-            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, off));
-        }
-        if ((tid & 31) == 0 && hi >= 0) {
-            atomicMin(&s_lo, lo);
-            atomicMax(&s_hi, hi);
-        }
-    }
-    __syncthreads();
-    const int lo = s_lo, hi = s_hi;
-    const bool in_smem = (hi >= lo) && (hi - lo + 1 <= wmax);
-    if (in_smem && col_ok) {
-        const int wrows = hi - lo + 1;
-        const float4 *xp = x + (int64_t)lo * nc4 + c0 + cl;
-        for (int r = rl; r < wrows; r += 4 * RPP) {      // 4 independent coalesced loads in flight
-            float4 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (r + u * RPP < wrows) v[u] = __ldg(xp + (int64_t)(r + u * RPP) * nc4);
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (r + u * RPP < wrows) xs[(r + u * RPP) * CB + cl] = v[u];
-        }
-    }
-    __syncthreads();
-    if (!col_ok) return;
-    for (int r = rl; r < nr; r += RPP) {
-        const int row = row0 + r;
-        const int s = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
-        const int64_t idx = (int64_t)row * nc4 + c0 + cl;
-        float4 zz = make_float4(0.f, 0.f, 0.f, 0.f), ww = zz;
-        if (z) zz = z[idx];                              // issued before the gathers
-        if (w) ww = w[idx];
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (in_smem) {
-            int j = s;
-            for (; j + 2 <= e; j += 2) {
-                const int ca = __ldg(colidx + j), cb = __ldg(colidx + j + 1);
-                const float va = __ldg(vals + j), vb = __ldg(vals + j + 1);
-                const float4 xa = xs[(ca - lo) * CB + cl];
-                const float4 xb = xs[(cb - lo) * CB + cl];
-                fma4(acc, va, xa);
-                fma4(acc, vb, xb);
-            }
-            if (j < e) fma4(acc, __ldg(vals + j), xs[(__ldg(colidx + j) - lo) * CB + cl]);
-        } else {
-            for (int j = s; j < e; ++j)
-                fma4(acc, __ldg(vals + j), ldg4(x + (int64_t)__ldg(colidx + j) * nc4 + c0 + cl));
-        }
-        float4 o = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
-        if (z) {
-            o.x = fmaf(beta, zz.x, o.x);
-            o.y = fmaf(beta, zz.y, o.y);
-            o.z = fmaf(beta, zz.z, o.z);
-            o.w = fmaf(beta, zz.w, o.w);
-        }
-        if (w) {
-            o.x += ww.x;
-            o.y += ww.y;
-            o.z += ww.z;
-            o.w += ww.w;
-        }
         y[idx] = o;
     }
 }
@@ -495,25 +386,6 @@ static int g_spmm_tx = 0, g_spmm_chunk = 0;      // 0 = automatic; set through m
 void set_spmm_shape(int tx, int chunk) { g_spmm_tx = tx; g_spmm_chunk = chunk; }
 static int g_spmm_mode = 0;   // 0 = automatic block size, 1/2/3 = force 256/512/1024-thread blocks (tuning runs)
 void set_spmm_mode(int v) { g_spmm_mode = v; }
-static int g_spmm_band = 0;   // experimental: measured SLOWER than the plain kernel (latency-bound phases), see profiles/README.md
-void set_spmm_band(int v) { g_spmm_band = v; }
-
-template <int CB>
-static int launch_band_t(int n_rows, const int32_t *rowptr, const int32_t *colidx, const float *vals,
-                         const float4 *x, float4 *y, const float4 *z, const float4 *w, float alpha, float beta,
-                         int nc4, int R, int wmax, cudaStream_t st) {
-    static bool attr_set = false;
-    const size_t smem = (size_t)wmax * CB * sizeof(float4);
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(spmm_band_kernel<CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        if (e != cudaSuccess) return set_err(MVB_ECUDA, "spmm_band: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set = true;
-    }
-    dim3 grid((n_rows + R - 1) / R, (nc4 + CB - 1) / CB);
-    spmm_band_kernel<CB><<<grid, 256, smem, st>>>(n_rows, rowptr, colidx, vals, x, y, z, w, alpha, beta, nc4, R, wmax);
-    return check_launch("mvb_spmm band");
-}
-
 int launch_spmm(int n_rows, int n_src_rows, const int32_t *rowptr, const int32_t *colidx, const float *vals,
                 const float *x, float *y, const float *z, const float *w, float alpha, float beta,
                 int64_t ncols, cudaStream_t st) {
@@ -529,17 +401,6 @@ int launch_spmm(int n_rows, int n_src_rows, const int32_t *rowptr, const int32_t
         float4 *y4 = reinterpret_cast<float4 *>(y);
         const float4 *z4 = reinterpret_cast<const float4 *>(z);
         const float4 *w4 = reinterpret_cast<const float4 *>(w);
-        if (g_spmm_band && n_rows >= 256 && nc4 >= 8) {
-            // shape the grid so that there are at least ~2 CTAs per SM: shrink the band before the slab
-            int R = 256, CB = 8;
-            auto nblocks = [&](int r, int cb) { return (int64_t)((n_rows + r - 1) / r) * ((nc4 + cb - 1) / cb); };
-            const int64_t want = (int64_t)num_sms() * 2;
-            while (R > 64 && nblocks(R, CB) < want) R >>= 1;
-            if (nblocks(R, CB) < want && nc4 >= 16) CB = 4;
-            const int wmax = (CB == 8) ? 576 : 1152;        // 72 KB window either way
-            if (CB == 8) return launch_band_t<8>(n_rows, rowptr, colidx, vals, x4, y4, z4, w4, alpha, beta, nc4, R, wmax, st);
-            return launch_band_t<4>(n_rows, rowptr, colidx, vals, x4, y4, z4, w4, alpha, beta, nc4, R, wmax, st);
-        }
         // block = TX column quads x (256 / TX) rows; every block walks `chunk` consecutive rows
         // measured sweep (scripts/spmm_tune.py, profiles/README.md): 256..512-byte slabs and 32-row
         // chunks beat one-row-per-block by 1.1x (B = 64) to 1.6x (B = 256): L2->SM traffic, not HBM,
@@ -609,7 +470,3 @@ extern "C" int mvb_set_spmm_mode(int mode) {
     return 0;
 }
 
-extern "C" int mvb_set_spmm_band(int enable) {
-    mvb::set_spmm_band(enable ? 1 : 0);
-    return 0;
-}

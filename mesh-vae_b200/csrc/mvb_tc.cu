@@ -843,7 +843,11 @@ int launch_wgrad_tc(const WgradArgs &a, int has_bias, int M4, int N4, int *npart
 extern "C" int mvb_set_tensor_cores(int enable) {
     const int old = mvb::tc_enabled();
     mvb::set_tc_enabled(enable ? 1 : 0);
-    if (enable >= 10 && enable < 20) mvb::set_tc_pg6(enable - 10);      // tuning hook: 11 / 12 / 13 / 16 = plane-group size 1 / 2 / 3 / 6
-    if (enable >= 20 && enable < 30) mvb::set_tc_cap(enable - 20);      // tuning hook: 21..24 = grid sized for 1..4 CTAs per SM
     return old;
+}
+
+extern "C" int mvb_set_tc_tuning(int plane_group, int ctas_per_sm) {
+    if (plane_group) mvb::set_tc_pg6(plane_group);
+    if (ctas_per_sm) mvb::set_tc_cap(ctas_per_sm);
+    return 0;
 }
