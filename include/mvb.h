@@ -161,22 +161,26 @@ int mvb_vae_reparam_bwd(int64_t n, const float *logvar, const float *eps, const 
 
 /* ---- A10/A11: loss epilogue  (models/cheb_VAE.py:321-346 loss_function; logpdf.py:7-8 KLD,
  *          :22-23 gaussian_nll, :24-28 softclip) -----------------------------------------------
- * recon  [N,B,C] fp32 VERTEX-MAJOR (the decoder output as the kernels produce it);
+ * recon  [N,B,recon_ld] fp32 VERTEX-MAJOR (the decoder output as the kernels produce it): recon_ld >= C
+ *        floats per (vertex, mesh) entry, the first C are the reconstruction (the 3-channel output layer
+ *        writes entries padded to 4 floats: passing it with recon_ld = 4 saves the slice copy);
  * x_gt   [B,N,C] mesh-major as main.py:70 delivers it, fp64 (x_is_f64 != 0; data.py:107) or fp32
  *        (inference.py:87);  mu/logvar [B,Z];  y_hat [B,ncls] softmax;  y [B,ncls] int64 one-hot;
  * log_sigma = softclip(1, -6) = 1.0009117 by default (models/cheb_VAE.py:328-329).
  * Outputs: loss[1] (fp64; mean_b(kld + rec - 2 log sum_c(y_hat*y))), kld[B] fp32, rec[B] fp64,
- * correct[1] int64, dnll [N,B,C] fp32 = (recon - x_gt)/sigma^2 (saved for backward).
+ * correct[1] int64, dnll [N,B,recon_ld] fp32 = (recon - x_gt)/sigma^2, zero in the padding (saved for
+ * backward).
  * Arithmetic is fp64 when x_gt is fp64 (as torch type promotion makes the reference do),
  * per-element fp32 with fp64 accumulation otherwise.  Deterministic (fixed-order reductions).
  * workspace: mvb_vae_loss_workspace_bytes(B, N) bytes. */
 size_t mvb_vae_loss_workspace_bytes(int B, int N);
-int mvb_vae_loss_fwd(int B, int N, int C, int Z, int ncls, const float *recon, const void *x_gt,
+int mvb_vae_loss_fwd(int B, int N, int C, int Z, int ncls, const float *recon, int recon_ld, const void *x_gt,
                      int x_is_f64, const float *mu, const float *logvar, const float *y_hat,
                      const int64_t *y, float log_sigma, double *loss, float *kld, double *rec,
                      int64_t *correct, float *dnll, void *workspace, size_t workspace_bytes,
                      void *stream);
-/* gloss: DEVICE pointer to the fp64 upstream gradient of `loss` (a scalar).
+/* gloss: DEVICE pointer to the fp64 upstream gradient of `loss` (a scalar).  C here is the entry width of
+ * dnll (the recon_ld of the forward call).
  * d_recon[N,B,C] = gloss/B * dnll ; d_mu = gloss/B * mu ; d_logvar = gloss/B * 0.5 (exp(logvar) - 1);
  * d_yhat[b,c] = gloss/B * (-2) * y[b,c] / sum_c(y_hat*y). Any output pointer may be NULL. */
 int mvb_vae_loss_bwd(int B, int N, int C, int Z, int ncls, const float *dnll, const float *mu,
@@ -196,6 +200,11 @@ int mvb_gaussian_nll_fwd(int64_t n, const float *mu, const void *x, int x_is_f64
                          void *out, void *stream);
 int mvb_gaussian_nll_bwd(int64_t n, const float *mu, const void *x, int x_is_f64, float log_sigma,
                          const void *gout, float *d_mu, void *stream);
+
+/* ---- input hand-off: mesh-major batch -> zero-padded vertex-major planes --------------------
+ * out[n, b, 0:Cp] = (x[b, n, 0:C], 0...)   x [B,N,C] as the loader delivers it (models/cheb_VAE.py:195-200
+ * reshape), out [N,B,Cp] with Cp >= C (4 for the 3-channel meshes): the layout every kernel works in. */
+int mvb_pack_vertex_major(int B, int N, int C, int Cp, const float *x, float *out, void *stream);
 
 /* ---- next row f3: per-batch reconstruction error  (main.py:88-93, :139-146; inference.py:100-127)
  * recon_mesh = out * std + mean (fp32) ; recon_mesh = bmm(recon_mesh * s, R) + m (fp64) ;

@@ -56,7 +56,8 @@ SIGNATURES = {
     "mvb_vae_reparam_fwd": (c_int, [c_int64, _vp, _vp, _vp, _vp, _vp]),
     "mvb_vae_reparam_bwd": (c_int, [c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvb_vae_loss_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "mvb_vae_loss_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, _vp, _vp, c_int, _vp, _vp, _vp, _vp, c_float,
+    "mvb_pack_vertex_major": (c_int, [c_int, c_int, c_int, c_int, _vp, _vp, _vp]),
+    "mvb_vae_loss_fwd": (c_int, [c_int, c_int, c_int, c_int, c_int, _vp, c_int, _vp, c_int, _vp, _vp, _vp, _vp, c_float,
                                  _vp, _vp, _vp, _vp, _vp, _vp, c_size_t, _vp]),
     "mvb_vae_loss_bwd": (c_int, [c_int, c_int, c_int, c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvb_kld_fwd": (c_int, [c_int, c_int, _vp, _vp, _vp, _vp]),

@@ -69,6 +69,7 @@ class cheb_VAE(nn.Module):
         # coarse levels: pool + conv + ReLU (+ pool) as one mesh-resident kernel (Fn.cheb_layer)
         self.fused_layers = True
         self.keep_encoder_conv_out = False
+        self._recon_padded = None
         self.encoder_conv_out = None
         self.A_num_nodes = tuple(int(n) for n in num_nodes)
         self.dropout_stream = Fn.DropoutStream()
@@ -106,6 +107,9 @@ class cheb_VAE(nn.Module):
 
     # ---- sub-networks (logical [B, N, F] tensors; physically vertex-major views) -----------------
     def encoder(self, x):
+        if x.is_cuda and not x.requires_grad and x.shape[2] % 4:
+            # 3-channel input: one kernel to the zero-padded vertex-major layout (the first conv pads its weight to match)
+            x = Fn.from_vertex_major(Fn.pack_input(x))
         for i in range(self.n_layers):
             x = self._layer(x, self.cheb[i], i, down=self.downsample_matrices[i])
         if self.keep_encoder_conv_out:
@@ -140,7 +144,17 @@ class cheb_VAE(nn.Module):
             lvl = self.n_layers - i - 1
             x = self._layer(x, self.cheb_dec[i], lvl, up=self.upsample_matrices[lvl])
         # quirk 1: the output conv runs the COARSEST operator on the finest mesh (models/cheb_VAE.py:288)
-        return self.cheb_dec[-1](x, self.A_edge_index[-1], self.A_norm[-1])
+        conv = self.cheb_dec[-1]
+        if x.is_cuda and not conv.fuse_relu:
+            # the 3-channel output stays in its 4-float entries: the returned [B,N,3] tensor is a view, and
+            # loss_function reads the padded buffer in place (handed over once through _recon_padded)
+            op = operators.from_edges(self.A_edge_index[-1], self.A_norm[-1], x.size(1), x.device)
+            y = Fn.cheb_conv(Fn.to_vertex_major(x), conv.weight, conv.bias, op, False, keep_padding=True)
+            fout = conv.weight.shape[2]
+            if y.shape[2] != fout:
+                self._recon_padded = y
+            return Fn.from_vertex_major(y)[..., :fout]
+        return conv(x, self.A_edge_index[-1], self.A_norm[-1])
 
     def sample(self, y, z):
         x = self.decoder(torch.cat([y, z], -1))
@@ -157,7 +171,12 @@ class cheb_VAE(nn.Module):
         return Fn.reparameterize(mu, logvar, eps)
 
     def loss_function(self, x, recon_x, z, mu_z, logvar_z, y, y_hat):
-        loss, kld, rec, correct = Fn.vae_loss(Fn.to_vertex_major(recon_x), x, mu_z, logvar_z, y_hat, y, self.log_sigma)
+        padded, self._recon_padded = self._recon_padded, None           # one-shot hand-over from decoder()
+        if padded is not None and recon_x.data_ptr() == padded.data_ptr() and recon_x.shape[1] == padded.shape[0]:
+            loss, kld, rec, correct = Fn.vae_loss(padded, x, mu_z, logvar_z, y_hat, y, self.log_sigma,
+                                                  channels=recon_x.shape[2])
+        else:
+            loss, kld, rec, correct = Fn.vae_loss(Fn.to_vertex_major(recon_x), x, mu_z, logvar_z, y_hat, y, self.log_sigma)
         return loss, correct, kld, rec
 
     def forward_recon(self, data, y, m_type="test", eps: Optional[torch.Tensor] = None):

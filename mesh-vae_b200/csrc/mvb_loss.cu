@@ -21,25 +21,25 @@ struct AccT<double> { typedef double type; };
 
 template <typename XT>
 __global__ void __launch_bounds__(256)
-vae_rec_partial_kernel(int B, int N, int C, int VCH, int BCH, const float *__restrict__ recon,
+vae_rec_partial_kernel(int B, int N, int C, int ld, int VCH, int BCH, const float *__restrict__ recon,
                        const XT *__restrict__ xgt, float log_sigma, float sigma,
                        double *__restrict__ partial, float *__restrict__ dnll) {
     typedef typename AccT<XT>::type AT;
     extern __shared__ double smem_d[];
     XT *Xs = reinterpret_cast<XT *>(smem_d);                     // [BCH][VCH*C]
-    float *Rs = reinterpret_cast<float *>(Xs + (size_t)BCH * VCH * C);  // [VCH][BCH*C]
+    float *Rs = reinterpret_cast<float *>(Xs + (size_t)BCH * VCH * C);  // [VCH][BCH*ld]  (ld >= C floats per entry)
     const int tid = threadIdx.x, nthreads = blockDim.x;
     const int v0 = blockIdx.x * VCH, b0 = blockIdx.y * BCH;
     const int nv = min(VCH, N - v0), nb = min(BCH, B - b0);
-    const int rw = nb * C;  // contiguous run per vertex in recon
+    const int rw = nb * ld; // contiguous run per vertex in recon (entries of ld floats, the first C are data)
     const int xw = nv * C;  // contiguous run per mesh in x_gt
     // both tiles through cp.async: every element of the block's two tiles is in flight at once (one exposed
     // latency instead of one per batch of register loads); a warp walks one contiguous run at a time
     {
         const int warp_ = tid >> 5, lane_ = tid & 31, nwarps_ = nthreads >> 5;
         for (int v = warp_; v < nv; v += nwarps_) {
-            const float *src = recon + ((int64_t)(v0 + v) * B + b0) * C;
-            float *dst = Rs + v * (BCH * C);
+            const float *src = recon + ((int64_t)(v0 + v) * B + b0) * ld;
+            float *dst = Rs + v * (BCH * ld);
             for (int e = lane_; e < rw; e += 32) cp_async<1>(dst + e, src + e);
         }
         for (int b = warp_; b < nb; b += nwarps_) {
@@ -65,7 +65,7 @@ vae_rec_partial_kernel(int B, int N, int C, int VCH, int BCH, const float *__res
         double s = 0.0;
         for (int e = lane; e < xw; e += 32) {
             const int v = e / C, c = e - v * C;
-            float *rp = Rs + v * (BCH * C) + b * C + c;
+            float *rp = Rs + v * (BCH * ld) + b * ld + c;
             const AT d = (AT)(*rp) - (AT)Xs[b * (VCH * C) + e];   // recon - x
             const AT t = d / sg;
             const AT nll = (AT)0.5 * t * t + cst;
@@ -79,7 +79,8 @@ vae_rec_partial_kernel(int B, int N, int C, int VCH, int BCH, const float *__res
     __syncthreads();
     for (int i = tid; i < nv * rw; i += nthreads) {
         const int v = i / rw, rem = i - v * rw;
-        dnll[((int64_t)(v0 + v) * B + b0) * C + rem] = Rs[v * (BCH * C) + rem];
+        const float val = (ld == C || rem % ld < C) ? Rs[v * (BCH * ld) + rem] : 0.f;      // padding entries carry no gradient
+        dnll[((int64_t)(v0 + v) * B + b0) * ld + rem] = val;
     }
 }
 
@@ -176,6 +177,27 @@ __global__ void vae_loss_bwd_small_kernel(int B, int Z, int ncls, const float *_
         float q = 0.f;
         for (int c = 0; c < ncls; ++c) q += y_hat[i * ncls + c] * (float)y[i * ncls + c];
         for (int c = 0; c < ncls; ++c) d_yhat[i * ncls + c] = s * (-2.f) * (float)y[i * ncls + c] / q;
+    }
+}
+
+// ---- input hand-off: [B,N,C] mesh-major -> [N,B,Cp] vertex-major, zero padded (one pass instead of transpose copy,
+// fill and padded copy) -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_vertex_major_kernel(int B, int N, int C, int Cp, const float *__restrict__ x, float *__restrict__ out) {
+    // block = 32 vertices x 8 meshes through shared memory: reads coalesced along a mesh's vertices, writes along
+    // a vertex's meshes
+    __shared__ float tile[8][32 * 8 + 1];
+    const int v0 = blockIdx.x * 32, b0 = blockIdx.y * 8;
+    const int nv = min(32, N - v0), nb = min(8, B - b0);
+    for (int i = threadIdx.x; i < nb * nv * C; i += blockDim.x) {
+        const int b = i / (nv * C), rem = i - b * (nv * C);
+        tile[b][rem] = __ldg(x + ((int64_t)(b0 + b) * N + v0) * C + rem);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nv * nb * Cp; i += blockDim.x) {
+        const int v = i / (nb * Cp), rem = i - v * (nb * Cp);
+        const int b = rem / Cp, c = rem - b * Cp;
+        out[((int64_t)(v0 + v) * B + b0) * Cp + rem] = c < C ? tile[b][v * C + c] : 0.f;
     }
 }
 
@@ -304,13 +326,13 @@ static inline unsigned ew_grid(int64_t n, int threads) {
     return (unsigned)b;
 }
 
-static void loss_tiles(int C, size_t xsize, int &VCH, int &BCH, size_t &smem) {
+static void loss_tiles(int C, int ld, size_t xsize, int &VCH, int &BCH, size_t &smem) {
     VCH = 32;
     BCH = 32;
-    smem = (size_t)VCH * BCH * C * (xsize + 4);
+    smem = (size_t)VCH * BCH * (C * xsize + ld * 4);
     while (smem > 48 * 1024 && VCH > 1) {
         VCH /= 2;
-        smem = (size_t)VCH * BCH * C * (xsize + 4);
+        smem = (size_t)VCH * BCH * (C * xsize + ld * 4);
     }
 }
 
@@ -324,19 +346,20 @@ extern "C" size_t mvb_vae_loss_workspace_bytes(int B, int N) {
     return nch * (size_t)B * sizeof(double);
 }
 
-extern "C" int mvb_vae_loss_fwd(int B, int N, int C, int Z, int ncls, const float *recon,
+extern "C" int mvb_vae_loss_fwd(int B, int N, int C, int Z, int ncls, const float *recon, int recon_ld,
                                 const void *x_gt, int x_is_f64, const float *mu,
                                 const float *logvar, const float *y_hat, const int64_t *y,
                                 float log_sigma, double *loss, float *kld, double *rec,
                                 int64_t *correct, float *dnll, void *workspace,
                                 size_t workspace_bytes, void *stream) {
     MVB_REQUIRE(B > 0 && N > 0 && C > 0 && Z > 0 && ncls > 0, "vae_loss_fwd: bad sizes");
+    MVB_REQUIRE(recon_ld >= C, "vae_loss_fwd: recon_ld=%d < C=%d", recon_ld, C);
     MVB_REQUIRE(recon && x_gt && mu && logvar && y_hat && y && loss && kld && rec && correct && dnll && workspace,
                 "vae_loss_fwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     int VCH, BCH;
     size_t smem;
-    loss_tiles(C, x_is_f64 ? 8 : 4, VCH, BCH, smem);
+    loss_tiles(C, recon_ld, x_is_f64 ? 8 : 4, VCH, BCH, smem);
     MVB_REQUIRE(VCH >= 8, "vae_loss_fwd: C=%d too large", C);
     const int nch = (N + VCH - 1) / VCH;
     if ((size_t)nch * B * sizeof(double) > workspace_bytes)
@@ -345,9 +368,9 @@ extern "C" int mvb_vae_loss_fwd(int B, int N, int C, int Z, int ncls, const floa
     const float sigma = expf(log_sigma);
     double *partial = reinterpret_cast<double *>(workspace);
     if (x_is_f64)
-        vae_rec_partial_kernel<double><<<grid, 256, smem, st>>>(B, N, C, VCH, BCH, recon, (const double *)x_gt, log_sigma, sigma, partial, dnll);
+        vae_rec_partial_kernel<double><<<grid, 256, smem, st>>>(B, N, C, recon_ld, VCH, BCH, recon, (const double *)x_gt, log_sigma, sigma, partial, dnll);
     else
-        vae_rec_partial_kernel<float><<<grid, 256, smem, st>>>(B, N, C, VCH, BCH, recon, (const float *)x_gt, log_sigma, sigma, partial, dnll);
+        vae_rec_partial_kernel<float><<<grid, 256, smem, st>>>(B, N, C, recon_ld, VCH, BCH, recon, (const float *)x_gt, log_sigma, sigma, partial, dnll);
     int rc = check_launch("mvb_vae_loss_fwd partial");
     if (rc) return rc;
     vae_loss_finalize_kernel<<<1, 256, 0, st>>>(B, Z, ncls, nch, partial, mu, logvar, y_hat, y, loss, kld, rec, correct);
@@ -449,4 +472,10 @@ extern "C" int mvb_recon_error(int B, int N, int ld, const float *recon, const f
     if (rc) return rc;
     mvb::recon_error_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, N, nch, psum, pmax, mean_err, max_err);
     return mvb::check_launch("mvb_recon_error finalize");
+}
+
+extern "C" int mvb_pack_vertex_major(int B, int N, int C, int Cp, const float *x, float *out, void *stream) {
+    MVB_REQUIRE(B > 0 && N > 0 && C > 0 && Cp >= C && C <= 8 && x && out, "pack_vertex_major: bad arguments");
+    mvb::pack_vertex_major_kernel<<<dim3((N + 31) / 32, (B + 7) / 8), 256, 0, (cudaStream_t)stream>>>(B, N, C, Cp, x, out);
+    return mvb::check_launch("mvb_pack_vertex_major");
 }

@@ -100,7 +100,7 @@ class _ChebConvFn(torch.autograd.Function):
 
 
 def cheb_conv(x_vm: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], op: MeshOperator,
-              relu: bool = False, pad_to_quads: bool = True) -> torch.Tensor:
+              relu: bool = False, pad_to_quads: bool = True, keep_padding: bool = False) -> torch.Tensor:
     """x_vm [N,B,Fin] -> [N,B,Fout] (vertex-major in, vertex-major out).
 
     Feature widths that are not a multiple of 4 (the 3-channel mesh coordinates at the encoder
@@ -109,16 +109,32 @@ def cheb_conv(x_vm: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Ten
     contractions run on the tcgen05 kernels instead of the scalar FFMA fallback.  Zero features /
     zero weight columns do not change any result; the padding ops are differentiable torch glue
     (autograd slices the padded weight gradient back)."""
-    fin, fout = x_vm.shape[2], weight.shape[2]
+    fin_x, fin, fout = x_vm.shape[2], weight.shape[1], weight.shape[2]
+    if fin_x != fin and not (fin_x > fin and fin_x == fin + (-fin) % 4):
+        raise _lib.MvbError(f"cheb_conv: x has {fin_x} features, weight expects {fin}")
     pin, pout = (-fin) % 4, (-fout) % 4
     if not pad_to_quads or (pin == 0 and pout == 0):
         return _ChebConvFn.apply(x_vm, weight, bias, op, relu)
-    if pin:
+    if pin and fin_x == fin:             # (an input packed by pack_input already carries the zero column)
         x_vm = torch.nn.functional.pad(x_vm, (0, pin))
     w = torch.nn.functional.pad(weight, (0, pout, 0, pin))
     b = bias if (bias is None or pout == 0) else torch.nn.functional.pad(bias, (0, pout))
     y = _ChebConvFn.apply(x_vm, w, b, op, relu)
+    if pout and keep_padding:
+        return y                         # [N,B,fout+pout]: the caller slices a view and hands the padded buffer to the loss
     return y[..., :fout] if pout else y
+
+
+def pack_input(x: torch.Tensor) -> torch.Tensor:
+    """[B,N,C] mesh-major input (no gradient) -> vertex-major [N,B,Cp] with Cp = C rounded up to 4, zero padded:
+    one kernel instead of the transpose copy + fill + padded copy."""
+    _req_cuda(x, "pack_input x")
+    b, n, c = x.shape
+    cp = c + (-c) % 4
+    x = x.contiguous()
+    out = torch.empty((n, b, cp), device=x.device, dtype=torch.float32)
+    check(lib.mvb_pack_vertex_major(b, n, c, cp, ptr(x), ptr(out), stream_ptr()), "mvb_pack_vertex_major")
+    return out
 
 
 class _PoolFn(torch.autograd.Function):
@@ -185,13 +201,14 @@ class _VaeLossFn(torch.autograd.Function):
     """mvb_vae_loss_fwd / _bwd  (models/cheb_VAE.py:321-346)."""
 
     @staticmethod
-    def forward(ctx, recon_vm, x_gt, mu, logvar, y_hat, y, log_sigma: float):
+    def forward(ctx, recon_vm, x_gt, mu, logvar, y_hat, y, log_sigma: float, channels: int):
         _req_cuda(recon_vm, "vae_loss recon")
         _req_cuda(x_gt, "vae_loss x_gt", None)
         if x_gt.dtype not in (torch.float32, torch.float64):
             raise _lib.MvbError(f"vae_loss: x_gt must be fp32 or fp64, got {x_gt.dtype}")
-        n, b, c = recon_vm.shape
-        if tuple(x_gt.shape) != (b, n, c):
+        n, b, ld = recon_vm.shape                    # entries of ld floats, the first `channels` are the reconstruction
+        c = channels
+        if tuple(x_gt.shape) != (b, n, c) or c > ld:
             raise _lib.MvbError(f"vae_loss: x_gt is {tuple(x_gt.shape)}, expected {(b, n, c)}")
         z = mu.shape[1]
         ncls = y_hat.shape[1]
@@ -207,11 +224,11 @@ class _VaeLossFn(torch.autograd.Function):
         dnll = torch.empty_like(recon_vm)
         ws_bytes = lib.mvb_vae_loss_workspace_bytes(b, n)
         ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-        check(lib.mvb_vae_loss_fwd(b, n, c, z, ncls, ptr(recon_vm), ptr(x_gt), 1 if f64 else 0, ptr(mu), ptr(logvar),
+        check(lib.mvb_vae_loss_fwd(b, n, c, z, ncls, ptr(recon_vm), ld, ptr(x_gt), 1 if f64 else 0, ptr(mu), ptr(logvar),
                                    ptr(y_hat), ptr(y), float(log_sigma), ptr(loss), ptr(kld), ptr(rec), ptr(correct),
                                    ptr(dnll), ptr(ws), ws_bytes, stream_ptr()), "mvb_vae_loss_fwd")
         ctx.save_for_backward(dnll, mu, logvar, y_hat, y)
-        ctx.dims = (b, n, c, z, ncls)
+        ctx.dims = (b, n, ld, z, ncls)
         ctx.set_materialize_grads(False)          # no zero tensors for the undefined grads of kld / rec / correct
         if not f64:                     # all-fp32 call (inference.py:87): the reference returns fp32
             loss, rec = loss.float(), rec.float()
@@ -230,12 +247,14 @@ class _VaeLossFn(torch.autograd.Function):
         d_yh = torch.empty_like(y_hat) if need[4] else None
         check(lib.mvb_vae_loss_bwd(b, n, c, z, ncls, ptr(dnll), ptr(mu), ptr(logvar), ptr(y_hat), ptr(y), ptr(g),
                                    ptr(d_recon), ptr(d_mu), ptr(d_lv), ptr(d_yh), stream_ptr()), "mvb_vae_loss_bwd")
-        return d_recon, None, d_mu, d_lv, d_yh, None, None
+        return d_recon, None, d_mu, d_lv, d_yh, None, None, None
 
 
-def vae_loss(recon_vm, x_gt, mu, logvar, y_hat, y, log_sigma: float = LOG_SIGMA_DEFAULT):
-    """-> (loss, kld[B], rec_loss[B], correct); only `loss` carries gradient (as main.py:80 uses it)."""
-    return _VaeLossFn.apply(recon_vm, x_gt, mu, logvar, y_hat, y, log_sigma)
+def vae_loss(recon_vm, x_gt, mu, logvar, y_hat, y, log_sigma: float = LOG_SIGMA_DEFAULT, channels: Optional[int] = None):
+    """-> (loss, kld[B], rec_loss[B], correct); only `loss` carries gradient (as main.py:80 uses it).
+    recon_vm [N,B,ld]; `channels` (default ld) < ld: the decoder's padded output buffer is read in place."""
+    return _VaeLossFn.apply(recon_vm, x_gt, mu, logvar, y_hat, y, log_sigma,
+                            int(recon_vm.shape[2] if channels is None else channels))
 
 
 class _KldFn(torch.autograd.Function):
