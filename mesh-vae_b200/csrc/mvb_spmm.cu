@@ -401,18 +401,27 @@ int launch_spmm(int n_rows, int n_src_rows, const int32_t *rowptr, const int32_t
         float4 *y4 = reinterpret_cast<float4 *>(y);
         const float4 *z4 = reinterpret_cast<const float4 *>(z);
         const float4 *w4 = reinterpret_cast<const float4 *>(w);
-        // block = TX column quads x (256 / TX) rows; every block walks `chunk` consecutive rows
-        // measured sweep (scripts/spmm_tune.py, profiles/README.md): 256..512-byte slabs and 32-row
-        // chunks beat one-row-per-block by 1.1x (B = 64) to 1.6x (B = 256): L2->SM traffic, not HBM,
-        // bounds this kernel, and the narrow slab lets L1 serve repeated neighbour rows
+        // block = TX column quads x (threads / TX) rows; every block walks `chunk` CONSECUTIVE rows of its
+        // 512-byte column slab (the operators are banded: L1 serves the repeated neighbour rows).
+        // The grid is ONE WAVE: exactly as many blocks as the GPU holds at once, each with an equal share of
+        // the rows.  The kernel is latency-bound, so a trailing partial wave costs as much as a full one:
+        // at 64 meshes the 64-row chunks gave 632 blocks = 2.13 waves and 17.3 us, 296 blocks of 136 rows
+        // give 14.7 us (0.54 -> 0.64 of the HBM peak; scripts/spmm_ab.py, profiles/README.md).
         int tx = g_spmm_tx, chunk = g_spmm_chunk;
         int nthreads = (g_spmm_mode == 2) ? 512 : (g_spmm_mode == 3 ? 1024 : 256);
-        if (g_spmm_mode == 0 && tx <= 0 && chunk <= 0 && nc4 >= 128 && nc4 < 512 && n_rows >= 2048) {
-            // mid-size planes (the level-0 steps at 64 meshes per GPU): 32 x 32-thread blocks, 64-row
-            // chunks: 18.7 us vs 20.7 us for the 256-thread shape (scripts/spmm_ab.py, profiles/README.md)
-            nthreads = 1024;
+        if (g_spmm_mode == 0 && tx <= 0 && chunk <= 0 && nc4 >= 32) {
             tx = 32;
-            chunk = 64;
+            const int gx1 = (nc4 + tx - 1) / tx;
+            for (nthreads = 1024; nthreads >= 256; nthreads >>= 1) {
+                const int gy1 = num_sms() * (2048 / nthreads) / gx1;
+                if (gy1 < 1) continue;
+                chunk = (n_rows + gy1 - 1) / gy1;
+                if (chunk >= 4 * (nthreads / tx) || nthreads == 256) break;     // >= 4 rows per warp, else smaller blocks
+            }
+            if (nthreads < 256) {            // more slabs than block slots (> 1184 slabs): several waves of 32-row chunks
+                nthreads = 256;
+                chunk = 0;
+            }
         }
         if (tx <= 0) {
             tx = (nc4 >= 512) ? 32 : 16;
@@ -422,7 +431,6 @@ int launch_spmm(int n_rows, int n_src_rows, const int32_t *rowptr, const int32_t
         const dim3 block(tx, nthreads / tx);
         if (chunk <= 0) chunk = 32;
         if (chunk < (int)block.y) chunk = block.y;
-        chunk = (chunk + block.y - 1) / block.y * block.y;
         const int64_t gy = ((int64_t)n_rows + chunk - 1) / chunk;
         const int64_t gx = (nc4 + tx - 1) / tx;
         if (gy > 65535) return set_err(MVB_EINVAL, "spmm: too many row chunks");

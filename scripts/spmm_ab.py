@@ -77,6 +77,8 @@ for lvl, B, F in cases:
     ref = sets[0][1].clone()
     variants = [(1, 0, 0), (0, 0, 0)] + [(m + st, tx, ch) for st in (0,) for m in (1, 2, 3) for tx in (16, 32)
                                           for ch in (64, 128, 256) if ch >= (256 << (m - 1)) // tx]
+    if os.environ.get("SPMM_VARIANTS"):      # "mode:tx:chunk,mode:tx:chunk,..."
+        variants = [tuple(int(t) for t in v.split(":")) for v in os.environ["SPMM_VARIANTS"].split(",")]
     for mode, tx, ch in variants:
         L.lib.mvb_set_spmm_mode(mode); L.lib.mvb_set_spmm_shape(tx, ch)
         sets[0][1].zero_()
