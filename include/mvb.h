@@ -212,11 +212,24 @@ int mvb_pack_vertex_major(int B, int N, int C, int Cp, const float *x, float *ou
  * recon [N,B,ld] fp32 vertex-major with ld >= 3 floats per (vertex, mesh) entry (the decoder output as
  * the kernels produce it, padded to 4); mean/std [N,3] fp32 (norm.npz); s [B], R [B,3,3], m [B,3] fp64
  * (Procrustes scale / rotation / translation, utils.py:58-156); gt [B,N,3] fp64 original meshes.
- * The reference copies the [B,N,3] reconstruction to the host for this every batch. */
+ * The reference copies the [B,N,3] reconstruction to the host for this every batch.
+ * Optional outputs (NULL = not wanted): vertex_err [B,N] fp32 = diff itself (evaluate() returns the
+ * concatenated per-vertex errors, main.py:146-148); mesh_out [B,N,3] fp32 = the back-transformed mesh
+ * (what evaluate(vis=True) / inference.py:131-140 write as OBJ files).  gt may be NULL when only
+ * mesh_out is wanted (the sex-changed mesh of main.py:162-164 has no ground truth): errors are 0 then. */
 size_t mvb_recon_error_workspace_bytes(int B, int N);
 int mvb_recon_error(int B, int N, int ld, const float *recon, const float *mean, const float *std, const double *s,
                     const double *R, const double *m, const double *gt, double *mean_err, double *max_err,
-                    void *workspace, size_t workspace_bytes, void *stream);
+                    float *vertex_err, float *mesh_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- next row f3: epoch statistics on the device  (main.py:60-65, 83-86, 93, 96; :135-137) ------
+ * acc[0] += loss * B; acc[1] += sum_b kld[b]; acc[2] += sum_b rec[b]; acc[3] += sum_b mean_err[b] (if given);
+ * acc[4] += correct (if given); acc[5] += B.   acc: 8 fp64 device accumulators, zeroed by the caller per epoch
+ * and read once at its end (the reference synchronises three times per batch, main.py:83-85).  With
+ * kld.mean()*B == sum kld etc. these are exactly the running totals of main.py.  loss: fp64 or fp32 scalar,
+ * rec: fp64 or fp32 [B] (as mvb_vae_loss_fwd returns them), correct: int64 scalar. */
+int mvb_epoch_meter_add(int B, const void *loss, int loss_is_f64, const float *kld, const void *rec, int rec_is_f64,
+                        const int64_t *correct, const double *mean_err, double *acc, void *stream);
 
 /* ---- next row f2: fused Adam on a flat parameter buffer  (main.py:251 torch.optim.Adam(lr,
  *          weight_decay), L2-style decay; main.py:81 optimizer.step()) --------------------------

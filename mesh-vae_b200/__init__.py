@@ -8,9 +8,10 @@ from .pool import SurfacePool, Pool
 from .cheb_vae import cheb_VAE
 from .cheb_cls import cheb_GCN
 from . import logpdf
+from . import formats, loader, loop
 
 __all__ = ["ChebConv_batch", "ChebConv", "SurfacePool", "Pool", "cheb_VAE", "cheb_GCN", "logpdf", "operators",
-           "functional", "MvbError"]
+           "functional", "formats", "loader", "loop", "MvbError"]
 __version__ = "0.1.0"
 
 

@@ -158,6 +158,7 @@ class cheb_VAE(nn.Module):
 
     def sample(self, y, z):
         x = self.decoder(torch.cat([y, z], -1))
+        self._recon_padded = None       # no loss follows a sampled decode: drop the hand-over reference at once
         return x.reshape(z.shape[0], -1, self.filters[0])
 
     def _draw_eps(self, shape, like):

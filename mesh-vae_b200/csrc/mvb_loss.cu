@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256)
 recon_error_partial_kernel(int B, int N, int ld, const float *__restrict__ recon, const float *__restrict__ mean,
                            const float *__restrict__ stdv, const double *__restrict__ sc, const double *__restrict__ R,
                            const double *__restrict__ m, const double *__restrict__ gt, double *__restrict__ psum,
-                           double *__restrict__ pmax) {
+                           double *__restrict__ pmax, float *__restrict__ vertex_err, float *__restrict__ mesh_out) {
     __shared__ double s_sum[256], s_max[256];
     const int b = blockIdx.y, tid = threadIdx.x;
     const int v = blockIdx.x * 256 + tid;
@@ -226,9 +226,18 @@ recon_error_partial_kernel(int B, int N, int ld, const float *__restrict__ recon
         const double *Rb = R + (int64_t)b * 9;
 #pragma unroll
         for (int j = 0; j < 3; ++j) q[j] = p[0] * Rb[j] + p[1] * Rb[3 + j] + p[2] * Rb[6 + j] + m[(int64_t)b * 3 + j];
-        const double *g = gt + ((int64_t)b * N + v) * 3;
-        const double d0 = q[0] - g[0], d1 = q[1] - g[1], d2 = q[2] - g[2];
-        err = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+        if (mesh_out) {                 // the back-transformed mesh itself (OBJ output of evaluate(vis) / inference.py)
+            float *o = mesh_out + ((int64_t)b * N + v) * 3;
+            o[0] = (float)q[0];
+            o[1] = (float)q[1];
+            o[2] = (float)q[2];
+        }
+        if (gt) {
+            const double *g = gt + ((int64_t)b * N + v) * 3;
+            const double d0 = q[0] - g[0], d1 = q[1] - g[1], d2 = q[2] - g[2];
+            err = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+            if (vertex_err) vertex_err[(int64_t)b * N + v] = (float)err;
+        }
     }
     s_sum[tid] = err;
     s_max[tid] = err;
@@ -257,6 +266,45 @@ __global__ void recon_error_finalize_kernel(int B, int N, int nchunks, const dou
     }
     mean_err[b] = s / (double)N;
     max_err[b] = mx;
+}
+
+// epoch statistics of the train / evaluate loops (main.py:83-86, :93, :135-137) kept on the device: one launch per
+// batch adds the batch's sums into 8 fp64 accumulators; the loop reads them ONCE per epoch instead of three
+// `.cpu()` synchronisations + a [B,N,3] read-back per batch.  acc = [loss*B, kld_sum, rec_sum, err_sum, correct, count, 0, 0]
+template <typename RecT>
+__global__ void __launch_bounds__(256)
+epoch_meter_kernel(int B, const double *__restrict__ loss, const float *__restrict__ loss32, const float *__restrict__ kld,
+                   const RecT *__restrict__ rec, const int64_t *__restrict__ correct, const double *__restrict__ mean_err,
+                   double *acc) {
+    __shared__ double sh[3][256];
+    const int tid = threadIdx.x;
+    double k = 0.0, r = 0.0, e = 0.0;
+    for (int b = tid; b < B; b += 256) {          // fixed order: deterministic sums
+        k += (double)kld[b];
+        r += (double)rec[b];
+        if (mean_err) e += mean_err[b];
+    }
+    sh[0][tid] = k;
+    sh[1][tid] = r;
+    sh[2][tid] = e;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (tid < off) {
+            sh[0][tid] += sh[0][tid + off];
+            sh[1][tid] += sh[1][tid + off];
+            sh[2][tid] += sh[2][tid + off];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const double l = loss ? *loss : (double)*loss32;
+        acc[0] += l * (double)B;
+        acc[1] += sh[0][0];
+        acc[2] += sh[1][0];
+        acc[3] += sh[2][0];
+        if (correct) acc[4] += (double)*correct;
+        acc[5] += (double)B;
+    }
 }
 
 // ---- reparameterisation ----------------------------------------------------------------------
@@ -459,19 +507,32 @@ extern "C" size_t mvb_recon_error_workspace_bytes(int B, int N) { return (size_t
 
 extern "C" int mvb_recon_error(int B, int N, int ld, const float *recon, const float *mean, const float *std, const double *s,
                                const double *R, const double *m, const double *gt, double *mean_err, double *max_err,
-                               void *workspace, size_t workspace_bytes, void *stream) {
-    MVB_REQUIRE(B > 0 && N > 0 && ld >= 3 && recon && mean && std && s && R && m && gt && mean_err && max_err && workspace,
+                               float *vertex_err, float *mesh_out, void *workspace, size_t workspace_bytes, void *stream) {
+    MVB_REQUIRE(B > 0 && N > 0 && ld >= 3 && recon && mean && std && s && R && m && mean_err && max_err && workspace,
                 "recon_error: bad arguments");
+    MVB_REQUIRE(gt || mesh_out, "recon_error: neither a ground truth nor a mesh output");
     const int nch = (N + 255) / 256;
     MVB_REQUIRE(workspace_bytes >= mvb_recon_error_workspace_bytes(B, N), "recon_error: workspace too small");
     double *psum = reinterpret_cast<double *>(workspace);
     double *pmax = psum + (size_t)nch * B;
     cudaStream_t st = (cudaStream_t)stream;
-    mvb::recon_error_partial_kernel<<<dim3(nch, B), 256, 0, st>>>(B, N, ld, recon, mean, std, s, R, m, gt, psum, pmax);
+    mvb::recon_error_partial_kernel<<<dim3(nch, B), 256, 0, st>>>(B, N, ld, recon, mean, std, s, R, m, gt, psum, pmax, vertex_err, mesh_out);
     int rc = mvb::check_launch("mvb_recon_error partial");
     if (rc) return rc;
     mvb::recon_error_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, N, nch, psum, pmax, mean_err, max_err);
     return mvb::check_launch("mvb_recon_error finalize");
+}
+
+extern "C" int mvb_epoch_meter_add(int B, const void *loss, int loss_is_f64, const float *kld, const void *rec, int rec_is_f64,
+                                   const int64_t *correct, const double *mean_err, double *acc, void *stream) {
+    MVB_REQUIRE(B > 0 && loss && kld && rec && acc, "epoch_meter_add: bad arguments");
+    const double *l64 = loss_is_f64 ? (const double *)loss : nullptr;
+    const float *l32 = loss_is_f64 ? nullptr : (const float *)loss;
+    if (rec_is_f64)
+        mvb::epoch_meter_kernel<double><<<1, 256, 0, (cudaStream_t)stream>>>(B, l64, l32, kld, (const double *)rec, correct, mean_err, acc);
+    else
+        mvb::epoch_meter_kernel<float><<<1, 256, 0, (cudaStream_t)stream>>>(B, l64, l32, kld, (const float *)rec, correct, mean_err, acc);
+    return mvb::check_launch("mvb_epoch_meter_add");
 }
 
 extern "C" int mvb_pack_vertex_major(int B, int N, int C, int Cp, const float *x, float *out, void *stream) {

@@ -106,7 +106,7 @@ class TrainEngine:
             if p.grad is None:
                 p.grad = v                      # the sink IS the gradient
         self.loss = torch.zeros((), device=self.dev, dtype=torch.float64)
-        self.kld = self.rec = self.correct = None
+        self.kld = self.rec = self.correct = self.recon = None
         self.use_graph = use_graph
         self.g_fb = self.g_opt = self.g_enc = None
         self._cut = self._cut_grad = None
@@ -135,6 +135,7 @@ class TrainEngine:
             # per-batch statistics of main.py:83-85: the tensors stay device-resident (static addresses under
             # graph replay); stats() reduces them on demand instead of inside every step
             self.kld, self.rec, self.correct = kld, rec, correct
+            self.recon = recon.detach()         # [B,N,3] view of the decoder buffer (no autograd graph attached)
             self._fwd_out = None
         if part == 0:
             loss.backward()
@@ -242,7 +243,7 @@ class TrainEngine:
 
     # ---- the public per-batch call (host buffers in, loss out) ---------------------------------
     def step(self, x_host: torch.Tensor, x_gt_host: torch.Tensor, y_host: torch.Tensor,
-             eps_host: Optional[torch.Tensor] = None) -> float:
+             eps_host: Optional[torch.Tensor] = None, sync: bool = True) -> Optional[float]:
         """x_host [B,N,3] f32, x_gt_host [B,N,3] f64/f32, y_host [B] int64 labels (pinned host memory for
         asynchronous copies).  Mirrors main.py:69-85: H2D, one-hot, step, loss read-back.  The ground truth
         travels on a second stream while the forward pass runs."""
@@ -261,7 +262,26 @@ class TrainEngine:
             self.x_gt.copy_(x_gt_host, non_blocking=True)
             self._gt_ready.record(self._copy_stream)
         self.device_step()
+        if not sync:                     # the epoch loop (loop.train_epoch) accumulates on the device instead
+            return None
         return float(self.loss)          # D2H read of the step's loss (synchronises)
+
+    def ragged_step(self, x: torch.Tensor, x_gt: torch.Tensor, y_hot: torch.Tensor, eps: Optional[torch.Tensor] = None):
+        """the last, smaller batch of an epoch (DataLoader without drop_last, main.py:256): same kernels, same flat
+        optimizer, not graph-replayed (the graphs are captured for `batch` meshes).  Device tensors in."""
+        for p, _ in self.loose:
+            p.grad = None
+        self.net.keep_encoder_conv_out = False
+        if eps is None:
+            eps = torch.normal(mean=0, std=1, size=(x.shape[0], self.net.z)).to(self.dev)
+        loss, correct, recon, (kld, rec, _), _ = self.net(x, x_gt, y_hot, m_type="train", eps=eps)
+        loss.backward()
+        if self.loose:
+            torch._foreach_copy_([v for _, v in self.loose], [p.grad for p, _ in self.loose])
+        if self.distributed:
+            dp.allreduce_sum_(self.opt.flat_g)
+        self._optim()
+        return loss.detach(), kld, rec, correct, recon.detach()
 
     def h2d_bytes(self) -> int:
         return (self.x.numel() * self.x.element_size() + self.x_gt.numel() * self.x_gt.element_size()

@@ -545,16 +545,19 @@ def cheb_layer(x_vm, weight, bias, l_op: MeshOperator, u_op: Optional[MeshOperat
 
 
 
-def recon_error(recon, mean, std, s, R, m, gt_mesh):
+def recon_error(recon, mean, std, s, R, m, gt_mesh, per_vertex: bool = False, mesh: bool = False):
     """Per-mesh reconstruction error of the train / evaluate / inference loops (main.py:88-93, :139-146;
     inference.py:100-127) on the device: recon [B,N,3] (any strides - the model's output is a view of the
     vertex-major decoder buffer and is read in place), mean/std [N,3] (norm.npz), s [B] / R [B,3,3] /
-    m [B,1,3] or [B,3] (Procrustes), gt_mesh [B,N,3].  -> (mean_err [B], max_err [B]) fp64 device tensors;
-    `mean_err.mean()` is main.py:93's `diff`."""
+    m [B,1,3] or [B,3] (Procrustes), gt_mesh [B,N,3] (None with mesh=True: only the back-transform).
+    -> (mean_err [B], max_err [B]) fp64 device tensors; `mean_err.mean()` is main.py:93's `diff`.
+    per_vertex=True appends diff [B,N] fp32 (main.py:146), mesh=True the back-transformed mesh [B,N,3] fp32."""
     _req_cuda(recon, "recon_error recon")
     b, n, c = recon.shape
     if c != 3:
         raise _lib.MvbError("recon_error: meshes have 3 coordinates")
+    if gt_mesh is None and not mesh:
+        raise _lib.MvbError("recon_error: no ground truth and no mesh output requested")
     rv = recon.permute(1, 0, 2)                      # [N,B,3] view
     if rv.stride(2) == 1 and rv.stride(0) == b * rv.stride(1) and rv.stride(1) >= 3:
         ld = rv.stride(1)                            # in place: entries of ld floats (3, or 4 for the padded decoder output)
@@ -564,11 +567,51 @@ def recon_error(recon, mean, std, s, R, m, gt_mesh):
     f32 = lambda t: torch.as_tensor(t).to(device=dev, dtype=torch.float32).contiguous()      # noqa: E731
     f64 = lambda t: torch.as_tensor(t).to(device=dev, dtype=torch.float64).contiguous()      # noqa: E731
     mean, std = f32(mean).reshape(n, 3), f32(std).reshape(n, 3)
-    s, R, m, gt = f64(s).reshape(b), f64(R).reshape(b, 3, 3), f64(m).reshape(b, 3), f64(gt_mesh).reshape(b, n, 3)
+    s, R, m = f64(s).reshape(b), f64(R).reshape(b, 3, 3), f64(m).reshape(b, 3)
+    gt = None if gt_mesh is None else f64(gt_mesh).reshape(b, n, 3)
     mean_err = torch.empty(b, device=dev, dtype=torch.float64)
     max_err = torch.empty(b, device=dev, dtype=torch.float64)
+    verr = torch.empty((b, n), device=dev, dtype=torch.float32) if (per_vertex and gt is not None) else None
+    mesh_out = torch.empty((b, n, 3), device=dev, dtype=torch.float32) if mesh else None
     ws_bytes = lib.mvb_recon_error_workspace_bytes(b, n)
     ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
     check(lib.mvb_recon_error(b, n, ld, ptr(rv), ptr(mean), ptr(std), ptr(s), ptr(R), ptr(m), ptr(gt), ptr(mean_err),
-                              ptr(max_err), ptr(ws), ws_bytes, stream_ptr()), "mvb_recon_error")
-    return mean_err, max_err
+                              ptr(max_err), ptr(verr), ptr(mesh_out), ptr(ws), ws_bytes, stream_ptr()), "mvb_recon_error")
+    out = (mean_err, max_err)
+    if per_vertex:
+        out += (verr,)
+    if mesh:
+        out += (mesh_out,)
+    return out
+
+
+class EpochMeter:
+    """Running totals of one epoch of main.py's train() / evaluate() (main.py:60-65, 83-86, 93, 96) on the device:
+    `add` is one launch and no synchronisation; `read` is the single device->host transfer of the epoch."""
+
+    def __init__(self, device):
+        self.acc = torch.zeros(8, device=device, dtype=torch.float64)
+
+    def reset(self):
+        self.acc.zero_()
+
+    def add(self, loss, kld, rec, correct=None, mean_err=None):
+        b = kld.shape[0]
+        if loss.dtype not in (torch.float32, torch.float64) or rec.dtype not in (torch.float32, torch.float64):
+            raise _lib.MvbError("EpochMeter.add: loss / rec must be fp32 or fp64")
+        kld = kld.detach().float().contiguous()
+        rec, loss = rec.detach().contiguous(), loss.detach().contiguous()
+        if correct is not None:
+            correct = correct.detach().to(torch.int64).contiguous()
+        if mean_err is not None:
+            mean_err = mean_err.detach().to(torch.float64).contiguous()
+        check(lib.mvb_epoch_meter_add(b, ptr(loss), int(loss.dtype == torch.float64), ptr(kld), ptr(rec),
+                                      int(rec.dtype == torch.float64), ptr(correct), ptr(mean_err), ptr(self.acc),
+                                      stream_ptr()), "mvb_epoch_meter_add")
+
+    def read(self):
+        """-> dict(loss, kld, rec_loss, error, accuracy, count): the per-sample means main.py returns"""
+        a = self.acc.cpu().numpy()
+        n = max(a[5], 1.0)
+        return {"loss": a[0] / n, "kld": a[1] / n, "rec_loss": a[2] / n, "error": a[3] / n, "accuracy": a[4] / n,
+                "count": int(a[5])}

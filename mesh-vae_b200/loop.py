@@ -1,0 +1,129 @@
+"""Epoch loops of the drivers with the host overheads removed.
+
+`train` and `evaluate` keep the signatures and return values of main.py:54-96 and :98-180.  What changes is
+where the per-batch bookkeeping happens: the reference synchronises three times per batch for the running
+totals (main.py:83-85), copies the [B,N,3] reconstruction to the host and runs the de-normalisation, the
+Procrustes back-transform (`bmm`) and the vertex errors there (main.py:88-94).  Here every batch ends with two
+launches on the device - `mvb_recon_error` on the decoder's buffer and `mvb_epoch_meter_add` into eight fp64
+accumulators - and the epoch ends with ONE read-back.  `train_epoch` is the same loop on the captured
+`engine.TrainEngine` step (fixed batch size replayed as a CUDA graph; the ragged last batch runs uncaptured).
+"""
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import formats
+from . import functional as Fn
+
+
+def _split(data):
+    x, x_gt, y, names, gt_mesh, R, m, s = data
+    return x, x_gt, y, names, gt_mesh, R, m, s
+
+
+def _norm(checkpoint_dir, norm, device):
+    mean, std = norm if norm is not None else formats.load_norm(checkpoint_dir)
+    return (torch.as_tensor(mean, dtype=torch.float32).to(device), torch.as_tensor(std, dtype=torch.float32).to(device))
+
+
+def _num_graphs(x):
+    return x.shape[0] if torch.is_tensor(x) else x.num_graphs
+
+
+def train(model, train_loader, optimizer, device, checkpoint_dir=None, norm=None):
+    """main.py:54-96.  -> (loss, kld, rec_loss, error, accuracy) per-sample means over the epoch (numpy float64
+    scalars: `.item()` works on each, as the driver expects of the accuracy).  `norm` = (mean, std) replaces the
+    norm.npz read."""
+    model.train()
+    mean, std = _norm(checkpoint_dir, norm, device)
+    meter = Fn.EpochMeter(device)
+    for data in train_loader:
+        x, x_gt, y, _, gt_mesh, R, m, s = _split(data)
+        x, x_gt = x.to(device, non_blocking=True), x_gt.to(device, non_blocking=True)
+        sex_hot = F.one_hot(y, num_classes=2).to(device, non_blocking=True)
+        optimizer.zero_grad()
+        loss, correct, out, z, _ = model(x, x_gt, sex_hot, m_type="train")
+        loss.backward()
+        optimizer.step()
+        mean_err, _ = Fn.recon_error(out.detach(), mean, std, s, R, m, gt_mesh)
+        meter.add(loss, z[0], z[1], correct, mean_err)
+    r = meter.read()
+    return r["loss"], r["kld"], r["rec_loss"], r["error"], np.float64(r["accuracy"])
+
+
+def train_epoch(engine, train_loader, checkpoint_dir=None, norm=None):
+    """`train` on the captured step: `engine.step(..., sync=False)` per full batch (host buffers in, nothing read
+    back), `engine.ragged_step` for a smaller last batch.  Same return tuple."""
+    dev = engine.dev
+    engine.net.train()
+    mean, std = _norm(checkpoint_dir, norm, dev)
+    meter = Fn.EpochMeter(dev)
+    for data in train_loader:
+        x, x_gt, y, _, gt_mesh, R, m, s = _split(data)
+        b = _num_graphs(x)
+        xt = (x if torch.is_tensor(x) else x.x).reshape(b, engine.n_vert, engine.feat)
+        if b == engine.batch:
+            engine.step(xt, x_gt.reshape(b, engine.n_vert, engine.feat), y, sync=False)
+            loss, kld, rec, correct, recon = engine.loss, engine.kld, engine.rec, engine.correct, engine.recon
+        else:
+            y_hot = F.one_hot(y, num_classes=engine.net.num_class).to(dev)
+            loss, kld, rec, correct, recon = engine.ragged_step(xt.to(dev), x_gt.reshape(b, engine.n_vert, engine.feat)
+                                                                .to(dev, engine.x_gt.dtype), y_hot)
+        mean_err, _ = Fn.recon_error(recon, mean, std, s, R, m, gt_mesh)
+        meter.add(loss, kld, rec, correct, mean_err)
+    r = meter.read()
+    return r["loss"], r["kld"], r["rec_loss"], r["error"], np.float64(r["accuracy"])
+
+
+def classifier_(net, x):
+    """main.py:42-49: predicted class of a batch of (normalised) meshes"""
+    return torch.argmax(net.classifier(net.encoder(x)), dim=1)
+
+
+def evaluate(n, model, test_loader, device, faces=None, checkpoint_dir=None, vis=False, norm=None):
+    """main.py:98-180.  -> (loss, kld, rec_loss, accuracy, errors [n_meshes, N] per-vertex distances, sex-change
+    success rate).  Per batch: forward, the sex-changed decode + re-classification (main.py:153-160), error kernel,
+    meter; nothing is read back before the end of the loop unless vis=True (OBJ files need the meshes)."""
+    model.eval()
+    mean, std = _norm(checkpoint_dir, norm, device)
+    meter = Fn.EpochMeter(device)
+    flipped = torch.zeros((), device=device, dtype=torch.int64)
+    errors = []
+    ok_dir = bad_dir = None
+    if vis:
+        save_path = os.path.join(checkpoint_dir, "mesh" + str(n))
+        ok_dir, bad_dir = os.path.join(save_path, "sex_change_S"), os.path.join(save_path, "sex_change_F")
+        os.makedirs(ok_dir, exist_ok=True)
+        os.makedirs(bad_dir, exist_ok=True)
+    with torch.no_grad():
+        for data in test_loader:
+            x, x_gt, y, names, gt_mesh, R, m, s = _split(data)
+            x, x_gt = x.to(device, non_blocking=True), x_gt.to(device, non_blocking=True)
+            sex_hot = F.one_hot(y, num_classes=2).to(device, non_blocking=True)
+            loss, correct, out, z, _ = model(x, x_gt, sex_hot, m_type="test")
+            res = Fn.recon_error(out, mean, std, s, R, m, gt_mesh, per_vertex=True, mesh=vis)
+            meter.add(loss, z[0], z[1], correct, res[0])
+            errors.append(res[2])
+            oppo = 1 - sex_hot
+            index_gt = torch.argmax(oppo, dim=1)
+            oppo_x = model.sample(oppo, z[2])
+            index_pred = classifier_(model, oppo_x)
+            flipped += (index_pred == index_gt).sum()
+            if not vis:
+                continue
+            oppo_mesh = Fn.recon_error(oppo_x, mean, std, s, R, m, None, mesh=True)[2].cpu().numpy()
+            recon_mesh, gt_np = res[3].cpu().numpy(), torch.as_tensor(gt_mesh).cpu().numpy()
+            hit = (index_pred == index_gt).cpu().numpy()
+            for i in range(len(names)):
+                base = names[i].split("/")[-1].split(".")[0]
+                d = ok_dir if hit[i] else bad_dir
+                formats.save_obj(os.path.join(d, base + "_recon.obj"), recon_mesh[i], faces)
+                formats.save_obj(os.path.join(d, base + "_gt.obj"), gt_np[i], faces)
+                formats.save_obj(os.path.join(d, base + ".obj"), oppo_mesh[i], faces)
+    r = meter.read()
+    total = max(r["count"], 1)
+    err = torch.cat(errors, 0).cpu().numpy() if errors else np.zeros((0, 0), dtype=np.float32)
+    return r["loss"], r["kld"], r["rec_loss"], np.float64(r["accuracy"]), err, int(flipped) / total
