@@ -211,7 +211,8 @@ int mvb_pack_vertex_major(int B, int N, int C, int Cp, const float *x, float *ou
  * diff = sqrt(((recon_mesh - gt_mesh)^2).sum(-1)) ; mean_err[b] = diff.mean(-1), max_err[b] = diff.max(-1).
  * recon [N,B,ld] fp32 vertex-major with ld >= 3 floats per (vertex, mesh) entry (the decoder output as
  * the kernels produce it, padded to 4); mean/std [N,3] fp32 (norm.npz); s [B], R [B,3,3], m [B,3] fp64
- * (Procrustes scale / rotation / translation, utils.py:58-156); gt [B,N,3] fp64 original meshes.
+ * (Procrustes scale / rotation / translation, utils.py:58-156); gt [B,N,3] original meshes, fp64 (gt_is_f64 != 0)
+ * or fp32 as the loader collates them (data.py:133 torch.Tensor(points)) - read without a conversion pass.
  * The reference copies the [B,N,3] reconstruction to the host for this every batch.
  * Optional outputs (NULL = not wanted): vertex_err [B,N] fp32 = diff itself (evaluate() returns the
  * concatenated per-vertex errors, main.py:146-148); mesh_out [B,N,3] fp32 = the back-transformed mesh
@@ -219,7 +220,7 @@ int mvb_pack_vertex_major(int B, int N, int C, int Cp, const float *x, float *ou
  * mesh_out is wanted (the sex-changed mesh of main.py:162-164 has no ground truth): errors are 0 then. */
 size_t mvb_recon_error_workspace_bytes(int B, int N);
 int mvb_recon_error(int B, int N, int ld, const float *recon, const float *mean, const float *std, const double *s,
-                    const double *R, const double *m, const double *gt, double *mean_err, double *max_err,
+                    const double *R, const double *m, const void *gt, int gt_is_f64, double *mean_err, double *max_err,
                     float *vertex_err, float *mesh_out, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- next row f3: epoch statistics on the device  (main.py:60-65, 83-86, 93, 96; :135-137) ------

@@ -75,7 +75,7 @@ SIGNATURES = {
     "mvb_vae_heads_bwd": (c_int, [c_int, c_int, c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_float, c_uint64, _vp,
                                   c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvb_recon_error_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "mvb_recon_error": (c_int, [c_int, c_int, c_int] + [_vp] * 11 + [_vp, c_size_t, _vp]),
+    "mvb_recon_error": (c_int, [c_int, c_int, c_int] + [_vp] * 7 + [c_int] + [_vp] * 4 + [_vp, c_size_t, _vp]),
     "mvb_epoch_meter_add": (c_int, [c_int, _vp, c_int, _vp, _vp, c_int, _vp, _vp, _vp, _vp]),
     "mvb_adam_step": (c_int, [c_int64, _vp, _vp, _vp, _vp, _vp, c_float, c_float, c_float, c_float, c_float, c_float,
                               _vp]),

@@ -208,10 +208,11 @@ pack_vertex_major_kernel(int B, int N, int C, int Cp, const float *__restrict__ 
 // The reference moves the whole [B,N,3] reconstruction to the host for this every batch; here it is one
 // pass over the vertex-major reconstruction on the device, per-(vertex chunk, mesh) partial sums / maxima
 // and an ordered final reduction.
+template <typename GtT>
 __global__ void __launch_bounds__(256)
 recon_error_partial_kernel(int B, int N, int ld, const float *__restrict__ recon, const float *__restrict__ mean,
                            const float *__restrict__ stdv, const double *__restrict__ sc, const double *__restrict__ R,
-                           const double *__restrict__ m, const double *__restrict__ gt, double *__restrict__ psum,
+                           const double *__restrict__ m, const GtT *__restrict__ gt, double *__restrict__ psum,
                            double *__restrict__ pmax, float *__restrict__ vertex_err, float *__restrict__ mesh_out) {
     __shared__ double s_sum[256], s_max[256];
     const int b = blockIdx.y, tid = threadIdx.x;
@@ -233,8 +234,8 @@ recon_error_partial_kernel(int B, int N, int ld, const float *__restrict__ recon
             o[2] = (float)q[2];
         }
         if (gt) {
-            const double *g = gt + ((int64_t)b * N + v) * 3;
-            const double d0 = q[0] - g[0], d1 = q[1] - g[1], d2 = q[2] - g[2];
+            const GtT *g = gt + ((int64_t)b * N + v) * 3;
+            const double d0 = q[0] - (double)g[0], d1 = q[1] - (double)g[1], d2 = q[2] - (double)g[2];
             err = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
             if (vertex_err) vertex_err[(int64_t)b * N + v] = (float)err;
         }
@@ -506,7 +507,7 @@ extern "C" int mvb_gaussian_nll_bwd(int64_t n, const float *mu, const void *x, i
 extern "C" size_t mvb_recon_error_workspace_bytes(int B, int N) { return (size_t)2 * ((N + 255) / 256) * B * sizeof(double); }
 
 extern "C" int mvb_recon_error(int B, int N, int ld, const float *recon, const float *mean, const float *std, const double *s,
-                               const double *R, const double *m, const double *gt, double *mean_err, double *max_err,
+                               const double *R, const double *m, const void *gt, int gt_is_f64, double *mean_err, double *max_err,
                                float *vertex_err, float *mesh_out, void *workspace, size_t workspace_bytes, void *stream) {
     MVB_REQUIRE(B > 0 && N > 0 && ld >= 3 && recon && mean && std && s && R && m && mean_err && max_err && workspace,
                 "recon_error: bad arguments");
@@ -516,7 +517,10 @@ extern "C" int mvb_recon_error(int B, int N, int ld, const float *recon, const f
     double *psum = reinterpret_cast<double *>(workspace);
     double *pmax = psum + (size_t)nch * B;
     cudaStream_t st = (cudaStream_t)stream;
-    mvb::recon_error_partial_kernel<<<dim3(nch, B), 256, 0, st>>>(B, N, ld, recon, mean, std, s, R, m, gt, psum, pmax, vertex_err, mesh_out);
+    if (gt_is_f64)
+        mvb::recon_error_partial_kernel<double><<<dim3(nch, B), 256, 0, st>>>(B, N, ld, recon, mean, std, s, R, m, (const double *)gt, psum, pmax, vertex_err, mesh_out);
+    else
+        mvb::recon_error_partial_kernel<float><<<dim3(nch, B), 256, 0, st>>>(B, N, ld, recon, mean, std, s, R, m, (const float *)gt, psum, pmax, vertex_err, mesh_out);
     int rc = mvb::check_launch("mvb_recon_error partial");
     if (rc) return rc;
     mvb::recon_error_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, N, nch, psum, pmax, mean_err, max_err);

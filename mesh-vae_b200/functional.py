@@ -564,19 +564,26 @@ def recon_error(recon, mean, std, s, R, m, gt_mesh, per_vertex: bool = False, me
     else:
         rv, ld = rv.contiguous(), 3
     dev = recon.device
-    f32 = lambda t: torch.as_tensor(t).to(device=dev, dtype=torch.float32).contiguous()      # noqa: E731
-    f64 = lambda t: torch.as_tensor(t).to(device=dev, dtype=torch.float64).contiguous()      # noqa: E731
+    # small operands: one asynchronous copy each (pinned host tensors make them truly asynchronous); the ground-truth
+    # meshes are read in the precision they arrive in (fp32 from the loader, data.py:133) - no conversion pass
+    f32 = lambda t: torch.as_tensor(t).to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()      # noqa: E731
+    f64 = lambda t: torch.as_tensor(t).to(device=dev, non_blocking=True).to(torch.float64).contiguous()        # noqa: E731
     mean, std = f32(mean).reshape(n, 3), f32(std).reshape(n, 3)
     s, R, m = f64(s).reshape(b), f64(R).reshape(b, 3, 3), f64(m).reshape(b, 3)
-    gt = None if gt_mesh is None else f64(gt_mesh).reshape(b, n, 3)
+    gt = None
+    if gt_mesh is not None:
+        gt = torch.as_tensor(gt_mesh)
+        if gt.dtype not in (torch.float32, torch.float64):
+            gt = gt.to(torch.float32)
+        gt = gt.to(dev, non_blocking=True).reshape(b, n, 3).contiguous()
     mean_err = torch.empty(b, device=dev, dtype=torch.float64)
     max_err = torch.empty(b, device=dev, dtype=torch.float64)
     verr = torch.empty((b, n), device=dev, dtype=torch.float32) if (per_vertex and gt is not None) else None
     mesh_out = torch.empty((b, n, 3), device=dev, dtype=torch.float32) if mesh else None
     ws_bytes = lib.mvb_recon_error_workspace_bytes(b, n)
     ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
-    check(lib.mvb_recon_error(b, n, ld, ptr(rv), ptr(mean), ptr(std), ptr(s), ptr(R), ptr(m), ptr(gt), ptr(mean_err),
-                              ptr(max_err), ptr(verr), ptr(mesh_out), ptr(ws), ws_bytes, stream_ptr()), "mvb_recon_error")
+    check(lib.mvb_recon_error(b, n, ld, ptr(rv), ptr(mean), ptr(std), ptr(s), ptr(R), ptr(m), ptr(gt),
+                              int(gt is not None and gt.dtype == torch.float64), ptr(mean_err), ptr(max_err), ptr(verr), ptr(mesh_out), ptr(ws), ws_bytes, stream_ptr()), "mvb_recon_error")
     out = (mean_err, max_err)
     if per_vertex:
         out += (verr,)

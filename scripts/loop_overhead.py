@@ -31,8 +31,8 @@ batches = []
 for i in range(4):
     x = torch.randn(B, n, 3, generator=g)
     batches.append((x.pin_memory(), x.double().pin_memory(), torch.randint(0, 2, (B,), generator=g), None,
-                    torch.randn(B, n, 3, generator=g), torch.randn(B, 3, 3, generator=g), torch.randn(B, 1, 3, generator=g),
-                    torch.rand(B, 1, generator=g) + 0.5))
+                    torch.randn(B, n, 3, generator=g).pin_memory(), torch.randn(B, 3, 3, generator=g).pin_memory(),
+                    torch.randn(B, 1, 3, generator=g).pin_memory(), (torch.rand(B, 1, generator=g) + 0.5).pin_memory()))
 
 
 def euclid(a, b):
