@@ -55,7 +55,12 @@ __host__ __device__ inline LayerSmem layer_smem(int N, int Fin, int Fout, int K,
     s.tB = o; o += rows * LDT;
     s.G = o; if (backward) o += n_out * (Fout + 4);
     s.W = o; o += K * Fin * Fout;
-    s.red = o; if (backward) o += LY_NT * 16;
+    if (backward) {           // dW partials: one per row split, or one per warp when a warp's lanes share blocks (shuffle-reduced)
+        const int nblk = (fin_local / 4) * (Fout / 4);
+        s.red = o; o += (nblk >= 32 ? LY_NT : (LY_NT / 32) * nblk) * 16;
+    } else {
+        s.red = o;
+    }
     s.csr = o; o += r4(N + 1) + 2 * r4(Lnnz);
     s.ucsr = o; if (Unnz > 0) o += r4((N > n_in ? N : n_in) + 1) + 2 * r4(Unnz);
     s.inv = o; if (backward) o += r4(N);
@@ -63,16 +68,28 @@ __host__ __device__ inline LayerSmem layer_smem(int N, int Fin, int Fout, int K,
     return s;
 }
 
+// CSR into shared memory: row pointers by cp.async, entries as packed (column, value) pairs - one 8-byte load per
+// neighbour in the gather loops instead of two 4-byte ones.  Visible after the caller's next wait + __syncthreads.
 __device__ __forceinline__ void stage_csr_async(float *smem, int nrows, int nnz, const int32_t *rp, const int32_t *ci,
-                                                const float *v, const int32_t *&srp, const int32_t *&sci, const float *&sv,
-                                                int tid) {
+                                                const float *v, const int32_t *&srp, const int2 *&sce, int tid) {
     int32_t *a = reinterpret_cast<int32_t *>(smem);
-    int32_t *b = a + r4(nrows + 1);
-    float *c = reinterpret_cast<float *>(b + r4(nnz));
+    int2 *b = reinterpret_cast<int2 *>(a + r4(nrows + 1));
     cp_async_words(a, rp, nrows + 1, tid, LY_NT);
-    cp_async_words(b, ci, nnz, tid, LY_NT);
-    cp_async_words(c, v, nnz, tid, LY_NT);
-    srp = a; sci = b; sv = c;
+    for (int base = 0; base < nnz; base += 4 * LY_NT) {          // 8 independent loads in flight per thread
+        int c[4];
+        float w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * LY_NT + tid;
+            if (i < nnz) { c[u] = __ldg(ci + i); w[u] = __ldg(v + i); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * LY_NT + tid;
+            if (i < nnz) b[i] = make_int2(c[u], __float_as_int(w[u]));
+        }
+    }
+    srp = a; sce = b;
 }
 
 __device__ __forceinline__ float4 ld4s(const float *p) { return *reinterpret_cast<const float4 *>(p); }
@@ -82,26 +99,28 @@ __device__ __forceinline__ void fma4s(float4 &a, float s, const float4 &x) {
 }
 
 // dst[v][q] = sum_j vals[j] * src[colidx[j]][q]  for the rows of a CSR held in shared memory
-__device__ __forceinline__ float4 gather_row(const float *src, int LDT, const int32_t *ci, const float *cv, int s, int e, int q) {
+__device__ __forceinline__ float4 gather_row(const float *src, int LDT, const int2 *ce, int s, int e, int q) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int j = s;
     for (; j + 2 <= e; j += 2) {
-        const int ca = ci[j], cb = ci[j + 1];
-        const float va = cv[j], vb = cv[j + 1];
-        const float4 xa = ld4s(src + ca * LDT + 4 * q), xb = ld4s(src + cb * LDT + 4 * q);
-        fma4s(acc, va, xa);
-        fma4s(acc, vb, xb);
+        const int2 ea = ce[j], eb = ce[j + 1];
+        const float4 xa = ld4s(src + ea.x * LDT + 4 * q), xb = ld4s(src + eb.x * LDT + 4 * q);
+        fma4s(acc, __int_as_float(ea.y), xa);
+        fma4s(acc, __int_as_float(eb.y), xb);
     }
-    if (j < e) fma4s(acc, cv[j], ld4s(src + ci[j] * LDT + 4 * q));
+    if (j < e) {
+        const int2 ea = ce[j];
+        fma4s(acc, __int_as_float(ea.y), ld4s(src + ea.x * LDT + 4 * q));
+    }
     return acc;
 }
 
 // one recurrence step in shared memory: old <- alpha * L cur - [k >= 2] old   (row arithmetic of the step kernels)
-__device__ __forceinline__ void recur_step(float *cur, float *old, int N, int lqf, int LDT, const int32_t *rp, const int32_t *ci,
-                                           const float *cv, int k, int tid) {
+__device__ __forceinline__ void recur_step(float *cur, float *old, int N, int lqf, int LDT, const int32_t *rp, const int2 *ce,
+                                           int k, int tid) {
     for (int i = tid; i < (N << lqf); i += LY_NT) {
         const int v = i >> lqf, q = i & ((1 << lqf) - 1);
-        const float4 acc = gather_row(cur, LDT, ci, cv, rp[v], rp[v + 1], q);
+        const float4 acc = gather_row(cur, LDT, ce, rp[v], rp[v + 1], q);
         float4 o;
         if (k == 1) {
             o = make_float4(1.f * acc.x, 1.f * acc.y, 1.f * acc.z, 1.f * acc.w);
@@ -129,21 +148,60 @@ __device__ __forceinline__ void stage_t0(const LayerArgs &a, float *sm, const La
     const int LDT = (4 << lqf) + 4;
     float *tA = sm + S.tA, *tB = sm + S.tB;
     if (a.Urp) {
-        const int32_t *urp, *uci;
-        const float *uv;
-        stage_csr_async(sm + S.ucsr, a.N, a.Unnz, a.Urp, a.Uci, a.Uv, urp, uci, uv, tid);
+        const int32_t *urp;
+        const int2 *uce;
+        stage_csr_async(sm + S.ucsr, a.N, a.Unnz, a.Urp, a.Uci, a.Uv, urp, uce, tid);
         stage_mesh_rows(tB, LDT, a.x, a.n_in, a.B, b, a.Fin, c0, lqf, tid);
         cp_async_wait_all();
         __syncthreads();
         for (int i = tid; i < (a.N << lqf); i += LY_NT) {
             const int v = i >> lqf, q = i & ((1 << lqf) - 1);
-            st4s(tA + v * LDT + 4 * q, gather_row(tB, LDT, uci, uv, urp[v], urp[v + 1], q));
+            st4s(tA + v * LDT + 4 * q, gather_row(tB, LDT, uce, urp[v], urp[v + 1], q));
         }
     } else {
         stage_mesh_rows(tA, LDT, a.x, a.N, a.B, b, a.Fin, c0, lqf, tid);
         cp_async_wait_all();
     }
     __syncthreads();
+}
+
+// One register tile of the contraction: acc[j] += T[row_j][:] . W_k[:, 4 cq .. 4 cq + 3] for the NJ valid rows of the
+// tile (rows are valid as a prefix; tiles of the last row groups are partial - the kernels are issue-bound, so rows
+// that do not exist must not be computed: at 79 vertices three of four tile rows would be padding)
+template <int NJ>
+__device__ __forceinline__ void contract_tile(const float *T, int LDT, const int *rows, const float *Wk, int Fout, int QF,
+                                              float4 *acc) {
+    const float *r[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) r[j] = T + rows[j] * LDT;
+    for (int i4 = 0; i4 < QF; ++i4) {
+        const float4 w0 = ld4s(Wk + (4 * i4 + 0) * Fout), w1 = ld4s(Wk + (4 * i4 + 1) * Fout);
+        const float4 w2 = ld4s(Wk + (4 * i4 + 2) * Fout), w3 = ld4s(Wk + (4 * i4 + 3) * Fout);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const float4 av = ld4s(r[j] + 4 * i4);
+            fma4s(acc[j], av.x, w0); fma4s(acc[j], av.y, w1); fma4s(acc[j], av.z, w2); fma4s(acc[j], av.w, w3);
+        }
+    }
+}
+
+// One register tile of P_k = G W_k^T (backward): p[j] = G[row_j][:] . Wt_k[:, 4 pq .. 4 pq + 3], Wt[k][o][i] in shared memory
+template <int NJ>
+__device__ __forceinline__ void pk_tile(const float *G, int LDG, const int *rows, const float *Wk, int Fin, int CQ, float4 *p) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) p[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int o4 = 0; o4 < CQ; ++o4) {
+        const float *wo = Wk + 4 * o4 * Fin;
+        const float4 t0 = ld4s(wo), t1 = ld4s(wo + Fin), t2 = ld4s(wo + 2 * Fin), t3 = ld4s(wo + 3 * Fin);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const float4 g = ld4s(G + rows[j] * LDG + 4 * o4);
+            p[j].x = fmaf(g.x, t0.x, fmaf(g.y, t1.x, fmaf(g.z, t2.x, fmaf(g.w, t3.x, p[j].x))));
+            p[j].y = fmaf(g.x, t0.y, fmaf(g.y, t1.y, fmaf(g.z, t2.y, fmaf(g.w, t3.y, p[j].y))));
+            p[j].z = fmaf(g.x, t0.z, fmaf(g.y, t1.z, fmaf(g.z, t2.z, fmaf(g.w, t3.z, p[j].z))));
+            p[j].w = fmaf(g.x, t0.w, fmaf(g.y, t1.w, fmaf(g.z, t2.w, fmaf(g.w, t3.w, p[j].w))));
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -157,10 +215,10 @@ cheb_layer_fwd_kernel(LayerArgs a, LayerSmem S) {
     const int Fin = a.Fin, Fout = a.Fout, K = a.K, N = a.N;
     const int LDT = Fin + 4, QF = Fin >> 2, lqf = ilog2(QF);
     float *Ws = sm + S.W;
-    const int32_t *lrp, *lci;
-    const float *lv;
+    const int32_t *lrp;
+    const int2 *lce;
     for (int i = tid; i < (K * Fin * Fout) >> 2; i += LY_NT) cp_async<4>(Ws + 4 * i, a.w + 4 * i);
-    stage_csr_async(sm + S.csr, N, a.Lnnz, a.Lrp, a.Lci, a.Lv, lrp, lci, lv, tid);
+    stage_csr_async(sm + S.csr, N, a.Lnnz, a.Lrp, a.Lci, a.Lv, lrp, lce, tid);
     stage_t0(a, sm, S, b, tid, 0, lqf);          // waits for every copy issued so far
 
     // contraction tiles: thread = (column quad cq, row group rg); tile t holds rows rg + j*NRG + t*4*NRG
@@ -181,29 +239,24 @@ cheb_layer_fwd_kernel(LayerArgs a, LayerSmem S) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[t][j] = make_float4(0.f, 0.f, 0.f, 0.f);
 
+    int nj[LY_MAXT];                                  // valid rows of each tile (a prefix of its 4 rows)
+#pragma unroll
+    for (int t = 0; t < LY_MAXT; ++t) nj[t] = (rr[t][0] >= 0) + (rr[t][1] >= 0) + (rr[t][2] >= 0) + (rr[t][3] >= 0);
     auto contract = [&](const float *T, int k) {
         const float *Wk = Ws + k * Fin * Fout + 4 * cq;
 #pragma unroll
         for (int t = 0; t < LY_MAXT; ++t) {
-            if (rr[t][0] < 0) break;
-            const float *r0 = T + rr[t][0] * LDT, *r1 = T + max(rr[t][1], 0) * LDT;
-            const float *r2 = T + max(rr[t][2], 0) * LDT, *r3 = T + max(rr[t][3], 0) * LDT;
-            for (int i4 = 0; i4 < QF; ++i4) {
-                const float4 a0 = ld4s(r0 + 4 * i4), a1 = ld4s(r1 + 4 * i4), a2 = ld4s(r2 + 4 * i4), a3 = ld4s(r3 + 4 * i4);
-                const float4 w0 = ld4s(Wk + (4 * i4 + 0) * Fout), w1 = ld4s(Wk + (4 * i4 + 1) * Fout);
-                const float4 w2 = ld4s(Wk + (4 * i4 + 2) * Fout), w3 = ld4s(Wk + (4 * i4 + 3) * Fout);
-                fma4s(acc[t][0], a0.x, w0); fma4s(acc[t][0], a0.y, w1); fma4s(acc[t][0], a0.z, w2); fma4s(acc[t][0], a0.w, w3);
-                fma4s(acc[t][1], a1.x, w0); fma4s(acc[t][1], a1.y, w1); fma4s(acc[t][1], a1.z, w2); fma4s(acc[t][1], a1.w, w3);
-                fma4s(acc[t][2], a2.x, w0); fma4s(acc[t][2], a2.y, w1); fma4s(acc[t][2], a2.z, w2); fma4s(acc[t][2], a2.w, w3);
-                fma4s(acc[t][3], a3.x, w0); fma4s(acc[t][3], a3.y, w1); fma4s(acc[t][3], a3.z, w2); fma4s(acc[t][3], a3.w, w3);
-            }
+            if (nj[t] == 4) contract_tile<4>(T, LDT, rr[t], Wk, Fout, QF, acc[t]);
+            else if (nj[t] == 3) contract_tile<3>(T, LDT, rr[t], Wk, Fout, QF, acc[t]);
+            else if (nj[t] == 2) contract_tile<2>(T, LDT, rr[t], Wk, Fout, QF, acc[t]);
+            else if (nj[t] == 1) contract_tile<1>(T, LDT, rr[t], Wk, Fout, QF, acc[t]);
         }
     };
 
     float *cur = sm + S.tA, *old = sm + S.tB;
     contract(cur, 0);
     for (int k = 1; k < K; ++k) {
-        recur_step(cur, old, N, lqf, LDT, lrp, lci, lv, k, tid);
+        recur_step(cur, old, N, lqf, LDT, lrp, lce, k, tid);
         __syncthreads();
         contract(old, k);
         float *t = cur; cur = old; old = t;
@@ -229,7 +282,7 @@ cheb_layer_fwd_kernel(LayerArgs a, LayerSmem S) {
 // b - the recurrences are independent per feature column, dW_k rows and dx columns of different
 // splits are disjoint, so the splits share nothing but the (re-staged) G and W.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(LY_NT)
+__global__ void __launch_bounds__(LY_NT, 2)       // 64 registers (no spills): two blocks per SM whenever shared memory allows
 cheb_layer_bwd_kernel(LayerArgs a, LayerSmem S) {
     extern __shared__ float4 lsm4[];
     float *sm = reinterpret_cast<float *>(lsm4);
@@ -240,10 +293,18 @@ cheb_layer_bwd_kernel(LayerArgs a, LayerSmem S) {
     const int LDT = 4 * QFl + 4, LDG = Fout + 4, CQ = Fout >> 2, lcq = ilog2(CQ);
     float *Ws = sm + S.W, *G = sm + S.G, *red = sm + S.red;
     int32_t *inv = reinterpret_cast<int32_t *>(sm + S.inv);
-    const int32_t *lrp, *lci;
-    const float *lv;
-    for (int i = tid; i < (K * Fin * Fout) >> 2; i += LY_NT) cp_async<4>(Ws + 4 * i, a.w + 4 * i);
-    stage_csr_async(sm + S.csr, N, a.Lnnz, a.Lrp, a.Lci, a.Lv, lrp, lci, lv, tid);
+    const int32_t *lrp;
+    const int2 *lce;
+    // W is only read by the P_k tiles of pass 2, four input features at a time: staged TRANSPOSED, Wt[k][o][i], so that
+    // the lanes of a warp (consecutive input-feature quads) read consecutive 16-byte pieces - the [k][i][o] layout put
+    // them 4 * Fout words apart, on the same banks (ncu: 16 wavefronts per load instead of 1-4)
+    if (a.out)
+        for (int i = tid; i < K * Fin * Fout; i += LY_NT) {
+            const int o = i % Fout, ki = i / Fout;                  // i = (k * Fin + in) * Fout + o
+            const int in = ki % Fin, k = ki / Fin;
+            Ws[(k * Fout + o) * Fin + in] = __ldg(a.w + i);
+        }
+    stage_csr_async(sm + S.csr, N, a.Lnnz, a.Lrp, a.Lci, a.Lv, lrp, lce, tid);
     stage_mesh_rows(G, LDG, a.dy, a.n_out, a.B, b, Fout, 0, lcq, tid);
     for (int v = tid; v < N; v += LY_NT) inv[v] = a.sel ? -1 : v;
     stage_t0(a, sm, S, b, tid, c0, lqf);
@@ -272,13 +333,28 @@ cheb_layer_bwd_kernel(LayerArgs a, LayerSmem S) {
             const float4 t = ld4s(T + v * LDT + 4 * iq), g = ld4s(G + r * LDG + 4 * oq);
             fma4s(c0_, t.x, g); fma4s(c1, t.y, g); fma4s(c2, t.z, g); fma4s(c3, t.w, g);
         }
+        // lanes of a warp that hold the same 4x4 block (NBLK < 32): fixed xor tree first, one partial per warp
+        for (int off = NBLK; off < 32; off <<= 1) {
+            c0_.x += __shfl_xor_sync(0xffffffffu, c0_.x, off); c0_.y += __shfl_xor_sync(0xffffffffu, c0_.y, off);
+            c0_.z += __shfl_xor_sync(0xffffffffu, c0_.z, off); c0_.w += __shfl_xor_sync(0xffffffffu, c0_.w, off);
+            c1.x += __shfl_xor_sync(0xffffffffu, c1.x, off); c1.y += __shfl_xor_sync(0xffffffffu, c1.y, off);
+            c1.z += __shfl_xor_sync(0xffffffffu, c1.z, off); c1.w += __shfl_xor_sync(0xffffffffu, c1.w, off);
+            c2.x += __shfl_xor_sync(0xffffffffu, c2.x, off); c2.y += __shfl_xor_sync(0xffffffffu, c2.y, off);
+            c2.z += __shfl_xor_sync(0xffffffffu, c2.z, off); c2.w += __shfl_xor_sync(0xffffffffu, c2.w, off);
+            c3.x += __shfl_xor_sync(0xffffffffu, c3.x, off); c3.y += __shfl_xor_sync(0xffffffffu, c3.y, off);
+            c3.z += __shfl_xor_sync(0xffffffffu, c3.z, off); c3.w += __shfl_xor_sync(0xffffffffu, c3.w, off);
+        }
+        const bool per_warp = NBLK < 32;
+        const int nparts = per_warp ? LY_NT / 32 : RS;
         __syncthreads();                      // red is free (the previous k's reduction has been read)
-        float *dst = red + (rs * NBLK + blk) * 16;
-        st4s(dst, c0_); st4s(dst + 4, c1); st4s(dst + 8, c2); st4s(dst + 12, c3);
+        if (!per_warp || (tid & 31) < NBLK) {
+            float *dst = red + ((per_warp ? (tid >> 5) : rs) * NBLK + blk) * 16;
+            st4s(dst, c0_); st4s(dst + 4, c1); st4s(dst + 8, c2); st4s(dst + 12, c3);
+        }
         __syncthreads();
-        for (int e = tid; e < NBLK * 16; e += LY_NT) {          // ordered sum over the row splits
+        for (int e = tid; e < NBLK * 16; e += LY_NT) {          // ordered sum over the partials
             float s = 0.f;
-            for (int p = 0; p < RS; ++p) s += red[p * NBLK * 16 + e];
+            for (int p = 0; p < nparts; ++p) s += red[p * NBLK * 16 + e];
             const int bk = e >> 4, m = (e >> 2) & 3, c = e & 3;
             const int i = c0 + 4 * (bk & (QFl - 1)) + m, o = 4 * (bk >> lqf) + c;
             dwp[((int64_t)k * Fin + i) * Fout + o] = s;
@@ -287,7 +363,7 @@ cheb_layer_bwd_kernel(LayerArgs a, LayerSmem S) {
     float *cur = sm + S.tA, *old = sm + S.tB;
     wgrad(cur, 0);
     for (int k = 1; k < K; ++k) {
-        recur_step(cur, old, N, lqf, LDT, lrp, lci, lv, k, tid);
+        recur_step(cur, old, N, lqf, LDT, lrp, lce, k, tid);
         __syncthreads();
         wgrad(old, k);
         float *t = cur; cur = old; old = t;
@@ -301,10 +377,10 @@ cheb_layer_bwd_kernel(LayerArgs a, LayerSmem S) {
     __syncthreads();
 
     // ---- pass 2: reverse recurrence in the same buffers ----
-    stage_csr_async(sm + S.csr, N, a.Lnnz, a.Ltrp, a.Ltci, a.Ltv, lrp, lci, lv, tid);      // L^T replaces L
-    const int32_t *utrp = nullptr, *utci = nullptr;
-    const float *utv = nullptr;
-    if (a.Utrp) stage_csr_async(sm + S.ucsr, a.n_in, a.Unnz, a.Utrp, a.Utci, a.Utv, utrp, utci, utv, tid);
+    stage_csr_async(sm + S.csr, N, a.Lnnz, a.Ltrp, a.Ltci, a.Ltv, lrp, lce, tid);      // L^T replaces L
+    const int32_t *utrp = nullptr;
+    const int2 *utce = nullptr;
+    if (a.Utrp) stage_csr_async(sm + S.ucsr, a.n_in, a.Unnz, a.Utrp, a.Utci, a.Utv, utrp, utce, tid);
     // P_k tiles: thread = (local input-feature quad pq, row group rg) over the n_out rows that carry gradient
     const int pq = tid & (QFl - 1), rg = tid >> lqf, NRG = LY_NT >> lqf;
     int rr[LY_MAXT][4];
@@ -317,24 +393,16 @@ cheb_layer_bwd_kernel(LayerArgs a, LayerSmem S) {
         }
     // dst[v] = P_k[v] - [sub] dst[v] on the rows with gradient (v = sel[r]); other rows are handled by the gather pass
     auto add_pk = [&](float *dst, int k, bool sub) {
-        const float *Wk = Ws + k * Fin * Fout + 4 * (q0 + pq) * Fout;          // rows 4 (q0 + pq) .. + 3 of W_k
+        const float *Wk = Ws + k * Fin * Fout + 4 * (q0 + pq);          // Wt[k][o][4 (q0 + pq) .. + 3]
 #pragma unroll
         for (int t = 0; t < LY_MAXT; ++t) {
             if (rr[t][0] < 0) break;
             float4 p[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) p[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int o4 = 0; o4 < CQ; ++o4) {
-                const float4 w0 = ld4s(Wk + 4 * o4), w1 = ld4s(Wk + Fout + 4 * o4), w2 = ld4s(Wk + 2 * Fout + 4 * o4), w3 = ld4s(Wk + 3 * Fout + 4 * o4);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 g = ld4s(G + max(rr[t][j], 0) * LDG + 4 * o4);
-                    p[j].x = fmaf(g.x, w0.x, fmaf(g.y, w0.y, fmaf(g.z, w0.z, fmaf(g.w, w0.w, p[j].x))));
-                    p[j].y = fmaf(g.x, w1.x, fmaf(g.y, w1.y, fmaf(g.z, w1.z, fmaf(g.w, w1.w, p[j].y))));
-                    p[j].z = fmaf(g.x, w2.x, fmaf(g.y, w2.y, fmaf(g.z, w2.z, fmaf(g.w, w2.w, p[j].z))));
-                    p[j].w = fmaf(g.x, w3.x, fmaf(g.y, w3.y, fmaf(g.z, w3.z, fmaf(g.w, w3.w, p[j].w))));
-                }
-            }
+            const int njt = 1 + (rr[t][1] >= 0) + (rr[t][2] >= 0) + (rr[t][3] >= 0);
+            if (njt == 4) pk_tile<4>(G, LDG, rr[t], Wk, Fin, CQ, p);
+            else if (njt == 3) pk_tile<3>(G, LDG, rr[t], Wk, Fin, CQ, p);
+            else if (njt == 2) pk_tile<2>(G, LDG, rr[t], Wk, Fin, CQ, p);
+            else pk_tile<1>(G, LDG, rr[t], Wk, Fin, CQ, p);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (rr[t][j] < 0) continue;
@@ -365,7 +433,7 @@ cheb_layer_bwd_kernel(LayerArgs a, LayerSmem S) {
         __syncthreads();
         for (int i = tid; i < (N << lqf); i += LY_NT) {
             const int v = i >> lqf, q = i & (QFl - 1);
-            const float4 acc = gather_row(g1, LDT, lci, lv, lrp[v], lrp[v + 1], q);
+            const float4 acc = gather_row(g1, LDT, lce, lrp[v], lrp[v + 1], q);
             float4 base = ld4s(g2 + v * LDT + 4 * q);
             if (inv[v] < 0) {                 // row without gradient: P_k = 0
                 if (has_g2) { base.x = -base.x; base.y = -base.y; base.z = -base.z; base.w = -base.w; }
@@ -383,7 +451,7 @@ cheb_layer_bwd_kernel(LayerArgs a, LayerSmem S) {
     if (a.Utrp) {
         for (int i = tid; i < (a.n_in << lqf); i += LY_NT) {
             const int c = i >> lqf, q = i & (QFl - 1);
-            const float4 v = gather_row(g1, LDT, utci, utv, utrp[c], utrp[c + 1], q);
+            const float4 v = gather_row(g1, LDT, utce, utrp[c], utrp[c + 1], q);
             *reinterpret_cast<float4 *>(a.out + ((int64_t)c * a.B + b) * Fin + c0 + 4 * q) = v;
         }
     } else {
@@ -421,11 +489,13 @@ layer_finalize_kernel(int B, int nw, int nb, const float *__restrict__ dwp, cons
 static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 // blocks per mesh: as many as keep every SM busy when the batch is small, while a block keeps >= `min_q` quads
-static int pick_splits(int B, int quads, int min_q) {
+static int pick_splits(int B, int quads, int min_q, int per_sm = 1) {
     int s = 1;
-    while (B * s * 2 <= num_sms() + num_sms() / 2 && quads / (s * 2) >= min_q) s *= 2;
+    while (B * s * 2 <= per_sm * (num_sms() + num_sms() / 2) && quads / (s * 2) >= min_q) s *= 2;
     return s;
 }
+static int g_layer_bwd_per_sm = 2;      // blocks per SM the backward grid is sized for (tuning: mvb_set_layer_tuning)
+void set_layer_tuning(int v) { if (v >= 1 && v <= 4) g_layer_bwd_per_sm = v; }
 
 static int layer_check(int N, int B, int Fin, int Fout, int K, int Lnnz, int n_in, int Unnz, int n_out, bool backward,
                        LayerSmem *S_out, int *splits_out) {
@@ -434,7 +504,9 @@ static int layer_check(int N, int B, int Fin, int Fout, int K, int Lnnz, int n_i
     const int QF = Fin / 4, CQ = Fout / 4;
     if (!pow2(QF) || !pow2(CQ)) return 0;
     // forward splits the output columns (each split redoes the cheap recurrence), backward the input features
-    const int splits = backward ? pick_splits(B, QF, 1) : pick_splits(B, CQ, 2);
+    // (the backward kernel fits two blocks per SM - 64 registers, feature-split shared memory - and its splits
+    // redo nothing, so its grid is sized for two blocks per SM: 4 splits at 64 meshes)
+    const int splits = backward ? pick_splits(B, QF, 1, g_layer_bwd_per_sm) : pick_splits(B, CQ, 2);
     const int ql = (backward ? QF : CQ) / splits;                 // local tile-column quads
     if (n_out > LY_MAXT * 4 * (LY_NT / ql)) return 0;
     if (backward && (QF / splits) * CQ > LY_NT) return 0;
@@ -448,6 +520,11 @@ static int layer_check(int N, int B, int Fin, int Fout, int K, int Lnnz, int n_i
 }  // namespace mvb
 
 using namespace mvb;
+
+extern "C" int mvb_set_layer_tuning(int bwd_blocks_per_sm) {
+    mvb::set_layer_tuning(bwd_blocks_per_sm);
+    return 0;
+}
 
 extern "C" int mvb_cheb_layer_supported(int N, int B, int Fin, int Fout, int K, int L_nnz, int n_in, int U_nnz, int n_out) {
     return layer_check(N, B, Fin, Fout, K, L_nnz, n_in, U_nnz, n_out, false, nullptr, nullptr) &&
