@@ -55,8 +55,9 @@ int mvb_set_tensor_cores(int enable);
  * default 2) and resident CTAs per SM its grid is sized for (1..4; default 4); 0 leaves a value unchanged.
  * Results are bit-identical for every setting. */
 int mvb_set_tc_tuning(int plane_group, int ctas_per_sm);
-/* blocks per SM the grid of the mesh-resident backward layer kernel is sized for (1..4, default 2): tuning hook */
-int mvb_set_layer_tuning(int bwd_blocks_per_sm);
+/* tuning hook of the mesh-resident backward layer: blocks per SM its grid is sized for (1..4, default 2); whether the
+ * weight-gradient and input-gradient halves run as two concurrent kernels (default 0: measured slower) */
+int mvb_set_layer_tuning(int bwd_blocks_per_sm, int bwd_concurrent);
 /* enable (default) / disable the fused multi-step recurrence kernels used when a level fits shared
  * memory (bit-identical to the step-by-step SpMM launches); a value >= 64 enables them with that
  * many threads per block (tuning hook; default 1024) */

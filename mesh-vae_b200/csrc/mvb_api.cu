@@ -247,6 +247,21 @@ struct JoinGuard {   // the side stream must rejoin on every exit path (a captur
     }
 };
 
+// the same fork / join for other translation units (mvb_layer.cu): returns the side stream or NULL
+namespace mvb {
+cudaStream_t side_fork(cudaStream_t st) {
+    SideStream *s = fork_side(st);
+    return s ? s->stream : nullptr;
+}
+void side_join(cudaStream_t side, cudaStream_t st) {
+    SideStream *s = side_stream();
+    if (side && s && s->stream == side) {
+        cudaEventRecord(s->join, s->stream);
+        cudaStreamWaitEvent(st, s->join, 0);
+    }
+}
+}  // namespace mvb
+
 extern "C" int mvb_cheb_bwd_uses_basis(int Fin, int Fout, int need_dx) { return adjoint_form(Fin, Fout, need_dx) ? 0 : 1; }
 
 extern "C" size_t mvb_cheb_bwd_workspace_bytes(int N, int B, int Fin, int Fout, int K, int n_active, int need_dx) {

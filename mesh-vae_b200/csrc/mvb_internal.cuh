@@ -140,4 +140,8 @@ int launch_fold_wgrad(int64_t rows, int Fin, int Fout, const float *x, const flo
 int launch_contract_tc(const ContractArgs &a, cudaStream_t st);
 int launch_wgrad_tc(const WgradArgs &a, int has_bias, int M4, int N4, int *nparts, cudaStream_t st);
 
+// fork a per-thread side stream from `st` (NULL: no overlap) / make `st` wait for it again (mvb_api.cu)
+cudaStream_t side_fork(cudaStream_t st);
+void side_join(cudaStream_t side, cudaStream_t st);
+
 }  // namespace mvb

@@ -304,10 +304,19 @@ cheb_layer_bwd_kernel(LayerArgs a, LayerSmem S) {
             const int in = ki % Fin, k = ki / Fin;
             Ws[(k * Fout + o) * Fin + in] = __ldg(a.w + i);
         }
-    stage_csr_async(sm + S.csr, N, a.Lnnz, a.Lrp, a.Lci, a.Lv, lrp, lce, tid);
+    // two modes besides "everything": a.dwp == NULL - input gradient only (pass 2), a.out == NULL - weight gradient
+    // only (pass 1).  The launcher runs them as two concurrent kernels: both are chains of short barrier-separated
+    // phases that leave most issue slots idle, and the weight gradient is off the critical path of the backward pass.
+    const bool want_dw = a.dwp != nullptr;
+    if (want_dw) stage_csr_async(sm + S.csr, N, a.Lnnz, a.Lrp, a.Lci, a.Lv, lrp, lce, tid);
     stage_mesh_rows(G, LDG, a.dy, a.n_out, a.B, b, Fout, 0, lcq, tid);
     for (int v = tid; v < N; v += LY_NT) inv[v] = a.sel ? -1 : v;
-    stage_t0(a, sm, S, b, tid, c0, lqf);
+    if (want_dw) {
+        stage_t0(a, sm, S, b, tid, c0, lqf);
+    } else {
+        cp_async_wait_all();
+        __syncthreads();
+    }
     if (a.sel)
         for (int r = tid; r < a.n_out; r += LY_NT) inv[__ldg(a.sel + r)] = r;
     if (a.relu)                                              // G = dY * [y > 0]
@@ -361,14 +370,16 @@ cheb_layer_bwd_kernel(LayerArgs a, LayerSmem S) {
         }
     };
     float *cur = sm + S.tA, *old = sm + S.tB;
-    wgrad(cur, 0);
-    for (int k = 1; k < K; ++k) {
-        recur_step(cur, old, N, lqf, LDT, lrp, lce, k, tid);
-        __syncthreads();
-        wgrad(old, k);
-        float *t = cur; cur = old; old = t;
+    if (want_dw) {
+        wgrad(cur, 0);
+        for (int k = 1; k < K; ++k) {
+            recur_step(cur, old, N, lqf, LDT, lrp, lce, k, tid);
+            __syncthreads();
+            wgrad(old, k);
+            float *t = cur; cur = old; old = t;
+        }
     }
-    if (a.dbp && blockIdx.y == 0 && tid < Fout) {
+    if (want_dw && a.dbp && blockIdx.y == 0 && tid < Fout) {
         float s = 0.f;
         for (int r = 0; r < a.n_out; ++r) s += G[r * LDG + tid];
         a.dbp[(int64_t)b * Fout + tid] = s;
@@ -495,7 +506,13 @@ static int pick_splits(int B, int quads, int min_q, int per_sm = 1) {
     return s;
 }
 static int g_layer_bwd_per_sm = 2;      // blocks per SM the backward grid is sized for (tuning: mvb_set_layer_tuning)
-void set_layer_tuning(int v) { if (v >= 1 && v <= 4) g_layer_bwd_per_sm = v; }
+// dW and dX halves of the backward layer as two concurrent kernels: OFF - measured 63 us for the pair against 59 us for
+// the single kernel at level 2 (both halves saturate the same shared-memory pipe; profiles/README.md)
+static int g_layer_bwd_concurrent = 0;
+void set_layer_tuning(int v, int conc) {
+    if (v >= 1 && v <= 4) g_layer_bwd_per_sm = v;
+    g_layer_bwd_concurrent = conc ? 1 : 0;
+}
 
 static int layer_check(int N, int B, int Fin, int Fout, int K, int Lnnz, int n_in, int Unnz, int n_out, bool backward,
                        LayerSmem *S_out, int *splits_out) {
@@ -521,8 +538,8 @@ static int layer_check(int N, int B, int Fin, int Fout, int K, int Lnnz, int n_i
 
 using namespace mvb;
 
-extern "C" int mvb_set_layer_tuning(int bwd_blocks_per_sm) {
-    mvb::set_layer_tuning(bwd_blocks_per_sm);
+extern "C" int mvb_set_layer_tuning(int bwd_blocks_per_sm, int bwd_concurrent) {
+    mvb::set_layer_tuning(bwd_blocks_per_sm, bwd_concurrent);
     return 0;
 }
 
@@ -606,10 +623,32 @@ extern "C" int mvb_cheb_layer_bwd(int N, int B, int Fin, int Fout, int K, const 
         if (e != cudaSuccess) return set_err(MVB_ECUDA, "cheb_layer_bwd: %s", cudaGetErrorString(e));
         granted = 200 * 1024;
     }
-    cheb_layer_bwd_kernel<<<dim3(B, splits), LY_NT, smem, (cudaStream_t)stream>>>(a, S);
-    int rc = check_launch("mvb_cheb_layer_bwd");
-    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
     const int nw = K * Fin * Fout, nb = dbias ? Fout : 0;
-    layer_finalize_kernel<<<(nw + nb + 255) / 256, 256, 0, (cudaStream_t)stream>>>(B, nw, nb, a.dwp, a.dbp, dweight, dbias);
+    cudaStream_t side = (dx && g_layer_bwd_concurrent) ? side_fork(st) : nullptr;
+    int rc;
+    if (side) {
+        // weight gradient (pass 1 + ordered sum over the meshes) on the side stream, input gradient (pass 2) on `st`
+        LayerArgs aw = a, ax = a;
+        aw.out = nullptr;
+        ax.dwp = nullptr;
+        ax.dbp = nullptr;
+        cheb_layer_bwd_kernel<<<dim3(B, splits), LY_NT, smem, st>>>(ax, S);
+        rc = check_launch("mvb_cheb_layer_bwd dx");
+        if (!rc) {
+            cheb_layer_bwd_kernel<<<dim3(B, splits), LY_NT, smem, side>>>(aw, S);
+            rc = check_launch("mvb_cheb_layer_bwd dw");
+        }
+        if (!rc) {
+            layer_finalize_kernel<<<(nw + nb + 255) / 256, 256, 0, side>>>(B, nw, nb, a.dwp, a.dbp, dweight, dbias);
+            rc = check_launch("mvb_cheb_layer_bwd finalize");
+        }
+        side_join(side, st);          // rejoin on every path: a captured graph must not end forked
+        return rc;
+    }
+    cheb_layer_bwd_kernel<<<dim3(B, splits), LY_NT, smem, st>>>(a, S);
+    rc = check_launch("mvb_cheb_layer_bwd");
+    if (rc) return rc;
+    layer_finalize_kernel<<<(nw + nb + 255) / 256, 256, 0, st>>>(B, nw, nb, a.dwp, a.dbp, dweight, dbias);
     return check_launch("mvb_cheb_layer_bwd finalize");
 }
