@@ -8,10 +8,11 @@ from .pool import SurfacePool, Pool
 from .cheb_vae import cheb_VAE
 from .cheb_cls import cheb_GCN
 from . import logpdf
-from . import formats, loader, loop
+from . import formats, loader, loop, mesh_ops
+from .model import get_model, scipy_to_torch_sparse
 
 __all__ = ["ChebConv_batch", "ChebConv", "SurfacePool", "Pool", "cheb_VAE", "cheb_GCN", "logpdf", "operators",
-           "functional", "formats", "loader", "loop", "MvbError"]
+           "functional", "formats", "loader", "loop", "mesh_ops", "get_model", "scipy_to_torch_sparse", "MvbError"]
 __version__ = "0.1.0"
 
 

@@ -41,3 +41,37 @@ def test_unchanged_reference_models_construct_on_native_modules():
                          npz=os.path.join(ROOT, "tests", "golden", "operators_template5k.npz"))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert "COMPAT_OK" in out.stdout, out.stdout + out.stderr
+
+
+SCRIPT_F1 = r"""
+import sys, os, tempfile
+sys.path.insert(0, {root!r})
+import meshvae_b200 as mvb
+mvb.install_compat()
+sys.path.insert(1, {ref!r})             # NO test shims: psbody / open3d / mesh_operations resolve inside compat/
+import numpy as np, torch
+import psbody.mesh, open3d, mesh_operations
+assert psbody.mesh.Mesh is mvb.mesh_ops.Mesh and mesh_operations.generate_transform_matrices is mvb.mesh_ops.generate_transform_matrices
+from model import get_model                      # the reference's own model.py (model.py:35-69), unchanged
+from config_parser import read_config            # and its own parser
+cfg = read_config(os.path.join({ref!r}, "files", "default.cfg"))
+cfg["template"] = os.path.join({ref!r}, "template", "template5k.obj")
+cfg["checkpoint_dir"] = tempfile.mkdtemp()
+net = get_model(cfg, "cpu")
+assert type(net).__module__ == "models.cheb_VAE" and sum(p.numel() for p in net.parameters()) == 712642
+assert os.path.exists(os.path.join(cfg["checkpoint_dir"], "initial_weight.pt"))
+g = np.load({npz!r})
+for i in range(4):                               # the operators the reference model holds are the golden ones
+    d, u = net.downsample_matrices[i], net.upsample_matrices[i]
+    assert np.array_equal(d._indices()[1].numpy(), g[f"D{{i}}_col"]) and np.array_equal(u._indices()[1].numpy(), g[f"U{{i}}_col"])
+    assert np.abs(u._values().numpy() - g[f"U{{i}}_val"]).max() <= 1e-6
+assert mvb.formats.read_config(os.path.join({ref!r}, "files", "default.cfg")) == read_config(os.path.join({ref!r}, "files", "default.cfg"))
+print("COMPAT_F1_OK")
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")
+def test_reference_get_model_runs_without_psbody_or_open3d():
+    code = SCRIPT_F1.format(root=ROOT, ref=REF, npz=os.path.join(ROOT, "tests", "golden", "operators_template5k.npz"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "COMPAT_F1_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
