@@ -7,6 +7,9 @@ Procrustes back-transform (`bmm`) and the vertex errors there (main.py:88-94).  
 launches on the device - `mvb_recon_error` on the decoder's buffer and `mvb_epoch_meter_add` into eight fp64
 accumulators - and the epoch ends with ONE read-back.  `train_epoch` is the same loop on the captured
 `engine.TrainEngine` step (fixed batch size replayed as a CUDA graph; the ragged last batch runs uncaptured).
+
+`estimate_diff`, `train_classifier` and `evaluate_classifier` are the counterparts for `crecon.py` (:64-150, :162-201):
+the sex classifier `cheb_GCN` trained on the residuals of the VAE's reconstruction under both labels.
 """
 import os
 from typing import Optional, Sequence
@@ -127,3 +130,78 @@ def evaluate(n, model, test_loader, device, faces=None, checkpoint_dir=None, vis
     total = max(r["count"], 1)
     err = torch.cat(errors, 0).cpu().numpy() if errors else np.zeros((0, 0), dtype=np.float32)
     return r["loss"], r["kld"], r["rec_loss"], np.float64(r["accuracy"]), err, int(flipped) / total
+
+
+# ---- crecon.py: classifier on reconstruction residuals ---------------------------------------------------------
+def estimate_diff(net, x, y, dtype, device=None):
+    """crecon.py:162-201.  x [B,N,3] normalised meshes (or one [N,3] mesh), y [B] labels.  Encodes, classifies, decodes
+    z_mean under the (true label when dtype == "train", else predicted) class and under the opposite one, and returns
+    (cat(x - recon_opposite, x - recon_same) [B,N,6], number of correct class predictions as a device tensor)."""
+    device = device if device is not None else next(net.parameters()).device
+    ori = x
+    if x.dim() == 2:
+        x = x.reshape(1, -1, 3)
+        ori = x
+        y = torch.as_tensor(y).reshape(1)
+    x, y = x.to(device), torch.as_tensor(y).to(device)
+    ori = ori.to(device)
+    with torch.no_grad():
+        h = net.encoder(x)
+        y_hat = net.classifier(h)
+        index_pred = torch.argmax(y_hat, dim=1)
+        correct = torch.sum(index_pred == y)
+        sex_hot = F.one_hot(index_pred if dtype != "train" else y, num_classes=2)
+        x_mean = net.z_mean(torch.cat([sex_hot, h], -1))
+        recon = net.sample(sex_hot, x_mean)
+        recon_oppo = net.sample(1 - sex_hot, x_mean)
+        diff = torch.cat((ori - recon_oppo, ori - recon), dim=-1)
+    return diff, correct
+
+
+def train_classifier(model, dvae, train_loader, len_dataset, optimizer, device, criterion):
+    """crecon.py:64-99 -> (summed batch losses / len_dataset, accuracy); totals stay on the device until the end"""
+    model.train()
+    dvae.eval()
+    tot = torch.zeros(3, device=device, dtype=torch.float64)          # loss sum, correct, count
+    for data in train_loader:
+        _, x_gt, label, _, _, _, _, _ = _split(data)
+        x_gt, label = x_gt.to(device, non_blocking=True).float(), label.to(device, non_blocking=True)
+        diff, _ = estimate_diff(dvae, x_gt.reshape(label.shape[0], -1, 3), label, "train", device)
+        optimizer.zero_grad()
+        pred = model(diff)
+        loss = criterion(pred, label)
+        loss.backward()
+        optimizer.step()
+        predicted = torch.argmax(pred.detach(), dim=-1)               # argmax of the softmax (crecon.py:89)
+        tot += torch.stack([loss.detach().double(), (predicted == label).sum().double(),
+                            torch.tensor(float(label.shape[0]), device=device, dtype=torch.float64)])
+    t = tot.cpu().numpy()
+    return t[0] / len_dataset, t[1] / max(t[2], 1.0)
+
+
+def evaluate_classifier(model, dvae, test_loader, len_dataset, device, criterion, err_file=False):
+    """crecon.py:103-150 -> (loss, accuracy, {file name: predicted label} of the misclassified meshes if err_file)"""
+    model.eval()
+    dvae.eval()
+    tot = torch.zeros(3, device=device, dtype=torch.float64)
+    wrong = []
+    with torch.no_grad():
+        for data in test_loader:
+            _, x_gt, label, names, _, _, _, _ = _split(data)
+            x_gt, label = x_gt.to(device, non_blocking=True).float(), label.to(device, non_blocking=True)
+            diff, _ = estimate_diff(dvae, x_gt.reshape(label.shape[0], -1, 3), label, "test", device)
+            pred = model(diff)
+            loss = criterion(pred, label)
+            predicted = torch.argmax(pred, dim=-1)
+            tot += torch.stack([loss.double(), (predicted == label).sum().double(),
+                                torch.tensor(float(label.shape[0]), device=device, dtype=torch.float64)])
+            if err_file:
+                wrong.append((list(names), predicted, label))
+    err = {}
+    for names, predicted, label in wrong:                              # read back after the loop
+        p, l = predicted.cpu().numpy().reshape(-1), label.cpu().numpy().reshape(-1)
+        for i, name in enumerate(names):
+            if p[i] != l[i]:
+                err[name] = str(p[i])
+    t = tot.cpu().numpy()
+    return t[0] / len_dataset, t[1] / max(t[2], 1.0), err

@@ -219,3 +219,60 @@ def test_epoch_meter_and_recon_error_outputs(mvb):
     assert rel_err(me, d.mean(-1)) < 1e-12 and rel_err(mx, d.max(-1).values) < 1e-12
     me2, mx2, mesh2 = Fn.recon_error(out.cuda(), mean, std, s, R, m, None, mesh=True)
     assert torch.equal(mesh2, mesh) and float(me2.abs().max()) == 0.0
+
+
+def test_crecon_classifier_loops_match_reference_restatement(mvb, ops):
+    """crecon.py:64-150, 162-201 restated on the oracle models vs loop.estimate_diff / train_classifier / evaluate_classifier"""
+    from meshvae_b200 import loop
+    A, D, U, nn_ = ops
+    dev = torch.device("cuda:0")
+    ds = SyntheticHips()
+    ref_vae, vae = _models(mvb, ops)
+    cfg = copy.deepcopy(O.DEFAULT_CONFIG)
+    ref_gcn = O.OracleChebGCN(6, copy.deepcopy(cfg), D, U, A, nn_)
+    ref_gcn.load_state_dict(seeded_state_dict(ref_gcn, 9))
+    gcn = mvb.cheb_GCN(6, copy.deepcopy(cfg), [d.to(dev) for d in D], [u.to(dev) for u in U], [a.to(dev) for a in A], nn_)
+    gcn.load_state_dict(seeded_state_dict(gcn, 9))
+    gcn = gcn.to(dev)
+    crit = torch.nn.CrossEntropyLoss()
+
+    def ref_diff(x, y, dtype):
+        with torch.no_grad():
+            h = ref_vae.encoder(x)
+            pred = torch.argmax(ref_vae.classifier(h), 1)
+            hot = F.one_hot(pred if dtype != "train" else y, num_classes=2)
+            zm = ref_vae.z_mean(torch.cat([hot, h], -1))
+            return torch.cat((x - ref_vae.sample(1 - hot, zm), x - ref_vae.sample(hot, zm)), -1)
+
+    def ref_epoch(train):
+        ref_vae.eval()
+        ref_gcn.train() if train else ref_gcn.eval()
+        opt = torch.optim.Adam(ref_gcn.parameters(), lr=1e-3)
+        tl, tot, cor, err = 0.0, 0, 0, {}
+        for batch, x_gt, label, names, *_ in _loader(mvb, ds):
+            x = x_gt.float()
+            with torch.set_grad_enabled(train):
+                pred = ref_gcn(ref_diff(x, label, "train" if train else "test"))
+                loss = crit(pred, label)
+            if train:
+                opt.zero_grad(); loss.backward(); opt.step()
+            tl += float(loss.detach())
+            p = torch.argmax(pred.detach(), -1)
+            tot += len(label); cor += int((p == label).sum())
+            err.update({n: str(int(pi)) for n, pi, li in zip(names, p, label) if pi != li})
+        return tl / len(ds), cor / tot, err
+
+    x0 = torch.stack([ds[i][1].float() for i in range(3)])
+    y0 = torch.tensor([ds[i][2] for i in range(3)])
+    d_gpu, c_gpu = loop.estimate_diff(vae.eval(), x0, y0, "test")
+    ref_vae.eval()
+    assert rel_err(d_gpu, ref_diff(x0, y0, "test")) < 1e-4 and d_gpu.shape == (3, 4998, 6)
+    d1, _ = loop.estimate_diff(vae, x0[0], int(y0[0]), "train")                 # single [N,3] mesh (crecon.py:165-167)
+    assert rel_err(d1, ref_diff(x0[:1], y0[:1], "train")) < 1e-4
+    want_e = ref_epoch(False)
+    got_e = loop.evaluate_classifier(gcn, vae, _loader(mvb, ds), len(ds), dev, crit, err_file=True)
+    assert abs(got_e[0] - want_e[0]) <= 1e-4 * max(1.0, abs(want_e[0])) and got_e[1] == want_e[1] and got_e[2] == want_e[2]
+    want_t = ref_epoch(True)
+    got_t = loop.train_classifier(gcn, vae, _loader(mvb, ds), len(ds), torch.optim.Adam(gcn.parameters(), lr=1e-3), dev, crit)
+    assert abs(got_t[0] - want_t[0]) <= 2e-3 * max(1.0, abs(want_t[0])), (got_t, want_t)
+    assert abs(got_t[1] - want_t[1]) <= 0.11                                       # one borderline mesh may flip over three Adam steps
