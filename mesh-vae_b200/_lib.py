@@ -39,6 +39,7 @@ SIGNATURES = {
     "mvb_launch_count": (c_int64, []),
     "mvb_set_tensor_cores": (c_int, [c_int]),
     "mvb_set_tc_tuning": (c_int, [c_int, c_int]),
+    "mvb_set_tc_balance": (c_int, [c_int]),
     "mvb_set_layer_tuning": (c_int, [c_int, c_int]),
     "mvb_set_spmm_shape": (c_int, [c_int, c_int]),
     "mvb_set_spmm_mode": (c_int, [c_int]),

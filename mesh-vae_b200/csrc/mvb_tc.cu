@@ -30,6 +30,8 @@ static int g_tc_pg6 = 2;           // planes staged at a time by the 6-plane for
 void set_tc_pg6(int v) { if (v == 1 || v == 2 || v == 3 || v == 6) g_tc_pg6 = v; }
 static int g_tc_cap = 4;           // resident CTAs per SM the row-GEMM grid is sized for (tuning: 1..4)
 void set_tc_cap(int v) { if (v >= 1 && v <= 4) g_tc_cap = v; }
+static int g_tc_balance = 0;       // row-GEMM grid = tiles / rounds instead of all block slots (tuning)
+void set_tc_balance(int v) { g_tc_balance = v ? 1 : 0; }
 void set_tc_enabled(int v) { g_tc_enabled = v; }
 int tc_enabled() { return g_tc_enabled; }
 
@@ -497,6 +499,10 @@ int launch_contract_tc(const ContractArgs &a, cudaStream_t st) {
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)num_sms() * per_sm;
     if (grid > ntiles) grid = ntiles;
+    if (g_tc_balance && grid > 0) {          // every block the same number of tiles
+        const int64_t rounds = (ntiles + grid - 1) / grid;
+        grid = (ntiles + rounds - 1) / rounds;
+    }
     int rc;
     if (packed) {
         rc = launch_rowgemm_t<0, 1>(t, (unsigned)grid, smem, st);
@@ -844,6 +850,11 @@ extern "C" int mvb_set_tensor_cores(int enable) {
     const int old = mvb::tc_enabled();
     mvb::set_tc_enabled(enable ? 1 : 0);
     return old;
+}
+
+extern "C" int mvb_set_tc_balance(int on) {
+    mvb::set_tc_balance(on);
+    return 0;
 }
 
 extern "C" int mvb_set_tc_tuning(int plane_group, int ctas_per_sm) {
