@@ -112,6 +112,8 @@ class TrainEngine:
         self._cut = self._cut_grad = None
         self.launches_per_step = None
         self._copy_stream = self._gt_ready = None
+        self._stage = self._ev_staged = self._ev_consumed = self._h_small = None
+        self._staged = False
         self._fwd_out = None
 
     # ---- device work of one step -------------------------------------------------------------
@@ -265,6 +267,62 @@ class TrainEngine:
         if not sync:                     # the epoch loop (loop.train_epoch) accumulates on the device instead
             return None
         return float(self.loss)          # D2H read of the step's loss (synchronises)
+
+    # ---- input double-buffering: batch i+1 travels to the device while step i computes ------------------------
+    def stage(self, x_host: torch.Tensor, x_gt_host: torch.Tensor, y_host: torch.Tensor,
+              eps_host: Optional[torch.Tensor] = None) -> None:
+        """Enqueue the host->device copies of the NEXT batch on the copy stream and return at once (pinned host
+        tensors).  The copies land in staging buffers; `step_prefetched` moves them into the step's static buffers
+        (device-to-device, a few microseconds) when the previous step no longer reads those."""
+        if self._stage is None:
+            self._stage = [torch.empty_like(t) for t in (self.x, self.x_gt, self.eps, self.y_hot)]
+            self._ev_staged, self._ev_consumed = torch.cuda.Event(), torch.cuda.Event()
+            self._ev_consumed.record(torch.cuda.current_stream())
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._gt_ready = torch.cuda.Event()
+        if self._h_small is None:
+            # pinned homes for the two small host-made operands: a copy from pageable memory would synchronise the
+            # copy stream on the host - behind the 11 MB of mesh data - before anything else could be launched
+            self._h_small = (torch.empty(self.eps.shape, dtype=self.eps.dtype).pin_memory(),
+                             torch.empty(self.y_hot.shape, dtype=self.y_hot.dtype).pin_memory())
+        else:
+            self._ev_staged.synchronize()           # the previous copies out of the pinned homes have been made
+        if eps_host is None:
+            eps_host = torch.normal(mean=0, std=1, size=(self.batch, self.net.z))
+        self._h_small[0].copy_(eps_host)
+        self._h_small[1].copy_(torch.nn.functional.one_hot(y_host, self.net.num_class))
+        cs = self._copy_stream
+        cs.wait_event(self._ev_consumed)            # the staging buffers have been emptied
+        with torch.cuda.stream(cs):
+            for dst, src in zip(self._stage, (x_host, x_gt_host, self._h_small[0], self._h_small[1])):
+                dst.copy_(src, non_blocking=True)
+            self._ev_staged.record(cs)
+        self._staged = True
+
+    def step_prefetched(self, next_batch=None, sync: bool = True) -> Optional[float]:
+        """One step on the batch handed to `stage()` earlier; `next_batch` = (x_host, x_gt_host, y_host[, eps_host]) is
+        staged while this step computes.  Same work per step as `step()` - every batch is copied from the host once
+        and the loss is read back - with the copy of batch i+1 overlapping the kernels of step i."""
+        if not self._staged:
+            raise RuntimeError("step_prefetched: no staged batch (call stage() first)")
+        main = torch.cuda.current_stream()
+        main.wait_event(self._ev_staged)
+        torch._foreach_copy_([self.x, self.x_gt, self.eps, self.y_hot], self._stage)
+        self._ev_consumed.record(main)
+        self._gt_ready.record(main)                  # the step graph's external wait node: the ground truth is in place
+        self._staged = False
+        self.device_step()                           # launched first: the copies below then overlap its kernels
+        if next_batch is not None:
+            self.stage(*next_batch)
+        if not sync:
+            return None
+        return float(self.loss)
+
+    def wait_staged(self) -> None:
+        """make the current stream wait for the staged copies (for timing: the interval then covers the H2D)"""
+        if self._staged:
+            torch.cuda.current_stream().wait_event(self._ev_staged)
 
     def ragged_step(self, x: torch.Tensor, x_gt: torch.Tensor, y_hot: torch.Tensor, eps: Optional[torch.Tensor] = None):
         """the last, smaller batch of an epoch (DataLoader without drop_last, main.py:256): same kernels, same flat

@@ -58,25 +58,42 @@ def train(model, train_loader, optimizer, device, checkpoint_dir=None, norm=None
 
 
 def train_epoch(engine, train_loader, checkpoint_dir=None, norm=None):
-    """`train` on the captured step: `engine.step(..., sync=False)` per full batch (host buffers in, nothing read
-    back), `engine.ragged_step` for a smaller last batch.  Same return tuple."""
+    """`train` on the captured step with the input double-buffered: while step i computes, batch i+1 is already on
+    its way to the device (`engine.stage` / `engine.step_prefetched`, nothing read back per batch);
+    `engine.ragged_step` for a smaller last batch.  Same return tuple."""
     dev = engine.dev
     engine.net.train()
     mean, std = _norm(checkpoint_dir, norm, dev)
     meter = Fn.EpochMeter(dev)
-    for data in train_loader:
-        x, x_gt, y, _, gt_mesh, R, m, s = _split(data)
+
+    def host_batch(data):
+        x, x_gt, y = data[0], data[1], data[2]
         b = _num_graphs(x)
         xt = (x if torch.is_tensor(x) else x.x).reshape(b, engine.n_vert, engine.feat)
+        return b, (xt, x_gt.reshape(b, engine.n_vert, engine.feat), y)
+
+    it = iter(train_loader)
+    cur = next(it, None)
+    staged = False
+    while cur is not None:
+        nxt = next(it, None)
+        b, hb = host_batch(cur)
+        _, _, _, _, gt_mesh, R, m, s = _split(cur)
         if b == engine.batch:
-            engine.step(xt, x_gt.reshape(b, engine.n_vert, engine.feat), y, sync=False)
+            if not staged:
+                engine.stage(*hb)
+            nb = host_batch(nxt) if nxt is not None else (0, None)
+            staged = nb[0] == engine.batch
+            engine.step_prefetched(nb[1] if staged else None, sync=False)
             loss, kld, rec, correct, recon = engine.loss, engine.kld, engine.rec, engine.correct, engine.recon
         else:
+            xt, x_gt, y = hb
             y_hot = F.one_hot(y, num_classes=engine.net.num_class).to(dev)
-            loss, kld, rec, correct, recon = engine.ragged_step(xt.to(dev), x_gt.reshape(b, engine.n_vert, engine.feat)
-                                                                .to(dev, engine.x_gt.dtype), y_hot)
+            loss, kld, rec, correct, recon = engine.ragged_step(xt.to(dev), x_gt.to(dev, engine.x_gt.dtype), y_hot)
+            staged = False
         mean_err, _ = Fn.recon_error(recon, mean, std, s, R, m, gt_mesh)
         meter.add(loss, kld, rec, correct, mean_err)
+        cur = nxt
     r = meter.read()
     return r["loss"], r["kld"], r["rec_loss"], r["error"], np.float64(r["accuracy"])
 

@@ -88,6 +88,29 @@ def test_graph_and_eager_engines_are_bit_identical():
     assert losses[0] == losses[1]
 
 
+def test_prefetched_steps_equal_plain_steps():
+    """input double-buffering (stage / step_prefetched) changes when the batch travels, not what is computed"""
+    import meshvae_b200 as mvb
+    from meshvae_b200.engine import TrainEngine
+    B = 3
+    batches = []
+    for s in range(5):
+        x, y, eps = seeded_batch(B, 4998, 500 + s)
+        batches.append((x.pin_memory(), x.double().pin_memory(), y, eps))
+    _, net, _ = _models(mvb, 0.0)
+    eng = TrainEngine(net, B)
+    eng.capture(warmup=1)
+    plain = [eng.step(x, xg, y, eps_host=e) for x, xg, y, e in batches]
+    _, net2, _ = _models(mvb, 0.0)
+    eng2 = TrainEngine(net2, B)
+    eng2.capture(warmup=1)
+    eng2.stage(*batches[0])
+    pre = [eng2.step_prefetched(batches[i + 1] if i + 1 < len(batches) else None) for i in range(len(batches))]
+    assert pre == plain
+    with pytest.raises(RuntimeError):
+        eng2.step_prefetched()                        # nothing staged
+
+
 def test_dropout_training_runs_and_decreases_loss():
     """dropout 0.2 as in files/default.cfg: masks change from replay to replay (device offset = Adam step
     counter) and the loss still goes down on a fixed batch."""
