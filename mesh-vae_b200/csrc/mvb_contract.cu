@@ -353,11 +353,12 @@ wgrad_kernel(WgradArgs a, int M, int has_bias, int M4, int N4, int LDT, int R, i
 // a_tr != 0: partial set A comes from the adjoint-basis backward, [S_0|..|S_{K-1}]^T x, stored
 // [K*fout][N4A] with N4A = round4(fin): element (k*fin + i, o) of dW is A[(k*fout + o)][i]; the bias
 // gradient then comes from the column-sum kernel, not from a "ones" row of A.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 wgrad_finalize_kernel(const float *__restrict__ partA, int nA, int M4A, const float *__restrict__ partB,
                       int nB, int M4B, int fin, int M, int n_out, int N4, int a_tr, int N4A, float *dweight,
                       float *dbias) {
-    __shared__ float red[8][33];
+    // 32 outputs x 32 partial lanes per block: ~10 partials per thread instead of ~40 (each a dependent L2 round trip)
+    __shared__ float red[32][33];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int total = (M + (dbias ? 1 : 0)) * n_out;
     const int i = blockIdx.x * 32 + tx;
@@ -368,17 +369,17 @@ wgrad_finalize_kernel(const float *__restrict__ partA, int nA, int M4A, const fl
         if (a_tr) {
             if (m < M) {
                 const size_t off = (size_t)(k * n_out + n) * N4A + (m - k * fin);
-                for (int p = ty; p < nA; p += 8) s += partA[(size_t)p * M4A * N4A + off];
+                for (int p = ty; p < nA; p += 32) s += partA[(size_t)p * M4A * N4A + off];
             }
         } else {
-            for (int p = ty; p < nA; p += 8) s += partA[(size_t)p * M4A * N4 + m * N4 + n];
+            for (int p = ty; p < nA; p += 32) s += partA[(size_t)p * M4A * N4 + m * N4 + n];
         }
         if (nB > 0) {
             const int mb = (m < M) ? (m - k * fin) : fin;          // bias row of B sits at index fin
             const float c = (m < M) ? ((k & 1) ? 0.f : ((k & 2) ? -1.f : 1.f)) : 1.f;
             if (c != 0.f) {
                 float sb = 0.f;
-                for (int p = ty; p < nB; p += 8) sb += partB[(size_t)p * M4B * N4 + mb * N4 + n];
+                for (int p = ty; p < nB; p += 32) sb += partB[(size_t)p * M4B * N4 + mb * N4 + n];
                 s += c * sb;
             }
         }
@@ -388,7 +389,7 @@ wgrad_finalize_kernel(const float *__restrict__ partA, int nA, int M4A, const fl
     if (ty == 0 && i < total) {
         float t = red[0][tx];
 #pragma unroll
-        for (int q = 1; q < 8; ++q) t += red[q][tx];
+        for (int q = 1; q < 32; ++q) t += red[q][tx];
         const int m = i / n_out, n = i - m * n_out;
         if (m < M)
             dweight[(size_t)m * n_out + n] = t;
@@ -691,7 +692,7 @@ int launch_wgrad_finalize(const float *partA, int nA, int M4A, const float *part
                           int fin, int M, int n_out, float *dweight, float *dbias, cudaStream_t st, int a_transposed) {
     const int total = (M + (dbias ? 1 : 0)) * n_out;
     const int N4 = round4(n_out);
-    wgrad_finalize_kernel<<<(total + 31) / 32, dim3(32, 8), 0, st>>>(partA, nA, M4A, partB, nB, M4B, fin, M, n_out,
+    wgrad_finalize_kernel<<<(total + 31) / 32, dim3(32, 32), 0, st>>>(partA, nA, M4A, partB, nB, M4B, fin, M, n_out,
                                                                     N4, a_transposed, round4(fin), dweight, dbias);
     return check_launch("mvb wgrad finalize");
 }

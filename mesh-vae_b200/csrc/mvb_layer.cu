@@ -473,27 +473,28 @@ cheb_layer_bwd_kernel(LayerArgs a, LayerSmem S) {
     }
 }
 
-// ordered sum of the per-mesh partials: dst[j] = sum_b part[b][j]
+// ordered sum of the per-mesh partials: dst[j] = sum_b part[b][j].  Block = 32 outputs x 8 mesh lanes (each lane sums
+// every 8th mesh, then a fixed-order sum over the lanes): B/8 dependent L2 round trips per thread instead of B.
 __global__ void __launch_bounds__(256)
 layer_finalize_kernel(int B, int nw, int nb, const float *__restrict__ dwp, const float *__restrict__ dbp,
                       float *__restrict__ dw, float *__restrict__ db) {
-    const int j = blockIdx.x * 256 + threadIdx.x;
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + tx;
+    float s = 0.f;
     if (j < nw) {
-        float s = 0.f;
-        int b = 0;
-        for (; b + 8 <= B; b += 8) {             // 8 loads in flight, summation order unchanged
-            float t[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) t[u] = __ldg(dwp + (int64_t)(b + u) * nw + j);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) s += t[u];
-        }
-        for (; b < B; ++b) s += __ldg(dwp + (int64_t)b * nw + j);
-        dw[j] = s;
+        for (int b = ty; b < B; b += 8) s += __ldg(dwp + (int64_t)b * nw + j);
     } else if (db && j - nw < nb) {
-        float s = 0.f;
-        for (int b = 0; b < B; ++b) s += __ldg(dbp + (int64_t)b * nb + (j - nw));
-        db[j - nw] = s;
+        for (int b = ty; b < B; b += 8) s += __ldg(dbp + (int64_t)b * nb + (j - nw));
+    }
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0) {
+        float t = red[0][tx];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) t += red[q][tx];
+        if (j < nw) dw[j] = t;
+        else if (db && j - nw < nb) db[j - nw] = t;
     }
 }
 
@@ -640,7 +641,7 @@ extern "C" int mvb_cheb_layer_bwd(int N, int B, int Fin, int Fout, int K, const 
             rc = check_launch("mvb_cheb_layer_bwd dw");
         }
         if (!rc) {
-            layer_finalize_kernel<<<(nw + nb + 255) / 256, 256, 0, side>>>(B, nw, nb, a.dwp, a.dbp, dweight, dbias);
+            layer_finalize_kernel<<<(nw + nb + 31) / 32, 256, 0, side>>>(B, nw, nb, a.dwp, a.dbp, dweight, dbias);
             rc = check_launch("mvb_cheb_layer_bwd finalize");
         }
         side_join(side, st);          // rejoin on every path: a captured graph must not end forked
@@ -649,6 +650,6 @@ extern "C" int mvb_cheb_layer_bwd(int N, int B, int Fin, int Fout, int K, const 
     cheb_layer_bwd_kernel<<<dim3(B, splits), LY_NT, smem, st>>>(a, S);
     rc = check_launch("mvb_cheb_layer_bwd");
     if (rc) return rc;
-    layer_finalize_kernel<<<(nw + nb + 255) / 256, 256, 0, st>>>(B, nw, nb, a.dwp, a.dbp, dweight, dbias);
+    layer_finalize_kernel<<<(nw + nb + 31) / 32, 256, 0, st>>>(B, nw, nb, a.dwp, a.dbp, dweight, dbias);
     return check_launch("mvb_cheb_layer_bwd finalize");
 }

@@ -40,11 +40,23 @@ vae_rec_partial_kernel(int B, int N, int C, int ld, int VCH, int BCH, const floa
         for (int v = warp_; v < nv; v += nwarps_) {
             const float *src = recon + ((int64_t)(v0 + v) * B + b0) * ld;
             float *dst = Rs + v * (BCH * ld);
-            for (int e = lane_; e < rw; e += 32) cp_async<1>(dst + e, src + e);
+            if ((rw & 3) == 0 && ((BCH * ld) & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+                for (int e = 4 * lane_; e < rw; e += 128) cp_async<4>(dst + e, src + e);      // 16-byte pieces (padded entries)
+            } else {
+                for (int e = lane_; e < rw; e += 32) cp_async<1>(dst + e, src + e);
+            }
         }
         for (int b = warp_; b < nb; b += nwarps_) {
             const XT *src = xgt + ((int64_t)(b0 + b) * N + v0) * C;
             XT *dst = Xs + b * (VCH * C);
+            constexpr int PER16 = 16 / (int)sizeof(XT);
+            if ((xw % PER16) == 0 && ((VCH * C) % PER16) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+                for (int e = PER16 * lane_; e < xw; e += 32 * PER16) {
+                    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + e);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src + e) : "memory");
+                }
+                continue;
+            }
             for (int e = lane_; e < xw; e += 32) {
                 if (sizeof(XT) == 8) {
                     const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + e);
@@ -59,7 +71,7 @@ vae_rec_partial_kernel(int B, int N, int C, int ld, int VCH, int BCH, const floa
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
     const AT sg = (AT)sigma;
-    const AT sg2 = sg * sg;
+    const AT inv_sg = (AT)1 / sg, inv_sg2 = (AT)1 / (sg * sg);     // two multiplies per element instead of two (fp64) divisions
     const AT cst = (AT)log_sigma + (AT)MVB_HALF_LOG_2PI;
     for (int b = warp; b < nb; b += nwarps) {
         double s = 0.0;
@@ -67,16 +79,25 @@ vae_rec_partial_kernel(int B, int N, int C, int ld, int VCH, int BCH, const floa
             const int v = e / C, c = e - v * C;
             float *rp = Rs + v * (BCH * ld) + b * ld + c;
             const AT d = (AT)(*rp) - (AT)Xs[b * (VCH * C) + e];   // recon - x
-            const AT t = d / sg;
+            const AT t = d * inv_sg;
             const AT nll = (AT)0.5 * t * t + cst;
             s += (double)nll;
-            *rp = (float)(d / sg2);
+            *rp = (float)(d * inv_sg2);
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
         if (lane == 0) partial[(int64_t)blockIdx.x * B + b0 + b] = s;
     }
     __syncthreads();
+    if (ld == 4 && C == 3) {          // padded mesh coordinates: one 16-byte entry per (vertex, mesh), pad lane zeroed
+        for (int i = tid; i < nv * nb; i += nthreads) {
+            const int v = i / nb, b = i - v * nb;
+            float4 r = *reinterpret_cast<const float4 *>(Rs + v * (BCH * 4) + b * 4);
+            r.w = 0.f;
+            *reinterpret_cast<float4 *>(dnll + ((int64_t)(v0 + v) * B + b0 + b) * 4) = r;
+        }
+        return;
+    }
     for (int i = tid; i < nv * rw; i += nthreads) {
         const int v = i / rw, rem = i - v * rw;
         const float val = (ld == C || rem % ld < C) ? Rs[v * (BCH * ld) + rem] : 0.f;      // padding entries carry no gradient
@@ -84,34 +105,52 @@ vae_rec_partial_kernel(int B, int N, int C, int ld, int VCH, int BCH, const floa
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 vae_loss_finalize_kernel(int B, int Z, int ncls, int nchunks, const double *__restrict__ partial,
                          const float *__restrict__ mu, const float *__restrict__ logvar,
                          const float *__restrict__ y_hat, const int64_t *__restrict__ y,
                          double *loss, float *kld, double *rec, int64_t *correct) {
-    __shared__ double s_sum[256];
-    __shared__ int s_cnt[256];
+    __shared__ double s_sum[1024];
+    __shared__ int s_cnt[1024];
     const int tid = threadIdx.x;
     double lsum = 0.0;
     int lcnt = 0;
-    // phase 1: a warp per mesh sums the vertex-chunk partials (lane-strided, fixed shuffle tree)
+    // phase 1: a warp per mesh sums the vertex-chunk partials (lane-strided, four independent loads in flight per
+    // lane, fixed shuffle tree); 32 warps: two meshes per warp at 64 meshes instead of eight
     const int wid = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
     for (int b = wid; b < B; b += nw) {
-        double r = 0.0;
-        for (int ch = lane; ch < nchunks; ch += 32) r += partial[(int64_t)ch * B + b];
+        double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+        int ch = lane;
+        for (; ch + 96 < nchunks; ch += 128) {
+            r0 += partial[(int64_t)ch * B + b];
+            r1 += partial[(int64_t)(ch + 32) * B + b];
+            r2 += partial[(int64_t)(ch + 64) * B + b];
+            r3 += partial[(int64_t)(ch + 96) * B + b];
+        }
+        for (; ch < nchunks; ch += 32) r0 += partial[(int64_t)ch * B + b];
+        double r = (r0 + r1) + (r2 + r3);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
         if (lane == 0) rec[b] = r;
     }
     __syncthreads();
-    // phase 2: a thread per mesh for the per-mesh terms
-    for (int b = tid; b < B; b += blockDim.x) {
-        const double r = rec[b];
+    // phase 2: 16 lanes per mesh for the per-mesh terms (the latent sums are lane-strided + a fixed xor tree; a single
+    // thread per mesh walked 2 Z dependent global loads)
+    constexpr int G = 16;
+    const int sub = tid & (G - 1);
+    for (int b0 = 0; b0 < B; b0 += blockDim.x / G) {
+        const int b = b0 + tid / G;
+        const bool ok = b < B;
         float k = 0.f;
-        for (int j = 0; j < Z; ++j) {
-            const float m = mu[b * Z + j], lv = logvar[b * Z + j];
-            k += 1.f + lv - m * m - expf(lv);
-        }
+        if (ok)
+            for (int j = sub; j < Z; j += G) {
+                const float m = mu[b * Z + j], lv = logvar[b * Z + j];
+                k += 1.f + lv - m * m - expf(lv);
+            }
+#pragma unroll
+        for (int off = G / 2; off > 0; off >>= 1) k += __shfl_xor_sync(0xffffffffu, k, off);
+        if (!ok || sub != 0) continue;
+        const double r = rec[b];
         k *= -0.5f;
         kld[b] = k;
         float q = 0.f;
@@ -189,6 +228,20 @@ pack_vertex_major_kernel(int B, int N, int C, int Cp, const float *__restrict__ 
     __shared__ float tile[8][32 * 8 + 1];
     const int v0 = blockIdx.x * 32, b0 = blockIdx.y * 8;
     const int nv = min(32, N - v0), nb = min(8, B - b0);
+    if (C == 3 && Cp == 4 && nv == 32 && nb == 8 && blockDim.x == 256) {
+        // the mesh coordinates: 96 contiguous floats per mesh in, one float4 entry per (vertex, mesh) out, no divisions
+        const int t = threadIdx.x;
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int i = t + u * 256, b = i / 96, rem = i - b * 96;
+            tile[b][rem] = __ldg(x + ((int64_t)(b0 + b) * N + v0) * 3 + rem);
+        }
+        __syncthreads();
+        const int v = t >> 3, b = t & 7;
+        const float4 o = make_float4(tile[b][3 * v], tile[b][3 * v + 1], tile[b][3 * v + 2], 0.f);
+        *reinterpret_cast<float4 *>(out + ((int64_t)(v0 + v) * B + b0 + b) * 4) = o;
+        return;
+    }
     for (int i = threadIdx.x; i < nb * nv * C; i += blockDim.x) {
         const int b = i / (nv * C), rem = i - b * (nv * C);
         tile[b][rem] = __ldg(x + ((int64_t)(b0 + b) * N + v0) * C + rem);
@@ -422,7 +475,7 @@ extern "C" int mvb_vae_loss_fwd(int B, int N, int C, int Z, int ncls, const floa
         vae_rec_partial_kernel<float><<<grid, 256, smem, st>>>(B, N, C, recon_ld, VCH, BCH, recon, (const float *)x_gt, log_sigma, sigma, partial, dnll);
     int rc = check_launch("mvb_vae_loss_fwd partial");
     if (rc) return rc;
-    vae_loss_finalize_kernel<<<1, 256, 0, st>>>(B, Z, ncls, nch, partial, mu, logvar, y_hat, y, loss, kld, rec, correct);
+    vae_loss_finalize_kernel<<<1, 1024, 0, st>>>(B, Z, ncls, nch, partial, mu, logvar, y_hat, y, loss, kld, rec, correct);
     return check_launch("mvb_vae_loss_fwd finalize");
 }
 
