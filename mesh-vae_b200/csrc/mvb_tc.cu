@@ -608,66 +608,90 @@ tc_wgrad_kernel(TcWgradArgs a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *slot;
-    const uint32_t idesc = make_idesc(128, a.n16, 1, 1);
+    // N-STACKING (Fout <= 16): the lo parts of dY go into columns 16..31 of the same 128-byte B rows, so ONE MMA with
+    // N = 32 yields A.[B_hi | B_lo]; two MMAs per K step (A_hi, A_lo) instead of three give all four hi/lo products, the
+    // epilogue adds the two column halves.  These MMAs cost the same whatever N is (the M = 128 operand is streamed from
+    // shared memory per instruction), and their count paces the kernel.
+    const bool nstack = FAST && a.n16 == 16;
+    const uint32_t idesc = make_idesc(128, nstack ? 32 : a.n16, 1, 1);
     const int64_t ntiles = (a.rows + R - 1) / R;
     const int dq4 = a.n_out >> 2;                      // float4 chunks per dY row (FAST only)
 
-    float4 pre[LPT * NPV];
-    float4 pred[4], prem[4];
-    auto prefetch = [&](int64_t row0) {
+    // register prefetch DEPTH tiles ahead.  Depth 3 for the narrow planes (10 KB per tile) measured no faster than depth 1
+    // (43.3 vs 42.7 us): the kernel is paced by the MMA instruction stream, not by memory latency - see N-stacking below
+    constexpr int DEPTH = 1;
+    float4 pre[DEPTH][LPT * NPV];
+    float4 pred[DEPTH][4], prem[DEPTH][4];
+    // everything about a thread's pieces of a tile that does not depend on the tile - row, shared-memory offsets,
+    // validity - is computed once: the per-tile code is then loads, the hi/lo split and stores (ncu: 11.2 M warp
+    // instructions for 4998 narrow tiles before, two integer divisions and a swizzle computation per piece per tile)
+    int trow[LPT];                       // row of T piece j within the tile, -1 = no piece
+    uint32_t toff[NPV][LPT];
+#pragma unroll
+    for (int j = 0; j < LPT; ++j) {
+        const int i = j * 128 + tid;
+        trow[j] = (FAST && i < 64 * Q4) ? i / Q4 : -1;
+#pragma unroll
+        for (int p = 0; p < NPV; ++p) toff[p][j] = trow[j] >= 0 ? b32_off(trow[j], p * W + (i - trow[j] * Q4) * 4, blk) : 0u;
+    }
+    int drow[4];
+    uint32_t doff[4], doff_lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = j * 128 + tid;
+        drow[j] = (FAST && i < R * dq4) ? i / dq4 : -1;
+        const int q = drow[j] >= 0 ? i - drow[j] * dq4 : 0;
+        doff[j] = drow[j] >= 0 ? b32_off(drow[j], q * 4, blk) : 0u;
+        doff_lo[j] = drow[j] >= 0 ? b32_off(drow[j], 16 + q * 4, blk) : 0u;       // N-stacked position of the lo part
+    }
+    auto prefetch = [&](const int d, int64_t row0) {
         const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
 #pragma unroll
         for (int p = 0; p < NPV; ++p) {
             const float4 *s4 = reinterpret_cast<const float4 *>((p == 0 ? a.in0 : a.in_rest + (int64_t)(p - 1) * a.rows * W) + row0 * W);
 #pragma unroll
-            for (int j = 0; j < LPT; ++j) {
-                const int i = j * 128 + tid;
-                pre[p * LPT + j] = (i < 64 * Q4 && (i / Q4) < nr) ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            for (int j = 0; j < LPT; ++j)
+                pre[d][p * LPT + j] = (trow[j] >= 0 && trow[j] < nr) ? __ldg(s4 + j * 128 + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         const float4 *d4 = reinterpret_cast<const float4 *>(a.dy + row0 * a.n_out);
         const float4 *m4 = reinterpret_cast<const float4 *>(a.mask ? a.mask + row0 * a.n_out : nullptr);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int i = j * 128 + tid;
-            const bool ok = i < R * dq4 && (i / dq4) < nr;
-            pred[j] = ok ? __ldg(d4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.mask) prem[j] = ok ? __ldg(m4 + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+            const bool ok = drow[j] >= 0 && drow[j] < nr;
+            pred[d][j] = ok ? __ldg(d4 + j * 128 + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.mask) prem[d][j] = ok ? __ldg(m4 + j * 128 + tid) : make_float4(1.f, 1.f, 1.f, 1.f);
         }
     };
-    auto commit = [&]() {
+    auto commit = [&](const int d) {
 #pragma unroll
         for (int p = 0; p < NPV; ++p) {
 #pragma unroll
             for (int j = 0; j < LPT; ++j) {
-                const int i = j * 128 + tid;
-                if (i < 64 * Q4) {
-                    const int r = i / Q4, q = i - r * Q4;
+                if (trow[j] >= 0) {
                     float4 h, l;
-                    split4(pre[p * LPT + j], h, l);
-                    const uint32_t off = b32_off(r, p * W + q * 4, blk);
-                    *reinterpret_cast<float4 *>(Thi + off) = h;
-                    *reinterpret_cast<float4 *>(Tlo + off) = l;
+                    split4(pre[d][p * LPT + j], h, l);
+                    *reinterpret_cast<float4 *>(Thi + toff[p][j]) = h;
+                    *reinterpret_cast<float4 *>(Tlo + toff[p][j]) = l;
                 }
             }
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int i = j * 128 + tid;
-            if (i < R * dq4) {
-                const int r = i / dq4, q = i - r * dq4;
-                float4 v = pred[j];
+            if (drow[j] >= 0) {
+                float4 v = pred[d][j];
                 if (a.mask) {
-                    v.x = prem[j].x > 0.f ? v.x : 0.f;
-                    v.y = prem[j].y > 0.f ? v.y : 0.f;
-                    v.z = prem[j].z > 0.f ? v.z : 0.f;
-                    v.w = prem[j].w > 0.f ? v.w : 0.f;
+                    v.x = prem[d][j].x > 0.f ? v.x : 0.f;
+                    v.y = prem[d][j].y > 0.f ? v.y : 0.f;
+                    v.z = prem[d][j].z > 0.f ? v.z : 0.f;
+                    v.w = prem[d][j].w > 0.f ? v.w : 0.f;
                 }
                 float4 h, l;
                 split4(v, h, l);
-                const uint32_t off = b32_off(r, q * 4, blk);
-                *reinterpret_cast<float4 *>(Dhi + off) = h;
-                *reinterpret_cast<float4 *>(Dlo + off) = l;
+                *reinterpret_cast<float4 *>(Dhi + doff[j]) = h;
+                if (nstack)
+                    *reinterpret_cast<float4 *>(Dhi + doff_lo[j]) = l;
+                else
+                    *reinterpret_cast<float4 *>(Dlo + doff[j]) = l;
             }
         }
     };
@@ -720,37 +744,47 @@ tc_wgrad_kernel(TcWgradArgs a) {
     uint32_t acc = 0, phase = 0;
     bool pending = false;
     int64_t t = blockIdx.x;
-    if (FAST && t < ntiles) prefetch(t * R);
-    for (; t < ntiles; t += gridDim.x) {
-        const int64_t row0 = t * R;
-        const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
-        if (pending) {   // the previous tile's MMAs must have finished reading shared memory
-            mbar_wait(bar, phase);
-            phase ^= 1;
-        }
-        if (FAST)
-            commit();
-        else
-            stage_generic(row0, nr);
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            for (int ks = 0; ks < R / 8; ++ks) {          // 8 activation rows per MMA = two 4-row K atoms
-                const uint64_t ah = make_desc(smem_u32(Thi) + ks * 1024, blk, 512, 1u);
-                const uint64_t al = make_desc(smem_u32(Tlo) + ks * 1024, blk, 512, 1u);
-                const uint64_t bh = make_desc(smem_u32(Dhi) + ks * 1024, blk, 512, 1u);
-                const uint64_t bl = make_desc(smem_u32(Dlo) + ks * 1024, blk, 512, 1u);
-                umma_tf32(tmem_base, al, bh, idesc, acc);
-                umma_tf32(tmem_base, ah, bl, idesc, 1);
-                umma_tf32(tmem_base, ah, bh, idesc, 1);
-                acc = 1;
+    if (FAST) {
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d)
+            if (t + (int64_t)d * gridDim.x < ntiles) prefetch(d, (t + (int64_t)d * gridDim.x) * R);
+    }
+    while (t < ntiles) {
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) {          // static register slots: the tile loop is unrolled DEPTH times
+            if (t >= ntiles) continue;
+            const int64_t row0 = t * R;
+            const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
+            if (pending) {   // the previous tile's MMAs must have finished reading shared memory
+                mbar_wait(bar, phase);
+                phase ^= 1;
             }
-            umma_commit(bar);
+            if (FAST)
+                commit(d);
+            else
+                stage_generic(row0, nr);
+            fence_proxy_async();
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                for (int ks = 0; ks < R / 8; ++ks) {          // 8 activation rows per MMA = two 4-row K atoms
+                    const uint64_t ah = make_desc(smem_u32(Thi) + ks * 1024, blk, 512, 1u);
+                    const uint64_t al = make_desc(smem_u32(Tlo) + ks * 1024, blk, 512, 1u);
+                    const uint64_t bh = make_desc(smem_u32(Dhi) + ks * 1024, blk, 512, 1u);
+                    const uint64_t bl = make_desc(smem_u32(Dlo) + ks * 1024, blk, 512, 1u);
+                    umma_tf32(tmem_base, al, bh, idesc, acc);
+                    if (!nstack) umma_tf32(tmem_base, ah, bl, idesc, 1);
+                    umma_tf32(tmem_base, ah, bh, idesc, 1);
+                    acc = 1;
+                }
+                umma_commit(bar);
+            }
+            pending = true;
+            const int64_t nx = t + (int64_t)DEPTH * gridDim.x;
+            if (FAST && nx < ntiles) prefetch(d, nx * R);     // overlaps this and the next DEPTH-1 tiles
+            t += gridDim.x;
         }
-        pending = true;
-        if (FAST && t + gridDim.x < ntiles) prefetch((t + gridDim.x) * R);   // overlaps this tile's MMAs
     }
     if (pending) {
         mbar_wait(bar, phase);
@@ -763,6 +797,12 @@ tc_wgrad_kernel(TcWgradArgs a) {
     for (int n0 = 0; n0 < a.n16; n0 += 16) {
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, v);
+        if (nstack) {                       // + A.B_lo from the upper column half
+            float v2[16];
+            tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + 16u, v2);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += v2[j];
+        }
         if (m < a.M4) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
