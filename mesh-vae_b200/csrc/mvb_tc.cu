@@ -310,6 +310,15 @@ tc_rowgemm_kernel(TcRowArgs a) {
 
     float4 pre[NV];
     float4 prem[Q4];
+    // tile-invariant part of a thread's pieces (row within the tile, swizzled shared-memory offset): computed once
+    int srow[Q4 > 0 ? Q4 : 1];
+    uint32_t soff[Q4 > 0 ? Q4 : 1];
+#pragma unroll
+    for (int j = 0; j < Q4; ++j) {
+        const int i = j * 128 + tid;
+        srow[j] = i / (Q4 > 0 ? Q4 : 1);
+        soff[j] = swz_off(srow[j], i - srow[j] * Q4, row_bytes);
+    }
     // global -> registers for plane group g of the tile starting at row0 (planar layout)
     auto prefetch = [&](int64_t row0, int g) {
         const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
@@ -319,16 +328,14 @@ tc_rowgemm_kernel(TcRowArgs a) {
             const float4 *s4 = reinterpret_cast<const float4 *>((p == 0 ? a.in0 : a.in_rest + (int64_t)(p - 1) * a.rows * (Q4 * 4)) + row0 * (Q4 * 4));
 #pragma unroll
             for (int j = 0; j < Q4; ++j) {
-                const int i = j * 128 + tid;
-                pre[pp * Q4 + j] = (i / Q4 < nr) ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                pre[pp * Q4 + j] = (srow[j] < nr) ? __ldg(s4 + j * 128 + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         if (a.mask && g == 0) {
             const float4 *m4 = reinterpret_cast<const float4 *>(a.mask + row0 * (Q4 * 4));
 #pragma unroll
             for (int j = 0; j < Q4; ++j) {
-                const int i = j * 128 + tid;
-                prem[j] = (i / Q4 < nr) ? __ldg(m4 + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+                prem[j] = (srow[j] < nr) ? __ldg(m4 + j * 128 + tid) : make_float4(1.f, 1.f, 1.f, 1.f);
             }
         }
     };
@@ -338,8 +345,6 @@ tc_rowgemm_kernel(TcRowArgs a) {
         for (int p = 0; p < NPR; ++p) {
 #pragma unroll
             for (int j = 0; j < Q4; ++j) {
-                const int i = j * 128 + tid;
-                const int r = i / Q4, q = i - r * Q4;
                 float4 v = pre[p * Q4 + j];
                 if (p == 0 && g == 0 && a.mask) {
                     v.x = prem[j].x > 0.f ? v.x : 0.f;
@@ -349,8 +354,8 @@ tc_rowgemm_kernel(TcRowArgs a) {
                 }
                 float4 h, l;
                 split4(v, h, l);
-                const uint32_t off = ONE_TILE ? swz_off(r, p * Q4 + q, row_bytes)
-                                              : (uint32_t)(p * a_plane) + swz_off(r, q, row_bytes);
+                const uint32_t off = ONE_TILE ? swz_off(srow[j], p * Q4 + (j * 128 + tid - srow[j] * Q4), row_bytes)
+                                              : (uint32_t)(p * a_plane) + soff[j];
                 *reinterpret_cast<float4 *>(Ahi + off) = h;
                 *reinterpret_cast<float4 *>(Alo + off) = l;
             }
