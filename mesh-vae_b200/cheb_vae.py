@@ -14,7 +14,7 @@ not present on the GPU box and because it can use the fused entry points:
     (models/cheb_VAE.py:316, `noise="cpu"`) or from the device generator (`noise="device"`,
     CUDA-graph capturable).
 """
-from typing import Optional, Sequence
+from typing import Optional
 
 import torch
 import torch.nn as nn

@@ -9,7 +9,7 @@ and a batch is what PyG's collater makes of a list of those: a `Batch` whose `.x
 LongTensor of labels and a list of names.  `edge_index` is read and ignored by the model (quirk 11): it is
 carried once, not replicated B times with offsets.
 """
-from typing import Iterator, List, Optional, Sequence
+from typing import Iterator, List, Sequence
 
 import numpy as np
 import torch

@@ -12,7 +12,6 @@ accumulators - and the epoch ends with ONE read-back.  `train_epoch` is the same
 the sex classifier `cheb_GCN` trained on the residuals of the VAE's reconstruction under both labels.
 """
 import os
-from typing import Optional, Sequence
 
 import numpy as np
 import torch
