@@ -75,3 +75,35 @@ def test_reference_get_model_runs_without_psbody_or_open3d():
     code = SCRIPT_F1.format(root=ROOT, ref=REF, npz=os.path.join(ROOT, "tests", "golden", "operators_template5k.npz"))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert "COMPAT_F1_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+SCRIPT_DRIVERS = r"""
+import sys
+sys.path.insert(0, {root!r})
+import meshvae_b200 as mvb
+mvb.install_compat()
+sys.path.insert(1, {ref!r})
+sys.path.insert(2, {plot!r})            # matplotlib only (absent from the image; the drivers never call it here)
+import torch
+import main, inference, crecon           # the reference's drivers, unchanged: every import resolves on compat/
+from torch_geometric.data import DataLoader, Data
+assert main.get_model.__module__ == "model" and main.Mesh is mvb.mesh_ops.Mesh
+class DS(torch.utils.data.Dataset):
+    def __len__(self): return 5
+    def __getitem__(self, i):
+        x = torch.full((7, 3), float(i))
+        return Data(x=x, y=x, edge_index=torch.zeros(2, 3, dtype=torch.long)), x.double(), i % 2, "f%d.obj" % i, x, torch.eye(3), torch.zeros(1, 3), torch.ones(1)
+batches = list(DataLoader(DS(), batch_size=2, shuffle=False, num_workers=0))
+assert len(batches) == 3
+x, x_gt, y, f, gt, R, m, s = batches[0]
+assert x.num_graphs == 2 and x.x.shape == (14, 3) and x_gt.shape == (2, 7, 3) and y.tolist() == [0, 1] and f == ["f0.obj", "f1.obj"]
+assert R.shape == (2, 3, 3) and m.shape == (2, 1, 3) and s.shape == (2, 1) and batches[2][0].num_graphs == 1
+print("COMPAT_DRIVERS_OK")
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present (GPU box)")
+def test_reference_drivers_import_on_compat():
+    code = SCRIPT_DRIVERS.format(root=ROOT, ref=REF, plot=os.path.join(ROOT, "oracle", "shims_plot"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "COMPAT_DRIVERS_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
