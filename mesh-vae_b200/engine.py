@@ -63,11 +63,12 @@ class TrainEngine:
         self.n_vert = net.adjacency_matrices[0].shape[0]
         self.feat = net.filters[0]
         # which parameters receive gradients is a property of the graph (dec_lin_1 is dead): probe once
-        self.x = torch.zeros(batch, self.n_vert, self.feat, device=self.dev)
-        self.x_gt = torch.zeros(batch, self.n_vert, self.feat, device=self.dev, dtype=x_gt_dtype)
-        self.y_hot = torch.zeros(batch, net.num_class, device=self.dev, dtype=torch.int64)
+        # the step's four input tensors are views of ONE flat device buffer (256-byte aligned pieces), so that the
+        # double-buffered path moves a staged batch into place with a single device-to-device copy
+        self._in_spec = [((batch, self.n_vert, self.feat), torch.float32), ((batch, self.n_vert, self.feat), x_gt_dtype),
+                         ((batch, net.z), torch.float32), ((batch, net.num_class), torch.int64)]
+        self._in_flat, (self.x, self.x_gt, self.eps, self.y_hot) = self._alloc_inputs()
         self.y_hot[:, 0] = 1
-        self.eps = torch.zeros(batch, net.z, device=self.dev)
         net.train()
         net.zero_grad(set_to_none=True)
         loss, *_ = net(self.x, self.x_gt, self.y_hot, m_type="train", eps=self.eps)
@@ -112,9 +113,26 @@ class TrainEngine:
         self._cut = self._cut_grad = None
         self.launches_per_step = None
         self._copy_stream = self._gt_ready = None
-        self._stage = self._ev_staged = self._ev_consumed = self._h_small = None
+        self._stage = self._stage_flat = self._ev_staged = self._ev_consumed = self._h_small = None
         self._staged = False
         self._fwd_out = None
+
+    def _alloc_inputs(self):
+        offs, n = [], 0
+        for shape, dt in self._in_spec:
+            offs.append(n)
+            nbytes = torch.empty((), dtype=dt).element_size()
+            for d in shape:
+                nbytes *= d
+            n += (nbytes + 255) // 256 * 256
+        flat = torch.zeros(n, device=self.dev, dtype=torch.uint8)
+        views = []
+        for (shape, dt), o in zip(self._in_spec, offs):
+            k = torch.empty((), dtype=dt).element_size()
+            for d in shape:
+                k *= d
+            views.append(flat[o:o + k].view(dt).view(shape))
+        return flat, views
 
     # ---- device work of one step -------------------------------------------------------------
     def _fwd(self):
@@ -275,7 +293,7 @@ class TrainEngine:
         tensors).  The copies land in staging buffers; `step_prefetched` moves them into the step's static buffers
         (device-to-device, a few microseconds) when the previous step no longer reads those."""
         if self._stage is None:
-            self._stage = [torch.empty_like(t) for t in (self.x, self.x_gt, self.eps, self.y_hot)]
+            self._stage_flat, self._stage = self._alloc_inputs()
             self._ev_staged, self._ev_consumed = torch.cuda.Event(), torch.cuda.Event()
             self._ev_consumed.record(torch.cuda.current_stream())
         if self._copy_stream is None:
@@ -308,7 +326,7 @@ class TrainEngine:
             raise RuntimeError("step_prefetched: no staged batch (call stage() first)")
         main = torch.cuda.current_stream()
         main.wait_event(self._ev_staged)
-        torch._foreach_copy_([self.x, self.x_gt, self.eps, self.y_hot], self._stage)
+        self._in_flat.copy_(self._stage_flat)         # one device-to-device copy for all four inputs
         self._ev_consumed.record(main)
         self._gt_ready.record(main)                  # the step graph's external wait node: the ground truth is in place
         self._staged = False
