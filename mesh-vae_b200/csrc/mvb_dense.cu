@@ -106,7 +106,9 @@ __device__ __forceinline__ void stage_async(float *dst, int ld, int tile_rows, i
 // forward: y = dropout(relu(x W^T + b)).  Block tile 64 rows x 8 outputs, the whole K extent (in
 // chunks of KC <= 640) staged in shared memory.
 // ---------------------------------------------------------------------------------------------
-constexpr int LF_TM = 64, LF_TN = 8;
+// (32 rows per block: at 64 meshes the grid is 2 x N/8 = 128-160 blocks on 148 SMs and a block stages half the
+// activation tile - the staging of x, not the arithmetic, is what a block's time goes into)
+constexpr int LF_TM = 32, LF_TN = 8, LF_RPT = LF_TM / 32;      // rows per thread: 256 threads = 8 outputs x 32 row groups
 
 template <int VEC>
 __global__ void __launch_bounds__(256)
@@ -120,7 +122,7 @@ linear_fwd_kernel(int M, int K, int N, const float *__restrict__ x, int x_vmf, c
     const int tid = threadIdx.x;
     const int m0 = blockIdx.y * LF_TM, n0 = blockIdx.x * LF_TN;
     const int rows = min(LF_TM, M - m0), cols = min(LF_TN, N - n0);
-    const int n = tid % LF_TN, r0 = (tid / LF_TN) * 2;
+    const int n = tid % LF_TN, r0 = (tid / LF_TN) * LF_RPT;
     const MatView xv = mat_view(x, M, K, x_vmf), wv = mat_view(W, N, K, 0);
     float acc0 = 0.f, acc1 = 0.f;
     for (int k0 = 0; k0 < K; k0 += KC) {
@@ -133,12 +135,15 @@ linear_fwd_kernel(int M, int K, int N, const float *__restrict__ x, int x_vmf, c
         __syncthreads();
         const float4 *w4 = reinterpret_cast<const float4 *>(ws + n * LD);
         const float4 *a4 = reinterpret_cast<const float4 *>(xs + r0 * LD);
-        const float4 *b4 = reinterpret_cast<const float4 *>(xs + (r0 + 1) * LD);
+        const float4 *b4 = reinterpret_cast<const float4 *>(xs + (r0 + LF_RPT - 1) * LD);
 #pragma unroll 4
         for (int k = 0; k < (kc4 >> 2); ++k) {
-            const float4 w = w4[k], a = a4[k], b = b4[k];
+            const float4 w = w4[k], a = a4[k];
             acc0 = fmaf(a.x, w.x, acc0); acc0 = fmaf(a.y, w.y, acc0); acc0 = fmaf(a.z, w.z, acc0); acc0 = fmaf(a.w, w.w, acc0);
-            acc1 = fmaf(b.x, w.x, acc1); acc1 = fmaf(b.y, w.y, acc1); acc1 = fmaf(b.z, w.z, acc1); acc1 = fmaf(b.w, w.w, acc1);
+            if (LF_RPT == 2) {
+                const float4 b = b4[k];
+                acc1 = fmaf(b.x, w.x, acc1); acc1 = fmaf(b.y, w.y, acc1); acc1 = fmaf(b.z, w.z, acc1); acc1 = fmaf(b.w, w.w, acc1);
+            }
         }
     }
     if (n >= cols) return;
@@ -146,7 +151,7 @@ linear_fwd_kernel(int M, int K, int N, const float *__restrict__ x, int x_vmf, c
     const uint64_t off = (uint64_t)(off_host + (off_dev ? *off_dev : 0));
     const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < LF_RPT; ++u) {
         const int r = r0 + u;
         if (r >= rows) break;
         float v = (u ? acc1 : acc0) + bv;
