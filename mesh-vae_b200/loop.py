@@ -8,6 +8,7 @@ launches on the device - `mvb_recon_error` on the decoder's buffer and `mvb_epoc
 accumulators - and the epoch ends with ONE read-back.  `train_epoch` is the same loop on the captured
 `engine.TrainEngine` step (fixed batch size replayed as a CUDA graph; the ragged last batch runs uncaptured).
 
+`inference` is the batch loop of `inference.py` (:55-157) with the same three report files and OBJ outputs.
 `estimate_diff`, `train_classifier` and `evaluate_classifier` are the counterparts for `crecon.py` (:64-150, :162-201):
 the sex classifier `cheb_GCN` trained on the residuals of the VAE's reconstruction under both labels.
 """
@@ -146,6 +147,50 @@ def evaluate(n, model, test_loader, device, faces=None, checkpoint_dir=None, vis
     total = max(r["count"], 1)
     err = torch.cat(errors, 0).cpu().numpy() if errors else np.zeros((0, 0), dtype=np.float32)
     return r["loss"], r["kld"], r["rec_loss"], np.float64(r["accuracy"]), err, int(flipped) / total
+
+
+def inference(net, output_path, mean, std, data_loader, faces, device, write_meshes=True):
+    """inference.py:55-157 without its dataset construction: for every batch the predicted class of the (normalised)
+    input, the reconstruction under that class and the sex-changed mesh under the opposite one; writes the
+    `<name>_recon.obj` / `<name>_gt.obj` / `<name>.obj` triples into `output_path/sex_change` and the three reports
+    `pred.json`, `error_list.json`, `inference.json` (formats.save_inference_reports).  The de-normalisation, the
+    Procrustes back-transform and the per-mesh mean / max errors run on the device (`mvb_recon_error`); the meshes come
+    back once per batch because they are written to disk.  -> the dict written to inference.json."""
+    net.eval()
+    mean, std = _norm(None, (mean, std), device)
+    out_dir = os.path.join(output_path, "sex_change")
+    os.makedirs(out_dir, exist_ok=True)
+    names_all, sex_all, mean_all, max_all = [], [], [], []
+    with torch.no_grad():
+        for data in data_loader:
+            x, x_gt, _, names, gt_mesh, R, m, s = _split(data)
+            b = _num_graphs(x)
+            x = x.to(device, non_blocking=True)
+            x_gt = x_gt.to(device, non_blocking=True).reshape(b, -1, 3).float()          # inference.py:73
+            pred = classifier_(net, x_gt)
+            sex_hot = F.one_hot(pred, num_classes=2)
+            _, _, out, z, _ = net(x, x_gt, sex_hot, m_type="test")
+            res = Fn.recon_error(out, mean, std, s, R, m, gt_mesh, mesh=write_meshes)
+            names_all += list(names)
+            sex_all.append(pred)
+            mean_all.append(res[0])
+            max_all.append(res[1])
+            if not write_meshes:
+                continue
+            oppo_x = net.sample(1 - sex_hot, z[2])
+            oppo_mesh = Fn.recon_error(oppo_x, mean, std, s, R, m, None, mesh=True)[2].cpu().numpy()
+            recon_mesh, gt_np = res[2].cpu().numpy(), torch.as_tensor(gt_mesh).cpu().numpy()
+            for i in range(b):
+                base = names[i].split("/")[-1].split(".")[0]
+                formats.save_obj(os.path.join(out_dir, base + "_recon.obj"), recon_mesh[i], faces)
+                formats.save_obj(os.path.join(out_dir, base + "_gt.obj"), gt_np[i], faces)
+                formats.save_obj(os.path.join(out_dir, base + ".obj"), oppo_mesh[i], faces)
+    sex = torch.cat(sex_all).cpu().numpy() if sex_all else np.zeros(0, dtype=np.int64)
+    e_mean = torch.cat(mean_all).cpu().numpy() if mean_all else np.zeros(0)
+    e_max = torch.cat(max_all).cpu().numpy() if max_all else np.zeros(0)
+    formats.save_inference_reports(output_path, names_all, sex, e_mean, e_max)
+    return {n.split("/").pop(): {"sex": int(sx), "reconstruction_error": {"mean": float(a), "max": float(c)}}
+            for n, sx, a, c in zip(names_all, sex, e_mean, e_max)}
 
 
 # ---- crecon.py: classifier on reconstruction residuals ---------------------------------------------------------

@@ -276,3 +276,42 @@ def test_crecon_classifier_loops_match_reference_restatement(mvb, ops):
     got_t = loop.train_classifier(gcn, vae, _loader(mvb, ds), len(ds), torch.optim.Adam(gcn.parameters(), lr=1e-3), dev, crit)
     assert abs(got_t[0] - want_t[0]) <= 2e-3 * max(1.0, abs(want_t[0])), (got_t, want_t)
     assert abs(got_t[1] - want_t[1]) <= 0.11                                       # one borderline mesh may flip over three Adam steps
+
+
+def test_inference_loop_reports_and_meshes(mvb, ops, tmp_path):
+    """inference.py:55-157 restated on the oracle vs loop.inference: predicted sex, per-mesh mean / max error, the three
+    JSON reports and the OBJ triples"""
+    import json
+    from meshvae_b200 import loop, formats
+    ds = SyntheticHips(n=6)
+    ref, net = _models(mvb, ops)
+    ref.eval()
+    mean, std = torch.FloatTensor(ds.mean), torch.FloatTensor(ds.std)
+    faces = np.load(OPERATORS_NPZ)["template_f"]
+    want = {}
+    with torch.no_grad():
+        for batch, x_gt, _, names, gt_mesh, R, m, s in _loader(mvb, ds):
+            b = batch.num_graphs
+            xg = x_gt.reshape(b, -1, 3).float()
+            pred = torch.argmax(ref.classifier(ref.encoder(xg)), 1)
+            hot = F.one_hot(pred, num_classes=2)
+            _, _, out, z, _ = ref(batch.x.reshape(b, -1, 3), xg, hot, m_type="test")
+            rm = torch.bmm((out * std + mean) * s.unsqueeze(1), R) + m
+            d = _euclid(rm.numpy(), gt_mesh.numpy())
+            for i, nme in enumerate(names):
+                want[nme.split("/").pop()] = (int(pred[i]), float(d[i].mean()), float(d[i].max()), rm[i].numpy())
+    got = loop.inference(net, str(tmp_path), mean, std, _loader(mvb, ds), faces, torch.device("cuda:0"))
+    assert set(got) == set(want)
+    for k, (sx, e_mean, e_max, mesh) in want.items():
+        assert got[k]["sex"] == sx
+        assert abs(got[k]["reconstruction_error"]["mean"] - e_mean) <= 1e-4 * e_mean
+        assert abs(got[k]["reconstruction_error"]["max"] - e_max) <= 1e-4 * e_max
+        v, f = formats.load_obj(str(tmp_path / "sex_change" / (k.split(".")[0] + "_recon.obj")))
+        assert np.array_equal(f, faces) and np.abs(v - mesh).max() <= 2e-4 * np.abs(mesh).max()
+    rep = json.load(open(tmp_path / "inference.json"))
+    assert set(rep) == set(want) and set(rep[k]) == {"sex", "reconstruction_error"}
+    pred = json.load(open(tmp_path / "pred.json"))
+    assert all(key.startswith("/scans/") and val in ("0", "1") for key, val in pred.items()) and len(pred) == 6
+    errs = json.load(open(tmp_path / "error_list.json"))
+    assert all(len(val.split(".")[1]) == 4 for val in errs.values())               # '.4f' (inference.py:122)
+    assert len(os.listdir(tmp_path / "sex_change")) == 18
