@@ -57,7 +57,7 @@ int mvb_set_tensor_cores(int enable);
 int mvb_set_tc_tuning(int plane_group, int ctas_per_sm);
 /* tuning: size the row-GEMM grid so that every block gets the same number of 128-row tiles (default 0) */
 int mvb_set_tc_balance(int on);
-/* tuning hook of the mesh-resident backward layer: blocks per SM its grid is sized for (1..4, default 2); whether the
+/* tuning hook of the mesh-resident backward layer: blocks per SM its grid is sized for (1..4, default 1); whether the
  * weight-gradient and input-gradient halves run as two concurrent kernels (default 0: measured slower) */
 int mvb_set_layer_tuning(int bwd_blocks_per_sm, int bwd_concurrent);
 /* enable (default) / disable the fused multi-step recurrence kernels used when a level fits shared

@@ -282,7 +282,7 @@ cheb_layer_fwd_kernel(LayerArgs a, LayerSmem S) {
 // b - the recurrences are independent per feature column, dW_k rows and dx columns of different
 // splits are disjoint, so the splits share nothing but the (re-staged) G and W.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(LY_NT, 2)       // 64 registers (no spills): two blocks per SM whenever shared memory allows
+__global__ void __launch_bounds__(LY_NT)
 cheb_layer_bwd_kernel(LayerArgs a, LayerSmem S) {
     extern __shared__ float4 lsm4[];
     float *sm = reinterpret_cast<float *>(lsm4);
@@ -506,7 +506,10 @@ static int pick_splits(int B, int quads, int min_q, int per_sm = 1) {
     while (B * s * 2 <= per_sm * (num_sms() + num_sms() / 2) && quads / (s * 2) >= min_q) s *= 2;
     return s;
 }
-static int g_layer_bwd_per_sm = 2;      // blocks per SM the backward grid is sized for (tuning: mvb_set_layer_tuning)
+// blocks per SM the backward grid is sized for (tuning: mvb_set_layer_tuning).  1: two feature splits per mesh at 64
+// meshes.  Sizing it for two blocks per SM (4 splits, kernel capped at 64 registers) measured 157 us against 149 us for
+// the four backward layers of a step: the per-block instruction count does not shrink with the split.
+static int g_layer_bwd_per_sm = 1;
 // dW and dX halves of the backward layer as two concurrent kernels: OFF - measured 63 us for the pair against 59 us for
 // the single kernel at level 2 (both halves saturate the same shared-memory pipe; profiles/README.md)
 static int g_layer_bwd_concurrent = 0;
@@ -522,8 +525,7 @@ static int layer_check(int N, int B, int Fin, int Fout, int K, int Lnnz, int n_i
     const int QF = Fin / 4, CQ = Fout / 4;
     if (!pow2(QF) || !pow2(CQ)) return 0;
     // forward splits the output columns (each split redoes the cheap recurrence), backward the input features
-    // (the backward kernel fits two blocks per SM - 64 registers, feature-split shared memory - and its splits
-    // redo nothing, so its grid is sized for two blocks per SM: 4 splits at 64 meshes)
+    // (the backward splits redo nothing - the recurrences are per feature column)
     const int splits = backward ? pick_splits(B, QF, 1, g_layer_bwd_per_sm) : pick_splits(B, CQ, 2);
     const int ql = (backward ? QF : CQ) / splits;                 // local tile-column quads
     if (n_out > LY_MAXT * 4 * (LY_NT / ql)) return 0;
