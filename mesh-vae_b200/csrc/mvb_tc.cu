@@ -577,15 +577,18 @@ __device__ __forceinline__ uint32_t b32_off(int r, int col, int blk) {
 
 // NPF > 0: planes of width 4*Q4 floats (4 or 16), Fout % 4 == 0: vector staging with register prefetch;
 // NPF == 0: generic scalar staging
+constexpr int WG_NT = 256;      // 8 warps: all of them stage tiles, warps 0-3 own the TMEM lanes of the epilogue (ncu: the
+                                // 128-thread version was paced by its own instruction stream at 8 warps per SM)
 template <int NPF, int Q4>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(WG_NT)
 tc_wgrad_kernel(TcWgradArgs a) {
     extern __shared__ __align__(1024) char smem_raw[];
     char *smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr bool FAST = NPF > 0;
     constexpr int NPV = FAST ? NPF : 1;
     constexpr int W = 4 * Q4;                          // plane width (FAST only)
-    constexpr int LPT = (64 * Q4 + 127) / 128;         // float4 loads per thread per plane per 64-row tile
+    constexpr int LPT = (64 * Q4 + WG_NT - 1) / WG_NT; // float4 loads per thread per plane per 64-row tile
+    constexpr int DJ = 512 / WG_NT;                    // dY pieces per thread (up to 64 rows x 8 quads)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int R = 64;                                  // activation rows (= UMMA K extent) per tile
     const int blk = R * 128;                           // one 32-feature block of the T tile: 8 KB
@@ -626,7 +629,7 @@ tc_wgrad_kernel(TcWgradArgs a) {
     // (43.3 vs 42.7 us): the kernel is paced by the MMA instruction stream, not by memory latency - see N-stacking below
     constexpr int DEPTH = 1;
     float4 pre[DEPTH][LPT * NPV];
-    float4 pred[DEPTH][4], prem[DEPTH][4];
+    float4 pred[DEPTH][DJ], prem[DEPTH][DJ];
     // everything about a thread's pieces of a tile that does not depend on the tile - row, shared-memory offsets,
     // validity - is computed once: the per-tile code is then loads, the hi/lo split and stores (ncu: 11.2 M warp
     // instructions for 4998 narrow tiles before, two integer divisions and a swizzle computation per piece per tile)
@@ -634,16 +637,16 @@ tc_wgrad_kernel(TcWgradArgs a) {
     uint32_t toff[NPV][LPT];
 #pragma unroll
     for (int j = 0; j < LPT; ++j) {
-        const int i = j * 128 + tid;
+        const int i = j * WG_NT + tid;
         trow[j] = (FAST && i < 64 * Q4) ? i / Q4 : -1;
 #pragma unroll
         for (int p = 0; p < NPV; ++p) toff[p][j] = trow[j] >= 0 ? b32_off(trow[j], p * W + (i - trow[j] * Q4) * 4, blk) : 0u;
     }
-    int drow[4];
-    uint32_t doff[4], doff_lo[4];
+    int drow[DJ];
+    uint32_t doff[DJ], doff_lo[DJ];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int i = j * 128 + tid;
+    for (int j = 0; j < DJ; ++j) {
+        const int i = j * WG_NT + tid;
         drow[j] = (FAST && i < R * dq4) ? i / dq4 : -1;
         const int q = drow[j] >= 0 ? i - drow[j] * dq4 : 0;
         doff[j] = drow[j] >= 0 ? b32_off(drow[j], q * 4, blk) : 0u;
@@ -656,15 +659,15 @@ tc_wgrad_kernel(TcWgradArgs a) {
             const float4 *s4 = reinterpret_cast<const float4 *>((p == 0 ? a.in0 : a.in_rest + (int64_t)(p - 1) * a.rows * W) + row0 * W);
 #pragma unroll
             for (int j = 0; j < LPT; ++j)
-                pre[d][p * LPT + j] = (trow[j] >= 0 && trow[j] < nr) ? __ldg(s4 + j * 128 + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
+                pre[d][p * LPT + j] = (trow[j] >= 0 && trow[j] < nr) ? __ldg(s4 + j * WG_NT + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         const float4 *d4 = reinterpret_cast<const float4 *>(a.dy + row0 * a.n_out);
         const float4 *m4 = reinterpret_cast<const float4 *>(a.mask ? a.mask + row0 * a.n_out : nullptr);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < DJ; ++j) {
             const bool ok = drow[j] >= 0 && drow[j] < nr;
-            pred[d][j] = ok ? __ldg(d4 + j * 128 + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.mask) prem[d][j] = ok ? __ldg(m4 + j * 128 + tid) : make_float4(1.f, 1.f, 1.f, 1.f);
+            pred[d][j] = ok ? __ldg(d4 + j * WG_NT + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.mask) prem[d][j] = ok ? __ldg(m4 + j * WG_NT + tid) : make_float4(1.f, 1.f, 1.f, 1.f);
         }
     };
     auto commit = [&](const int d) {
@@ -681,7 +684,7 @@ tc_wgrad_kernel(TcWgradArgs a) {
             }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < DJ; ++j) {
             if (drow[j] >= 0) {
                 float4 v = pred[d][j];
                 if (a.mask) {
@@ -706,11 +709,11 @@ tc_wgrad_kernel(TcWgradArgs a) {
         const int per_plane = R * a.in_w;
         const int t_total = a.in_planes * per_plane;
         const int total = t_total + R * a.n_out;          // T planes, then the dY tile
-        for (int base = 0; base < total; base += 8 * 128) {
+        for (int base = 0; base < total; base += 8 * WG_NT) {
             float v[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int i = base + u * 128 + tid;
+                const int i = base + u * WG_NT + tid;
                 v[u] = 0.f;
                 if (i < t_total) {
                     const int p = i / per_plane, e = i - p * per_plane;
@@ -726,7 +729,7 @@ tc_wgrad_kernel(TcWgradArgs a) {
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int i = base + u * 128 + tid;
+                const int i = base + u * WG_NT + tid;
                 float h, l;
                 split_tf32(v[u], h, l);
                 if (i < t_total) {
@@ -799,7 +802,7 @@ tc_wgrad_kernel(TcWgradArgs a) {
     // D[m = feature (or bias row)][n = fo] -> per-CTA partial block [M4][N4]
     const int m = warp * 32 + lane;
     float *part = a.partials + (size_t)blockIdx.x * a.M4 * a.N4;
-    for (int n0 = 0; n0 < a.n16; n0 += 16) {
+    for (int n0 = 0; warp < 4 && n0 < a.n16; n0 += 16) {      // TMEM lanes 0..127 belong to warps 0..3
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, v);
         if (nstack) {                       // + A.B_lo from the upper column half
@@ -827,7 +830,7 @@ static int launch_wgrad_t(const TcWgradArgs &t, unsigned grid, size_t smem, cuda
         if (e != cudaSuccess) return set_err(MVB_ECUDA, "tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    tc_wgrad_kernel<NPF, Q4><<<grid, 128, smem, st>>>(t);
+    tc_wgrad_kernel<NPF, Q4><<<grid, WG_NT, smem, st>>>(t);
     return check_launch("mvb tc_wgrad");
 }
 
