@@ -51,29 +51,11 @@ int64_t mvb_launch_count(void);
 /* enable (default) / disable the tcgen05 3xTF32 tensor-core kernels for the dense contractions;
  * disabled, the strict-fp32 FFMA kernels run everywhere.  Returns the previous setting. */
 int mvb_set_tensor_cores(int enable);
-/* tuning hook for the tcgen05 row GEMM: planes of the 6-plane contraction staged at a time (1, 2, 3 or 6;
- * default 2) and resident CTAs per SM its grid is sized for (1..4; default 4); 0 leaves a value unchanged.
- * Results are bit-identical for every setting. */
-int mvb_set_tc_tuning(int plane_group, int ctas_per_sm);
-/* tuning: size the row-GEMM grid so that every block gets the same number of 128-row tiles (default 0) */
-int mvb_set_tc_balance(int on);
-/* tuning hook of the mesh-resident backward layer: blocks per SM its grid is sized for (1..4, default 1); whether the
- * weight-gradient and input-gradient halves run as two concurrent kernels (default 0: measured slower) */
-int mvb_set_layer_tuning(int bwd_blocks_per_sm, int bwd_concurrent);
-/* enable (default) / disable the fused multi-step recurrence kernels used when a level fits shared
- * memory (bit-identical to the step-by-step SpMM launches); a value >= 64 enables them with that
- * many threads per block (tuning hook; default 1024) */
-int mvb_set_fused_recurrence(int enable);
-/* tuning hook: force the SpMM block shape (tx column quads per block row, chunk = consecutive rows
- * walked by one block); 0, 0 restores the automatic choice */
-int mvb_set_spmm_shape(int tx, int chunk);
-/* tuning hook: SpMM block size, 0 = automatic, 1/2/3 = force 256/512/1024 threads.  Results are
- * bit-identical for every shape (same per-row summation order). */
-int mvb_set_spmm_mode(int mode);
-/* enable (default) / disable running the weight-gradient branch of mvb_cheb_bwd on an internal
- * side stream, forked from and joined back into `stream` with events (capturable: the two
- * branches become parallel branches of a CUDA graph).  Returns the previous setting. */
-int mvb_set_overlap(int enable);
+/* Tuning hooks for A/B measurement runs (scripts/, tests) - not part of the operator API.  spec is a list
+ * "key=a[,b];key=..." (keys: tc_tuning, tc_balance, layer_tuning, fused_recurrence, spmm_shape, spmm_mode, overlap,
+ * mesh_tc; documented next to mvb_tune in csrc/mvb_api.cu).  Results are bit-identical for every setting of the
+ * grid-shape keys; mesh_tc / fused_recurrence select between implementations tested against each other. */
+int mvb_tune(const char *spec);
 
 /* step-engine plumbing: cudaStreamWaitEvent(stream, event, cudaEventWaitExternal).  Legal during stream
  * capture (becomes an external event-wait node): each replay of the captured graph waits for the latest
@@ -256,19 +238,23 @@ int mvb_adam_step(int64_t n, float *p, const float *g, float *m, float *v, int64
  *   x [n_in,B,Fin] (n_in == N unless U [N x n_in] is given), y [n_out,B,Fout] (n_out == N unless
  *   sel[n_out] is given: output row r is conv row sel[r] - D is such a selection,
  *   mesh_operations.py:72-85: one 1.0 per row).
- * mvb_cheb_layer_supported: 1 when the level fits (Fin, Fout multiples of 4 and powers of two up to
- *   64, per-mesh planes + operators within 200 KB of shared memory), else 0 - the caller then uses
+ * Two implementations behind the same entry points: the tensor-core mesh kernels (csrc/mvb_mesh_tc.cu: 16 / 32-wide
+ *   features, up to 1280 vertices - levels 1-3 of the template; a cluster of 1-2 CTAs per mesh keeps the basis planes
+ *   in shared memory in the UMMA operand layout and contracts them with tcgen05.mma into TMEM accumulators) and the
+ *   FFMA mesh kernels (csrc/mvb_layer.cu: any multiple-of-4 width, a few hundred vertices).
+ * mvb_cheb_layer_supported: 1 when one of them covers the level in both directions, else 0 - the caller then uses
  *   mvb_pool_* + mvb_cheb_*.
  * Backward: nothing but x and y is kept from the forward pass (the basis is recomputed in shared
  *   memory).  dweight / dbias OVERWRITTEN; dx [n_in,B,Fin] may be NULL.  L^T / U^T as in
- *   mvb_cheb_bwd / mvb_pool_bwd.  workspace: mvb_cheb_layer_bwd_workspace_bytes (per-mesh partials,
- *   summed in mesh order by a second kernel: deterministic). */
+ *   mvb_cheb_bwd / mvb_pool_bwd.  workspace: mvb_cheb_layer_bwd_workspace_bytes(N, B, Fin, Fout, K, has_up = U given)
+ *   (per-mesh partials summed in mesh order by a second kernel, or the S_k planes of the adjoint form for the
+ *   streaming weight-gradient reduction: deterministic either way). */
 int mvb_cheb_layer_supported(int N, int B, int Fin, int Fout, int K, int L_nnz, int n_in, int U_nnz, int n_out);
 int mvb_cheb_layer_fwd(int N, int B, int Fin, int Fout, int K, const int32_t *L_rowptr, const int32_t *L_colidx,
                        const float *L_vals, int L_nnz, int n_in, const int32_t *U_rowptr, const int32_t *U_colidx,
                        const float *U_vals, int U_nnz, int n_out, const int32_t *sel, const float *x,
                        const float *weight, const float *bias, int relu, float *y, void *stream);
-size_t mvb_cheb_layer_bwd_workspace_bytes(int B, int Fin, int Fout, int K);
+size_t mvb_cheb_layer_bwd_workspace_bytes(int N, int B, int Fin, int Fout, int K, int has_up);
 int mvb_cheb_layer_bwd(int N, int B, int Fin, int Fout, int K, const int32_t *L_rowptr, const int32_t *L_colidx,
                        const float *L_vals, const int32_t *Lt_rowptr, const int32_t *Lt_colidx, const float *Lt_vals,
                        int L_nnz, int n_in, const int32_t *U_rowptr, const int32_t *U_colidx, const float *U_vals,

@@ -38,13 +38,7 @@ SIGNATURES = {
     "mvb_device_cc": (c_int, []),
     "mvb_launch_count": (c_int64, []),
     "mvb_set_tensor_cores": (c_int, [c_int]),
-    "mvb_set_tc_tuning": (c_int, [c_int, c_int]),
-    "mvb_set_tc_balance": (c_int, [c_int]),
-    "mvb_set_layer_tuning": (c_int, [c_int, c_int]),
-    "mvb_set_spmm_shape": (c_int, [c_int, c_int]),
-    "mvb_set_spmm_mode": (c_int, [c_int]),
-    "mvb_set_fused_recurrence": (c_int, [c_int]),
-    "mvb_set_overlap": (c_int, [c_int]),
+    "mvb_tune": (c_int, [c_char_p]),
     "mvb_stream_wait_external_event": (c_int, [_vp, _vp]),
     "mvb_csr_from_coo_host": (c_int, [c_int64, c_int64, c_int64, _vp, _vp, _vp, c_int, _vp, _vp, _vp]),
     "mvb_spmm": (c_int, [c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_float, c_float, c_int64, _vp]),
@@ -68,7 +62,7 @@ SIGNATURES = {
     "mvb_gaussian_nll_bwd": (c_int, [c_int64, _vp, _vp, c_int, c_float, _vp, _vp, _vp]),
     "mvb_cheb_layer_supported": (c_int, [c_int] * 9),
     "mvb_cheb_layer_fwd": (c_int, [c_int] * 5 + [_vp, _vp, _vp, c_int, c_int, _vp, _vp, _vp, c_int, c_int, _vp, _vp, _vp, _vp, c_int, _vp, _vp]),
-    "mvb_cheb_layer_bwd_workspace_bytes": (c_size_t, [c_int] * 4),
+    "mvb_cheb_layer_bwd_workspace_bytes": (c_size_t, [c_int] * 6),
     "mvb_cheb_layer_bwd": (c_int, [c_int] * 5 + [_vp] * 6 + [c_int, c_int] + [_vp] * 6 + [c_int, c_int] + [_vp] * 9 + [c_size_t, _vp]),
     "mvb_linear_fwd": (c_int, [c_int, c_int, c_int, _vp, c_int, _vp, _vp, c_int, c_float, c_uint64, _vp, c_int64, _vp, c_int, _vp]),
     "mvb_linear_bwd": (c_int, [c_int, c_int, c_int, _vp, c_int, _vp, _vp, _vp, c_int, c_int, c_float, _vp, _vp, _vp, _vp]),
@@ -96,6 +90,11 @@ def last_error() -> str:
 def check(rc: int, what: str = ""):
     if rc != 0:
         raise MvbError(f"{what or 'mvb call'} failed (code {rc}): {last_error()}")
+
+
+def tune(spec: str):
+    """A/B tuning hooks (include/mvb.h: mvb_tune), e.g. tune("spmm_mode=1;mesh_tc=1,2")"""
+    check(lib.mvb_tune(spec.encode()), "mvb_tune")
 
 
 def ptr(t):

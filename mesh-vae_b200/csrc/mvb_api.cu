@@ -2,6 +2,7 @@
 // Chebyshev convolution forward / backward compositions.  See include/mvb.h for the contract and
 // the reference symbols (file:line) each entry point replaces.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <atomic>
 #include <vector>
 #include "mvb_internal.cuh"
@@ -46,7 +47,6 @@ extern "C" const char *mvb_last_error(void) { return err_buf(); }
 namespace mvb { long long launch_count(); }
 extern "C" int64_t mvb_launch_count(void) { return (int64_t)mvb::launch_count(); }
 
-extern "C" int mvb_set_overlap(int enable);
 
 extern "C" int mvb_device_cc(void) {
     int dev = 0, major = 0, minor = 0;
@@ -537,8 +537,49 @@ extern "C" int mvb_stream_wait_external_event(void *stream, void *event) {
     return MVB_OK;
 }
 
-extern "C" int mvb_set_overlap(int enable) {
-    const int old = g_overlap;
-    g_overlap = enable ? 1 : 0;
-    return old;
+// ---------------------------------------------------------------------------------------------
+// tuning hooks for A/B runs (scripts/, tests): NOT part of the operator API.  spec = "key=a[,b];key=..."
+//   tc_tuning=pg,cap   planes staged at a time by the 6-plane row GEMM (1,2,3,6) / resident CTAs per SM (1..4)
+//   tc_balance=0|1     equal tile counts per row-GEMM block
+//   layer_tuning=p,c   FFMA mesh-layer backward: blocks per SM, concurrent halves
+//   fused_recurrence=v 0 off, 1 on, >= 64 on with that many threads
+//   spmm_shape=tx,chunk / spmm_mode=m   SpMM block shape / size (0 = automatic)
+//   overlap=0|1        side-stream fork inside mvb_cheb_bwd
+//   mesh_tc=e,c        tensor-core mesh layers on/off, CTAs per mesh (0 = automatic)
+//   mesh_dbg=bits      timing probes of the tensor-core mesh forward kernel (1 no MMAs, 2 no recurrence, 4 no epilogue):
+//                      results are then wrong - scripts/mesh_tc_probe.py only
+// ---------------------------------------------------------------------------------------------
+extern "C" int mvb_tune(const char *spec) {
+    MVB_REQUIRE(spec != nullptr, "mvb_tune: null spec");
+    const char *p = spec;
+    while (*p) {
+        char key[32];
+        int n = 0, v[2] = {0, 0}, nv = 0;
+        while (*p && *p != '=' && *p != ';' && n < 31) key[n++] = *p++;
+        key[n] = 0;
+        if (*p == '=') {
+            ++p;
+            while (nv < 2) {
+                char *end = nullptr;
+                v[nv] = (int)strtol(p, &end, 10);
+                if (end == p) break;
+                ++nv;
+                p = end;
+                if (*p == ',') ++p; else break;
+            }
+        }
+        while (*p && *p != ';') ++p;
+        if (*p == ';') ++p;
+        if (!strcmp(key, "tc_tuning")) { if (v[0]) set_tc_pg6(v[0]); if (v[1]) set_tc_cap(v[1]); }
+        else if (!strcmp(key, "tc_balance")) set_tc_balance(v[0]);
+        else if (!strcmp(key, "layer_tuning")) set_layer_tuning(v[0], v[1]);
+        else if (!strcmp(key, "fused_recurrence")) set_recur_fused(v[0]);
+        else if (!strcmp(key, "spmm_shape")) set_spmm_shape(v[0], v[1]);
+        else if (!strcmp(key, "spmm_mode")) set_spmm_mode(v[0] & 15);
+        else if (!strcmp(key, "overlap")) g_overlap = v[0] ? 1 : 0;
+        else if (!strcmp(key, "mesh_tc")) set_mesh_tc(v[0], v[1]);
+        else if (!strcmp(key, "mesh_dbg")) set_mesh_dbg(v[0]);
+        else if (key[0]) return set_err(MVB_EINVAL, "mvb_tune: unknown key '%s'", key);
+    }
+    return MVB_OK;
 }

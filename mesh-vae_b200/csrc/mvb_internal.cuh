@@ -140,6 +140,32 @@ int launch_fold_wgrad(int64_t rows, int Fin, int Fout, const float *x, const flo
 int launch_contract_tc(const ContractArgs &a, cudaStream_t st);
 int launch_wgrad_tc(const WgradArgs &a, int has_bias, int M4, int N4, int *nparts, cudaStream_t st);
 
+// tuning setters behind mvb_tune (mvb_api.cu)
+void set_tc_pg6(int v);
+void set_tc_cap(int v);
+void set_tc_balance(int v);
+void set_layer_tuning(int v, int conc);
+void set_recur_fused(int v);
+void set_spmm_shape(int tx, int chunk);
+void set_spmm_mode(int v);
+void set_mesh_tc(int enable, int c);
+void set_mesh_dbg(int v);
+
+// mesh-resident tensor-core layers (mvb_mesh_tc.cu): 1 = handled / supported, 0 = shape not covered, < 0 = error
+int mesh_tc_fwd_supported(int N, int B, int Fin, int Fout, int K, int Lnnz, int n_in, int n_out);
+int mesh_tc_bwd_supported(int N, int B, int Fin, int Fout, int K, int Lnnz, int n_in, int n_out, int has_up);
+size_t mesh_tc_bwd_workspace_bytes(int N, int B, int Fin, int Fout, int K, int has_up);
+int launch_mesh_tc_fwd(int N, int B, int Fin, int Fout, int K, const int32_t *Lrp, const int32_t *Lci, const float *Lv, int Lnnz,
+                       int n_in, const int32_t *Urp, const int32_t *Uci, const float *Uv, int n_out, const int32_t *sel,
+                       const float *x, const float *w, const float *bias, int relu, float *y, cudaStream_t st);
+int launch_mesh_tc_bwd(int N, int B, int Fin, int Fout, int K, const int32_t *Ltrp, const int32_t *Ltci, const float *Ltv, int Lnnz,
+                       int n_in, const int32_t *Urp, const int32_t *Uci, const float *Uv, const int32_t *Utrp, const int32_t *Utci,
+                       const float *Utv, int n_out, const int32_t *sel, const float *x, const float *w, const float *y_for_relu,
+                       const float *dy, float *dx, float *dweight, float *dbias, void *workspace, size_t workspace_bytes,
+                       cudaStream_t st);
+// ordered sum over the meshes of per-mesh partials (mvb_layer.cu): dw[j] = sum_b dwp[b][j], db likewise
+int launch_layer_finalize(int B, int nw, int nb, const float *dwp, const float *dbp, float *dw, float *db, cudaStream_t st);
+
 // fork a per-thread side stream from `st` (NULL: no overlap) / make `st` wait for it again (mvb_api.cu)
 cudaStream_t side_fork(cudaStream_t st);
 void side_join(cudaStream_t side, cudaStream_t st);

@@ -537,22 +537,31 @@ static int layer_check(int N, int B, int Fin, int Fout, int K, int Lnnz, int n_i
     return 1;
 }
 
+int launch_layer_finalize(int B, int nw, int nb, const float *dwp, const float *dbp, float *dw, float *db, cudaStream_t st) {
+    if (nw + nb <= 0) return MVB_OK;
+    layer_finalize_kernel<<<(nw + nb + 31) / 32, 256, 0, st>>>(B, nw, nb, dwp, dbp, dw, db);
+    return check_launch("mvb layer finalize");
+}
+
 }  // namespace mvb
 
 using namespace mvb;
 
-extern "C" int mvb_set_layer_tuning(int bwd_blocks_per_sm, int bwd_concurrent) {
-    mvb::set_layer_tuning(bwd_blocks_per_sm, bwd_concurrent);
-    return 0;
-}
 
 extern "C" int mvb_cheb_layer_supported(int N, int B, int Fin, int Fout, int K, int L_nnz, int n_in, int U_nnz, int n_out) {
-    return layer_check(N, B, Fin, Fout, K, L_nnz, n_in, U_nnz, n_out, false, nullptr, nullptr) &&
-           layer_check(N, B, Fin, Fout, K, L_nnz, n_in, U_nnz, n_out, true, nullptr, nullptr);
+    // every layer has two implementations: the tensor-core mesh kernels (mvb_mesh_tc.cu; 16 / 32-wide features,
+    // up to 1280 vertices) and the FFMA mesh kernels of this file (any multiple of 4, levels of a few hundred vertices)
+    const bool fwd = mesh_tc_fwd_supported(N, B, Fin, Fout, K, L_nnz, n_in, n_out) ||
+                     layer_check(N, B, Fin, Fout, K, L_nnz, n_in, U_nnz, n_out, false, nullptr, nullptr);
+    const bool bwd = mesh_tc_bwd_supported(N, B, Fin, Fout, K, L_nnz, n_in, n_out, U_nnz > 0) ||
+                     layer_check(N, B, Fin, Fout, K, L_nnz, n_in, U_nnz, n_out, true, nullptr, nullptr);
+    return fwd && bwd;
 }
 
-extern "C" size_t mvb_cheb_layer_bwd_workspace_bytes(int B, int Fin, int Fout, int K) {
-    return ((size_t)B * K * Fin * Fout + (size_t)B * Fout) * sizeof(float);
+extern "C" size_t mvb_cheb_layer_bwd_workspace_bytes(int N, int B, int Fin, int Fout, int K, int has_up) {
+    const size_t ffma = ((size_t)B * K * Fin * Fout + (size_t)B * Fout) * sizeof(float);
+    const size_t tc = mesh_tc_bwd_workspace_bytes(N, B, Fin, Fout, K, has_up);
+    return ffma > tc ? ffma : tc;
 }
 
 static bool al16p(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -564,6 +573,11 @@ extern "C" int mvb_cheb_layer_fwd(int N, int B, int Fin, int Fout, int K, const 
     MVB_REQUIRE(L_rowptr && x && weight && y, "cheb_layer_fwd: null pointer");
     MVB_REQUIRE(U_rowptr || n_in == N, "cheb_layer_fwd: n_in=%d != N=%d without an up-sampling operator", n_in, N);
     MVB_REQUIRE(sel || n_out == N, "cheb_layer_fwd: n_out=%d != N=%d without a row selection", n_out, N);
+    if (al16p(x) && al16p(weight) && al16p(y)) {
+        const int tc = launch_mesh_tc_fwd(N, B, Fin, Fout, K, L_rowptr, L_colidx, L_vals, L_nnz, n_in, U_rowptr, U_colidx, U_vals,
+                                          n_out, sel, x, weight, bias, relu, y, (cudaStream_t)stream);
+        if (tc != 0) return tc < 0 ? tc : MVB_OK;
+    }
     LayerSmem S;
     int splits = 1;
     if (!layer_check(N, B, Fin, Fout, K, L_nnz, n_in, U_rowptr ? U_nnz : 0, n_out, false, &S, &splits))
@@ -599,13 +613,19 @@ extern "C" int mvb_cheb_layer_bwd(int N, int B, int Fin, int Fout, int K, const 
     MVB_REQUIRE(U_rowptr || n_in == N, "cheb_layer_bwd: n_in != N without an up-sampling operator");
     MVB_REQUIRE(!U_rowptr || !dx || Ut_rowptr, "cheb_layer_bwd: dx requested without U^T");
     MVB_REQUIRE(sel || n_out == N, "cheb_layer_bwd: n_out != N without a row selection");
+    if (al16p(x) && al16p(weight) && al16p(dy) && (!y_for_relu || al16p(y_for_relu)) && (!dx || al16p(dx)) && al16p(workspace)) {
+        const int tc = launch_mesh_tc_bwd(N, B, Fin, Fout, K, Lt_rowptr, Lt_colidx, Lt_vals, L_nnz, n_in, U_rowptr, U_colidx, U_vals,
+                                          Ut_rowptr, Ut_colidx, Ut_vals, n_out, sel, x, weight, y_for_relu, dy, dx, dweight, dbias,
+                                          workspace, workspace_bytes, (cudaStream_t)stream);
+        if (tc != 0) return tc < 0 ? tc : MVB_OK;
+    }
     LayerSmem S;
     int splits = 1;
     if (!layer_check(N, B, Fin, Fout, K, L_nnz, n_in, U_rowptr ? U_nnz : 0, n_out, true, &S, &splits))
         return set_err(MVB_EINVAL, "cheb_layer_bwd: shape N=%d Fin=%d Fout=%d K=%d not supported", N, Fin, Fout, K);
     if (!al16p(x) || !al16p(weight) || !al16p(dy) || (y_for_relu && !al16p(y_for_relu)) || (dx && !al16p(dx)))
         return set_err(MVB_EALIGN, "cheb_layer_bwd: tensors must be 16-byte aligned");
-    const size_t need = mvb_cheb_layer_bwd_workspace_bytes(B, Fin, Fout, K);
+    const size_t need = ((size_t)B * K * Fin * Fout + (size_t)B * Fout) * sizeof(float);
     if (workspace_bytes < need) return set_err(MVB_EWORKSPACE, "cheb_layer_bwd: workspace %zu < %zu", workspace_bytes, need);
     LayerArgs a;
     memset(&a, 0, sizeof(a));
@@ -652,6 +672,5 @@ extern "C" int mvb_cheb_layer_bwd(int N, int B, int Fin, int Fout, int K, const 
     cheb_layer_bwd_kernel<<<dim3(B, splits), LY_NT, smem, st>>>(a, S);
     rc = check_launch("mvb_cheb_layer_bwd");
     if (rc) return rc;
-    layer_finalize_kernel<<<(nw + nb + 31) / 32, 256, 0, st>>>(B, nw, nb, a.dwp, a.dbp, dweight, dbias);
-    return check_launch("mvb_cheb_layer_bwd finalize");
+    return launch_layer_finalize(B, nw, nb, a.dwp, a.dbp, dweight, dbias, st);
 }

@@ -462,19 +462,3 @@ int launch_spmm(int n_rows, int n_src_rows, const int32_t *rowptr, const int32_t
 }
 
 }  // namespace mvb
-
-extern "C" int mvb_set_fused_recurrence(int enable) {
-    mvb::set_recur_fused(enable);
-    return 0;
-}
-
-extern "C" int mvb_set_spmm_shape(int tx, int chunk) {
-    mvb::set_spmm_shape(tx, chunk);
-    return 0;
-}
-
-extern "C" int mvb_set_spmm_mode(int mode) {
-    mvb::set_spmm_mode(mode & 15);
-    return 0;
-}
-

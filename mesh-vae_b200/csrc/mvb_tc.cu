@@ -22,6 +22,7 @@
 // stores bank-conflict free.
 #include <stdlib.h>
 #include "mvb_internal.cuh"
+#include "mvb_tcgen05.cuh"
 
 namespace mvb {
 
@@ -34,102 +35,6 @@ static int g_tc_balance = 0;       // row-GEMM grid = tiles / rounds instead of 
 void set_tc_balance(int v) { g_tc_balance = v ? 1 : 0; }
 void set_tc_enabled(int v) { g_tc_enabled = v; }
 int tc_enabled() { return g_tc_enabled; }
-
-// ---------------------------------------------------------------------------------------------
-// PTX helpers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t ncols) {  // one full warp
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // same warp
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// 32 lanes x 16 consecutive 32-bit columns: thread i of the warp gets TMEM lane (base_lane + i)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout, sm_100 "version 1")
-//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
-//   [46,48) version = 1 | [61,64) layout type (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)layout_type << 61;
-    return d;
-}
-// instruction descriptor for kind::tf32, fp32 accumulate (cute::UMMA::InstrDescriptor):
-//   [4,6) c_format = 1 (F32) | [7,10) a_format = 2 (TF32) | [10,13) b_format = 2 | [15] a_major | [16] b_major
-//   [17,23) N >> 3 | [24,29) M >> 4        (major: 0 = K-major, 1 = MN-major)
-__device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
-    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-    lo = x - hi;
-}
-__device__ __forceinline__ void split4(const float4 &v, float4 &hi, float4 &lo) {
-    split_tf32(v.x, hi.x, lo.x);
-    split_tf32(v.y, hi.y, lo.y);
-    split_tf32(v.z, hi.z, lo.z);
-    split_tf32(v.w, hi.w, lo.w);
-}
-// byte offset of 16-byte chunk q of row r inside a swizzled tile whose rows are row_bytes (64 / 128) long
-__device__ __forceinline__ uint32_t swz_off(int r, int q, int row_bytes) {
-    const int x = (row_bytes == 128) ? (r & 7) : ((r >> 1) & 3);
-    return (uint32_t)(r * row_bytes + ((q ^ x) << 4));
-}
 
 // ---------------------------------------------------------------------------------------------
 // row GEMM:  out = act(A . Bm + bias)
@@ -898,15 +803,4 @@ extern "C" int mvb_set_tensor_cores(int enable) {
     const int old = mvb::tc_enabled();
     mvb::set_tc_enabled(enable ? 1 : 0);
     return old;
-}
-
-extern "C" int mvb_set_tc_balance(int on) {
-    mvb::set_tc_balance(on);
-    return 0;
-}
-
-extern "C" int mvb_set_tc_tuning(int plane_group, int ctas_per_sm) {
-    if (plane_group) mvb::set_tc_pg6(plane_group);
-    if (ctas_per_sm) mvb::set_tc_cap(ctas_per_sm);
-    return 0;
 }

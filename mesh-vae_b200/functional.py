@@ -514,7 +514,7 @@ class _ChebLayerFn(torch.autograd.Function):
         sw, sb = ctx.sinks
         dw = _grad_out(sw, w)
         db = (sb if sb is not None else torch.empty(fout, device=w.device, dtype=torch.float32)) if ctx.has_bias else None
-        ws_bytes = lib.mvb_cheb_layer_bwd_workspace_bytes(b, fin, fout, k)
+        ws_bytes = lib.mvb_cheb_layer_bwd_workspace_bytes(n, b, fin, fout, k, 1 if u is not None else 0)
         ws = torch.empty(ws_bytes, device=w.device, dtype=torch.uint8)
         check(lib.mvb_cheb_layer_bwd(n, b, fin, fout, k, ptr(l_op.rowptr), ptr(l_op.colidx), ptr(l_op.vals), ptr(l_op.rowptr_t),
                                      ptr(l_op.colidx_t), ptr(l_op.vals_t), l_op.nnz, n_in,

@@ -10,7 +10,7 @@ dev = torch.device("cuda:0")
 _, net, A, nn_ = bench.build_model(dev)
 L = mvb._lib
 flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
-L.lib.mvb_set_fused_recurrence(0)      # step-by-step recurrence: identical across variants, isolates the contraction
+L.tune(f"fused_recurrence={0}")      # step-by-step recurrence: identical across variants, isolates the contraction
 for lvl, B, F in [(0, 64, 16), (1, 64, 16), (1, 256, 16)]:
     n = nn_[lvl]
     ei, norm = mvb.ChebConv_batch.norm(A[lvl]._indices(), n)
@@ -20,7 +20,7 @@ for lvl, B, F in [(0, 64, 16), (1, 64, 16), (1, 256, 16)]:
     bias = torch.randn(16, device=dev)
     ref = None
     for pg, cap in ((6, 4), (2, 4), (2, 3), (2, 2), (2, 1), (3, 2), (3, 1)):
-        L.lib.mvb_set_tc_tuning(pg, cap)
+        L.tune(f"tc_tuning={pg},{cap}")
         basis = torch.empty(5, n, B, F, device=dev); y = torch.empty(n, B, 16, device=dev)
         ms = {}
         for cold in (True, False):
@@ -35,4 +35,4 @@ for lvl, B, F in [(0, 64, 16), (1, 64, 16), (1, 256, 16)]:
             ms[cold] = sum(t) / len(t) * 1e3
         if ref is None: ref = y.clone()
         print(f"lvl{lvl} B{B} F{F} plane group {pg} cap {cap}: cheb_fwd cold {ms[True]:6.1f} us  warm {ms[False]:6.1f} us  max|dy| vs pg6 {float((y-ref).abs().max()):.2e}")
-L.lib.mvb_set_tc_tuning(2, 4); L.lib.mvb_set_fused_recurrence(1)
+L.tune(f"tc_tuning={2},{4}"); L.tune(f"fused_recurrence={1}")

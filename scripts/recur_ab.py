@@ -17,7 +17,7 @@ for lvl, B, F in [(1, 64, 16), (1, 64, 32), (2, 64, 16), (1, 256, 16)]:
     w = torch.randn(6, F, 16, device=dev) * 0.1
     ref = None
     for nt in (0, 256, 512, 768, 1024):
-        L.lib.mvb_set_fused_recurrence(nt)
+        L.tune(f"fused_recurrence={nt}")
         basis = torch.empty(5, n, B, F, device=dev); y = torch.empty(n, B, 16, device=dev)
         ms = {}
         for cold in (True, False):
@@ -33,4 +33,4 @@ for lvl, B, F in [(1, 64, 16), (1, 64, 32), (2, 64, 16), (1, 256, 16)]:
             ms[cold] = sum(t) / len(t) * 1e3
         if ref is None: ref = basis.clone()
         print(f"lvl{lvl} B{B} F{F} threads={nt:4d} ({L.lib.mvb_launch_count()-c0} launches): recurrence+contraction cold {ms[True]:6.1f} us  warm {ms[False]:6.1f} us  identical={torch.equal(basis, ref)}")
-L.lib.mvb_set_fused_recurrence(1)
+L.tune(f"fused_recurrence={1}")

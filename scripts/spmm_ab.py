@@ -72,7 +72,7 @@ for lvl, B, F in cases:
     sets = [(torch.randn(n, B, F, device=dev), torch.empty(n, B, F, device=dev), torch.randn(n, B, F, device=dev))
             for _ in range(nsets)]
     print(f"--- lvl{lvl} B{B} F{F}: {alg/1e6:.1f} MB per launch, {nsets} rotating operand sets")
-    L.lib.mvb_set_spmm_mode(1); L.lib.mvb_set_spmm_shape(0, 0)
+    L.tune(f"spmm_mode={1}"); L.tune(f"spmm_shape={0},{0}")
     launch(op, n, *sets[0][:1], sets[0][1], sets[0][2], B * F)
     ref = sets[0][1].clone()
     variants = [(1, 0, 0), (0, 0, 0)] + [(m + st, tx, ch) for st in (0,) for m in (1, 2, 3) for tx in (16, 32)
@@ -80,11 +80,11 @@ for lvl, B, F in cases:
     if os.environ.get("SPMM_VARIANTS"):      # "mode:tx:chunk,mode:tx:chunk,..."
         variants = [tuple(int(t) for t in v.split(":")) for v in os.environ["SPMM_VARIANTS"].split(",")]
     for mode, tx, ch in variants:
-        L.lib.mvb_set_spmm_mode(mode); L.lib.mvb_set_spmm_shape(tx, ch)
+        L.tune(f"spmm_mode={mode}"); L.tune(f"spmm_shape={tx},{ch}")
         sets[0][1].zero_()
         launch(op, n, sets[0][0], sets[0][1], sets[0][2], B * F)
         same = torch.equal(sets[0][1], ref)
         single, train = time_variant(op, n, B, F, sets)
         print(f"mode={mode} tx={tx:2d} chunk={ch:4d}: single {single:6.1f} us ({alg/single/1e3:5.0f} GB/s)   "
               f"train {train:6.1f} us ({alg/train/1e3:5.0f} GB/s = {alg/train/1e3/6548.2:.2f} of peak)   identical={same}")
-L.lib.mvb_set_spmm_mode(0); L.lib.mvb_set_spmm_shape(0, 0)
+L.tune(f"spmm_mode={0}"); L.tune(f"spmm_shape={0},{0}")

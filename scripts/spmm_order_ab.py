@@ -36,7 +36,7 @@ for cluster in (0, 32, 64, 128):
         op = mvb.operators.from_edges(ei_p.contiguous(), norm.clone(), n, dev)
     for B, F in [(64, 16), (256, 16), (64, 4)]:
         for shape in [(0, 0), (32, 64), (32, 128), (16, 64)]:
-            L.lib.mvb_set_spmm_mode(3 if shape != (0, 0) else 0); L.lib.mvb_set_spmm_shape(*shape)
+            L.tune(f"spmm_mode={3 if shape != (0, 0) else 0}"); L.tune(f"spmm_shape={shape[0]},{shape[1]}")
             us, gbs = timeit(op, B, F)
             print(f"cluster {cluster:3d} B{B} F{F} shape {shape}: {us:6.1f} us {gbs:6.0f} GB/s ({gbs/6548.2:.2f})")
-L.lib.mvb_set_spmm_mode(0); L.lib.mvb_set_spmm_shape(0, 0)
+L.tune(f"spmm_mode={0}"); L.tune(f"spmm_shape={0},{0}")

@@ -16,10 +16,9 @@ ap.add_argument("--batch", type=int, default=64)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 mvb, net, A, nn_ = bench.build_model(dev)
-# tuning hooks for A/B runs: MVB_TUNE="mvb_set_tc_balance=1;mvb_set_tc_tuning=2,3"
-for call in filter(None, os.environ.get("MVB_TUNE", "").split(";")):
-    name, args = call.split("=")
-    getattr(mvb._lib.lib, name)(*[int(v) for v in args.split(",")])
+# tuning hooks for A/B runs: MVB_TUNE="tc_balance=1;tc_tuning=2,3;mesh_tc=0" (include/mvb.h: mvb_tune)
+if os.environ.get("MVB_TUNE"):
+    mvb._lib.tune(os.environ["MVB_TUNE"])
 from meshvae_b200.engine import TrainEngine  # noqa: E402
 eng = TrainEngine(net, a.batch)
 eng.capture(warmup=3)

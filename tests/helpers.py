@@ -41,3 +41,21 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     if denom == 0.0:
         return float((a - b).abs().max())
     return float((a - b).abs().max()) / denom
+
+
+def elem_err(a: torch.Tensor, b: torch.Tensor, rtol: float = 1e-4, atol_rms: float = 1e-4) -> float:
+    """Per-element mixed tolerance: max over the elements of |a-b| / (rtol*|b| + atol_rms*rms(b)); the check passes when
+    the value is <= 1.  Unlike rel_err (a max-norm bound per tensor) a small entry next to large ones must itself be
+    right to rtol, up to an absolute floor tied to the tensor's RMS (fp32 sums of ~1e2..1e5 terms of that magnitude
+    cannot be reproduced below it in a different summation order)."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    if a.shape != b.shape:
+        raise AssertionError(f"shape mismatch {tuple(a.shape)} vs {tuple(b.shape)}")
+    if b.numel() == 0:
+        return 0.0
+    rms = float(b.pow(2).mean().sqrt())
+    den = rtol * b.abs() + atol_rms * rms
+    if rms == 0.0:
+        return float((a - b).abs().max()) / atol_rms if float((a - b).abs().max()) > 0 else 0.0
+    return float(((a - b).abs() / den).max())

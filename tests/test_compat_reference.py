@@ -1,14 +1,15 @@
 """Delivery mode 1 (import-path drop-in): the UNCHANGED reference model files import and construct on
-top of `compat/`.  Needs /root/reference, so it only runs in the build container; forward passes need
-a GPU, which the build container lacks - the GPU parity tests cover the same native modules."""
+top of `compat/`.  Needs the reference tree (/root/reference in the build container, or its staged unmodified copy
+oracle/_ref/reference); forward + backward of these same files on a B200: tests/test_gpu_dropin.py."""
 import os
 import subprocess
 import sys
 import pytest
 
 from tests.helpers import ROOT
+from oracle.ref_loader import reference_root
 
-REF = os.environ.get("MVB_REFERENCE", "/root/reference")
+REF = reference_root() or "/nonexistent"       # /root/reference (build container) or the staged oracle/_ref/reference
 
 SCRIPT = r"""
 import sys, copy
