@@ -228,6 +228,11 @@ int mvb_epoch_meter_add(int B, const void *loss, int loss_is_f64, const float *k
 int mvb_adam_step(int64_t n, float *p, const float *g, float *m, float *v, int64_t *step, float lr,
                   float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                   void *stream);
+/* The same update with the hyper-parameters in DEVICE memory, hyper[6] = {lr, beta1, beta2, eps, weight_decay,
+ * grad_scale}: a captured step follows main.py's per-epoch learning-rate schedule (main.py:266-269 rewrites
+ * optimizer.param_groups[..]['lr']) and a restored optimizer state without re-capture. */
+int mvb_adam_step_hp(int64_t n, float *p, const float *g, float *m, float *v, int64_t *step, const float *hyper,
+                     void *stream);
 
 /* ---- A12 fused: one whole encoder / decoder layer of a COARSE level per launch ---------------
  * (models/cheb_VAE.py:264-265  x = relu(cheb[i](x, L)); x = pool(x, D)   and

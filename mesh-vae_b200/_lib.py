@@ -75,6 +75,7 @@ SIGNATURES = {
     "mvb_epoch_meter_add": (c_int, [c_int, _vp, c_int, _vp, _vp, c_int, _vp, _vp, _vp, _vp]),
     "mvb_adam_step": (c_int, [c_int64, _vp, _vp, _vp, _vp, _vp, c_float, c_float, c_float, c_float, c_float, c_float,
                               _vp]),
+    "mvb_adam_step_hp": (c_int, [c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

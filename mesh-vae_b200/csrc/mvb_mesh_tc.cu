@@ -30,6 +30,8 @@
 namespace mvb {
 
 constexpr int MT_NT = 1024;          // threads per CTA: the recurrence is a chain of shared-memory latencies
+constexpr int MT_NC = MT_NT - 32;    // ... of which the last warp only issues the MMAs (and so never delays a step)
+constexpr int MT_ISSUER = MT_NC;     // thread that issues tcgen05.mma / tcgen05.commit
 
 struct MeshTcArgs {
     int N, B, Fin, Fout, K;
@@ -42,10 +44,11 @@ struct MeshTcArgs {
     float *out;
     int C;                                                        // CTAs per mesh
     int dbg;                                                      // probe bits (mvb_tune mesh_dbg): 1 no MMAs, 2 no recurrence, 4 no epilogue
+    unsigned long long *prof;                                     // debug: phase time stamps of CTA 0 (mvb_debug_mesh_prof), else NULL
     int tiles;                                                    // ceil(N / 128)
     int tmem_cols;
     // shared-memory offsets (bytes from the 1024-aligned base)
-    int o_pa, o_pb, o_lo, o_bhi, o_blo, o_rp, o_ce, o_inv, o_bar, total;
+    int o_pa, o_pb, o_lo, o_lo2, o_bhi, o_blo, o_rp, o_ce, o_inv, o_bar, total;      // o_lo2 == o_lo: single lo plane
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -65,33 +68,86 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t addr, const float4 &v) {
     asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-template <int WL>
-__device__ __forceinline__ uint32_t swz(int r, int q) {
-    constexpr int RB = WL * 4;
-    const int x = (RB == 128) ? (r & 7) : (RB == 64 ? ((r >> 1) & 3) : ((r >> 2) & 1));
-    return (uint32_t)(r * RB + ((q ^ x) << 4));
+// ---- shared memory through 32-bit shared-space addresses: the planes are reached through run-time offsets and swapped
+// pointers, for which the compiler falls back to GENERIC loads (LD.E: ncu showed every gather waiting on the long
+// scoreboard, 45 us per level-1 layer); explicit ld.shared / st.shared keeps them on the LDS / STS path ----
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts4(uint32_t a, const float4 &v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ int2 lds_i2(uint32_t a) {
+    int2 v;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_i2(uint32_t a, int x, int y) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ int lds_i(uint32_t a) {
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds_f(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_i(uint32_t a, int v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+
+// Swizzled byte offset of 16-byte chunk q of row r: r*RB + ((q ^ x(r)) << 4) with x(r) = the row bits the UMMA swizzle
+// mode XORs in.  As r*RB has no bits below 5 + log2(WL/8), this is (r*RB | x(r) << 4) ^ (q << 4): the row part is
+// precomputed per operator entry (row_code), the quad part per thread.
+__device__ __forceinline__ void prof_stamp(unsigned long long *prof, int slot) {
+    if (prof && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        prof[slot] = t;
+    }
 }
 
-__device__ __forceinline__ float4 lds4(const char *p) { return *reinterpret_cast<const float4 *>(p); }
-__device__ __forceinline__ void sts4(char *p, const float4 &v) { *reinterpret_cast<float4 *>(p) = v; }
+template <int WL>
+__device__ __forceinline__ uint32_t row_code(int r) {
+    constexpr int RB = WL * 4;
+    const int x = (RB == 128) ? (r & 7) : (RB == 64 ? ((r >> 1) & 3) : ((r >> 2) & 1));
+    return (uint32_t)(r * RB) | (uint32_t)(x << 4);
+}
+template <int WL>
+__device__ __forceinline__ uint32_t swz(int r, int q) { return row_code<WL>(r) ^ (uint32_t)(q << 4); }
+
 __device__ __forceinline__ void fma4m(float4 &a, float s, const float4 &x) {
     a.x = fmaf(s, x.x, a.x); a.y = fmaf(s, x.y, a.y); a.z = fmaf(s, x.z, a.z); a.w = fmaf(s, x.w, a.w);
 }
 
-// sum_j vals[j] * src[col[j]][quad q] over the staged CSR row [s, e) - the fmaf order of the step kernels
-template <int WL>
-__device__ __forceinline__ float4 gather_swz(const char *src, const int2 *ce, int s, int e, int q) {
+// sum_j vals[j] * src[col[j]][quad] over the staged CSR row [s, e): entries are (row_code(col), value) pairs; the fmaf
+// order is the CSR order of the step kernels (mvb_spmm.cu), four gathers in flight
+__device__ __forceinline__ float4 gather_rc(uint32_t src, uint32_t ce, int s, int e, uint32_t qs) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int j = s;
-    for (; j + 2 <= e; j += 2) {
-        const int2 ea = ce[j], eb = ce[j + 1];
-        const float4 xa = lds4(src + swz<WL>(ea.x, q)), xb = lds4(src + swz<WL>(eb.x, q));
-        fma4m(acc, __int_as_float(ea.y), xa);
-        fma4m(acc, __int_as_float(eb.y), xb);
+    for (; j + 4 <= e; j += 4) {
+        const int2 e0 = lds_i2(ce + 8u * j), e1 = lds_i2(ce + 8u * j + 8u), e2 = lds_i2(ce + 8u * j + 16u), e3 = lds_i2(ce + 8u * j + 24u);
+        const float4 x0 = lds4(src + ((uint32_t)e0.x ^ qs)), x1 = lds4(src + ((uint32_t)e1.x ^ qs));
+        const float4 x2 = lds4(src + ((uint32_t)e2.x ^ qs)), x3 = lds4(src + ((uint32_t)e3.x ^ qs));
+        fma4m(acc, __int_as_float(e0.y), x0);
+        fma4m(acc, __int_as_float(e1.y), x1);
+        fma4m(acc, __int_as_float(e2.y), x2);
+        fma4m(acc, __int_as_float(e3.y), x3);
+    }
+    if (j + 2 <= e) {
+        const int2 e0 = lds_i2(ce + 8u * j), e1 = lds_i2(ce + 8u * j + 8u);
+        const float4 x0 = lds4(src + ((uint32_t)e0.x ^ qs)), x1 = lds4(src + ((uint32_t)e1.x ^ qs));
+        fma4m(acc, __int_as_float(e0.y), x0);
+        fma4m(acc, __int_as_float(e1.y), x1);
+        j += 2;
     }
     if (j < e) {
-        const int2 ea = ce[j];
-        fma4m(acc, __int_as_float(ea.y), lds4(src + swz<WL>(ea.x, q)));
+        const int2 e0 = lds_i2(ce + 8u * j);
+        fma4m(acc, __int_as_float(e0.y), lds4(src + ((uint32_t)e0.x ^ qs)));
     }
     return acc;
 }
@@ -102,57 +158,10 @@ __device__ __forceinline__ float4 lo_of(const float4 &v) {
     return l;
 }
 
-// all MMAs of recurrence step k: every 128-row tile of the plane against W_k's rows of this CTA (3xTF32)
+// operator into shared memory: rows[v] = (start, end) of row v, entries (row_code(column), value)
 template <int WL>
-__device__ __forceinline__ void issue_step_mmas(const MeshTcArgs &a, uint32_t tmem_base, const char *plane, const char *lo,
-                                                const char *bhi, const char *blo, int k, int ncols_acc, uint32_t idesc) {
-    constexpr int RB = WL * 4;
-    constexpr uint32_t LT = (RB == 128) ? 2u : (RB == 64 ? 4u : 6u);
-    constexpr uint32_t SBO = 8u * RB;
-    const uint32_t b_tile = (uint32_t)(ncols_acc * RB);
-    for (int t = 0; t < a.tiles; ++t) {
-#pragma unroll
-        for (int j = 0; j < WL / 8; ++j) {
-            const uint64_t ah = make_desc(smem_u32(plane) + t * 128 * RB + j * 32, 16, SBO, LT);
-            const uint64_t al = make_desc(smem_u32(lo) + t * 128 * RB + j * 32, 16, SBO, LT);
-            const uint64_t bh = make_desc(smem_u32(bhi) + k * b_tile + j * 32, 16, SBO, LT);
-            const uint64_t bl = make_desc(smem_u32(blo) + k * b_tile + j * 32, 16, SBO, LT);
-            const uint32_t d = tmem_base + (uint32_t)(t * ncols_acc);
-            umma_tf32(d, al, bh, idesc, (k > 0 || j > 0) ? 1u : 0u);     // small terms first
-            umma_tf32(d, ah, bl, idesc, 1u);
-            umma_tf32(d, ah, bh, idesc, 1u);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// forward
-// ---------------------------------------------------------------------------------------------
-template <int WL>
-__global__ void __launch_bounds__(MT_NT, 1)
-cheb_mesh_tc_fwd_kernel(const MeshTcArgs a) {
-    extern __shared__ __align__(1024) char mt_smem_raw[];
-    char *sm = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(mt_smem_raw) + 1023) & ~(uintptr_t)1023);
-    constexpr int RB = WL * 4, QL = WL / 4;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int c = (a.C > 1) ? (int)cluster_ctarank() : 0;
-    const int b = (a.C > 1) ? blockIdx.x / a.C : blockIdx.x;
-    const int N = a.N, Fin = a.Fin, Fout = a.Fout, K = a.K;
-    char *pa = sm + a.o_pa, *pb = sm + a.o_pb, *plo = sm + a.o_lo;
-    char *bhi = sm + a.o_bhi, *blo = sm + a.o_blo;
-    int32_t *rp = reinterpret_cast<int32_t *>(sm + a.o_rp);
-    int2 *ce = reinterpret_cast<int2 *>(sm + a.o_ce);
-    int32_t *inv = reinterpret_cast<int32_t *>(sm + a.o_inv);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(sm + a.o_bar);
-    uint32_t *slot = reinterpret_cast<uint32_t *>(bar + 1);
-
-    if (warp == 0) tmem_alloc(slot, (uint32_t)a.tmem_cols);
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        fence_barrier_init();
-    }
-    // ---- stage the operator: row pointers, packed (column, value) entries ----
-    for (int i = tid; i <= N; i += MT_NT) rp[i] = __ldg(a.Lrp + i);
+__device__ __forceinline__ void stage_operator(const MeshTcArgs &a, uint32_t rows, uint32_t ce, int tid) {
+    for (int v = tid; v < a.N; v += MT_NT) sts_i2(rows + 8u * v, __ldg(a.Lrp + v), __ldg(a.Lrp + v + 1));
     for (int base = 0; base < a.Lnnz; base += 4 * MT_NT) {
         int cc[4];
         float vv[4];
@@ -164,9 +173,112 @@ cheb_mesh_tc_fwd_kernel(const MeshTcArgs a) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int i = base + u * MT_NT + tid;
-            if (i < a.Lnnz) ce[i] = make_int2(cc[u], __float_as_int(vv[u]));
+            if (i < a.Lnnz) sts_i2(ce + 8u * i, (int)row_code<WL>(cc[u]), __float_as_int(vv[u]));
         }
     }
+}
+
+// one recurrence step out of shared memory: old <- alpha * L cur - [k >= 2] old (and its lo part); `bar` / `phase`:
+// the MMAs issued after the previous step still read `lo` (and, one step earlier, `old`) - wait before the first store
+template <int WL>
+__device__ __forceinline__ void recur_step(uint32_t cur, uint32_t old, uint32_t plo, uint32_t rows, uint32_t ce, int N, int k,
+                                           uint64_t *bar, uint32_t phase, bool wait_mma, int tid, float *gout, int64_t gstride) {
+    constexpr int QL = WL / 4;
+    bool waited = !wait_mma;
+    for (int i = tid; i < N * QL; i += MT_NC) {
+        if (tid >= MT_NC) break;            // the issuer warp
+        const int v = i / QL, q = i % QL;
+        const int2 se = lds_i2(rows + 8u * v);
+        const uint32_t qs = (uint32_t)(q << 4);
+        const float4 acc = gather_rc(cur, ce, se.x, se.y, qs);
+        const uint32_t off = row_code<WL>(v) ^ qs;
+        float4 o;
+        if (k == 1) {
+            o = make_float4(1.f * acc.x, 1.f * acc.y, 1.f * acc.z, 1.f * acc.w);
+        } else {
+            const float4 z = lds4(old + off);
+            o.x = fmaf(-1.f, z.x, 2.f * acc.x); o.y = fmaf(-1.f, z.y, 2.f * acc.y);
+            o.z = fmaf(-1.f, z.z, 2.f * acc.z); o.w = fmaf(-1.f, z.w, 2.f * acc.w);
+        }
+        if (!waited) {
+            mbar_wait(bar, phase);
+            waited = true;
+        }
+        sts4(old + off, o);
+        sts4(plo + off, lo_of(o));
+        if (gout) *reinterpret_cast<float4 *>(gout + (int64_t)v * gstride + 4 * q) = o;
+    }
+    if (!waited) mbar_wait(bar, phase);
+}
+
+// all MMAs of recurrence step k: every 128-row tile of the plane against W_k's rows of this CTA (3xTF32).  Issued by
+// ONE thread of the warp that takes no part in the recurrence (MT_ISSUER): the descriptors of a step differ only in
+// their 14-bit start-address field, so the per-tile work is a 64-bit add per operand.
+template <int WL>
+__device__ __forceinline__ void issue_step_mmas(const MeshTcArgs &a, uint32_t tmem_base, uint32_t plane, uint32_t lo,
+                                                uint32_t bhi, uint32_t blo, int k, int ncols_acc, uint32_t idesc) {
+    constexpr int RB = WL * 4;
+    constexpr uint32_t LT = (RB == 128) ? 2u : (RB == 64 ? 4u : 6u);
+    constexpr uint32_t SBO = 8u * RB;
+    const uint32_t b_tile = (uint32_t)(ncols_acc * RB);
+    const uint64_t ah0 = make_desc(plane, 16, SBO, LT), al0 = make_desc(lo, 16, SBO, LT);
+    const uint64_t bh0 = make_desc(bhi + k * b_tile, 16, SBO, LT), bl0 = make_desc(blo + k * b_tile, 16, SBO, LT);
+    for (int t = 0; t < a.tiles; ++t) {
+        const uint32_t d = tmem_base + (uint32_t)(t * ncols_acc);
+#pragma unroll
+        for (int j = 0; j < WL / 8; ++j) {
+            const uint64_t ao = (uint64_t)((t * 128 * RB + j * 32) >> 4), bo = (uint64_t)((j * 32) >> 4);
+            umma_tf32(d, al0 + ao, bh0 + bo, idesc, (k > 0 || j > 0) ? 1u : 0u);     // small terms first
+            umma_tf32(d, ah0 + ao, bl0 + bo, idesc, 1u);
+            umma_tf32(d, ah0 + ao, bh0 + bo, idesc, 1u);
+        }
+    }
+}
+
+// 16-column TMEM chunks [lo, hi) that cover the columns [c0, c0 + H) of a W-column accumulator
+__device__ __forceinline__ int chunk_lo(int c0) { return c0 & ~15; }
+__device__ __forceinline__ int chunk_hi(int c0, int H, int W) { const int e = (c0 + H + 15) & ~15; return e < W ? e : W; }
+
+// T_0 = U x through the coarse rows staged (unswizzled, [n_in][FL floats]) at `tmp`; U's entries are read from global
+// memory (used once).  Row arithmetic of the pooling SpMM: 1.f * sum_j v_j x_j in CSR order.
+__device__ __forceinline__ float4 upsample_row(const MeshTcArgs &a, uint32_t tmp, int v, int q, int FQ) {
+    const int s = __ldg(a.Urp + v), e = __ldg(a.Urp + v + 1);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = s; j < e; ++j) fma4m(acc, __ldg(a.Uv + j), lds4(tmp + (uint32_t)((__ldg(a.Uci + j) * FQ + q) * 16)));
+    return make_float4(1.f * acc.x, 1.f * acc.y, 1.f * acc.z, 1.f * acc.w);
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+template <int WL>
+__global__ void __launch_bounds__(MT_NT, 1)
+cheb_mesh_tc_fwd_kernel(const MeshTcArgs a) {
+    extern __shared__ __align__(1024) char mt_smem_raw[];
+    const uint32_t sm = (smem_u32(mt_smem_raw) + 1023u) & ~1023u;
+    constexpr int RB = WL * 4, QL = WL / 4;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int c = (a.C > 1) ? (int)cluster_ctarank() : 0;
+    const int b = (a.C > 1) ? blockIdx.x / a.C : blockIdx.x;
+    const int N = a.N, Fin = a.Fin, Fout = a.Fout, K = a.K;
+    const uint32_t pa = sm + a.o_pa, pb = sm + a.o_pb, plo = sm + a.o_lo, plo2 = sm + a.o_lo2;
+    const bool lo2 = a.o_lo2 != a.o_lo;                  // lo parts of odd steps in their own plane
+    const uint32_t bhi = sm + a.o_bhi, blo = sm + a.o_blo;
+    const uint32_t rows = sm + a.o_rp, ce = sm + a.o_ce, inv = sm + a.o_inv;
+    char *smg = mt_smem_raw + (sm - smem_u32(mt_smem_raw));       // generic view of the aligned base (barrier, TMEM slot)
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smg + a.o_bar);
+    uint32_t *slot = reinterpret_cast<uint32_t *>(bar + 2);            // bar[0]: commits of even steps (all steps without lo2), bar[1]: odd
+
+    prof_stamp(a.prof, 0);
+    if (warp == 0) tmem_alloc(slot, (uint32_t)a.tmem_cols);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        fence_barrier_init();
+    }
+    prof_stamp(a.prof, 1);
+    stage_operator<WL>(a, rows, ce, tid);
+    prof_stamp(a.prof, 2);
     // ---- B operands: Bt_k[n][kd] = W_k[c*WL + kd][n], K-major, swizzled like the planes, hi / lo ----
     for (int i = tid; i < K * WL * Fout; i += MT_NT) {
         const int n = i % Fout, kk = i / Fout;
@@ -175,12 +287,13 @@ cheb_mesh_tc_fwd_kernel(const MeshTcArgs a) {
         float h, l;
         split_tf32(wv, h, l);
         const uint32_t off = (uint32_t)(k * Fout * RB) + swz<WL>(n, kd >> 2) + (uint32_t)((kd & 3) << 2);
-        *reinterpret_cast<float *>(bhi + off) = h;
-        *reinterpret_cast<float *>(blo + off) = l;
+        sts_f(bhi + off, h);
+        sts_f(blo + off, l);
     }
     if (a.sel) {
-        for (int v = tid; v < N; v += MT_NT) inv[v] = -1;
+        for (int v = tid; v < N; v += MT_NT) sts_i(inv + 4u * v, -1);
     }
+    prof_stamp(a.prof, 3);
     // ---- T_0 into plane A (+ its lo part) ----
     const int64_t xrow = (int64_t)a.B * Fin;               // floats between consecutive vertices of one mesh
     const float *xb = a.x + (int64_t)b * Fin + c * WL;
@@ -196,17 +309,13 @@ cheb_mesh_tc_fwd_kernel(const MeshTcArgs a) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int i = base + u * MT_NT + tid;
-                if (i < a.n_in * QL) sts4(pb + (size_t)i * 16, v[u]);
+                if (i < a.n_in * QL) sts4(pb + (uint32_t)i * 16u, v[u]);
             }
         }
         __syncthreads();
         for (int i = tid; i < N * QL; i += MT_NT) {
             const int v = i / QL, q = i % QL;
-            const int s = __ldg(a.Urp + v), e = __ldg(a.Urp + v + 1);
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int j = s; j < e; ++j)
-                fma4m(acc, __ldg(a.Uv + j), lds4(pb + ((size_t)__ldg(a.Uci + j) * QL + q) * 16));
-            const float4 o = make_float4(1.f * acc.x, 1.f * acc.y, 1.f * acc.z, 1.f * acc.w);
+            const float4 o = upsample_row(a, pb, v, q, QL);
             const uint32_t off = swz<WL>(v, q);
             sts4(pa + off, o);
             sts4(plo + off, lo_of(o));
@@ -230,58 +339,50 @@ cheb_mesh_tc_fwd_kernel(const MeshTcArgs a) {
             }
         }
     }
+    prof_stamp(a.prof, 4);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    prof_stamp(a.prof, 5);
     if (a.sel) {
-        for (int r = tid; r < a.n_out; r += MT_NT) inv[__ldg(a.sel + r)] = r;
+        for (int r = tid; r < a.n_out; r += MT_NT) sts_i(inv + 4u * (uint32_t)__ldg(a.sel + r), r);
     }
     const uint32_t tmem_base = *slot;
     const uint32_t idesc = make_idesc(128, Fout, 0, 0);
-    uint32_t phase = 0;
     const bool mma_on = !(a.dbg & 1);
-    if (tid == 0 && mma_on) {
+    if (tid == MT_ISSUER && mma_on) {
         issue_step_mmas<WL>(a, tmem_base, pa, plo, bhi, blo, 0, Fout, idesc);
         umma_commit(bar);
     }
-    // ---- recurrence steps: T_k into `old` (over T_{k-2}), its MMAs overlap the next step ----
-    char *cur = pa, *old = pb;
+    // ---- recurrence steps: T_k into `old` (over T_{k-2}), its MMAs overlap the next step.  Before its first store a
+    // thread waits for the MMAs that still read what it overwrites: those of step k-1 (single lo plane), or - with the
+    // second lo plane - only those of step k-2, committed to the barrier of this step's parity ----
+    uint32_t cur = pa, old = pb;
     for (int k = 1; k < K; ++k) {
-        bool waited = !mma_on;
-        for (int i = tid; i < ((a.dbg & 2) ? 0 : N * QL); i += MT_NT) {
-            const int v = i / QL, q = i % QL;
-            const float4 acc = gather_swz<WL>(cur, ce, rp[v], rp[v + 1], q);
-            const uint32_t off = swz<WL>(v, q);
-            float4 o;
-            if (k == 1) {
-                o = make_float4(1.f * acc.x, 1.f * acc.y, 1.f * acc.z, 1.f * acc.w);
-            } else {
-                const float4 z = lds4(old + off);
-                o.x = fmaf(-1.f, z.x, 2.f * acc.x); o.y = fmaf(-1.f, z.y, 2.f * acc.y);
-                o.z = fmaf(-1.f, z.z, 2.f * acc.z); o.w = fmaf(-1.f, z.w, 2.f * acc.w);
-            }
-            if (!waited) {               // the MMAs of step k-1 read `lo` (and, two steps back, `old`): done before we overwrite
-                mbar_wait(bar, phase);
-                waited = true;
-            }
-            sts4(old + off, o);
-            sts4(plo + off, lo_of(o));
-        }
-        if (!waited) mbar_wait(bar, phase);
-        phase ^= 1;
+        const uint32_t lo_k = (lo2 && (k & 1)) ? plo2 : plo;
+        uint64_t *bar_w = lo2 ? bar + (k & 1) : bar;
+        const uint32_t par_w = lo2 ? (uint32_t)(((k >> 1) + 1) & 1) : (uint32_t)((k - 1) & 1);
+        recur_step<WL>(cur, old, lo_k, rows, ce, (a.dbg & 2) ? 0 : N, k, bar_w, par_w, mma_on && !(lo2 && k < 2), tid, nullptr, 0);
+        prof_stamp(a.prof, 4 + 2 * k);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0 && mma_on) {
+        prof_stamp(a.prof, 5 + 2 * k);
+        if (tid == MT_ISSUER && mma_on) {
             tc_fence_after();
-            issue_step_mmas<WL>(a, tmem_base, old, plo, bhi, blo, k, Fout, idesc);
-            umma_commit(bar);
+            issue_step_mmas<WL>(a, tmem_base, old, lo_k, bhi, blo, k, Fout, idesc);
+            umma_commit(lo2 ? bar + (k & 1) : bar);
         }
-        char *t = cur; cur = old; old = t;
+        const uint32_t t = cur; cur = old; old = t;
     }
-    if (mma_on) mbar_wait(bar, phase);
+    prof_stamp(a.prof, 20);
+    if (mma_on) {          // the last commit (tcgen05.commit tracks every MMA issued before it)
+        const int kl = K - 1;
+        mbar_wait(lo2 ? bar + (kl & 1) : bar, lo2 ? (uint32_t)((kl >> 1) & 1) : (uint32_t)(kl & 1));
+    }
     tc_fence_after();
+    prof_stamp(a.prof, 21);
 
     // ---- epilogue: TMEM -> registers -> bias / ReLU -> the rows D keeps ----
     const int quarter = warp & 3, group = warp >> 2;            // a warp reads TMEM lanes [32 (warp % 4), +32)
@@ -290,7 +391,7 @@ cheb_mesh_tc_fwd_kernel(const MeshTcArgs a) {
     } else if (a.C == 1) {
         for (int t = group; t < a.tiles; t += NG) {
             const int row = t * 128 + quarter * 32 + lane;
-            const int ro = (row < N) ? (a.sel ? inv[row] : row) : -1;
+            const int ro = (row < N) ? (a.sel ? lds_i(inv + 4u * row) : row) : -1;
             for (int n0 = 0; n0 < Fout; n0 += 16) {
                 float v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * Fout + n0), v);
@@ -309,50 +410,63 @@ cheb_mesh_tc_fwd_kernel(const MeshTcArgs a) {
             }
         }
     } else {
-        // K-split partials: this CTA finalises the output columns [c*H, (c+1)*H), H = Fout / 2.  Buffers (over the dead
-        // planes): mine[row][H] (local), theirs[row][H] (written by the partner through DSMEM).
+        // K-split partials: this CTA finalises the output columns [c*H, (c+1)*H), H = Fout / 2.  Phase A: the partner's
+        // column half of every row goes into ITS buffer theirs[row][H] (over the dead plane B) through DSMEM; phase B
+        // (after the cluster barrier): own half from TMEM + the partner's contribution -> bias / ReLU -> global.
         const int H = Fout >> 1, HQ = H >> 2;
-        char *mine = pa, *theirs = pb;
+        const uint32_t theirs = pb;
         cluster_sync_all();                      // the partner's MMAs no longer read its planes
-        const uint32_t peer = (uint32_t)(c ^ 1);
-        const uint32_t theirs_remote = map_to_cta(smem_u32(theirs), peer);
+        prof_stamp(a.prof, 16);
+        const uint32_t theirs_remote = map_to_cta(theirs, (uint32_t)(c ^ 1));
+        const int ps = (c ^ 1) * H;              // first column of the partner's half
         for (int t = group; t < a.tiles; t += NG) {
             const int row = t * 128 + quarter * 32 + lane;
-            for (int n0 = 0; n0 < Fout; n0 += 16) {
+            for (int n0 = chunk_lo(ps); n0 < chunk_hi(ps, H, Fout); n0 += 16) {
                 float v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * Fout + n0), v);
                 if (row < N) {
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
-                        const int col = n0 + 4 * j4;                 // H is a multiple of 8: a quad never straddles the halves
-                        const int h = col / H, qh = (col - h * H) >> 2;
-                        const float4 val = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-                        const uint32_t off = (uint32_t)((row * HQ + qh) * 16);
-                        if (h == c) sts4(mine + off, val);
-                        else st_cluster_f4(theirs_remote + off, val);
+                        const int col = n0 + 4 * j4 - ps;                    // column inside the partner's half
+                        if (col >= 0 && col < H)
+                            st_cluster_f4(theirs_remote + (uint32_t)((row * HQ + (col >> 2)) * 16),
+                                          make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
                     }
                 }
             }
         }
+        prof_stamp(a.prof, 17);
         cluster_sync_all();                      // both halves are in place
-        for (int i = tid; i < N * HQ; i += MT_NT) {
-            const int row = i / HQ, qh = i % HQ;
-            const int ro = a.sel ? inv[row] : row;
-            if (ro < 0) continue;
-            const float4 m = lds4(mine + (size_t)i * 16), o = lds4(theirs + (size_t)i * 16);
-            const int col = c * H + 4 * qh;
-            float4 v = (c == 0) ? make_float4(m.x + o.x, m.y + o.y, m.z + o.z, m.w + o.w)
-                                : make_float4(o.x + m.x, o.y + m.y, o.z + m.z, o.w + m.w);   // rank 0's partial first on both CTAs
-            if (a.bias) {
-                v.x += __ldg(a.bias + col); v.y += __ldg(a.bias + col + 1); v.z += __ldg(a.bias + col + 2); v.w += __ldg(a.bias + col + 3);
+        prof_stamp(a.prof, 18);
+        for (int t = group; t < a.tiles; t += NG) {
+            const int row = t * 128 + quarter * 32 + lane;
+            const int ro = (row < N) ? (a.sel ? lds_i(inv + 4u * row) : row) : -1;
+            for (int n0 = chunk_lo(c * H); n0 < chunk_hi(c * H, H, Fout); n0 += 16) {
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * Fout + n0), v);
+                if (ro >= 0) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        const int col = n0 + 4 * j4 - c * H;                 // column inside this CTA's half
+                        if (col < 0 || col >= H) continue;
+                        const float4 o = lds4(theirs + (uint32_t)((row * HQ + (col >> 2)) * 16));
+                        float4 r = make_float4(v[4 * j4] + o.x, v[4 * j4 + 1] + o.y, v[4 * j4 + 2] + o.z, v[4 * j4 + 3] + o.w);
+                        const int gc = c * H + col;
+                        if (a.bias) {
+                            r.x += __ldg(a.bias + gc); r.y += __ldg(a.bias + gc + 1); r.z += __ldg(a.bias + gc + 2); r.w += __ldg(a.bias + gc + 3);
+                        }
+                        if (a.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+                        *reinterpret_cast<float4 *>(a.out + ((int64_t)ro * a.B + b) * Fout + gc) = r;
+                    }
+                }
             }
-            if (a.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            *reinterpret_cast<float4 *>(a.out + ((int64_t)ro * a.B + b) * Fout + col) = v;
         }
     }
+    prof_stamp(a.prof, 22);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+    prof_stamp(a.prof, 23);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -377,42 +491,28 @@ template <int WL>
 __global__ void __launch_bounds__(MT_NT, 1)
 cheb_mesh_tc_bwd_kernel(const MeshTcBwdArgs g) {
     extern __shared__ __align__(1024) char mt_smem_raw[];
-    char *sm = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(mt_smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t sm = (smem_u32(mt_smem_raw) + 1023u) & ~1023u;
     const MeshTcArgs &a = g.m;
     constexpr int RB = WL * 4, QL = WL / 4;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int c = (a.C > 1) ? (int)cluster_ctarank() : 0;
     const int b = (a.C > 1) ? blockIdx.x / a.C : blockIdx.x;
     const int N = a.N, Fin = a.Fin, Fout = a.Fout, K = a.K;
-    char *pa = sm + a.o_pa, *pb = sm + a.o_pb, *plo = sm + a.o_lo;
-    char *bhi = sm + a.o_bhi, *blo = sm + a.o_blo;
-    int32_t *rp = reinterpret_cast<int32_t *>(sm + a.o_rp);
-    int2 *ce = reinterpret_cast<int2 *>(sm + a.o_ce);
-    int32_t *inv = reinterpret_cast<int32_t *>(sm + a.o_inv);
-    float *red = reinterpret_cast<float *>(sm + g.o_red);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(sm + a.o_bar);
-    uint32_t *slot = reinterpret_cast<uint32_t *>(bar + 1);
+    const uint32_t pa = sm + a.o_pa, pb = sm + a.o_pb, plo = sm + a.o_lo, plo2 = sm + a.o_lo2;
+    const bool lo2 = a.o_lo2 != a.o_lo;                  // lo parts of odd steps in their own plane
+    const uint32_t bhi = sm + a.o_bhi, blo = sm + a.o_blo;
+    const uint32_t rows = sm + a.o_rp, ce = sm + a.o_ce, inv = sm + a.o_inv, red = sm + g.o_red;
+    char *smg = mt_smem_raw + (sm - smem_u32(mt_smem_raw));
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smg + a.o_bar);
+    uint32_t *slot = reinterpret_cast<uint32_t *>(bar + 2);            // bar[0]: commits of even steps (all steps without lo2), bar[1]: odd
 
     if (warp == 0) tmem_alloc(slot, (uint32_t)a.tmem_cols);
     if (tid == 0) {
         mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
         fence_barrier_init();
     }
-    for (int i = tid; i <= N; i += MT_NT) rp[i] = __ldg(a.Lrp + i);
-    for (int base = 0; base < a.Lnnz; base += 4 * MT_NT) {
-        int cc[4];
-        float vv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = base + u * MT_NT + tid;
-            if (i < a.Lnnz) { cc[u] = __ldg(a.Lci + i); vv[u] = __ldg(a.Lv + i); }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = base + u * MT_NT + tid;
-            if (i < a.Lnnz) ce[i] = make_int2(cc[u], __float_as_int(vv[u]));
-        }
-    }
+    stage_operator<WL>(a, rows, ce, tid);
     // B operands of dX += S_k W_k^T: Bt_k[n = fi][kd = fo - c*WL] = W_k[fi][fo]
     for (int i = tid; i < K * Fin * WL; i += MT_NT) {
         const int kd = i % WL, kk = i / WL;
@@ -421,42 +521,37 @@ cheb_mesh_tc_bwd_kernel(const MeshTcBwdArgs g) {
         float h, l;
         split_tf32(wv, h, l);
         const uint32_t off = (uint32_t)(k * Fin * RB) + swz<WL>(n, kd >> 2) + (uint32_t)((kd & 3) << 2);
-        *reinterpret_cast<float *>(bhi + off) = h;
-        *reinterpret_cast<float *>(blo + off) = l;
+        sts_f(bhi + off, h);
+        sts_f(blo + off, l);
     }
-    for (int v = tid; v < N; v += MT_NT) inv[v] = a.sel ? -1 : v;
+    for (int v = tid; v < N; v += MT_NT) sts_i(inv + 4u * v, a.sel ? -1 : v);
     // ---- T_0 = U x of this CTA's share of the input features, straight to global (operand of the weight gradient) ----
     if (a.Urp && g.T0) {
         const int FL = Fin / a.C, FQ = FL >> 2;
         const float *xb = a.x + (int64_t)b * Fin + c * FL;
         const int64_t xrow = (int64_t)a.B * Fin;
         for (int i = tid; i < a.n_in * FQ; i += MT_NT)
-            sts4(pb + (size_t)i * 16, __ldg(reinterpret_cast<const float4 *>(xb + (int64_t)(i / FQ) * xrow) + (i % FQ)));
+            sts4(pb + (uint32_t)i * 16u, __ldg(reinterpret_cast<const float4 *>(xb + (int64_t)(i / FQ) * xrow) + (i % FQ)));
         __syncthreads();
         for (int i = tid; i < N * FQ; i += MT_NT) {
             const int v = i / FQ, q = i % FQ;
-            const int s = __ldg(a.Urp + v), e = __ldg(a.Urp + v + 1);
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int j = s; j < e; ++j)
-                fma4m(acc, __ldg(a.Uv + j), lds4(pb + ((size_t)__ldg(a.Uci + j) * FQ + q) * 16));
-            *reinterpret_cast<float4 *>(g.T0 + ((int64_t)v * a.B + b) * Fin + c * FL + 4 * q) =
-                make_float4(1.f * acc.x, 1.f * acc.y, 1.f * acc.z, 1.f * acc.w);
+            *reinterpret_cast<float4 *>(g.T0 + ((int64_t)v * a.B + b) * Fin + c * FL + 4 * q) = upsample_row(a, pb, v, q, FQ);
         }
     }
     __syncthreads();
     if (a.sel) {
-        for (int r = tid; r < a.n_out; r += MT_NT) inv[__ldg(a.sel + r)] = r;
+        for (int r = tid; r < a.n_out; r += MT_NT) sts_i(inv + 4u * (uint32_t)__ldg(a.sel + r), r);
         __syncthreads();
     }
     // ---- S_0 = G ----
     const int64_t plane_g = (int64_t)N * a.B * Fout;           // floats per S plane in global memory
+    const int64_t grow = (int64_t)a.B * Fout;
     {
         const float *dyb = g.dy + (int64_t)b * Fout + c * WL;
         const float *yb = g.y ? g.y + (int64_t)b * Fout + c * WL : nullptr;
-        const int64_t grow = (int64_t)a.B * Fout;
         for (int i = tid; i < N * QL; i += MT_NT) {
             const int v = i / QL, q = i % QL;
-            const int r = inv[v];
+            const int r = lds_i(inv + 4u * v);
             float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r >= 0) {
                 o = __ldg(reinterpret_cast<const float4 *>(dyb + (int64_t)r * grow) + q);
@@ -478,8 +573,7 @@ cheb_mesh_tc_bwd_kernel(const MeshTcBwdArgs g) {
     tc_fence_after();
     const uint32_t tmem_base = *slot;
     const uint32_t idesc = make_idesc(128, Fin, 0, 0);
-    uint32_t phase = 0;
-    if (tid == 0) {
+    if (tid == MT_ISSUER) {
         issue_step_mmas<WL>(a, tmem_base, pa, plo, bhi, blo, 0, Fin, idesc);
         umma_commit(bar);
     }
@@ -488,108 +582,102 @@ cheb_mesh_tc_bwd_kernel(const MeshTcBwdArgs g) {
         constexpr int NP = MT_NT / WL;
         const int col = tid % WL, part = tid / WL;
         float s = 0.f;
-        for (int v = part; v < N; v += NP) s += *reinterpret_cast<const float *>(pa + swz<WL>(v, col >> 2) + ((col & 3) << 2));
-        red[part * WL + col] = s;
+        for (int v = part; v < N; v += NP) s += lds_f(pa + swz<WL>(v, col >> 2) + (uint32_t)((col & 3) << 2));
+        sts_f(red + 4u * (uint32_t)(part * WL + col), s);
         __syncthreads();
         if (tid < WL) {
             float t = 0.f;
-            for (int p = 0; p < NP; ++p) t += red[p * WL + tid];
+            for (int p = 0; p < NP; ++p) t += lds_f(red + 4u * (uint32_t)(p * WL + tid));
             g.dbp[(int64_t)b * Fout + c * WL + tid] = t;
         }
     }
-    char *cur = pa, *old = pb;
+    uint32_t cur = pa, old = pb;
     for (int k = 1; k < K; ++k) {
-        bool waited = false;
-        float *sk = g.S + (int64_t)k * plane_g + (int64_t)b * Fout + c * WL;
-        for (int i = tid; i < N * QL; i += MT_NT) {
-            const int v = i / QL, q = i % QL;
-            const float4 acc = gather_swz<WL>(cur, ce, rp[v], rp[v + 1], q);
-            const uint32_t off = swz<WL>(v, q);
-            float4 o;
-            if (k == 1) {
-                o = make_float4(1.f * acc.x, 1.f * acc.y, 1.f * acc.z, 1.f * acc.w);
-            } else {
-                const float4 z = lds4(old + off);
-                o.x = fmaf(-1.f, z.x, 2.f * acc.x); o.y = fmaf(-1.f, z.y, 2.f * acc.y);
-                o.z = fmaf(-1.f, z.z, 2.f * acc.z); o.w = fmaf(-1.f, z.w, 2.f * acc.w);
-            }
-            if (!waited) {
-                mbar_wait(bar, phase);
-                waited = true;
-            }
-            sts4(old + off, o);
-            sts4(plo + off, lo_of(o));
-            *reinterpret_cast<float4 *>(sk + (int64_t)v * a.B * Fout + 4 * q) = o;
-        }
-        if (!waited) mbar_wait(bar, phase);
-        phase ^= 1;
+        const uint32_t lo_k = (lo2 && (k & 1)) ? plo2 : plo;
+        uint64_t *bar_w = lo2 ? bar + (k & 1) : bar;
+        const uint32_t par_w = lo2 ? (uint32_t)(((k >> 1) + 1) & 1) : (uint32_t)((k - 1) & 1);
+        recur_step<WL>(cur, old, lo_k, rows, ce, N, k, bar_w, par_w, !(lo2 && k < 2), tid,
+                       g.S + (int64_t)k * plane_g + (int64_t)b * Fout + c * WL, grow);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
+        if (tid == MT_ISSUER) {
             tc_fence_after();
-            issue_step_mmas<WL>(a, tmem_base, old, plo, bhi, blo, k, Fin, idesc);
-            umma_commit(bar);
+            issue_step_mmas<WL>(a, tmem_base, old, lo_k, bhi, blo, k, Fin, idesc);
+            umma_commit(lo2 ? bar + (k & 1) : bar);
         }
-        char *t = cur; cur = old; old = t;
+        const uint32_t t = cur; cur = old; old = t;
     }
-    mbar_wait(bar, phase);
+    {
+        const int kl = K - 1;
+        mbar_wait(lo2 ? bar + (kl & 1) : bar, lo2 ? (uint32_t)((kl >> 1) & 1) : (uint32_t)(kl & 1));
+    }
     tc_fence_after();
 
     if (a.out) {
-        // dT_0 [N][H] of this CTA's input-feature half into `mine` (C = 2: + the partner's partial), then [U^T], dx
+        // dT_0: this CTA finalises the input-feature columns [c*H, (c+1)*H), H = Fin / C.  C = 2: the partner's half of
+        // the K-split partial goes into ITS buffer theirs[row][H] through DSMEM (phase A); phase B adds own half (TMEM)
+        // and the partner's contribution; with an up-sampling prologue the sum is kept in shared memory for U^T.
         const int quarter = warp & 3, group = warp >> 2;
         constexpr int NG = MT_NT / 128;
         const int H = Fin / a.C, HQ = H >> 2;
-        char *mine = pa, *theirs = pb;
-        uint32_t theirs_remote = 0;
+        const uint32_t mine = pa, theirs = pb;
         if (a.C > 1) {
             cluster_sync_all();
-            theirs_remote = map_to_cta(smem_u32(theirs), (uint32_t)(c ^ 1));
+            const uint32_t theirs_remote = map_to_cta(theirs, (uint32_t)(c ^ 1));
+            const int ps = (c ^ 1) * H;
+            for (int t = group; t < a.tiles; t += NG) {
+                const int row = t * 128 + quarter * 32 + lane;
+                for (int n0 = chunk_lo(ps); n0 < chunk_hi(ps, H, Fin); n0 += 16) {
+                    float v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * Fin + n0), v);
+                    if (row < N) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const int col = n0 + 4 * j4 - ps;
+                            if (col >= 0 && col < H)
+                                st_cluster_f4(theirs_remote + (uint32_t)((row * HQ + (col >> 2)) * 16),
+                                              make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]));
+                        }
+                    }
+                }
+            }
+            cluster_sync_all();
         } else {
             __syncthreads();
         }
         for (int t = group; t < a.tiles; t += NG) {
             const int row = t * 128 + quarter * 32 + lane;
-            for (int n0 = 0; n0 < Fin; n0 += 16) {
+            for (int n0 = chunk_lo(c * H); n0 < chunk_hi(c * H, H, Fin); n0 += 16) {
                 float v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(t * Fin + n0), v);
                 if (row < N) {
 #pragma unroll
                     for (int j4 = 0; j4 < 4; ++j4) {
-                        const int col = n0 + 4 * j4;
-                        const int h = col / H, qh = (col - h * H) >> 2;
-                        const float4 val = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-                        const uint32_t off = (uint32_t)((row * HQ + qh) * 16);
-                        if (h == c) sts4(mine + off, val);
-                        else st_cluster_f4(theirs_remote + off, val);
+                        const int col = n0 + 4 * j4 - c * H;
+                        if (col < 0 || col >= H) continue;
+                        const uint32_t off = (uint32_t)((row * HQ + (col >> 2)) * 16);
+                        float4 r = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+                        if (a.C > 1) {
+                            const float4 o = lds4(theirs + off);
+                            r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+                        }
+                        if (g.Utrp) sts4(mine + off, r);
+                        else *reinterpret_cast<float4 *>(a.out + ((int64_t)row * a.B + b) * Fin + c * H + col) = r;
                     }
                 }
             }
         }
-        if (a.C > 1) {
-            cluster_sync_all();
-            for (int i = tid; i < N * HQ; i += MT_NT) {          // rank 0's partial first on both CTAs
-                const float4 m = lds4(mine + (size_t)i * 16), o = lds4(theirs + (size_t)i * 16);
-                sts4(mine + (size_t)i * 16, (c == 0) ? make_float4(m.x + o.x, m.y + o.y, m.z + o.z, m.w + o.w)
-                                                     : make_float4(o.x + m.x, o.y + m.y, o.z + m.z, o.w + m.w));
-            }
-        }
-        __syncthreads();
         if (g.Utrp) {
+            __syncthreads();
             for (int i = tid; i < a.n_in * HQ; i += MT_NT) {
                 const int ci = i / HQ, qh = i % HQ;
                 const int s = __ldg(g.Utrp + ci), e = __ldg(g.Utrp + ci + 1);
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int j = s; j < e; ++j)
-                    fma4m(acc, __ldg(g.Utv + j), lds4(mine + ((size_t)__ldg(g.Utci + j) * HQ + qh) * 16));
+                    fma4m(acc, __ldg(g.Utv + j), lds4(mine + (uint32_t)((__ldg(g.Utci + j) * HQ + qh) * 16)));
                 *reinterpret_cast<float4 *>(a.out + ((int64_t)ci * a.B + b) * Fin + c * H + 4 * qh) =
                     make_float4(1.f * acc.x, 1.f * acc.y, 1.f * acc.z, 1.f * acc.w);
-            }
-        } else {
-            for (int i = tid; i < N * HQ; i += MT_NT) {
-                const int row = i / HQ, qh = i % HQ;
-                *reinterpret_cast<float4 *>(a.out + ((int64_t)row * a.B + b) * Fin + c * H + 4 * qh) = lds4(mine + (size_t)i * 16);
             }
         }
     }
@@ -605,6 +693,7 @@ static int g_mesh_tc = 1;            // 0: the FFMA mesh-resident kernels of mvb
 static int g_mesh_tc_c = 0;          // 0: automatic cluster size, 1 / 2: forced
 static int g_mesh_dbg = 0;           // probe bits for timing attribution (results are then WRONG): see MeshTcArgs::dbg
 void set_mesh_dbg(int v) { g_mesh_dbg = v; }
+static unsigned long long *g_mesh_prof = nullptr;
 void set_mesh_tc(int enable, int c) { g_mesh_tc = enable ? 1 : 0; g_mesh_tc_c = (c == 1 || c == 2) ? c : 0; }
 
 static int pow2_cols_m(int n) {
@@ -638,10 +727,17 @@ static bool mesh_tc_layout(MeshTcArgs &a, int width_in, int width_acc, int C) {
     a.o_lo = o; o += plane;
     a.o_bhi = o; o += al(a.K * width_acc * RB, 1024);
     a.o_blo = o; o += al(a.K * width_acc * RB, 1024);
-    a.o_rp = o; o += al((a.N + 1) * 4, 16);
+    a.o_rp = o; o += al(a.N * 8, 16);
     a.o_ce = o; o += al(a.Lnnz * 8, 16);
     a.o_inv = o; o += al(a.N * 4, 16);
-    a.o_bar = o; o += 16;
+    a.o_bar = o; o += 32;
+    // a second lo plane (lo parts of even / odd steps apart) when there is room: a step then only waits for the MMAs
+    // issued TWO steps earlier - never in practice - instead of the ones issued just before it
+    a.o_lo2 = a.o_lo;
+    if ((size_t)o + plane + 4096 + 1024 <= 227 * 1024) {
+        o = al(o, 1024);
+        a.o_lo2 = o; o += plane;
+    }
     a.total = o;
     return (size_t)a.total + 1024 <= 227 * 1024;
 }
@@ -727,6 +823,7 @@ int launch_mesh_tc_fwd(int N, int B, int Fin, int Fout, int K, const int32_t *Lr
     a.n_out = n_out; a.sel = sel;
     a.x = x; a.w = w; a.bias = bias; a.relu = relu; a.out = y;
     a.dbg = g_mesh_dbg;
+    a.prof = g_mesh_prof;
     const int c = pick_mesh_c(a, Fin, Fout);
     if (!c) return 0;
     int rc;
@@ -870,3 +967,7 @@ int launch_mesh_tc_bwd(int N, int B, int Fin, int Fout, int K, const int32_t *Lt
 }
 
 }  // namespace mvb
+
+// debug hook (scripts/mesh_tc_probe.py; not in include/mvb.h): 24 uint64 %globaltimer stamps of CTA 0 of the next
+// tensor-core mesh forward launches are written to `buf` (device memory); NULL switches it off
+extern "C" void mvb_debug_mesh_prof(void *buf) { mvb::g_mesh_prof = reinterpret_cast<unsigned long long *>(buf); }

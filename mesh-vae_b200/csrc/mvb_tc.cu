@@ -480,7 +480,7 @@ __device__ __forceinline__ uint32_t b32_off(int r, int col, int blk) {
     return (uint32_t)(b * blk + r * 128 + (((c >> 1) ^ (r & 3)) << 5) + ((c & 1) << 4) + ((col & 3) << 2));
 }
 
-// NPF > 0: planes of width 4*Q4 floats (4 or 16), Fout % 4 == 0: vector staging with register prefetch;
+// NPF > 0: planes of width 4*Q4 floats (4, 16 or 32), Fout % 4 == 0: vector staging with register prefetch;
 // NPF == 0: generic scalar staging
 constexpr int WG_NT = 256;      // 8 warps: all of them stage tiles, warps 0-3 own the TMEM lanes of the epilogue (ncu: the
                                 // 128-thread version was paced by its own instruction stream at 8 warps per SM)
@@ -744,7 +744,8 @@ int launch_wgrad_tc(const WgradArgs &a, int has_bias, int M4, int N4, int *npart
     if (!g_tc_enabled) return 0;
     const int M = a.in_planes * a.in_w;
     if (M + (has_bias ? 1 : 0) > 128 || M4 > 128 || a.n_out > 32 || a.rows < 256) return 0;
-    const bool fast = ((a.in_w == 16 && a.in_planes <= 6) || (a.in_w == 4 && a.in_planes <= 8)) && (a.n_out % 4 == 0) && aligned16(a.in0) &&
+    const bool fast = ((a.in_w == 16 && a.in_planes <= 6) || (a.in_w == 4 && a.in_planes <= 8) || (a.in_w == 32 && a.in_planes <= 3)) &&
+                      (a.n_out % 4 == 0) && aligned16(a.in0) &&
                       (a.in_planes == 1 || aligned16(a.in_rest)) && aligned16(a.dy) && (!a.mask || aligned16(a.mask));
     static const bool allow_generic = getenv("MVB_TC_PACKED") != nullptr;
     if (!fast && !allow_generic) return 0;
@@ -771,6 +772,12 @@ int launch_wgrad_tc(const WgradArgs &a, int has_bias, int M4, int N4, int *npart
     int rc;
     if (!fast) {
         rc = launch_wgrad_t<0, 1>(t, (unsigned)grid, smem, st);
+    } else if (a.in_w == 32) {
+        switch (a.in_planes) {
+            case 1: rc = launch_wgrad_t<1, 8>(t, (unsigned)grid, smem, st); break;
+            case 2: rc = launch_wgrad_t<2, 8>(t, (unsigned)grid, smem, st); break;
+            default: rc = launch_wgrad_t<3, 8>(t, (unsigned)grid, smem, st); break;
+        }
     } else if (a.in_w == 16) {
         switch (a.in_planes) {
             case 1: rc = launch_wgrad_t<1, 4>(t, (unsigned)grid, smem, st); break;

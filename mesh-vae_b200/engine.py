@@ -18,6 +18,19 @@ from . import _lib, dp
 from ._lib import lib, check, ptr, stream_ptr
 
 
+class _HyperGroup(dict):
+    """optimizer.param_groups[0] of torch.optim.Adam: item assignment reaches the device-resident hyper-parameters"""
+
+    def __init__(self, opt):
+        super().__init__(lr=opt.lr, betas=opt.betas, eps=opt.eps, weight_decay=opt.weight_decay, amsgrad=False)
+        self._opt = opt
+
+    def __setitem__(self, key, value):
+        super().__setitem__(key, value)
+        if key in ("lr", "betas", "eps", "weight_decay"):
+            setattr(self._opt, key, value)
+
+
 class FlatAdam:
     """Adam(lr, betas, eps, weight_decay) with torch.optim.Adam's arithmetic (main.py:251) as one
     fused kernel over a flat parameter buffer; parameters are re-pointed to views of that buffer."""
@@ -40,16 +53,46 @@ class FlatAdam:
         self.m = torch.zeros_like(self.flat_p)
         self.v = torch.zeros_like(self.flat_p)
         self.step_count = torch.zeros((), device=dev, dtype=torch.int64)
-        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        # hyper-parameters live in DEVICE memory (lr, beta1, beta2, eps, weight_decay, grad_scale): the kernel reads them
+        # at run time, so a captured step graph follows `opt.lr = ...` / `set_lr()` (the per-epoch schedule of
+        # main.py:266-269) and formats.load_adam_state_dict without re-capture
+        self._hp_host = [float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay), 1.0]
+        self.hyper = torch.tensor(self._hp_host, device=dev, dtype=torch.float32)
+        # the view torch.optim.Adam offers to main.py:266-269 (`for p in optimizer.param_groups: p['lr'] = ...`)
+        self.param_groups = [_HyperGroup(self)]
+
+    def _set_hp(self, i: int, v: float):
+        v = float(v)
+        if self._hp_host[i] != v:
+            self._hp_host[i] = v
+            self.hyper[i:i + 1].copy_(torch.tensor([v], dtype=torch.float32), non_blocking=False)
+
+    lr = property(lambda self: self._hp_host[0], lambda self, v: self._set_hp(0, v))
+    eps = property(lambda self: self._hp_host[3], lambda self, v: self._set_hp(3, v))
+    weight_decay = property(lambda self: self._hp_host[4], lambda self, v: self._set_hp(4, v))
+    grad_scale = property(lambda self: self._hp_host[5], lambda self, v: self._set_hp(5, v))
+
+    @property
+    def betas(self):
+        return (self._hp_host[1], self._hp_host[2])
+
+    @betas.setter
+    def betas(self, b):
+        self._set_hp(1, b[0])
+        self._set_hp(2, b[1])
+
+    def set_lr(self, lr: float):
+        """learning rate of the NEXT step, captured graphs included"""
+        self.lr = lr
 
     def pack_grads(self):
         """one multi-tensor copy of the per-parameter gradients into the flat exchange buffer"""
         dp.pack_grads(self.params, self.grad_views)
 
     def step(self, grad_scale: float = 1.0):
-        check(lib.mvb_adam_step(self.n, ptr(self.flat_p), ptr(self.flat_g), ptr(self.m), ptr(self.v),
-                                ptr(self.step_count), self.lr, self.betas[0], self.betas[1], self.eps,
-                                self.weight_decay, grad_scale, stream_ptr()), "mvb_adam_step")
+        self.grad_scale = grad_scale
+        check(lib.mvb_adam_step_hp(self.n, ptr(self.flat_p), ptr(self.flat_g), ptr(self.m), ptr(self.v),
+                                   ptr(self.step_count), ptr(self.hyper), stream_ptr()), "mvb_adam_step_hp")
 
 
 class TrainEngine:

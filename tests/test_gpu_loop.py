@@ -9,7 +9,8 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from tests.helpers import OPERATORS_NPZ, seeded_state_dict, rel_err
+from tests.helpers import OPERATORS_NPZ, GOLDEN, seeded_state_dict, rel_err
+from tests.synthetic import SyntheticHips, ref_train as _ref_train, ref_evaluate as _ref_evaluate, _euclid
 from oracle import mesh_vae_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -27,37 +28,6 @@ def ops():
     return O.load_operators(OPERATORS_NPZ)
 
 
-class _Data:
-    def __init__(self, x):
-        self.x, self.y, self.edge_index = x, x, torch.zeros(2, 1, dtype=torch.long)
-
-
-class SyntheticHips(torch.utils.data.Dataset):
-    """MeshData-shaped items (data.py:103-111): template + smooth noise, random similarity transforms"""
-
-    def __init__(self, n=N_MESH, seed=3):
-        d = np.load(OPERATORS_NPZ)
-        tv = d["template_v"]
-        rng = np.random.default_rng(seed)
-        self.aligned = [tv + rng.normal(size=tv.shape) * 0.8 for _ in range(n)]              # "mtx2" of the Procrustes fit
-        self.mean, self.std = np.mean(self.aligned, 0), np.std(self.aligned, 0) + 1e-3
-        self.R, self.s, self.m, self.ori = [], [], [], []
-        for a in self.aligned:
-            q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
-            s, m = rng.uniform(0.5, 2.0), rng.normal(size=(1, 3)) * 10
-            self.R.append(torch.FloatTensor(q)); self.s.append(torch.FloatTensor([s])); self.m.append(torch.FloatTensor(m))
-            self.ori.append(torch.Tensor((a * s) @ q + m + rng.normal(size=a.shape) * 0.05))   # the original scan
-        self.labels = [int(v) for v in rng.integers(0, 2, n)]
-
-    def __len__(self):
-        return len(self.aligned)
-
-    def __getitem__(self, i):
-        ori = (torch.tensor(self.aligned[i]) - torch.tensor(self.mean)) / torch.tensor(self.std)   # float64, data.py:106
-        return (_Data(ori.float()), ori, self.labels[i], f"/scans/hip_{'fm'[self.labels[i]]}_{i}.obj", self.ori[i],
-                self.R[i], self.m[i], self.s[i])
-
-
 def _models(mvb, ops, dropout=0.0):
     A, D, U, nn_ = ops
     cfg = copy.deepcopy(O.DEFAULT_CONFIG)
@@ -69,61 +39,6 @@ def _models(mvb, ops, dropout=0.0):
                        model=cfg["model"])
     net.load_state_dict(seeded_state_dict(net, 7))
     return ref, net.to(dev)
-
-
-def _euclid(a, b):
-    return np.sqrt(((a - b) ** 2).sum(-1))          # main.py:51-52
-
-
-def _ref_train(model, loader, optimizer, mean, std):
-    """main.py:54-96 restated on the oracle model (host bookkeeping per batch, as the reference does it)"""
-    model.train()
-    tot = dict(n=0, loss=0.0, kld=0.0, rec=0.0, err=0.0, correct=0)
-    for batch, x_gt, y, _, gt_mesh, R, m, s in loader:
-        b = batch.num_graphs
-        x = batch.x.reshape(b, -1, 3)
-        hot = F.one_hot(y, num_classes=2)
-        optimizer.zero_grad()
-        loss, correct, out, z, _ = model(x, x_gt, hot, m_type="train")
-        loss.backward()
-        optimizer.step()
-        tot["n"] += b
-        tot["loss"] += loss.detach().numpy() * b
-        tot["kld"] += z[0].mean().detach().numpy() * b
-        tot["rec"] += z[1].mean().detach().numpy() * b
-        tot["correct"] += int(correct)
-        rm = torch.bmm((out.detach() * std + mean) * s.unsqueeze(1), R) + m
-        tot["err"] += _euclid(rm.numpy(), gt_mesh.numpy()).mean() * b
-    n = tot["n"]
-    return tot["loss"] / n, tot["kld"] / n, tot["rec"] / n, tot["err"] / n, tot["correct"] / n
-
-
-def _ref_evaluate(model, loader, mean, std):
-    """main.py:98-180 restated (vis=False)"""
-    model.eval()
-    tot = dict(n=0, loss=0.0, kld=0.0, rec=0.0, correct=0, acc=0)
-    errors, metas = [], []
-    with torch.no_grad():
-        for batch, x_gt, y, _, gt_mesh, R, m, s in loader:
-            b = batch.num_graphs
-            x = batch.x.reshape(b, -1, 3)
-            hot = F.one_hot(y, num_classes=2)
-            loss, correct, out, z, _ = model(x, x_gt, hot, m_type="test")
-            tot["n"] += b
-            tot["loss"] += loss.numpy() * b
-            tot["kld"] += z[0].mean().numpy() * b
-            tot["rec"] += z[1].mean().numpy() * b
-            tot["correct"] += int(correct)
-            rm = torch.bmm((out * std + mean) * s.unsqueeze(1), R) + m
-            errors.append(_euclid(rm.numpy(), gt_mesh.numpy()))
-            oppo = 1 - hot
-            oppo_x = model.sample(oppo, z[2])
-            pred = torch.argmax(model.classifier(model.encoder(oppo_x)), 1)
-            tot["acc"] += int((pred == torch.argmax(oppo, 1)).sum())
-            metas.append((torch.bmm((oppo_x * std + mean) * s.unsqueeze(1), R) + m).numpy())
-    n = tot["n"]
-    return (tot["loss"] / n, tot["kld"] / n, tot["rec"] / n, tot["correct"] / n, np.concatenate(errors, 0), tot["acc"] / n,
-            np.concatenate(metas, 0))
 
 
 def _loader(mvb, ds):
@@ -315,3 +230,37 @@ def test_inference_loop_reports_and_meshes(mvb, ops, tmp_path):
     errs = json.load(open(tmp_path / "error_list.json"))
     assert all(len(val.split(".")[1]) == 4 for val in errs.values())               # '.4f' (inference.py:122)
     assert len(os.listdir(tmp_path / "sex_change")) == 18
+
+
+def test_train_and_evaluate_match_the_references_own_loops(mvb, ops, tmp_path):
+    """f3 pin: loop.train / loop.evaluate against the return tuples of the reference's OWN main.train (main.py:54-96)
+    and main.evaluate (main.py:98-179), run unchanged by tests/golden/make_golden_loops.py on the same dataset,
+    parameters, optimizer and noise seed: evaluate, two training epochs, evaluate."""
+    from meshvae_b200 import loop
+    gl = np.load(os.path.join(GOLDEN, "golden_loops.npz"))
+    ds = SyntheticHips(n=10, seed=3)
+    mean, std = torch.FloatTensor(ds.mean), torch.FloatTensor(ds.std)
+    _, net = _models(mvb, ops)
+    dev = torch.device("cuda:0")
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=5e-4)
+    torch.manual_seed(4321)
+
+    def check_eval(tag):
+        loss, kld, rec, correct, errors, acc = loop.evaluate(0, net, _loader(mvb, ds), dev, norm=(mean, std))
+        want = gl[f"{tag}_scalars"]
+        for g, w, name in zip((loss, kld, rec, correct, acc), want, ("loss", "kld", "rec", "correct", "acc")):
+            assert abs(float(g) - float(w)) <= 2e-4 * max(1.0, abs(float(w))), (tag, name, float(g), float(w))
+        we = gl[f"{tag}_errors"]
+        assert errors.shape == we.shape and np.abs(errors - we).max() <= 2e-4 * we.max(), tag
+
+    check_eval("eval0")
+    for e in range(2):
+        got = loop.train(net, _loader(mvb, ds), opt, dev, norm=(mean, std))
+        for g, w, name in zip(got, gl[f"train{e}"], ("loss", "kld", "rec", "err", "acc")):
+            assert abs(float(g) - float(w)) <= 2e-4 * max(1.0, abs(float(w))), (e, name, float(g), float(w))
+    # after 6 Adam steps single weights may sit a step apart (sign-like first updates, see above): the epoch statistics
+    # of the second evaluation are compared at 1e-3
+    loss, kld, rec, correct, errors, acc = loop.evaluate(0, net, _loader(mvb, ds), dev, norm=(mean, std))
+    want = gl["eval1_scalars"]
+    assert abs(float(loss) - want[0]) <= 1e-3 * abs(want[0]) and abs(float(rec) - want[2]) <= 1e-3 * abs(want[2])
+    assert np.abs(errors - gl["eval1_errors"]).max() <= 5e-3 * gl["eval1_errors"].max()
