@@ -56,6 +56,13 @@ int mvb_set_tensor_cores(int enable);
  * mesh_tc; documented next to mvb_tune in csrc/mvb_api.cu).  Results are bit-identical for every setting of the
  * grid-shape keys; mesh_tc / fused_recurrence select between implementations tested against each other. */
 int mvb_tune(const char *spec);
+/* Deferred side chains: with mvb_tune("defer_wgrad=1") the weight-gradient reductions of mvb_cheb_layer_bwd run on an
+ * internal per-device side stream and are joined into the caller's stream lazily (after the next such chain has been
+ * started) instead of before the call returns - they then overlap the next layer's backward kernel.  The caller must
+ * (1) keep every buffer of the call (workspace, x, dweight, dbias) alive and untouched until it has called
+ * mvb_side_join(stream), which makes `stream` wait for the pending chain, and (2) call it before reading any gradient
+ * and before a stream capture ends.  Default off: every call joins before it returns. */
+int mvb_side_join(void *stream);
 
 /* step-engine plumbing: cudaStreamWaitEvent(stream, event, cudaEventWaitExternal).  Legal during stream
  * capture (becomes an external event-wait node): each replay of the captured graph waits for the latest

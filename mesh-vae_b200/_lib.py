@@ -39,6 +39,7 @@ SIGNATURES = {
     "mvb_launch_count": (c_int64, []),
     "mvb_set_tensor_cores": (c_int, [c_int]),
     "mvb_tune": (c_int, [c_char_p]),
+    "mvb_side_join": (c_int, [_vp]),
     "mvb_stream_wait_external_event": (c_int, [_vp, _vp]),
     "mvb_csr_from_coo_host": (c_int, [c_int64, c_int64, c_int64, _vp, _vp, _vp, c_int, _vp, _vp, _vp]),
     "mvb_spmm": (c_int, [c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_float, c_float, c_int64, _vp]),
@@ -96,6 +97,22 @@ def check(rc: int, what: str = ""):
 def tune(spec: str):
     """A/B tuning hooks (include/mvb.h: mvb_tune), e.g. tune("spmm_mode=1;mesh_tc=1,2")"""
     check(lib.mvb_tune(spec.encode()), "mvb_tune")
+
+
+# Deferred side chains (include/mvb.h: mvb_side_join): while on, the tensors a chain still reads are parked here until
+# the join, so that the caching allocator cannot hand their memory to a later kernel of the main stream
+_deferred = {"on": False, "keep": []}
+
+
+def defer_side_chains(on: bool):
+    _deferred["on"] = bool(on)
+    tune(f"defer_wgrad={1 if on else 0}")
+
+
+def side_join():
+    """make the current stream wait for the pending side chain and release the parked tensors"""
+    check(lib.mvb_side_join(stream_ptr()), "mvb_side_join")
+    _deferred["keep"].clear()
 
 
 def ptr(t):

@@ -262,6 +262,84 @@ void side_join(cudaStream_t side, cudaStream_t st) {
 }
 }  // namespace mvb
 
+// ---------------------------------------------------------------------------------------------
+// Deferred side chains.  The weight-gradient reduction of a mesh-resident layer (tc_wgrad + finalize kernels, 10-20 us)
+// is not on the critical path of the backward pass: nothing reads dW / db before the optimizer.  In deferred mode
+// (mvb_tune "defer_wgrad=1", switched on by the step engine around its backward pass) such a chain is forked onto a
+// per-device side stream and joined back into the caller's stream only AFTER the next chain's producer kernel has been
+// enqueued (lazy_fork), or by mvb_side_join - so it overlaps the following layer's backward kernel; in a captured CUDA
+// graph the two become parallel branches.  Off (default): the chain is joined before the call returns.
+// The state is per device and process-wide (autograd runs backward functions on its own thread).
+// ---------------------------------------------------------------------------------------------
+#include <mutex>
+namespace mvb {
+struct LazySide {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    bool tried = false, ok = false, pending = false;
+};
+static LazySide g_lazy[64];
+static std::mutex g_lazy_mu;
+static int g_defer_wgrad = 0;
+void set_defer_wgrad(int v) { g_defer_wgrad = v ? 1 : 0; }
+
+static LazySide *lazy_side() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    LazySide &s = g_lazy[dev];
+    if (!s.tried) {
+        s.tried = true;
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess)
+            s.ok = true;
+        else
+            cudaGetLastError();
+    }
+    return s.ok ? &s : nullptr;
+}
+
+// make `st` wait for a pending chain (if any)
+static void lazy_join_locked(LazySide *s, cudaStream_t st) {
+    if (s && s->pending) {
+        cudaStreamWaitEvent(st, s->join, 0);
+        s->pending = false;
+    }
+}
+
+// Call AFTER the producer kernel of the chain has been enqueued on `st`.  Joins the previous chain into `st`, forks the
+// side stream from `st`; returns the stream to enqueue the chain on, or NULL (not deferred / unavailable): run it on `st`.
+cudaStream_t lazy_fork(cudaStream_t st) {
+    if (!g_defer_wgrad) return nullptr;
+    std::lock_guard<std::mutex> lk(g_lazy_mu);
+    LazySide *s = lazy_side();
+    if (!s) return nullptr;
+    lazy_join_locked(s, st);
+    if (cudaEventRecord(s->fork, st) != cudaSuccess || cudaStreamWaitEvent(s->stream, s->fork, 0) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return s->stream;
+}
+
+// the chain has been enqueued on `side`: record its end; it is joined by the next lazy_fork or by mvb_side_join
+void lazy_done(cudaStream_t side, cudaStream_t st) {
+    if (!side) return;
+    std::lock_guard<std::mutex> lk(g_lazy_mu);
+    LazySide *s = lazy_side();
+    if (!s || s->stream != side) return;
+    cudaEventRecord(s->join, s->stream);
+    s->pending = true;
+    if (!g_defer_wgrad) lazy_join_locked(s, st);
+}
+}  // namespace mvb
+
+extern "C" int mvb_side_join(void *stream) {
+    std::lock_guard<std::mutex> lk(mvb::g_lazy_mu);
+    mvb::lazy_join_locked(mvb::lazy_side(), (cudaStream_t)stream);
+    return MVB_OK;
+}
+
 extern "C" int mvb_cheb_bwd_uses_basis(int Fin, int Fout, int need_dx) { return adjoint_form(Fin, Fout, need_dx) ? 0 : 1; }
 
 extern "C" size_t mvb_cheb_bwd_workspace_bytes(int N, int B, int Fin, int Fout, int K, int n_active, int need_dx) {
@@ -546,6 +624,7 @@ extern "C" int mvb_stream_wait_external_event(void *stream, void *event) {
 //   spmm_shape=tx,chunk / spmm_mode=m   SpMM block shape / size (0 = automatic)
 //   overlap=0|1        side-stream fork inside mvb_cheb_bwd
 //   mesh_tc=e,c        tensor-core mesh layers on/off, CTAs per mesh (0 = automatic)
+//   defer_wgrad=0|1    weight-gradient chains of the mesh layers joined lazily (engine only; see mvb_side_join)
 //   mesh_dbg=bits      timing probes of the tensor-core mesh forward kernel (1 no MMAs, 2 no recurrence, 4 no epilogue):
 //                      results are then wrong - scripts/mesh_tc_probe.py only
 // ---------------------------------------------------------------------------------------------
@@ -579,6 +658,7 @@ extern "C" int mvb_tune(const char *spec) {
         else if (!strcmp(key, "overlap")) g_overlap = v[0] ? 1 : 0;
         else if (!strcmp(key, "mesh_tc")) set_mesh_tc(v[0], v[1]);
         else if (!strcmp(key, "mesh_dbg")) set_mesh_dbg(v[0]);
+        else if (!strcmp(key, "defer_wgrad")) set_defer_wgrad(v[0]);
         else if (key[0]) return set_err(MVB_EINVAL, "mvb_tune: unknown key '%s'", key);
     }
     return MVB_OK;

@@ -166,6 +166,10 @@ int launch_mesh_tc_bwd(int N, int B, int Fin, int Fout, int K, const int32_t *Lt
 // ordered sum over the meshes of per-mesh partials (mvb_layer.cu): dw[j] = sum_b dwp[b][j], db likewise
 int launch_layer_finalize(int B, int nw, int nb, const float *dwp, const float *dbp, float *dw, float *db, cudaStream_t st);
 
+// deferred side chains (mvb_api.cu): see lazy_fork / lazy_done / mvb_side_join
+cudaStream_t lazy_fork(cudaStream_t st);
+void lazy_done(cudaStream_t side, cudaStream_t st);
+
 // fork a per-thread side stream from `st` (NULL: no overlap) / make `st` wait for it again (mvb_api.cu)
 cudaStream_t side_fork(cudaStream_t st);
 void side_join(cudaStream_t side, cudaStream_t st);

@@ -936,14 +936,14 @@ int launch_mesh_tc_bwd(int N, int B, int Fin, int Fout, int K, const int32_t *Lt
         default: rc = launch_mesh_bwd_t<32>(g, st); break;
     }
     if (rc) return rc;
-    if (dbias) {
-        rc = launch_layer_finalize(B, 0, Fout, nullptr, g.dbp, nullptr, dbias, st);
-        if (rc) return rc;
-    }
+    // db and dW off the critical path: on the deferred side chain when the step engine has switched it on
+    cudaStream_t side = lazy_fork(st);
+    cudaStream_t ws_st = side ? side : st;
+    if (dbias) rc = launch_layer_finalize(B, 0, Fout, nullptr, g.dbp, nullptr, dbias, ws_st);
     // dW_k[i][o] = sum_rows T_0[row][i] S_k[row][o]: streaming tensor-core reduction over all meshes, plane groups
     const int64_t rows = (int64_t)N * B;
     const int grp = wgrad_group(K, Fout);
-    for (int k0 = 0; k0 < K; k0 += grp) {
+    for (int k0 = 0; k0 < K && !rc; k0 += grp) {
         const int np = K - k0 < grp ? K - k0 : grp;
         WgradArgs wa;
         memset(&wa, 0, sizeof(wa));
@@ -958,11 +958,13 @@ int launch_mesh_tc_bwd(int N, int B, int Fin, int Fout, int K, const int32_t *Lt
         wa.partial_bytes = al256(wgrad_partial_bytes(np * Fout, Fin));
         ws += wa.partial_bytes;
         int nA = 0, m4A = 0;
-        rc = launch_wgrad_partials(wa, 0, &nA, &m4A, st);
-        if (rc) return rc;
-        rc = launch_wgrad_finalize(wa.partials, nA, m4A, nullptr, 0, 0, Fin, np * Fin, Fout, dweight + (int64_t)k0 * Fin * Fout, nullptr, st, 1);
-        if (rc) return rc;
+        rc = launch_wgrad_partials(wa, 0, &nA, &m4A, ws_st);
+        if (!rc)
+            rc = launch_wgrad_finalize(wa.partials, nA, m4A, nullptr, 0, 0, Fin, np * Fin, Fout, dweight + (int64_t)k0 * Fin * Fout, nullptr,
+                                       ws_st, 1);
     }
+    lazy_done(side, st);          // on every path: a captured graph must not end forked
+    if (rc) return rc;
     return 1;
 }
 

@@ -20,6 +20,19 @@ def shard_bounds(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
     return rank * per, (rank + 1) * per
 
 
+def ragged_bounds(global_batch: int, rank: int, world: int) -> Tuple[int, int]:
+    """slice of a global batch that does NOT divide evenly (the last batch of an epoch without drop_last): as even as
+    it can be; a rank may own nothing"""
+    return global_batch * rank // world, global_batch * (rank + 1) // world
+
+
+def ragged_weight(global_batch: int, rank: int, world: int) -> float:
+    """factor for a rank's local-MEAN gradient so that (sum over ranks) / world is the gradient of the mean over the
+    whole global batch: local_count * world / global_batch (0 for a rank whose slice is empty)"""
+    lo, hi = ragged_bounds(global_batch, rank, world)
+    return (hi - lo) * world / float(global_batch)
+
+
 def live_parameters(params: Sequence[torch.nn.Parameter]) -> List[torch.nn.Parameter]:
     """parameters that received a gradient (dec_lin_1 of cheb_VAE never does, quirk 7; torch's Adam
     skips such parameters, and so does the flat exchange buffer)"""

@@ -200,6 +200,16 @@ class TrainEngine:
             self.kld, self.rec, self.correct = kld, rec, correct
             self.recon = recon.detach()         # [B,N,3] view of the decoder buffer (no autograd graph attached)
             self._fwd_out = None
+        _lib.defer_side_chains(True)          # weight-gradient chains of the mesh layers overlap the next layer (joined below)
+        try:
+            sel = self._backward_part(part, loss if part in (0, 1) else None)
+        finally:
+            _lib.side_join()
+            _lib.defer_side_chains(False)
+        if sel:       # autograd-routed gradients into their views (all of them live in bucket 2)
+            torch._foreach_copy_([v for _, v in sel], [p.grad for p, _ in sel])
+
+    def _backward_part(self, part: int, loss):
         if part == 0:
             loss.backward()
             self._cut = None
@@ -214,8 +224,7 @@ class TrainEngine:
             sel = [(p, v) for p, v in self.loose if id(p) in self._enc_ids]
             torch.autograd.backward([self._cut], [self._cut_grad])
             self._cut = self._cut_grad = None
-        if sel:       # autograd-routed gradients into their views (all of them live in bucket 2)
-            torch._foreach_copy_([v for _, v in sel], [p.grad for p, _ in sel])
+        return sel
 
     def _fwd_bwd(self):
         self._fwd()
@@ -385,9 +394,14 @@ class TrainEngine:
         if self._staged:
             torch.cuda.current_stream().wait_event(self._ev_staged)
 
-    def ragged_step(self, x: torch.Tensor, x_gt: torch.Tensor, y_hot: torch.Tensor, eps: Optional[torch.Tensor] = None):
+    def ragged_step(self, x: torch.Tensor, x_gt: torch.Tensor, y_hot: torch.Tensor, eps: Optional[torch.Tensor] = None,
+                    grad_weight: float = 1.0):
         """the last, smaller batch of an epoch (DataLoader without drop_last, main.py:256): same kernels, same flat
-        optimizer, not graph-replayed (the graphs are captured for `batch` meshes).  Device tensors in."""
+        optimizer, not graph-replayed (the graphs are captured for `batch` meshes).  Device tensors in.
+        Data parallel: EVERY rank must take this path for the same step (one all-reduce of the whole flat buffer, where
+        the graph path issues two bucketed ones - loop.train_epoch decides from the global batch size); `grad_weight`
+        = dp.ragged_weight(...) makes the average over ranks the gradient of the global-batch mean when the slices
+        are unequal (0 for a rank that only holds a stand-in item)."""
         for p, _ in self.loose:
             p.grad = None
         self.net.keep_encoder_conv_out = False
@@ -398,6 +412,8 @@ class TrainEngine:
         if self.loose:
             torch._foreach_copy_([v for _, v in self.loose], [p.grad for p, _ in self.loose])
         if self.distributed:
+            if grad_weight != 1.0:
+                self.opt.flat_g.mul_(float(grad_weight))
             dp.allreduce_sum_(self.opt.flat_g)
         self._optim()
         return loss.detach(), kld, rec, correct, recon.detach()

@@ -523,6 +523,12 @@ class _ChebLayerFn(torch.autograd.Function):
                                      u.nnz if u else 0, n_out, ptr(d_op.colidx) if d_op is not None else None, ptr(x_vm), ptr(w),
                                      ptr(y) if ctx.relu else None, ptr(dy), ptr(dx), ptr(dw), ptr(db), ptr(ws), ws_bytes,
                                      stream_ptr()), "mvb_cheb_layer_bwd")
+        if _lib._deferred["on"]:
+            if sw is not None and (sb is not None or not ctx.has_bias):
+                # the weight-gradient chain may still be running on the side stream: it reads ws / x and writes the sinks
+                _lib._deferred["keep"].append((ws, x_vm, w, dy, dw, db))
+            else:
+                _lib.side_join()          # gradients handed back to autograd must be complete on this stream
         return dx, _ret(sw, dw), _ret(sb, db), None, None, None, None
 
 

@@ -85,6 +85,12 @@ class ShardedMeshLoader:
         n = len(self.dataset)
         return n // g if self.drop_last else (n + g - 1) // g
 
+    def global_chunk_sizes(self) -> List[int]:
+        """items of every GLOBAL batch of an epoch (identical on all ranks): the step engine takes its replayed-graph
+        path only for full global batches - a decision every rank must make alike, or their collectives mismatch"""
+        g, n = self.batch_size * self.world, len(self.dataset)
+        return [min(g, n - i * g) for i in range(len(self))]
+
     def index_batches(self) -> Iterator[np.ndarray]:
         order = self.global_order()
         g = self.batch_size * self.world
@@ -93,7 +99,7 @@ class ShardedMeshLoader:
             if len(chunk) % self.world == 0:
                 lo, hi = dp.shard_bounds(len(chunk), self.rank, self.world)
             else:                                   # ragged final global batch: as even as it can be
-                lo, hi = len(chunk) * self.rank // self.world, len(chunk) * (self.rank + 1) // self.world
+                lo, hi = dp.ragged_bounds(len(chunk), self.rank, self.world)
             mine = chunk[lo:hi]
             yield mine if len(mine) else chunk[:1]
 

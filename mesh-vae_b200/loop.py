@@ -16,9 +16,10 @@ import os
 
 import numpy as np
 import torch
+import torch.distributed as dist
 import torch.nn.functional as F
 
-from . import formats
+from . import dp, formats
 from . import functional as Fn
 
 
@@ -72,25 +73,48 @@ def train_epoch(engine, train_loader, checkpoint_dir=None, norm=None):
         xt = (x if torch.is_tensor(x) else x.x).reshape(b, engine.n_vert, engine.feat)
         return b, (xt, x_gt.reshape(b, engine.n_vert, engine.feat), y)
 
+    # Which path a step takes - the replayed graphs (bucketed all-reduces) or the uncaptured ragged step (one
+    # all-reduce) - must be the SAME on every rank: it is decided from the size of the GLOBAL batch (a loader that
+    # knows it: ShardedMeshLoader.global_chunk_sizes), else by agreement (a MIN all-reduce of "my slice is full").
+    world, rank = engine.world, (dist.get_rank() if engine.world > 1 else 0)
+    sizes = train_loader.global_chunk_sizes() if hasattr(train_loader, "global_chunk_sizes") else None
+
+    def full_everywhere(i, b):
+        if world == 1:
+            return b == engine.batch, 1.0
+        if sizes is not None:
+            g = sizes[i]
+            return g == engine.batch * world, dp.ragged_weight(g, rank, world)
+        flag = torch.tensor([1 if b == engine.batch else 0, b], device=dev, dtype=torch.int64)
+        both = [torch.zeros_like(flag) for _ in range(world)]
+        dist.all_gather(both, flag)
+        g = int(sum(int(t[1]) for t in both))
+        return all(int(t[0]) for t in both), b * world / float(max(g, 1))
+
     it = iter(train_loader)
     cur = next(it, None)
     staged = False
+    i = 0
+    cur_full = full_everywhere(0, host_batch(cur)[0]) if cur is not None else (False, 1.0)
     while cur is not None:
         nxt = next(it, None)
         b, hb = host_batch(cur)
+        nxt_full = full_everywhere(i + 1, host_batch(nxt)[0]) if nxt is not None else (False, 1.0)
         _, _, _, _, gt_mesh, R, m, s = _split(cur)
-        if b == engine.batch:
+        if cur_full[0]:
             if not staged:
                 engine.stage(*hb)
-            nb = host_batch(nxt) if nxt is not None else (0, None)
-            staged = nb[0] == engine.batch
-            engine.step_prefetched(nb[1] if staged else None, sync=False)
+            staged = nxt is not None and nxt_full[0]
+            engine.step_prefetched(host_batch(nxt)[1] if staged else None, sync=False)
             loss, kld, rec, correct, recon = engine.loss, engine.kld, engine.rec, engine.correct, engine.recon
         else:
             xt, x_gt, y = hb
             y_hot = F.one_hot(y, num_classes=engine.net.num_class).to(dev)
-            loss, kld, rec, correct, recon = engine.ragged_step(xt.to(dev), x_gt.to(dev, engine.x_gt.dtype), y_hot)
+            loss, kld, rec, correct, recon = engine.ragged_step(xt.to(dev), x_gt.to(dev, engine.x_gt.dtype), y_hot,
+                                                                grad_weight=cur_full[1])
             staged = False
+        i += 1
+        cur_full = nxt_full
         mean_err, _ = Fn.recon_error(recon, mean, std, s, R, m, gt_mesh)
         meter.add(loss, kld, rec, correct, mean_err)
         cur = nxt

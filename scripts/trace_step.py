@@ -38,7 +38,7 @@ evs.sort(key=lambda e: e.time_range.start)
 steps, cur = [], []
 for e in evs:
     cur.append(e)
-    if "adam_kernel" in e.name:
+    if "adam_kernel" in e.name or "adam_hp_kernel" in e.name:
         steps.append(cur)
         cur = []
 st = steps[1] if len(steps) > 1 else steps[0]
