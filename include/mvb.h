@@ -57,8 +57,8 @@ int mvb_set_tensor_cores(int enable);
  * grid-shape keys; mesh_tc / fused_recurrence select between implementations tested against each other. */
 int mvb_tune(const char *spec);
 /* Deferred side chains: with mvb_tune("defer_wgrad=1") the weight-gradient reductions of mvb_cheb_layer_bwd run on an
- * internal per-device side stream and are joined into the caller's stream lazily (after the next such chain has been
- * started) instead of before the call returns - they then overlap the next layer's backward kernel.  The caller must
+ * internal per-device side stream (as does the weight-gradient branch of mvb_cheb_bwd) and are NOT joined into the
+ * caller's stream before the call returns - they then overlap the following layers' backward kernels.  The caller must
  * (1) keep every buffer of the call (workspace, x, dweight, dbias) alive and untouched until it has called
  * mvb_side_join(stream), which makes `stream` wait for the pending chain, and (2) call it before reading any gradient
  * and before a stream capture ends.  Default off: every call joins before it returns. */
@@ -240,6 +240,24 @@ int mvb_adam_step(int64_t n, float *p, const float *g, float *m, float *v, int64
  * optimizer.param_groups[..]['lr']) and a restored optimizer state without re-capture. */
 int mvb_adam_step_hp(int64_t n, float *p, const float *g, float *m, float *v, int64_t *step, const float *hyper,
                      void *stream);
+
+/* ---- A3 + A5 fused on the step-by-step path: Chebyshev convolution + row selection -------------------------------
+ * (the encoder loop body  x = relu(cheb[i](x, L)); x = pool(x, D)  models/cheb_VAE.py:264-265, at the levels too large
+ *  for the mesh-resident kernels: level 0 of the template; D is a row selection, mesh_operations.py:72-85.)
+ * y_sel [n_sel,B,Fout] = act(conv(x))[sel]: only the rows D keeps (1/4) are contracted and written.  basis as for
+ * mvb_cheb_fwd ((K-1) planes [N,B,Fin], all rows - kept for the backward pass).
+ * mvb_cheb_sel_bwd: dW / db of such a layer when its input needs NO gradient (the first encoder layer: the basis form
+ * dW_k = T_k^T G, db = 1^T G, G = dy_sel * [y_sel > 0] reduced over the selected rows only - G is zero elsewhere).
+ * mvb_cheb_sel_supported: 1 for the plane widths of the tensor-core kernels (Fin 4 / 16 / 32, Fout % 4 == 0, <= 32), else 0 -
+ * the caller then composes mvb_cheb_fwd + mvb_pool_fwd. */
+int mvb_cheb_sel_supported(int N, int B, int Fin, int Fout, int K, int n_sel);
+int mvb_cheb_sel_fwd(int N, int B, int Fin, int Fout, int K, int nnz, const int32_t *rowptr, const int32_t *colidx,
+                     const float *vals, const float *x, const float *weight, const float *bias, int relu, int n_sel,
+                     const int32_t *sel, float *basis, float *y_sel, void *stream);
+size_t mvb_cheb_sel_bwd_workspace_bytes(int Fin, int Fout, int K);
+int mvb_cheb_sel_bwd(int N, int B, int Fin, int Fout, int K, const float *x, const float *basis, const float *y_sel_for_relu,
+                     const float *dy_sel, int n_sel, const int32_t *sel, float *dweight, float *dbias, void *workspace,
+                     size_t workspace_bytes, void *stream);
 
 /* ---- A12 fused: one whole encoder / decoder layer of a COARSE level per launch ---------------
  * (models/cheb_VAE.py:264-265  x = relu(cheb[i](x, L)); x = pool(x, D)   and

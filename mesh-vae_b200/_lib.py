@@ -61,6 +61,10 @@ SIGNATURES = {
     "mvb_kld_bwd": (c_int, [c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mvb_gaussian_nll_fwd": (c_int, [c_int64, _vp, _vp, c_int, c_float, _vp, _vp]),
     "mvb_gaussian_nll_bwd": (c_int, [c_int64, _vp, _vp, c_int, c_float, _vp, _vp, _vp]),
+    "mvb_cheb_sel_supported": (c_int, [c_int] * 6),
+    "mvb_cheb_sel_fwd": (c_int, [c_int] * 6 + [_vp] * 6 + [c_int, c_int] + [_vp] * 4),
+    "mvb_cheb_sel_bwd_workspace_bytes": (c_size_t, [c_int] * 3),
+    "mvb_cheb_sel_bwd": (c_int, [c_int] * 5 + [_vp] * 4 + [c_int] + [_vp] * 4 + [c_size_t, _vp]),
     "mvb_cheb_layer_supported": (c_int, [c_int] * 9),
     "mvb_cheb_layer_fwd": (c_int, [c_int] * 5 + [_vp, _vp, _vp, c_int, c_int, _vp, _vp, _vp, c_int, c_int, _vp, _vp, _vp, _vp, c_int, _vp, _vp]),
     "mvb_cheb_layer_bwd_workspace_bytes": (c_size_t, [c_int] * 6),

@@ -98,6 +98,12 @@ class cheb_VAE(nn.Module):
                                                                            l_op, u_op, d_op):
                 y = Fn.cheb_layer(Fn.to_vertex_major(x), conv.weight, conv.bias, l_op, u_op, d_op, relu=True)
                 return Fn.from_vertex_major(y)
+            if u_op is None and fout % 4 == 0:
+                # level 0 (too large for a mesh-resident kernel): conv + ReLU + row selection, only the rows D keeps are
+                # contracted / reduced over (first encoder layer: its input needs no gradient)
+                xv = Fn.to_vertex_major(x)
+                if Fn.cheb_conv_sel_supported(xv, conv.weight, l_op, d_op):
+                    return Fn.from_vertex_major(Fn.cheb_conv_sel(xv, conv.weight, conv.bias, l_op, d_op, relu=True))
         if up is not None:
             x = self.pool(x, up)
         x = self._act(conv, conv(x, self.A_edge_index[lvl], self.A_norm[lvl]))

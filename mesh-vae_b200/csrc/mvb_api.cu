@@ -189,6 +189,100 @@ extern "C" int mvb_cheb_fwd(int N, int B, int Fin, int Fout, int K, int n_active
     return MVB_OK;
 }
 
+static inline size_t align_up_c(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// Chebyshev convolution followed by a row selection (the encoder loop body at the levels that do not fit a
+// mesh-resident kernel: x = relu(cheb[i](x, L)); x = pool(x, D), models/cheb_VAE.py:264-265, D = one 1.0 per row,
+// mesh_operations.py:72-85).  Only the rows D keeps are contracted and written (1/4 of them at every level), and the
+// backward pass - the basis form for a layer whose input needs no gradient, i.e. the first encoder layer - reduces
+// dW / db over those rows only: dY is zero everywhere else.  Tensor-core kernels only (4 / 16 / 32-wide planes).
+// ---------------------------------------------------------------------------------------------
+static bool sel_shape_ok(int N, int B, int Fin, int Fout, int K, int n_sel) {
+    if (!tc_enabled() || N < 1 || B < 1 || K < 1 || n_sel < 1 || n_sel > N) return false;
+    if (!((Fin == 4 && K <= 8) || (Fin == 16 && K <= 6) || (Fin == 32 && K <= 3))) return false;     // planar layouts of tc_rowgemm / tc_wgrad
+    if (Fout % 4 || Fout > 32 || (int64_t)n_sel * B < 256) return false;
+    if (K * Fin + 1 > 128) return false;
+    return true;
+}
+
+extern "C" int mvb_cheb_sel_supported(int N, int B, int Fin, int Fout, int K, int n_sel) {
+    return sel_shape_ok(N, B, Fin, Fout, K, n_sel) ? 1 : 0;
+}
+
+extern "C" int mvb_cheb_sel_fwd(int N, int B, int Fin, int Fout, int K, int nnz, const int32_t *rowptr, const int32_t *colidx,
+                                const float *vals, const float *x, const float *weight, const float *bias, int relu, int n_sel,
+                                const int32_t *sel, float *basis, float *y_sel, void *stream) {
+    MVB_REQUIRE(sel_shape_ok(N, B, Fin, Fout, K, n_sel), "cheb_sel_fwd: shape N=%d B=%d Fin=%d Fout=%d K=%d n_sel=%d not supported", N, B, Fin,
+                Fout, K, n_sel);
+    MVB_REQUIRE(x && weight && y_sel && sel && (K == 1 || (basis && rowptr)), "cheb_sel_fwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t ncols = (int64_t)B * Fin;
+    const int64_t plane = (int64_t)N * ncols;
+    int rc = (K > 1) ? launch_cheb_recur_fwd(N, nnz, K, rowptr, colidx, vals, x, basis, ncols, st) : 1;
+    if (rc < 0) return rc;
+    for (int k = 1; k < K && rc == 0; ++k) {
+        float *tk = basis + (int64_t)(k - 1) * plane;
+        const float *tkm1 = (k == 1) ? x : basis + (int64_t)(k - 2) * plane;
+        const float *tkm2 = (k == 1) ? nullptr : (k == 2 ? x : basis + (int64_t)(k - 3) * plane);
+        int rc2 = launch_spmm(N, N, rowptr, colidx, vals, tkm1, tk, tkm2, nullptr, k == 1 ? 1.f : 2.f, -1.f, ncols, st);
+        if (rc2) return rc2;
+    }
+    ContractArgs a;
+    fill_contract(a);
+    a.rows = (int64_t)n_sel * B;
+    a.in_planes = K;
+    a.in_w = Fin;
+    a.in0 = x;
+    a.in_rest = basis;
+    a.wmat = weight;
+    a.bias = bias;
+    a.relu = relu;
+    a.out_planes = 1;
+    a.out_w = Fout;
+    a.out = y_sel;
+    a.row_sel = sel;
+    a.sel_group = B;
+    a.plane_rows = (int64_t)N * B;
+    rc = launch_contract_tc(a, st);
+    if (rc < 0) return rc;
+    if (rc == 0) return set_err(MVB_EINVAL, "cheb_sel_fwd: the tensor-core contraction does not cover this call (alignment?)");
+    return MVB_OK;
+}
+
+extern "C" size_t mvb_cheb_sel_bwd_workspace_bytes(int Fin, int Fout, int K) {
+    return align_up_c(wgrad_partial_bytes(K * Fin, Fout), 256);
+}
+
+extern "C" int mvb_cheb_sel_bwd(int N, int B, int Fin, int Fout, int K, const float *x, const float *basis,
+                                const float *y_sel_for_relu, const float *dy_sel, int n_sel, const int32_t *sel, float *dweight,
+                                float *dbias, void *workspace, size_t workspace_bytes, void *stream) {
+    MVB_REQUIRE(sel_shape_ok(N, B, Fin, Fout, K, n_sel), "cheb_sel_bwd: shape not supported");
+    MVB_REQUIRE(x && dy_sel && sel && dweight && workspace && (K == 1 || basis), "cheb_sel_bwd: null pointer");
+    const size_t need = mvb_cheb_sel_bwd_workspace_bytes(Fin, Fout, K);
+    if (workspace_bytes < need) return set_err(MVB_EWORKSPACE, "cheb_sel_bwd: workspace %zu < %zu", workspace_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    WgradArgs wa;
+    memset(&wa, 0, sizeof(wa));
+    wa.rows = (int64_t)n_sel * B;
+    wa.in_planes = K;
+    wa.in_w = Fin;
+    wa.in0 = x;
+    wa.in_rest = basis;
+    wa.dy = dy_sel;
+    wa.mask = y_sel_for_relu;
+    wa.n_out = Fout;
+    wa.partials = reinterpret_cast<float *>(workspace);
+    wa.partial_bytes = need;
+    wa.row_sel = sel;
+    wa.sel_group = B;
+    wa.plane_rows = (int64_t)N * B;
+    int nA = 0, m4A = 0;
+    int rc = launch_wgrad_partials(wa, dbias != nullptr, &nA, &m4A, st);
+    if (rc) return rc;
+    return launch_wgrad_finalize(wa.partials, nA, m4A, nullptr, 0, 0, Fin, K * Fin, Fout, dweight, dbias, st);
+}
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // per-host-thread side stream + fork/join events for intra-call concurrency
@@ -266,9 +360,10 @@ void side_join(cudaStream_t side, cudaStream_t st) {
 // Deferred side chains.  The weight-gradient reduction of a mesh-resident layer (tc_wgrad + finalize kernels, 10-20 us)
 // is not on the critical path of the backward pass: nothing reads dW / db before the optimizer.  In deferred mode
 // (mvb_tune "defer_wgrad=1", switched on by the step engine around its backward pass) such a chain is forked onto a
-// per-device side stream and joined back into the caller's stream only AFTER the next chain's producer kernel has been
-// enqueued (lazy_fork), or by mvb_side_join - so it overlaps the following layer's backward kernel; in a captured CUDA
-// graph the two become parallel branches.  Off (default): the chain is joined before the call returns.
+// per-device side stream (the chains of successive layers queue up there, each started by an event on the caller's
+// stream once its producer kernel has been enqueued) and joined back only by mvb_side_join - so they fill the idle
+// SMs / memory bandwidth under the following layers' latency-bound kernels; in a captured CUDA graph they form a
+// parallel branch.  Off (default): the chain is joined before the call returns.
 // The state is per device and process-wide (autograd runs backward functions on its own thread).
 // ---------------------------------------------------------------------------------------------
 #include <mutex>
@@ -289,7 +384,12 @@ static LazySide *lazy_side() {
     LazySide &s = g_lazy[dev];
     if (!s.tried) {
         s.tried = true;
-        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess &&
+        // LOWEST priority: when a chain and a kernel of the caller's stream are ready together (the input-gradient
+        // contraction next to the weight-gradient reduction of the same layer), the block scheduler serves the caller's
+        // kernel first - the chain takes what is left (a captured graph keeps the priority as a kernel-node attribute)
+        int least = 0, greatest = 0;
+        if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { least = 0; cudaGetLastError(); }
+        if (cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, least) == cudaSuccess &&
             cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess)
             s.ok = true;
@@ -307,14 +407,13 @@ static void lazy_join_locked(LazySide *s, cudaStream_t st) {
     }
 }
 
-// Call AFTER the producer kernel of the chain has been enqueued on `st`.  Joins the previous chain into `st`, forks the
-// side stream from `st`; returns the stream to enqueue the chain on, or NULL (not deferred / unavailable): run it on `st`.
+// Call AFTER the producer kernel of the chain has been enqueued on `st`.  Makes the side stream wait for that point of
+// `st`; returns the stream to enqueue the chain on, or NULL (not deferred / unavailable): run it on `st`.
 cudaStream_t lazy_fork(cudaStream_t st) {
     if (!g_defer_wgrad) return nullptr;
     std::lock_guard<std::mutex> lk(g_lazy_mu);
     LazySide *s = lazy_side();
     if (!s) return nullptr;
-    lazy_join_locked(s, st);
     if (cudaEventRecord(s->fork, st) != cudaSuccess || cudaStreamWaitEvent(s->stream, s->fork, 0) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
@@ -322,7 +421,8 @@ cudaStream_t lazy_fork(cudaStream_t st) {
     return s->stream;
 }
 
-// the chain has been enqueued on `side`: record its end; it is joined by the next lazy_fork or by mvb_side_join
+// the chain has been enqueued on `side`: record its end (the side stream is in order: the latest record covers every
+// earlier chain); joined by mvb_side_join
 void lazy_done(cudaStream_t side, cudaStream_t st) {
     if (!side) return;
     std::lock_guard<std::mutex> lk(g_lazy_mu);
@@ -523,11 +623,57 @@ static int cheb_bwd_adjoint(int N, int B, int Fin, int Fout, int K, int n_active
             if (rc2) return rc2;
         }
     }
-    // weight-gradient branch on the side stream, input-gradient contraction on the main stream
+    // weight-gradient branch on a side stream, input-gradient contraction on the main stream.  Deferred mode (step
+    // engine): the branch is joined lazily - nothing reads dW before the optimizer - so the contraction that the next
+    // layer waits for no longer shares the memory system with it; otherwise forked and joined within this call.
     cudaStream_t wst = st;
-    SideStream *side = fork_side(st);
-    if (side) wst = side->stream;
+    cudaStream_t lazy = lazy_fork(st);
+    SideStream *side = lazy ? nullptr : fork_side(st);
+    if (lazy) wst = lazy;
+    else if (side) wst = side->stream;
     JoinGuard join_guard{side, st};
+    struct LazyGuard {
+        cudaStream_t s, main;
+        ~LazyGuard() { lazy_done(s, main); }
+    } lazy_guard{lazy, st};
+    // the input-gradient contraction is launched FIRST (the next layer waits for it; in deferred mode the
+    // weight-gradient chain behind it then only takes the block slots it leaves free)
+    if (rows_act > 0) {      // dX = sum_k S_k W_k^T
+        ContractArgs a;
+        fill_contract(a);
+        a.rows = rows_act;
+        a.in_planes = K;
+        a.in_w = Fout;
+        a.in0 = G;
+        a.in_rest = S;
+        a.wmat = weight;
+        a.w_transposed = 2;
+        a.out_planes = 1;
+        a.out_w = Fin;
+        a.out = dx;
+        rc = launch_contract(a, st);
+        if (rc) return rc;
+    }
+    if (rows_in > 0) {       // empty rows: dX = G (sum_k c_k W_k)^T
+        rc = launch_fold_dx(rows_in, K, Fin, Fout, G + rows_act * Fout, weight, dx + rows_act * Fin, st);
+        if (rc < 0) return rc;
+        if (rc == 0) {
+        ContractArgs a;
+        fill_contract(a);
+        a.rows = rows_in;
+        a.in_planes = 1;
+        a.in_w = Fout;
+        a.in0 = G + rows_act * Fout;
+        a.wmat = weight;
+        a.w_transposed = 1;
+        a.w_fold = K;
+        a.out_planes = 1;
+        a.out_w = Fin;
+        a.out = dx + rows_act * Fin;
+        rc = launch_contract(a, st);
+        if (rc) return rc;
+        }
+    }
     int nA = 0, m4A = 0, nB = 0, m4B = 0;
     if (rows_act > 0) {      // A = [S_0|..|S_{K-1}]^T x   ([K*Fout, Fin]; dW_k[i][o] = A[k*Fout + o][i])
         WgradArgs wa;
@@ -564,41 +710,6 @@ static int cheb_bwd_adjoint(int N, int B, int Fin, int Fout, int K, int n_active
     }
     rc = launch_wgrad_finalize(partA, nA, m4A, partB, nB, m4B, Fin, K * Fin, Fout, dweight, nullptr, wst, 1);
     if (rc) return rc;
-    if (rows_act > 0) {      // dX = sum_k S_k W_k^T
-        ContractArgs a;
-        fill_contract(a);
-        a.rows = rows_act;
-        a.in_planes = K;
-        a.in_w = Fout;
-        a.in0 = G;
-        a.in_rest = S;
-        a.wmat = weight;
-        a.w_transposed = 2;
-        a.out_planes = 1;
-        a.out_w = Fin;
-        a.out = dx;
-        rc = launch_contract(a, st);
-        if (rc) return rc;
-    }
-    if (rows_in > 0) {       // empty rows: dX = G (sum_k c_k W_k)^T
-        rc = launch_fold_dx(rows_in, K, Fin, Fout, G + rows_act * Fout, weight, dx + rows_act * Fin, st);
-        if (rc < 0) return rc;
-        if (rc == 1) return MVB_OK;
-        ContractArgs a;
-        fill_contract(a);
-        a.rows = rows_in;
-        a.in_planes = 1;
-        a.in_w = Fout;
-        a.in0 = G + rows_act * Fout;
-        a.wmat = weight;
-        a.w_transposed = 1;
-        a.w_fold = K;
-        a.out_planes = 1;
-        a.out_w = Fin;
-        a.out = dx + rows_act * Fin;
-        rc = launch_contract(a, st);
-        if (rc) return rc;
-    }
     return MVB_OK;
 }
 

@@ -236,6 +236,7 @@ int launch_contract(const ContractArgs &a, cudaStream_t st) {
     }
     const int M = a.in_planes * a.in_w, Nn = a.out_planes * a.out_w;
     MVB_REQUIRE(M > 0 && Nn > 0, "contract: empty shape");
+    MVB_REQUIRE(!a.row_sel, "contract: a row selection needs the tensor-core path (see mvb_cheb_sel_supported)");
     const int M4 = round4(M), N4 = round4(Nn), LD = pad_ld(M4), NT = N4 / 4;
     int TR = 4, R = 128;
     while ((R / TR) * NT > 512 && R > 32) R /= 2;
@@ -508,6 +509,7 @@ int launch_wgrad_partials(const WgradArgs &a, int has_bias, int *nparts, int *m4
         const int rc = launch_wgrad_tc(a, has_bias, M4, N4, nparts, st);
         if (rc != 0) return rc < 0 ? rc : MVB_OK;
     }
+    MVB_REQUIRE(!a.row_sel, "wgrad: a row selection needs the tensor-core path (see mvb_cheb_sel_supported)");
     const int G = MT * NT;
     MVB_REQUIRE(G <= 512, "wgrad: K*Fin x Fout = %d x %d too large for the register-tiled reduction", M, a.n_out);
     const int threads = G * ngroups;

@@ -104,6 +104,12 @@ struct ContractArgs {
     int relu;
     int out_planes, out_w;
     float *out;
+    // optional row selection (the down-sampling D folded into the contraction, models/cheb_VAE.py:264-265): output row
+    // r = m * sel_group + b reads input row row_sel[m] * sel_group + b of every plane; planes are plane_rows rows long.
+    // Tensor-core path only (launch_contract_tc); NULL = all rows in order.
+    const int32_t *row_sel;
+    int sel_group;
+    int64_t plane_rows;
 };
 int launch_contract(const ContractArgs &a, cudaStream_t st);
 
@@ -119,6 +125,10 @@ struct WgradArgs {
     int n_out;            // Fout
     float *partials;      // workspace
     size_t partial_bytes;
+    // optional row selection for the tcat planes (dy / mask are dense over the selected rows): see ContractArgs
+    const int32_t *row_sel;
+    int sel_group;
+    int64_t plane_rows;
 };
 size_t wgrad_partial_bytes(int M, int n_out);
 int launch_wgrad_partials(const WgradArgs &a, int has_bias, int *nparts, int *m4_out, cudaStream_t st);
@@ -138,6 +148,7 @@ int launch_fold_wgrad(int64_t rows, int Fin, int Fout, const float *x, const flo
 
 // tcgen05 paths (mvb_tc.cu): return 1 = handled, 0 = shape unsupported (use FFMA), < 0 = error
 int launch_contract_tc(const ContractArgs &a, cudaStream_t st);
+int tc_enabled();
 int launch_wgrad_tc(const WgradArgs &a, int has_bias, int M4, int N4, int *nparts, cudaStream_t st);
 
 // tuning setters behind mvb_tune (mvb_api.cu)

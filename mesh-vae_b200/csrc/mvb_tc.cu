@@ -53,7 +53,16 @@ struct TcRowArgs {
     int tmem_cols;
     int tile_w;                   // floats per staged tile row (16 or 32)
     int tile_planes;              // number of staged tiles (= in_planes when planar, 1 when packed)
+    const int32_t *row_sel;       // optional input-row selection (ContractArgs), planar layouts only
+    int sel_group;
+    int64_t plane_rows;           // rows of one input plane (== rows without a selection)
 };
+
+// input row of output row r under a row selection: row_sel[r / group] * group + r % group
+__device__ __forceinline__ int64_t sel_row(const int32_t *row_sel, int group, int64_t r) {
+    const int64_t m = r / group;
+    return (int64_t)__ldg(row_sel + m) * group + (r - m * group);
+}
 
 // B operand: Bt[n][kd] (n = output column, kd = logical K index p*in_w + i), K-major, swizzled like A,
 // hi/lo split.  kd maps to (tile plane, column) = (kd / tile_w, kd % tile_w) - for the packed layout
@@ -228,6 +237,22 @@ tc_rowgemm_kernel(TcRowArgs a) {
     auto prefetch = [&](int64_t row0, int g) {
         const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
 #pragma unroll
+        if (a.row_sel) {          // selected rows: the pieces of a tile row stay contiguous, the rows are gathered
+            int64_t src[Q4 > 0 ? Q4 : 1];
+#pragma unroll
+            for (int j = 0; j < Q4; ++j) src[j] = (srow[j] < nr) ? sel_row(a.row_sel, a.sel_group, row0 + srow[j]) : 0;
+#pragma unroll
+            for (int pp = 0; pp < NPR; ++pp) {
+                const int p = g * NPR + pp;
+                const float4 *b4 = reinterpret_cast<const float4 *>(p == 0 ? a.in0 : a.in_rest + (int64_t)(p - 1) * a.plane_rows * (Q4 * 4));
+#pragma unroll
+                for (int j = 0; j < Q4; ++j) {
+                    const int i = j * 128 + tid;
+                    pre[pp * Q4 + j] = (srow[j] < nr) ? __ldg(b4 + src[j] * Q4 + (i - srow[j] * Q4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        } else {
+#pragma unroll
         for (int pp = 0; pp < NPR; ++pp) {
             const int p = g * NPR + pp;
             const float4 *s4 = reinterpret_cast<const float4 *>((p == 0 ? a.in0 : a.in_rest + (int64_t)(p - 1) * a.rows * (Q4 * 4)) + row0 * (Q4 * 4));
@@ -235,6 +260,7 @@ tc_rowgemm_kernel(TcRowArgs a) {
             for (int j = 0; j < Q4; ++j) {
                 pre[pp * Q4 + j] = (srow[j] < nr) ? __ldg(s4 + j * 128 + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+        }
         }
         if (a.mask && g == 0) {
             const float4 *m4 = reinterpret_cast<const float4 *>(a.mask + row0 * (Q4 * 4));
@@ -375,7 +401,11 @@ int launch_contract_tc(const ContractArgs &a, cudaStream_t st) {
     const bool packed = allow_packed && !(planar && vec_ok) && Kd <= 32;
     if (!(planar && vec_ok) && !packed) return 0;
     if (!aligned16(a.out)) return 0;
+    if (a.row_sel && (packed || a.mask || a.sel_group < 1)) return 0;
     TcRowArgs t;
+    t.row_sel = a.row_sel;
+    t.sel_group = a.sel_group;
+    t.plane_rows = a.row_sel ? a.plane_rows : a.rows;
     t.rows = a.rows;
     t.in_planes = a.in_planes;
     t.in_w = w;
@@ -472,6 +502,9 @@ struct TcWgradArgs {
     int M4, N4;                    // partial block layout [M4][N4] expected by the finalize kernel
     float *partials;
     int tmem_cols;
+    const int32_t *row_sel;        // optional selection of the T rows (WgradArgs); dy / mask are dense over the selected rows
+    int sel_group;
+    int64_t plane_rows;
 };
 
 // byte offset of logical (row r, feature column col) in a BASE32B tile made of 32-column blocks of blk bytes
@@ -559,12 +592,27 @@ tc_wgrad_kernel(TcWgradArgs a) {
     }
     auto prefetch = [&](const int d, int64_t row0) {
         const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
+        if (a.row_sel) {
+            int64_t src[LPT];
+#pragma unroll
+            for (int j = 0; j < LPT; ++j) src[j] = (trow[j] >= 0 && trow[j] < nr) ? sel_row(a.row_sel, a.sel_group, row0 + trow[j]) : 0;
+#pragma unroll
+            for (int p = 0; p < NPV; ++p) {
+                const float4 *b4 = reinterpret_cast<const float4 *>(p == 0 ? a.in0 : a.in_rest + (int64_t)(p - 1) * a.plane_rows * W);
+#pragma unroll
+                for (int j = 0; j < LPT; ++j) {
+                    const int i = j * WG_NT + tid;
+                    pre[d][p * LPT + j] = (trow[j] >= 0 && trow[j] < nr) ? __ldg(b4 + src[j] * Q4 + (i - trow[j] * Q4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        } else {
 #pragma unroll
         for (int p = 0; p < NPV; ++p) {
             const float4 *s4 = reinterpret_cast<const float4 *>((p == 0 ? a.in0 : a.in_rest + (int64_t)(p - 1) * a.rows * W) + row0 * W);
 #pragma unroll
             for (int j = 0; j < LPT; ++j)
                 pre[d][p * LPT + j] = (trow[j] >= 0 && trow[j] < nr) ? __ldg(s4 + j * WG_NT + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         }
         const float4 *d4 = reinterpret_cast<const float4 *>(a.dy + row0 * a.n_out);
         const float4 *m4 = reinterpret_cast<const float4 *>(a.mask ? a.mask + row0 * a.n_out : nullptr);
@@ -749,7 +797,11 @@ int launch_wgrad_tc(const WgradArgs &a, int has_bias, int M4, int N4, int *npart
                       (a.in_planes == 1 || aligned16(a.in_rest)) && aligned16(a.dy) && (!a.mask || aligned16(a.mask));
     static const bool allow_generic = getenv("MVB_TC_PACKED") != nullptr;
     if (!fast && !allow_generic) return 0;
+    if (a.row_sel && (!fast || a.sel_group < 1)) return 0;
     TcWgradArgs t;
+    t.row_sel = a.row_sel;
+    t.sel_group = a.sel_group;
+    t.plane_rows = a.row_sel ? a.plane_rows : a.rows;
     t.rows = a.rows;
     t.in_planes = a.in_planes;
     t.in_w = a.in_w;

@@ -96,6 +96,11 @@ class _ChebConvFn(torch.autograd.Function):
                                ptr(basis) if (basis is not None and basis.numel()) else None, ptr(w), ptr(y) if ctx.relu else None,
                                ptr(dy), ptr(dx),
                                ptr(dw), ptr(db), ptr(ws), ws_bytes, stream_ptr()), "mvb_cheb_bwd")
+        if _lib._deferred["on"]:
+            if sw is not None and (sb is not None or not ctx.has_bias):
+                _lib._deferred["keep"].append((ws, x_vm, basis, w, y, dy, dw, db))      # read / written by the pending side chain
+            else:
+                _lib.side_join()
         return dx, _ret(sw, dw), _ret(sb, db), None, None
 
 
@@ -123,6 +128,69 @@ def cheb_conv(x_vm: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Ten
     if pout and keep_padding:
         return y                         # [N,B,fout+pout]: the caller slices a view and hands the padded buffer to the loss
     return y[..., :fout] if pout else y
+
+
+class _ChebConvSelFn(torch.autograd.Function):
+    """mvb_cheb_sel_fwd / mvb_cheb_sel_bwd: ChebConv (+bias, ReLU) followed by the row selection of a down-sampling
+    operator (models/cheb_VAE.py:264-265) for a layer whose input needs no gradient (the first encoder layer)."""
+
+    @staticmethod
+    def forward(ctx, x_vm, weight, bias, op: MeshOperator, d_op: MeshOperator, relu: bool):
+        _req_cuda(x_vm, "cheb_conv_sel x")
+        n, b, fin = x_vm.shape
+        k, _, fout = weight.shape
+        x_vm, w = x_vm.contiguous(), weight.contiguous()
+        bb = None if bias is None else bias.contiguous()
+        n_sel = d_op.n_rows
+        basis = torch.empty((max(k - 1, 0), n, b, fin), device=x_vm.device, dtype=torch.float32)
+        y = torch.empty((n_sel, b, fout), device=x_vm.device, dtype=torch.float32)
+        check(lib.mvb_cheb_sel_fwd(n, b, fin, fout, k, op.nnz, ptr(op.rowptr), ptr(op.colidx), ptr(op.vals), ptr(x_vm), ptr(w),
+                                   ptr(bb), 1 if relu else 0, n_sel, ptr(d_op.colidx), ptr(basis) if basis.numel() else None,
+                                   ptr(y), stream_ptr()), "mvb_cheb_sel_fwd")
+        ctx.d_op, ctx.relu, ctx.has_bias = d_op, relu, bias is not None
+        ctx.sinks = (_sink(weight), _sink(bias))
+        ctx.save_for_backward(x_vm, basis, w, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_vm, basis, w, y = ctx.saved_tensors
+        n, b, fin = x_vm.shape
+        k, _, fout = w.shape
+        dy = dy.contiguous()
+        sw, sb = ctx.sinks
+        dw = _grad_out(sw, w)
+        db = (sb if sb is not None else torch.empty(fout, device=w.device, dtype=torch.float32)) if ctx.has_bias else None
+        ws_bytes = lib.mvb_cheb_sel_bwd_workspace_bytes(fin, fout, k)
+        ws = torch.empty(ws_bytes, device=w.device, dtype=torch.uint8)
+        check(lib.mvb_cheb_sel_bwd(n, b, fin, fout, k, ptr(x_vm), ptr(basis) if basis.numel() else None, ptr(y) if ctx.relu else None,
+                                   ptr(dy), ctx.d_op.n_rows, ptr(ctx.d_op.colidx), ptr(dw), ptr(db), ptr(ws), ws_bytes, stream_ptr()),
+              "mvb_cheb_sel_bwd")
+        return None, _ret(sw, dw), _ret(sb, db), None, None, None
+
+
+def cheb_conv_sel_supported(x_vm: torch.Tensor, weight: torch.Tensor, op: MeshOperator, d_op: Optional[MeshOperator]) -> bool:
+    """the conv + row-selection kernels cover this layer: a selection D, an input without gradient, plane widths of
+    the tensor-core kernels (3 input channels count as 4: zero padded)"""
+    if d_op is None or not d_op.is_selection or x_vm.requires_grad or not x_vm.is_cuda:
+        return False
+    if op.n_active != op.n_rows or op.n_rows != x_vm.shape[0]:
+        return False
+    k, fin, fout = weight.shape
+    finp = fin + (-fin) % 4
+    return bool(lib.mvb_cheb_sel_supported(op.n_rows, x_vm.shape[1], finp, fout, k, d_op.n_rows))
+
+
+def cheb_conv_sel(x_vm: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], op: MeshOperator, d_op: MeshOperator,
+                  relu: bool = True) -> torch.Tensor:
+    """x_vm [N,B,Fin] (no gradient) -> [n_sel,B,Fout] = act(conv(x))[rows D keeps]; see cheb_conv for the zero padding of
+    3-channel inputs (the padded weight's gradient is sliced back by autograd)."""
+    fin_x, fin = x_vm.shape[2], weight.shape[1]
+    pin = (-fin) % 4
+    if pin and fin_x == fin:
+        x_vm = torch.nn.functional.pad(x_vm, (0, pin))
+    w = torch.nn.functional.pad(weight, (0, 0, 0, pin)) if pin else weight
+    return _ChebConvSelFn.apply(x_vm, w, bias, op, d_op, relu)
 
 
 def pack_input(x: torch.Tensor) -> torch.Tensor:
