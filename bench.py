@@ -64,51 +64,138 @@ def emit(line: dict):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU reference arm / cpu_baseline: the oracle port of the reference training step
+# CPU reference arm / cpu_baseline: the UNCHANGED reference through the leaf shims, else the oracle port
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step_rate(batch: int, steps: int, warmup: int, threads: int):
-    """meshes/s of the CPU port of main.py:67-85 (forward, backward, Adam) with the oracle
-    restatement of cheb_VAE; default.cfg hyper-parameters, dropout 0.2, x_gt fp64, seed 666."""
-    from oracle import mesh_vae_oracle as O     # the checker, used here ONLY as the timed CPU baseline
-    torch.set_num_threads(threads)
-    torch.manual_seed(666)
+def physical_cores() -> int:
+    """physical cores of the box (hyper-threads hurt the scatter/gather-bound reference step)"""
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+        if n:
+            return int(n)
+    except Exception:  # noqa: BLE001
+        pass
+    return max(1, (os.cpu_count() or 2) // 2) if (os.cpu_count() or 1) > 8 else (os.cpu_count() or 1)
+
+
+def _cpu_model(workload: str):
+    """-> (kind, step(batch) callable factory).  kind "reference": the reference's own models/cheb_VAE.py /
+    models/cheb_cls.py, imported unchanged from /root/reference or the staged copy oracle/_ref/reference
+    (oracle/make_ref.py) on top of the leaf shims in oracle/shims; "port": the oracle restatement (no reference tree)."""
+    from oracle import ref_loader
+    from oracle import mesh_vae_oracle as O     # fixture loader / port: the checker, used here ONLY as the timed CPU baseline
     A, D, U, nn_ = O.load_operators(OPERATORS_NPZ)
     cfg = copy.deepcopy(O.DEFAULT_CONFIG)
-    net = O.OracleChebVAE(3, cfg, D, U, A, nn_)
-    net.train()
-    opt = torch.optim.Adam(net.parameters(), lr=cfg["learning_rate"], weight_decay=cfg["weight_decay"])
+    ref = ref_loader.use_reference_on_shims()
+    torch.manual_seed(666)
+    if ref is not None:
+        from models.cheb_VAE import cheb_VAE            # the reference's own file
+        from models.cheb_cls import cheb_GCN
+        from torch_geometric.data import Data
+        vae = cheb_VAE(3, copy.deepcopy(cfg), D, U, A, nn_, model=cfg["model"])
+        gcn = cheb_GCN(6, copy.deepcopy(cfg), D, U, A, nn_) if workload == "cls" else None
+        wrap = lambda x: Data(x=x.reshape(-1, x.shape[-1]), edge_index=None, num_graphs=x.shape[0])      # noqa: E731
+        kind = "reference"
+    else:
+        vae = O.OracleChebVAE(3, copy.deepcopy(cfg), D, U, A, nn_)
+        gcn = O.OracleChebGCN(6, copy.deepcopy(cfg), D, U, A, nn_) if workload == "cls" else None
+        wrap = lambda x: x      # noqa: E731
+        kind = "port"
+    return kind, vae, gcn, wrap, nn_, cfg
+
+
+def cpu_reference_step_rate(batch: int, steps: int, warmup: int, threads: int, workload: str = "train"):
+    """meshes/s (median step) of the reference's CPU path for one of the bench workloads:
+    train - main.py:67-85 (forward, backward, Adam; default.cfg, dropout 0.2, x_gt fp64);
+    infer - inference.py:88-114 per batch (classifier pass, test-mode forward, opposite-sex sample; no_grad);
+    cls   - crecon.py:80-88 (cheb_GCN forward on [B,4998,6], CrossEntropyLoss, backward, Adam).
+    -> (meshes/s, median ms/step, kind)"""
+    torch.set_num_threads(threads)
+    kind, vae, gcn, wrap, nn_, cfg = _cpu_model(workload)
     g = torch.Generator().manual_seed(0)
     x = torch.randn(batch, nn_[0], 3, generator=g)
     x_gt = x.double()
     y = torch.nn.functional.one_hot(torch.randint(0, 2, (batch,), generator=g), 2)
+    if workload == "train":
+        vae.train()
+        opt = torch.optim.Adam(vae.parameters(), lr=cfg["learning_rate"], weight_decay=cfg["weight_decay"])
+
+        def step():
+            opt.zero_grad()
+            loss, *_ = vae(wrap(x), x_gt, y, m_type="train")
+            loss.backward()
+            opt.step()
+            float(loss)
+    elif workload == "infer":
+        vae.eval()
+
+        def step():
+            with torch.no_grad():
+                h = vae.encoder(x)
+                y_hot = torch.nn.functional.one_hot(vae.classifier(h).argmax(1), 2)
+                loss, _, recon, (_, _, z_), _ = vae(wrap(x), x, y_hot, m_type="test")
+                vae.sample((1 - y_hot).float(), z_)
+                float(loss)
+    else:
+        gcn.train()
+        opt = torch.optim.Adam(gcn.parameters(), lr=1e-3, weight_decay=5e-4)
+        x6 = torch.randn(batch, nn_[0], 6, generator=g)
+        yl = torch.randint(0, 2, (batch,), generator=g)
+
+        def step():
+            opt.zero_grad()
+            loss = torch.nn.functional.cross_entropy(gcn(x6), yl)
+            loss.backward()
+            opt.step()
+            float(loss)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        opt.zero_grad()
-        loss, *_ = net(x, x_gt, y, m_type="train")
-        loss.backward()
-        opt.step()
-        float(loss)
+        step()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    total = sum(times)
-    return batch * len(times) / total, 1e3 * total / len(times)
+    med = statistics.median(times)
+    return batch / med, 1e3 * med, kind
+
+
+WORKLOAD_TEXT = {
+    "train": "cheb_VAE default.cfg train step (fwd+bwd+Adam), 4998-vertex template, fp32 (x_gt fp64)",
+    "infer": "inference.py per-batch device work (classifier pass + test-mode forward + opposite-sex sample), cheb_VAE default.cfg, fp32",
+    "cls": "cheb_GCN (crecon.py) train step on [B,4998,6] (fwd, CrossEntropyLoss, bwd, Adam), K=6, fp32",
+}
+METRICS = {"train": METRIC, "infer": "inference_meshes_per_sec", "cls": "cls_train_meshes_per_sec"}
+
+
+def cpu_baseline_block(workload: str, steps: int, warmup: int = 3):
+    """the `cpu_baseline` object: the reference's CPU path on this box's host cores, all physical cores and one thread"""
+    cores = physical_cores()
+    val, ms, kind = cpu_reference_step_rate(16, steps, warmup, cores, workload)
+    n1 = max(4, steps // 6)
+    v1, ms1, _ = cpu_reference_step_rate(16, n1, 1, 1, workload)
+    return {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d timed 16-mesh steps (files/default.cfg batch_size) of the %s, median %.0f ms/step, torch threads = %d "
+                      "physical cores (os.cpu_count() = %s); 1 thread: %.1f meshes/s (median of %d steps, %.0f ms/step)"
+                      % (steps, "reference's own model files on the leaf shims (oracle/shims)" if kind == "reference" else
+                         "oracle CPU port of the reference (no reference tree on this box)", ms, cores, os.cpu_count(), v1, n1, ms1),
+            "value_1thread": v1, "ms_per_step": ms}
 
 
 def run_reference(args, rank):
     if rank != 0:
         return 0
-    threads = os.cpu_count() or 1
+    cores = physical_cores()
     sample_batch = 16       # files/default.cfg:26 batch_size - the reference's own CPU-runnable case
-    val, ms = cpu_reference_step_rate(sample_batch, args.steps, args.warmup, threads)
-    sample = (f"{sample_batch}-mesh steps (files/default.cfg batch_size) of the cheb_VAE train step "
-              f"(fwd+bwd+Adam), oracle CPU port of the reference, {args.steps} timed steps")
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+    steps = max(args.steps, 20)
+    val, ms, kind = cpu_reference_step_rate(sample_batch, steps, args.warmup, cores, args.workload)
+    sample = (f"{sample_batch}-mesh steps (files/default.cfg batch_size): {WORKLOAD_TEXT[args.workload]}; "
+              + ("the reference's own model files, unchanged, on the leaf shims of oracle/shims" if kind == "reference"
+                 else "oracle CPU port of the reference (no reference tree on this box)")
+              + f"; median of {steps} timed steps, {cores} torch threads (physical cores)")
+    line = {"impl": "reference", "metric": METRICS[args.workload], "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cheb_VAE default.cfg train step, 4998-vertex template, fp32 (x_gt fp64)",
-                       "batch_per_step": sample_batch, "device": "host CPU"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": WORKLOAD_TEXT[args.workload], "batch_per_step": sample_batch, "device": "host CPU"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -116,22 +203,57 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------------
-# clocks
+# clocks: NVML polled from a thread every few ms (a 0.1-0.3 s timed region still yields tens of samples);
+# nvidia-smi -lms as the fallback
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index: int, period_s: float = 0.004):
+        self.index, self.period = index, period_s
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.rows, self.proc, self.thread, self._stop, self.how = [], None, None, False, None
+
+    def _nvml_loop(self, nv, h):
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(h))
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = self.index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                phys = int(vis.split(",")[self.index])
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            self.how = "nvml"
+            return
+        except Exception:  # noqa: BLE001
+            pass
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            self.how = "nvidia-smi"
         except Exception:  # noqa: BLE001
             self.proc = None
 
@@ -140,29 +262,32 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:  # noqa: BLE001
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            parts = [p.strip() for p in r.split(",")]
-            if len(parts) < 6:
-                continue
+        if self.how == "nvml":
+            self._stop = True
+            self.thread.join(timeout=1)
+        elif self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
             try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, parts[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                self.proc.wait(timeout=2)
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for r in self.rows:
+                parts = [p.strip() for p in r.split(",")]
+                if len(parts) < 6:
+                    continue
+                try:
+                    self.sm.append(float(parts[0])); self.mx.append(float(parts[1]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, parts[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source (nvml / nvidia-smi unavailable)"], "samples": 0}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.how}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -97,3 +97,79 @@ def ref_evaluate(model, loader, mean, std):
             np.concatenate(metas, 0))
 
 
+
+
+# ---------------------------------------------------------------------------------------------
+# "hip-bone-shaped" synthetic scans (SURVEY.md 8(d) loss-curve inputs) and the reference's data preparation
+# ---------------------------------------------------------------------------------------------
+def procrustes(data1, data2):
+    """Restatement of the reference's utils.procrustes (utils.py:58-156; scipy's procrustes that also returns the
+    similarity transform): both sets centred and scaled to unit Frobenius norm, data2 rotated / scaled onto data1.
+    -> (mtx1, mtx2, disparity, [R, norm2 / s, mean2]).  Pinned against the reference's function by
+    tests/test_cpu_formats.py::test_procrustes_restatement_matches_reference."""
+    from scipy.linalg import orthogonal_procrustes
+    mtx1 = np.array(data1, dtype=np.double, copy=True)
+    mtx2 = np.array(data2, dtype=np.double, copy=True)
+    mean2 = np.mean(mtx2, 0)
+    mtx1 -= np.mean(mtx1, 0)
+    mtx2 -= np.mean(mtx2, 0)
+    norm1, norm2 = np.linalg.norm(mtx1), np.linalg.norm(mtx2)
+    mtx1 /= norm1
+    mtx2 /= norm2
+    R, s = orthogonal_procrustes(mtx1, mtx2)
+    mtx2 = np.dot(mtx2, R.T) * s
+    return mtx1, mtx2, float(np.sum(np.square(mtx1 - mtx2))), [R, norm2 / s, mean2]
+
+
+def hip_like_scans(n, seed=666):
+    """n scans [N,3] of the template under 8 smooth deformation modes (low-order polynomials of the centred template
+    coordinates, amplitudes ~ N(0, 3 mm)), 0.5 mm vertex noise, a random rotation <= 10 degrees, scale U(0.9, 1.1) and a
+    translation; labels = sign of the first amplitude (so that the classifier term is learnable)."""
+    tv = np.load(OPERATORS_NPZ)["template_v"].astype(np.float64)
+    c = tv - tv.mean(0)
+    u = c / np.abs(c).max()
+    x, y, z = u[:, 0:1], u[:, 1:2], u[:, 2:3]
+    e = np.eye(3)
+    modes = [x * e[0], y * e[1], z * e[2], (x * y) * e[2], (y * z) * e[0], (z * x) * e[1], (x * x - y * y) * e[0], (y * y - z * z) * e[2]]
+    rng = np.random.default_rng(seed)
+    scans, labels = [], []
+    for _ in range(n):
+        a = rng.normal(size=8) * 3.0
+        shape = tv + sum(ai * m for ai, m in zip(a, modes)) + rng.normal(size=tv.shape) * 0.5
+        axis = rng.normal(size=3)
+        axis /= np.linalg.norm(axis)
+        ang = np.deg2rad(rng.uniform(0, 10))
+        Kx = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+        Rm = np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx
+        scans.append(rng.uniform(0.9, 1.1) * shape @ Rm.T + rng.normal(size=(1, 3)) * 20)
+        labels.append(int(a[0] > 0))
+    return tv, scans, labels
+
+
+class HipLikeDataset(torch.utils.data.Dataset):
+    """MeshData-shaped items (data.py:103-111) made the way data.py:120-184 makes them: Procrustes fit of every scan
+    against the template, per-vertex z-score with the mean / std of the fitted set, (R, s, m) kept for the
+    back-transform of main.py:88-91."""
+
+    def __init__(self, n=256, seed=666, data_cls=None, procrustes_fn=procrustes):
+        tv, scans, labels = hip_like_scans(n, seed)
+        fitted, self.R, self.s, self.m, self.ori = [], [], [], [], []
+        for sc in scans:
+            _, mtx2, _, res = procrustes_fn(tv, sc)
+            fitted.append(mtx2.copy())
+            self.ori.append(torch.Tensor(sc))
+            self.R.append(torch.FloatTensor(res[0]))
+            self.s.append(torch.FloatTensor([res[1]]))
+            self.m.append(torch.FloatTensor(np.array([res[2]])))
+        self.aligned = fitted
+        self.mean, self.std = np.mean(fitted, axis=0), np.std(fitted, axis=0)          # data.py:166-170
+        self.labels = labels
+        self.data_cls = data_cls or _Data
+
+    def __len__(self):
+        return len(self.aligned)
+
+    def __getitem__(self, i):
+        ori = (torch.tensor(self.aligned[i]) - torch.tensor(self.mean)) / torch.tensor(self.std)      # data.py:106
+        return (self.data_cls(x=ori.float(), y=ori.float(), edge_index=torch.zeros(2, 1, dtype=torch.long)), ori, self.labels[i],
+                f"/scans/hip_{'fm'[self.labels[i]]}_{i}.obj", self.ori[i], self.R[i], self.m[i], self.s[i])
