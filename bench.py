@@ -385,6 +385,82 @@ def spmm_roofline(mvb, A, nn_, batch, dev, peaks, reps=6):
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
 
 
+# per-mesh algorithmic bytes of the level-0 / level-1 layers (fp32): "stepwise" = every kernel of
+# the step-by-step decomposition reads / writes its operands once (SURVEY 8(d) formulas), "fused" = layer input + output
+# (+ what the backward pass must re-read).  (fwd stepwise, fwd fused, bwd stepwise, bwd fused); pools of the layer included.
+LAYER_BYTES = {
+    "enc0 (level 0, 3->16, +D0)": (2818892 + 414876, 639748, 679728 + 414876, 679728),
+    "dec3 (level 0, U0+, 16->16)": (8016812 + 539820, 899644, 10255916 + 539820, 2818876),
+    "enc1 (level 1, 16->16, +D1)": (2005020 + 103792, 225004, 2565020 + 103792, 705004),
+    "dec2 (level 1, U1+, 16->16)": (2005020 + 135036, 225004, 2565020 + 135036, 705004),
+}
+STEP_BYTES_STEPWISE, STEP_BYTES_FUSED = 52.68e6, 13.04e6          # whole training step per mesh (SURVEY Appendix B totals)
+
+
+def layer_rooflines(mvb, net, nn_, batch, dev, peak_gbs, reps=12):
+    """The four layers that carry ~95 % of the step's bytes, each as the model runs it (one call of the fused / composed
+    layer, forward and backward), replayed from a CUDA graph with the L2 flushed before every replay (cold operands),
+    one CUDA-event pair per replay on the replay stream.  achieved = stepwise algorithmic bytes / time: a fused layer
+    moves fewer bytes than the stepwise model counts, so its fraction of the HBM peak may exceed what a stepwise chain
+    could reach - `fused_frac` is the same time against the fused lower bound."""
+    Fn, ops = mvb.functional, mvb.operators
+    out = []
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    st = torch.cuda.current_stream()
+    specs = [("enc0 (level 0, 3->16, +D0)", 0, net.cheb[0], None, net.downsample_matrices[0]),
+             ("dec3 (level 0, U0+, 16->16)", 0, net.cheb_dec[3], net.upsample_matrices[0], None),
+             ("enc1 (level 1, 16->16, +D1)", 1, net.cheb[1], None, net.downsample_matrices[1]),
+             ("dec2 (level 1, U1+, 16->16)", 1, net.cheb_dec[2], net.upsample_matrices[1], None)]
+    for name, lvl, conv, up, down in specs:
+        n_in = up.shape[1] if up is not None else nn_[lvl]
+        fin = conv.weight.shape[1]
+        first = name.startswith("enc0")
+        x = torch.randn(batch, n_in, fin, device=dev)
+        if not first:
+            x.requires_grad_()
+        with torch.no_grad():
+            xin = Fn.from_vertex_major(Fn.pack_input(x)) if first else x
+        y = net._layer(xin, conv, lvl, up=up, down=down)
+        gy = torch.randn_like(y)
+        params = [conv.weight, conv.bias] + ([] if first else [x])
+
+        def fwd():
+            with torch.no_grad():
+                net._layer(xin, conv, lvl, up=up, down=down)
+
+        def bwd():
+            torch.autograd.grad(y, params, gy, retain_graph=True, allow_unused=True)      # (engine sinks: dW lands in the flat buffer)
+        times = {}
+        for tag, fn in (("fwd", fwd), ("bwd", bwd)):
+            side = torch.cuda.Stream()
+            side.wait_stream(st)
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    fn()
+            st.wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            ts = []
+            for i in range(reps + 3):
+                flush.fill_(float(i))
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record(st)
+                g.replay()
+                s1.record(st)
+                s1.synchronize()
+                if i >= 3:
+                    ts.append(s0.elapsed_time(s1))
+            times[tag] = statistics.median(ts)
+        b = LAYER_BYTES[name]
+        for tag, sw, fu in (("fwd", b[0], b[1]), ("bwd", b[2], b[3])):
+            gbs = batch * sw / (times[tag] * 1e-3) / 1e9
+            out.append({"layer": name, "pass": tag, "ms": times[tag], "stepwise_bytes": batch * sw, "fused_bytes": batch * fu,
+                        "achieved_gbs": gbs, "frac": gbs / peak_gbs, "fused_frac": batch * fu / (times[tag] * 1e-3) / 1e9 / peak_gbs})
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - this framework has no CPU path (use --impl reference for the CPU arm)")
@@ -465,19 +541,30 @@ def run_ours(args, rank, world, local_rank):
     if os.path.exists(ppath):
         peaks = json.load(open(ppath))
     roof = spmm_roofline(mvb, A, nn_, B, dev, peaks)
+    peak_gbs = peaks.get("hbm_gbs", 6650.0)
+    layers = layer_rooflines(mvb, net, nn_, B, dev, peak_gbs) if world == 1 else None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    tensor_pipe = None
+    if os.path.exists(tpath):
+        try:
+            tensor_pipe = json.load(open(tpath)).get("tensor_pipe")
+        except Exception:  # noqa: BLE001
+            tensor_pipe = None
+    step_s = dev_ms * 1e-3 / args.steps
+    step_roof = {"stepwise_frac": B * STEP_BYTES_STEPWISE / step_s / 1e9 / peak_gbs,
+                 "fused_frac": B * STEP_BYTES_FUSED / step_s / 1e9 / peak_gbs,
+                 "stepwise_bytes_per_mesh": STEP_BYTES_STEPWISE, "fused_bytes_per_mesh": STEP_BYTES_FUSED,
+                 "note": "whole step against the HBM peak: bytes of the step-by-step kernel model / of the layer-fused lower bound "
+                         "(SURVEY.md Appendix B) divided by the device-timed step"}
     total_meshes = B * world * args.steps
     value = total_meshes / (dev_ms * 1e-3)
     e2e_val = total_meshes / (e2e_ms * 1e-3)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        n_cpu_steps = 120          # ~10 s of host work: the rate moved between 150 and 310 meshes/s on 12-step samples
-        cv, cms = cpu_reference_step_rate(16, n_cpu_steps, 3, threads)
-        cpu = {"value": cv, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "%d timed 16-mesh train steps (fwd+bwd+Adam) of the oracle CPU port, %.0f ms/step" % (n_cpu_steps, cms)}
+        cpu = cpu_baseline_block("train", steps=40)          # ~15-25 s of host work; median step
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "cheb_VAE files/default.cfg training step (fwd+bwd+allreduce+Adam), "
                                    "4998-vertex template, K=6, filters 16,16,16,32,32, dropout 0.2, x_gt fp64",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
@@ -489,7 +576,8 @@ def run_ours(args, rank, world, local_rank):
                     "d2h_bytes_per_step": eng.d2h_bytes(), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(eng.launches_per_step) * args.steps,
             "gpu_launches_per_step": int(eng.launches_per_step),
-            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+            "clocks": clocks, "roofline": roof, "roofline_layers": layers, "roofline_step": step_roof,
+            "tensor_pipe": tensor_pipe, "cpu_baseline": cpu}
     emit(line)
     return 0
 
@@ -526,21 +614,57 @@ def _time_graph(fn, steps, warmup, dev):
     return sum(a.elapsed_time(b) for a, b in evs) / steps
 
 
+def _time_graph_e2e(fn, h2d, d2h, steps, warmup, dev):
+    """end-to-end per step: the step's input copied from pinned host memory, the captured graph replayed, the step's
+    result read back to the host - all inside one CUDA-event pair (L2 flushed before it)"""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    st = torch.cuda.current_stream()
+    tot = 0.0
+    for i in range(warmup + steps):
+        flush.fill_(float(i))
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        h2d()
+        g.replay()
+        d2h()
+        b.record(st)
+        b.synchronize()
+        if i >= warmup:
+            tot += a.elapsed_time(b)
+    return tot / steps
+
+
 def run_secondary(args, local_rank):
     """--workload infer: the device work of inference.py:63-131 per batch (classifier pass, full test-mode
     forward, opposite-sex sample: 2 encoder + 2 decoder passes, no_grad).  --workload cls: one cheb_GCN
-    training step as crecon.py:80-88 runs it (forward on [B,4998,6], CrossEntropyLoss, backward, Adam)."""
+    training step as crecon.py:80-88 runs it (forward on [B,4998,6], CrossEntropyLoss, backward, Adam).
+    --workload dropin: delivery mode 1 - the reference's OWN cheb_VAE class (imported unchanged on compat/), accelerate(),
+    torch.optim.Adam: what a user who only swaps the import path gets (eager PyTorch autograd around the native ops)."""
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     mvb, net, A, nn_ = build_model(dev)
     L = mvb._lib.lib
     B = args.batch
     g = torch.Generator().manual_seed(5)
+    sampler = ClockSampler(local_rank)
+    h2d_bytes = d2h_bytes = 0
     if args.workload == "infer":
         net.eval()
-        x = torch.randn(B, nn_[0], 3, generator=g).to(dev)
-        y0 = torch.zeros(B, 2, dtype=torch.int64, device=dev)
+        x_h = torch.randn(B, nn_[0], 3, generator=g).pin_memory()
+        x = x_h.to(dev)
         out = {}
+        res_h = torch.empty(B, dtype=torch.int64).pin_memory()
 
         def fn():
             with torch.no_grad():
@@ -550,21 +674,25 @@ def run_secondary(args, local_rank):
                 loss, _, recon, (_, _, z_), _ = net(x, x, y_hot, m_type="test")      # inference.py:97
                 out["oppo"] = net.sample((1 - y_hot).float(), z_)                    # inference.py:114
                 out["loss"] = loss
+                out["pred"] = yh.argmax(1)
         c0 = L.mvb_launch_count()
+        sampler.start()
         ms = _time_graph(fn, args.steps, args.warmup, dev)
         launches = (L.mvb_launch_count() - c0) // 4          # 3 warm-up calls + the capture
-        work = ("inference.py per-batch device work: classifier pass + test-mode forward + opposite-sex sample "
-                "(2 encoder + 2 decoder passes, no_grad), cheb_VAE default.cfg, fp32")
-        metric = "inference_meshes_per_sec"
+        e2e_ms = _time_graph_e2e(fn, lambda: x.copy_(x_h, non_blocking=True), lambda: res_h.copy_(out["pred"], non_blocking=True),
+                                 args.steps, args.warmup, dev)
+        h2d_bytes, d2h_bytes = x_h.numel() * 4, res_h.numel() * 8
         assert torch.isfinite(out["loss"]) and torch.isfinite(out["oppo"]).all()
-    else:
+    elif args.workload == "cls":
         cfg = {"n_layers": 4, "polygon_order": [6, 6, 6, 6, 6], "num_conv_filters": [16, 16, 16, 32, 32], "num_classes": 2}
         cls = mvb.cheb_GCN(6, cfg, net.downsample_matrices, net.upsample_matrices, net.adjacency_matrices, nn_).to(dev)
         cls.train()
-        x = torch.randn(B, nn_[0], 6, generator=g).to(dev)
-        y = torch.randint(0, 2, (B,), generator=g).to(dev)
+        x_h = torch.randn(B, nn_[0], 6, generator=g).pin_memory()
+        y_h = torch.randint(0, 2, (B,), generator=g).pin_memory()
+        x, y = x_h.to(dev), y_h.to(dev)
         opt = torch.optim.Adam(cls.parameters(), lr=1e-3, weight_decay=5e-4, capturable=True)
         out = {}
+        res_h = torch.empty((), dtype=torch.float32).pin_memory()
 
         def fn():
             opt.zero_grad(set_to_none=True)
@@ -573,26 +701,97 @@ def run_secondary(args, local_rank):
             opt.step()
             out["loss"] = loss.detach()
         c0 = L.mvb_launch_count()
+        sampler.start()
         ms = _time_graph(fn, args.steps, args.warmup, dev)
         launches = (L.mvb_launch_count() - c0) // 4
-        work = "cheb_GCN (crecon.py) training step: forward on [B,4998,6], CrossEntropyLoss, backward, Adam; K=6, fp32"
-        metric = "cls_train_meshes_per_sec"
+
+        def h2d():
+            x.copy_(x_h, non_blocking=True)
+            y.copy_(y_h, non_blocking=True)
+        e2e_ms = _time_graph_e2e(fn, h2d, lambda: res_h.copy_(out["loss"], non_blocking=True), args.steps, args.warmup, dev)
+        h2d_bytes, d2h_bytes = x_h.numel() * 4 + y_h.numel() * 8, 4
         assert torch.isfinite(out["loss"])
+    else:       # dropin
+        from oracle import ref_loader          # locates the staged reference tree only (nothing of the oracle runs here)
+        ref = ref_loader.reference_root()
+        if ref is None:
+            emit({"metric": "dropin_train_meshes_per_sec", "unavailable": "no reference tree on this box (oracle/make_ref.py stages it)"})
+            return 0
+        mvb.install_compat()
+        sys.path.insert(1, ref)
+        sys.path.insert(2, os.path.join(ROOT, "oracle", "shims"))       # the open3d / psbody leaves of utils.py only
+        from models.cheb_VAE import cheb_VAE as RefVAE                  # the reference's own class, unchanged
+        cfg = {"n_layers": 4, "num_hidden": 512, "polygon_order": [6, 6, 6, 6, 6], "num_conv_filters": [16, 16, 16, 32, 32],
+               "num_classes": 2, "num_style": 16, "dropout": 0.2, "model": "optimal_sigma_VAE"}
+        torch.manual_seed(666)
+        rnet = RefVAE(3, cfg, net.downsample_matrices, net.upsample_matrices, net.adjacency_matrices, nn_, model=cfg["model"]).to(dev)
+        mvb.accelerate(rnet)
+        rnet.train()
+        from torch_geometric.data import Data
+        opt = torch.optim.Adam(rnet.parameters(), lr=1e-3, weight_decay=5e-4)
+        x_h = torch.randn(B, nn_[0], 3, generator=g).pin_memory()
+        xgt_h = x_h.double().pin_memory()
+        y_h = torch.randint(0, 2, (B,), generator=g).pin_memory()
+        st = torch.cuda.current_stream()
+        flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+
+        def step():                                  # main.py:67-85, eager: H2D, one-hot, forward, backward, Adam, loss read-back
+            x = x_h.to(dev, non_blocking=True)
+            x_gt = xgt_h.to(dev, non_blocking=True)
+            hot = torch.nn.functional.one_hot(y_h, 2).to(dev, non_blocking=True)
+            opt.zero_grad()
+            loss, *_ = rnet(Data(x=x.reshape(-1, 3), edge_index=None, num_graphs=B), x_gt, hot, m_type="train")
+            loss.backward()
+            opt.step()
+            return float(loss)
+        c0 = L.mvb_launch_count()
+        for _ in range(max(3, args.warmup)):
+            step()
+        launches = (L.mvb_launch_count() - c0) // max(3, args.warmup)
+        sampler.start()
+        tot = 0.0
+        for i in range(args.steps):
+            flush.fill_(float(i))
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st)
+            last = step()
+            b.record(st)
+            b.synchronize()
+            tot += a.elapsed_time(b)
+        ms = e2e_ms = tot / args.steps
+        h2d_bytes, d2h_bytes = x_h.numel() * 4 + xgt_h.numel() * 8 + B * 2 * 8, 8
+        assert np.isfinite(last)
+    clocks = sampler.stop()
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_baseline_block("train" if args.workload == "dropin" else args.workload, steps=30)
+    work = {"infer": WORKLOAD_TEXT["infer"], "cls": WORKLOAD_TEXT["cls"],
+            "dropin": "the reference's own cheb_VAE class (unchanged, imported on compat/) + accelerate() + torch.optim.Adam, eager "
+                      "training step as main.py:67-85 runs it (H2D, forward, backward, optimizer, loss read-back), batch fp32 / x_gt fp64"}[args.workload]
+    metric = {"infer": METRICS["infer"], "cls": METRICS["cls"], "dropin": "dropin_train_meshes_per_sec"}[args.workload]
     line = {"metric": metric, "value": B / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": work, "batch_per_gpu": B, "cuda_graph": True,
+            "data": "synthetic", "config": {"workload": work, "batch_per_gpu": B, "cuda_graph": args.workload != "dropin",
                                             "l2": "flushed between timed steps (256 MiB write, outside the event pairs)"},
-            "gpu_launches_per_step": int(launches), "gpu_launches": int(launches) * args.steps}
+            "e2e": {"value": B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+                    "ms_per_step": e2e_ms},
+            "gpu_launches_per_step": int(launches), "gpu_launches": int(launches) * args.steps, "clocks": clocks, "cpu_baseline": cpu}
     emit(line)
     return 0
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="train", choices=["train", "infer", "cls"],
-                    help="train = the headline cheb_VAE step (BASELINE configs[1]/[2]); infer / cls = configs[3] / [4]")
+    ap.add_argument("--workload", default="train", choices=["train", "infer", "cls", "dropin"],
+                    help="train = the headline cheb_VAE step (BASELINE configs[1]/[2]); infer / cls = configs[3] / [4]; "
+                         "dropin = the reference's own model class on the import-path drop-in (eager)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch meshes per GPU (default 64); strong: --global-batch meshes split over the GPUs "
+                         "(SURVEY 8(e): global 512 -> 512/N per rank)")
+    ap.add_argument("--global-batch", type=int, default=512)
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="meshes per GPU per step")
@@ -605,9 +804,15 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        if args.workload == "dropin":
+            args.workload = "train"
         if args.steps > 40:
             args.steps = 40
         return run_reference(args, rank)
+    if args.scaling == "strong":
+        if args.global_batch % world:
+            raise SystemExit(f"bench.py: global batch {args.global_batch} does not divide over {world} GPUs")
+        args.batch = args.global_batch // world
     if args.workload != "train":
         if rank != 0:
             return 0

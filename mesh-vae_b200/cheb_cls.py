@@ -53,6 +53,10 @@ class cheb_GCN(nn.Module):
             if not conv.fuse_relu:      # F.relu of cheb_cls.py:97, fused into the conv epilogue otherwise
                 x = F.relu(x)
             x = Pool(x, self.downsample_matrices[i])
+        if x.is_cuda:
+            # x.reshape(B, -1) of cheb_cls.py:101 read straight from the vertex-major buffer; both Linears native
+            h = Fn.linear(Fn.to_vertex_major(x), self.enc_lin.weight, self.enc_lin.bias, relu=True, x_vm=True)
+            return Fn.linear(h, self.cls_layer.weight, self.cls_layer.bias)
         x = x.reshape(b, self.enc_lin.in_features)
         return self.cls_layer(F.relu(self.enc_lin(x)))
 

@@ -133,6 +133,15 @@ class cheb_VAE(nn.Module):
         return float(self.dropout.p) if self.training else 0.0
 
     def classifier(self, x):
+        if self.fused_dense and x.is_cuda and not x.requires_grad and not (self.training and self.dropout.p > 0):
+            # inference.py:88 / main.py:42-49 (classifier_): softmax(classifier_layer(x)) from the heads kernel
+            # (its other outputs are discarded); no cuBLAS / ATen launch on the forward-only path
+            outs = []
+            for i in range(0, x.shape[0], Fn.VAE_HEADS_MAX_BATCH):
+                xi = x[i:i + Fn.VAE_HEADS_MAX_BATCH]
+                y0 = torch.zeros((xi.shape[0], self.num_class), device=x.device, dtype=torch.int64)
+                outs.append(Fn.vae_heads(xi, y0, None, self.classifier_layer, self.z_mean, self.z_log_var)[0])
+            return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
         return F.softmax(self.classifier_layer(self.dropout(x)), dim=1)
 
     def decoder(self, z):
@@ -197,7 +206,7 @@ class cheb_VAE(nn.Module):
         x = x.reshape(batch_size, -1, self.filters[0])
         self.dropout_stream.advance()
         h = self.encoder(x)
-        if self.fused_dense and h.is_cuda and batch_size <= Fn.VAE_HEADS_MAX_BATCH:
+        if self.fused_dense and h.is_cuda:
             if m_type == "train" and eps is None:
                 eps = self._draw_eps((batch_size, self.z), h)
             y_hat, x_mean, x_var, z_, z = Fn.vae_heads(h, y, eps if m_type == "train" else None, self.classifier_layer,

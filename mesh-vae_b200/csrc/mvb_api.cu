@@ -24,16 +24,18 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int num_sms() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
-        else
-            cached = 148;
+    static int cached[64] = {0};
+    const int d = device_slot();
+    if (cached[d] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) == cudaSuccess && n > 0)
+            cached[d] = n;
+        else {
+            cudaGetLastError();
+            cached[d] = 148;
+        }
     }
-    return cached;
+    return cached[d];
 }
 
 }  // namespace mvb

@@ -218,11 +218,10 @@ template <int TR>
 static int launch_contract_t(const ContractArgs &a, int M, int Nn, int M4, int N4, int LD, int R,
                              int NT, int in_vec, int out_vec, int grid, int threads, size_t smem,
                              cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(contract_kernel<TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return set_err(MVB_ECUDA, "contract: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set = true;
+    static DevFlags optin;
+    {
+        const int rc_attr = smem_optin(contract_kernel<TR>, 200 * 1024, optin, "contract");
+        if (rc_attr) return rc_attr;
     }
     contract_kernel<TR><<<grid, threads, smem, st>>>(a, M, Nn, M4, N4, LD, R, NT, in_vec, out_vec);
     return check_launch("mvb contract");
@@ -517,11 +516,10 @@ int launch_wgrad_partials(const WgradArgs &a, int has_bias, int *nparts, int *m4
     MVB_REQUIRE((size_t)grid * M4 * N4 * sizeof(float) <= a.partial_bytes, "wgrad: workspace too small");
     const size_t smem = ((size_t)R * LDT + (size_t)R * N4 + (size_t)ngroups * M4 * N4) * sizeof(float);
     MVB_REQUIRE(smem <= 200 * 1024, "wgrad: shared memory %zu too large", smem);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return set_err(MVB_ECUDA, "wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set = true;
+    static DevFlags optin;
+    {
+        const int rc_attr = smem_optin(wgrad_kernel, 200 * 1024, optin, "wgrad");
+        if (rc_attr) return rc_attr;
     }
     const int in_vec = (a.in_w % 4 == 0) && aligned16(a.in0) && (a.in_planes == 1 || aligned16(a.in_rest));
     const int dy_vec = (a.n_out % 4 == 0) && aligned16(a.dy) && (!a.mask || aligned16(a.mask));

@@ -536,15 +536,9 @@ using namespace mvb;
 static bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template <typename KernelT>
-static int ensure_smem(KernelT kernel, size_t bytes, size_t *granted, const char *what) {
-    if (bytes <= *granted) return MVB_OK;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        return set_err(MVB_ECUDA, "%s: cudaFuncSetAttribute(%zu bytes): %s", what, bytes, cudaGetErrorString(e));
-    }
-    *granted = bytes;
-    return MVB_OK;
+static int ensure_smem(KernelT kernel, size_t bytes, DevFlags *granted, const char *what) {
+    if (bytes <= 48 * 1024) return MVB_OK;
+    return smem_optin(kernel, bytes, *granted, what);
 }
 
 extern "C" int mvb_linear_fwd(int M, int K, int N, const float *x, int x_vm_f, const float *W, const float *bias,
@@ -558,7 +552,7 @@ extern "C" int mvb_linear_fwd(int M, int K, int N, const float *x, int x_vm_f, c
     const int KC = K4 < 640 ? K4 : 640;
     const bool vec = (K % 4 == 0) && (x_vm_f == 0 || x_vm_f % 4 == 0) && al16(x) && al16(W);
     const size_t smem = (size_t)(LF_TM + LF_TN) * (KC + 4) * sizeof(float);
-    static size_t granted4 = 48 * 1024, granted1 = 48 * 1024;
+    static DevFlags granted4, granted1;
     int rc = vec ? ensure_smem(linear_fwd_kernel<4>, smem, &granted4, "linear_fwd") : ensure_smem(linear_fwd_kernel<1>, smem, &granted1, "linear_fwd");
     if (rc) return rc;
     dim3 grid((N + LF_TN - 1) / LF_TN, (M + LF_TM - 1) / LF_TM);
@@ -586,7 +580,7 @@ extern "C" int mvb_linear_bwd(int M, int K, int N, const float *x, int x_vm_f, c
     const size_t smem = nB ? (smA > smB ? smA : smB) : smA;
     const bool vn = (N % 4 == 0) && (y_vm_f == 0 || y_vm_f % 4 == 0) && al16(gy) && (!relu || al16(y));
     const bool vk = (K % 4 == 0) && (x_vm_f == 0 || x_vm_f % 4 == 0) && al16(x) && al16(W);
-    static size_t granted[4] = {48 * 1024, 48 * 1024, 48 * 1024, 48 * 1024};
+    static DevFlags granted[4];
     const float scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
     int rc;
 #define MVB_LBWD(VN_, VK_, SLOT)                                                                                             \
@@ -615,7 +609,7 @@ extern "C" int mvb_vae_heads_fwd(int B, int H, int Z, int C, const float *h, con
     MVB_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "vae_heads_fwd: dropout p=%f outside [0,1)", p_drop);
     const size_t smem = (size_t)(2 * (C + H) + (C + 2 * Z) * (C + H + 1)) * sizeof(float);
     MVB_REQUIRE(smem <= 220 * 1024, "vae_heads_fwd: H=%d too large", H);
-    static size_t granted = 48 * 1024;
+    static DevFlags granted;
     int rc = ensure_smem(vae_heads_fwd_kernel, smem, &granted, "vae_heads_fwd");
     if (rc) return rc;
     vae_heads_fwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(B, H, Z, C, h, y_onehot, eps, Wc, bc, Wm, bm, Wv, bv, p_drop,
@@ -637,7 +631,7 @@ extern "C" int mvb_vae_heads_bwd(int B, int H, int Z, int C, const float *h, con
     const size_t smB = (size_t)(B * nout + 2 * B * 33 + 4 + small_in_words(B, Z, C)) * sizeof(float);
     const size_t smem = smA > smB ? smA : smB;
     MVB_REQUIRE(smem <= 220 * 1024, "vae_heads_bwd: batch %d / H=%d too large for one pass", B, H);
-    static size_t granted = 48 * 1024;
+    static DevFlags granted;
     int rc = ensure_smem(vae_heads_bwd_kernel, smem, &granted, "vae_heads_bwd");
     if (rc) return rc;
     const int nbg = (B + HB_ROWS - 1) / HB_ROWS;

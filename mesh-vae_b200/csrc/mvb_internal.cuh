@@ -31,7 +31,33 @@ inline int check_launch(const char *what) {
     return MVB_OK;
 }
 
-int num_sms();  // cached multiprocessor count of the current device (148 on B200)
+int num_sms();  // multiprocessor count of the CURRENT device, cached per device (148 on B200)
+
+// Function attributes (the opt-in for > 48 KB of dynamic shared memory) are per DEVICE: a process that drives several
+// GPUs must set them on each.  DevFlags keeps one bit / one size per device ordinal for a call site.
+inline int device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        dev = 0;
+    }
+    return (dev >= 0 && dev < 64) ? dev : 0;
+}
+struct DevFlags {
+    size_t granted[64] = {0};
+};
+template <typename KernelT>
+inline int smem_optin(KernelT kernel, size_t bytes, DevFlags &f, const char *what) {
+    const int d = device_slot();
+    if (bytes <= f.granted[d]) return MVB_OK;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(MVB_ECUDA, "%s: cudaFuncSetAttribute(%zu bytes): %s", what, bytes, cudaGetErrorString(e));
+    }
+    f.granted[d] = bytes;
+    return MVB_OK;
+}
 
 #ifdef __CUDACC__
 // global -> shared copy with U independent loads in flight per thread.  A plain

@@ -591,12 +591,11 @@ extern "C" int mvb_cheb_layer_fwd(int N, int B, int Fin, int Fout, int K, const 
     a.n_out = n_out; a.sel = sel;
     a.x = x; a.w = weight; a.bias = bias; a.relu = relu; a.out = y;
     a.splits = splits;
-    static size_t granted = 48 * 1024;
+    static DevFlags optin;
     const size_t smem = (size_t)S.total * 4;
-    if (smem > granted) {
-        cudaError_t e = cudaFuncSetAttribute(cheb_layer_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return set_err(MVB_ECUDA, "cheb_layer_fwd: %s", cudaGetErrorString(e));
-        granted = 200 * 1024;
+    if (smem > 48 * 1024) {
+        const int rc_attr = smem_optin(cheb_layer_fwd_kernel, 200 * 1024, optin, "cheb_layer_fwd");
+        if (rc_attr) return rc_attr;
     }
     cheb_layer_fwd_kernel<<<dim3(B, splits), LY_NT, smem, (cudaStream_t)stream>>>(a, S);
     return check_launch("mvb_cheb_layer_fwd");
@@ -639,12 +638,11 @@ extern "C" int mvb_cheb_layer_bwd(int N, int B, int Fin, int Fout, int K, const 
     a.dwp = reinterpret_cast<float *>(workspace);
     a.dbp = a.dwp + (size_t)B * K * Fin * Fout;
     a.splits = splits;
-    static size_t granted = 48 * 1024;
+    static DevFlags optin;
     const size_t smem = (size_t)S.total * 4;
-    if (smem > granted) {
-        cudaError_t e = cudaFuncSetAttribute(cheb_layer_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return set_err(MVB_ECUDA, "cheb_layer_bwd: %s", cudaGetErrorString(e));
-        granted = 200 * 1024;
+    if (smem > 48 * 1024) {
+        const int rc_attr = smem_optin(cheb_layer_bwd_kernel, 200 * 1024, optin, "cheb_layer_bwd");
+        if (rc_attr) return rc_attr;
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int nw = K * Fin * Fout, nb = dbias ? Fout : 0;

@@ -742,26 +742,10 @@ static bool mesh_tc_layout(MeshTcArgs &a, int width_in, int width_acc, int C) {
     return (size_t)a.total + 1024 <= 227 * 1024;
 }
 
-// per-device one-time attributes (a process may drive several devices)
-template <typename KernelT>
-static int ensure_smem_attr(KernelT kernel, bool *done, const char *what) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64) dev = 0;
-    if (done[dev]) return MVB_OK;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        return set_err(MVB_ECUDA, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
-    }
-    done[dev] = true;
-    return MVB_OK;
-}
-
 template <int WL>
 static int launch_mesh_fwd_t(const MeshTcArgs &a, cudaStream_t st) {
-    static bool done[64] = {false};
-    int rc = ensure_smem_attr(cheb_mesh_tc_fwd_kernel<WL>, done, "cheb_mesh_tc_fwd");
+    static DevFlags optin;
+    int rc = smem_optin(cheb_mesh_tc_fwd_kernel<WL>, 227 * 1024, optin, "cheb_mesh_tc_fwd");
     if (rc) return rc;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -838,8 +822,8 @@ int launch_mesh_tc_fwd(int N, int B, int Fin, int Fout, int K, const int32_t *Lr
 
 template <int WL>
 static int launch_mesh_bwd_t(const MeshTcBwdArgs &g, cudaStream_t st) {
-    static bool done[64] = {false};
-    int rc = ensure_smem_attr(cheb_mesh_tc_bwd_kernel<WL>, done, "cheb_mesh_tc_bwd");
+    static DevFlags optin;
+    int rc = smem_optin(cheb_mesh_tc_bwd_kernel<WL>, 227 * 1024, optin, "cheb_mesh_tc_bwd");
     if (rc) return rc;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

@@ -343,14 +343,14 @@ int launch_cheb_recur_fwd(int N, int nnz, int K, const int32_t *rowptr, const in
     if (K < 2 || !recur_shape(N, nnz, ncols, x, basis, &cs4, &smem, &nnz_smem)) return 0;
     const int nc4 = (int)(ncols / 4);
     const int grid = (nc4 + cs4 - 1) / cs4;
-    static bool attr1 = false, attr2 = false;
+    static DevFlags optin1, optin2;
     cudaError_t e = cudaSuccess;
     if (cs4 == 2) {
-        if (!attr2) { e = cudaFuncSetAttribute(cheb_recur_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr2 = true; }
+        if (smem_optin(cheb_recur_fwd_kernel<2>, 200 * 1024, optin2, "cheb_recur_fwd_kernel")) e = cudaErrorInvalidValue;
         if (e == cudaSuccess)
             cheb_recur_fwd_kernel<2><<<grid, g_recur_threads, smem, st>>>(N, K, rowptr, colidx, vals, (const float4 *)x, (float4 *)basis, nc4, nnz_smem);
     } else {
-        if (!attr1) { e = cudaFuncSetAttribute(cheb_recur_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr1 = true; }
+        if (smem_optin(cheb_recur_fwd_kernel<1>, 200 * 1024, optin1, "cheb_recur_fwd_kernel")) e = cudaErrorInvalidValue;
         if (e == cudaSuccess)
             cheb_recur_fwd_kernel<1><<<grid, g_recur_threads, smem, st>>>(N, K, rowptr, colidx, vals, (const float4 *)x, (float4 *)basis, nc4, nnz_smem);
     }
@@ -366,14 +366,14 @@ int launch_cheb_recur_bwd(int N, int nnz, int K, const int32_t *rowptr_t, const 
     if (K < 2 || !recur_shape(N, nnz, ncols, P, dx, &cs4, &smem, &nnz_smem)) return 0;
     const int nc4 = (int)(ncols / 4);
     const int grid = (nc4 + cs4 - 1) / cs4;
-    static bool attr1 = false, attr2 = false;
+    static DevFlags optin1, optin2;
     cudaError_t e = cudaSuccess;
     if (cs4 == 2) {
-        if (!attr2) { e = cudaFuncSetAttribute(cheb_recur_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr2 = true; }
+        if (smem_optin(cheb_recur_bwd_kernel<2>, 200 * 1024, optin2, "cheb_recur_bwd_kernel")) e = cudaErrorInvalidValue;
         if (e == cudaSuccess)
             cheb_recur_bwd_kernel<2><<<grid, g_recur_threads, smem, st>>>(N, K, rowptr_t, colidx_t, vals_t, (const float4 *)P, (float4 *)dx, nc4, nnz_smem);
     } else {
-        if (!attr1) { e = cudaFuncSetAttribute(cheb_recur_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr1 = true; }
+        if (smem_optin(cheb_recur_bwd_kernel<1>, 200 * 1024, optin1, "cheb_recur_bwd_kernel")) e = cudaErrorInvalidValue;
         if (e == cudaSuccess)
             cheb_recur_bwd_kernel<1><<<grid, g_recur_threads, smem, st>>>(N, K, rowptr_t, colidx_t, vals_t, (const float4 *)P, (float4 *)dx, nc4, nnz_smem);
     }

@@ -373,11 +373,10 @@ static int pow2_cols(int n) {
 
 template <int W, int NP, int PG = NP>
 static int launch_rowgemm_t(const TcRowArgs &t, unsigned grid, size_t smem, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_rowgemm_kernel<W, NP, PG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return set_err(MVB_ECUDA, "tc_rowgemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set = true;
+    static DevFlags optin;
+    {
+        const int rc_attr = smem_optin(tc_rowgemm_kernel<W, NP, PG>, 200 * 1024, optin, "tc_rowgemm");
+        if (rc_attr) return rc_attr;
     }
     tc_rowgemm_kernel<W, NP, PG><<<grid, 128, smem, st>>>(t);
     return check_launch("mvb tc_rowgemm");
@@ -777,11 +776,10 @@ tc_wgrad_kernel(TcWgradArgs a) {
 
 template <int NPF, int Q4>
 static int launch_wgrad_t(const TcWgradArgs &t, unsigned grid, size_t smem, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel<NPF, Q4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return set_err(MVB_ECUDA, "tc_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set = true;
+    static DevFlags optin;
+    {
+        const int rc_attr = smem_optin(tc_wgrad_kernel<NPF, Q4>, 200 * 1024, optin, "tc_wgrad");
+        if (rc_attr) return rc_attr;
     }
     tc_wgrad_kernel<NPF, Q4><<<grid, WG_NT, smem, st>>>(t);
     return check_launch("mvb tc_wgrad");

@@ -97,12 +97,14 @@ class FlatAdam:
 
 class TrainEngine:
     def __init__(self, net, batch: int, lr=1e-3, weight_decay=5e-4, x_gt_dtype=torch.float64, use_graph=True,
-                 distributed: Optional[bool] = None):
+                 distributed: Optional[bool] = None, graph_comm: bool = True):
         self.net = net
         self.dev = next(net.parameters()).device
         self.batch = batch
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         self.distributed = (self.world > 1) if distributed is None else distributed
+        self.graph_comm = graph_comm            # data parallel: capture the all-reduces inside the step graph
+        self.one_graph = False
         self.n_vert = net.adjacency_matrices[0].shape[0]
         self.feat = net.filters[0]
         # which parameters receive gradients is a property of the graph (dec_lin_1 is dead): probe once
@@ -159,6 +161,19 @@ class TrainEngine:
         self._stage = self._stage_flat = self._ev_staged = self._ev_consumed = self._h_small = None
         self._staged = False
         self._fwd_out = None
+
+    def release(self):
+        """Detach the engine from the model: remove the gradient sinks (while they are installed the backward kernels
+        OVERWRITE the flat gradient buffer and hand `None` to autograd - a torch optimizer driving the same net afterwards
+        would skip those parameters, and gradient accumulation would not accumulate) and give the dropout streams back
+        their host counter.  Parameters stay views of the flat parameter buffer (values preserved)."""
+        for p in self.opt.params:
+            if hasattr(p, "_mvb_grad_sink"):
+                del p._mvb_grad_sink
+            p.grad = None
+        if hasattr(self.net, "dropout_stream"):
+            self.net.dropout_stream.offset_dev = None
+        self.g_fb = self.g_opt = self.g_enc = None
 
     def _alloc_inputs(self):
         offs, n = [], 0
@@ -270,6 +285,42 @@ class TrainEngine:
         # all captures on ONE stream: autograd replays a node's backward on the stream of its forward, so the
         # encoder backward (its own graph when the gradient buckets are split) must be captured on that stream
         cap = torch.cuda.Stream()
+        self.one_graph = not self.distributed
+        if self.distributed and self.graph_comm:
+            # Data parallel, ONE graph: the bucketed NCCL all-reduces are captured with the step (NCCL enqueues on its own
+            # stream; fork / join become graph edges), so a step is a single replay - no host launch between backward,
+            # exchange and optimizer, and the big bucket still overlaps the encoder backward.
+            try:
+                warm = torch.zeros(8, device=self.dev)
+                dist.all_reduce(warm)                       # communicator set-up outside the capture
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=cap):
+                    self._fwd()
+                    check(lib.mvb_stream_wait_external_event(stream_ptr(), self._gt_ready.cuda_event), "mvb_stream_wait_external_event")
+                    if self.split:
+                        self._loss_bwd(1)
+                        w1 = dist.all_reduce(self.opt.flat_g[self.split:], op=dist.ReduceOp.SUM, async_op=True)
+                        self._loss_bwd(2)
+                        w2 = dist.all_reduce(self.opt.flat_g[:self.split], op=dist.ReduceOp.SUM, async_op=True)
+                        w1.wait()
+                        w2.wait()
+                    else:
+                        self._loss_bwd(0)
+                        dist.all_reduce(self.opt.flat_g, op=dist.ReduceOp.SUM)
+                    self._optim()
+                self.g_fb, self.one_graph = g, True
+                self.launches_per_step = lib.mvb_launch_count() - c0
+                torch.cuda.synchronize()
+                return
+            except Exception as e:  # noqa: BLE001  (a build of torch / NCCL that cannot capture collectives): three graphs below
+                import warnings
+                warnings.warn(f"TrainEngine: the data-parallel step could not be captured as one graph ({e}); "
+                              "falling back to three graphs with host-launched all-reduces")
+                torch.cuda.synchronize()
+                self.opt.flat_p.copy_(state[0]); self.opt.m.copy_(state[1]); self.opt.v.copy_(state[2])
+                self.opt.step_count.copy_(state[3])
+                c0 = lib.mvb_launch_count()
         self.g_fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_fb, stream=cap):
             self._fwd()
@@ -290,6 +341,9 @@ class TrainEngine:
 
     def device_step(self):
         """one training step on inputs already resident in the static device buffers"""
+        if self.use_graph and self.one_graph:
+            self.g_fb.replay()               # the whole step, collectives included
+            return
         if self.use_graph:
             self.g_fb.replay()
         else:

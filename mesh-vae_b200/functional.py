@@ -395,7 +395,11 @@ class DropoutStream:
         self.offset_dev: Optional[torch.Tensor] = None     # int64 scalar on the device, or None
 
     def advance(self):
-        self.offset_host += 1
+        # with a device counter attached (the engine points it at Adam's step counter, which every step - replayed or
+        # eager - increments) the host offset must stay frozen: advancing both would hand two different steps the same
+        # sum, i.e. the same masks at every site
+        if self.offset_dev is None:
+            self.offset_host += 1
 
     def site(self, site_id: int):
         return ((self.seed + 0x9E3779B97F4A7C15 * (site_id + 1)) & 0xFFFFFFFFFFFFFFFF, self.offset_dev, self.offset_host)
@@ -519,9 +523,22 @@ class _VaeHeadsFn(torch.autograd.Function):
 
 def vae_heads(h, y_onehot, eps, classifier, z_mean, z_log_var, p: float = 0.0, rng=_NO_RNG):
     """-> (y_hat, mu, logvar, z, cat(y, z)); `classifier`, `z_mean`, `z_log_var` are the model's
-    nn.Linear modules (their Parameters receive the gradients); eps=None means z = mu (test mode)."""
-    return _VaeHeadsFn.apply(h, y_onehot, eps, classifier.weight, classifier.bias, z_mean.weight, z_mean.bias,
-                             z_log_var.weight, z_log_var.bias, float(p), rng)
+    nn.Linear modules (their Parameters receive the gradients); eps=None means z = mu (test mode).
+    Batches beyond VAE_HEADS_MAX_BATCH meshes (the one-launch backward keeps the batch's small gradients in shared
+    memory) run in chunks of that size: the outputs are concatenated and autograd adds the chunks' parameter gradients
+    (no gradient sinks on that path - the kernels OVERWRITE their dW outputs)."""
+    args = (classifier.weight, classifier.bias, z_mean.weight, z_mean.bias, z_log_var.weight, z_log_var.bias)
+    b = h.shape[0]
+    if b <= VAE_HEADS_MAX_BATCH:
+        return _VaeHeadsFn.apply(h, y_onehot, eps, *args, float(p), rng)
+    if p > 0:
+        raise _lib.MvbError(f"vae_heads: dropout with more than {VAE_HEADS_MAX_BATCH} meshes per call is not supported "
+                            "(the mask is keyed by the row index inside a call)")
+    plain = tuple(t.view_as(t) for t in args)          # non-leaf aliases: no sink attribute, autograd accumulates
+    outs = [_VaeHeadsFn.apply(h[i:i + VAE_HEADS_MAX_BATCH], y_onehot[i:i + VAE_HEADS_MAX_BATCH],
+                              None if eps is None else eps[i:i + VAE_HEADS_MAX_BATCH], *plain, 0.0, rng)
+            for i in range(0, b, VAE_HEADS_MAX_BATCH)]
+    return tuple(torch.cat([o[j] for o in outs], 0) for j in range(5))
 
 
 # ---------------------------------------------------------------------------------------------

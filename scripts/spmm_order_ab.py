@@ -5,6 +5,56 @@ sys.path.insert(0, ROOT)
 import torch
 import meshvae_b200 as mvb
 import bench
+import numpy as np
+
+
+def locality_order(n: int, rows, cols, fixed_prefix: int = 0, cluster: int = 64) -> np.ndarray:
+    """A vertex order in which every run of `cluster` consecutive rows is a compact patch of the mesh:
+    order[i] = original index of the vertex placed at row i.  Patches are grown breadth-first from seeds
+    taken on the boundary of the previous patches and are aligned to multiples of `cluster` (the row chunk
+    one SpMM block walks), so the neighbours gathered by a block are ~1.6 x its own rows instead of ~3 x
+    in the template's order - they then stay in the block's L1.  The first `fixed_prefix` vertices keep
+    their place (the reference's output layer applies the coarsest operator to vertices 0..19 of the
+    finest mesh, models/cheb_VAE.py:288).  Pure graph algorithm, deterministic, host side, init time."""
+    from collections import deque
+    rows = np.asarray(rows)
+    cols = np.asarray(cols)
+    nbrs = [[] for _ in range(n)]
+    for a, b in zip(rows.tolist(), cols.tolist()):
+        if a != b:
+            nbrs[a].append(b)
+    visited = np.zeros(n, dtype=bool)
+    order = list(range(fixed_prefix))
+    visited[:fixed_prefix] = True
+    frontier = deque(w for v in range(fixed_prefix) for w in nbrs[v])
+    while len(order) < n:
+        want = cluster - (len(order) % cluster)
+        seed = None
+        while frontier:
+            cand = frontier.popleft()
+            if not visited[cand]:
+                seed = cand
+                break
+        if seed is None:
+            seed = int(np.argmin(visited))
+        q = deque([seed])
+        visited[seed] = True
+        members = []
+        while q and len(members) < want:
+            v = q.popleft()
+            members.append(v)
+            for w in nbrs[v]:
+                if not visited[w]:
+                    visited[w] = True
+                    q.append(w)
+        for w in q:                      # reached but not placed: seeds of the next patches
+            visited[w] = False
+            frontier.append(w)
+        order.extend(members)
+    return np.asarray(order, dtype=np.int64)
+
+
+
 dev = torch.device("cuda:0")
 _, net, A, nn_ = bench.build_model(dev)
 L = mvb._lib
@@ -30,7 +80,7 @@ for cluster in (0, 32, 64, 128):
     if cluster == 0:
         op = op0
     else:
-        order = mvb.operators.locality_order(n, ei[1].cpu().numpy(), ei[0].cpu().numpy(), 20, cluster)
+        order = locality_order(n, ei[1].cpu().numpy(), ei[0].cpu().numpy(), 20, cluster)
         inv = torch.empty(n, dtype=torch.long); inv[torch.from_numpy(order)] = torch.arange(n)
         ei_p = inv.to(ei.device)[ei]
         op = mvb.operators.from_edges(ei_p.contiguous(), norm.clone(), n, dev)

@@ -171,3 +171,30 @@ def test_recon_error_matches_reference_arithmetic():
     assert rel_err(got_mean, torch.from_numpy(ref_mean)) < 1e-12 and rel_err(got_max, torch.from_numpy(ref_max)) < 1e-12
     got2, _ = Fn.recon_error(out_d.contiguous(), mean, std, s, R, m, gt)          # contiguous [B,N,3] input: copied path
     assert torch.equal(got2, got_mean)
+
+
+def test_vae_heads_beyond_one_launch_batch(Fn):
+    """more meshes than the one-launch heads kernel holds (VAE_HEADS_MAX_BATCH): chunked calls, gradients summed by
+    autograd - the strong-scaling shapes (512 / 256 meshes per GPU) stay on the native kernels"""
+    b, hd, z, c = Fn.VAE_HEADS_MAX_BATCH + 44, 512, 16, 2
+    h = _rand(b, hd, seed=1)
+    y = F.one_hot(torch.randint(0, c, (b,), generator=torch.Generator().manual_seed(2)), c)
+    eps = _rand(b, z, seed=3)
+    mods = [torch.nn.Linear(hd, c), torch.nn.Linear(hd + c, z), torch.nn.Linear(hd + c, z)]
+    gmods = [torch.nn.Linear(hd, c).cuda(), torch.nn.Linear(hd + c, z).cuda(), torch.nn.Linear(hd + c, z).cuda()]
+    for m, g in zip(mods, gmods):
+        g.load_state_dict(m.state_dict())
+    hr = h.clone().requires_grad_()
+    y_hat = torch.softmax(mods[0](hr), 1)
+    hc = torch.cat([y.float(), hr], 1)
+    mu, lv = mods[1](hc), mods[2](hc)
+    zz = mu + eps * torch.exp(0.5 * lv)
+    loss = (y_hat * _rand(b, c, seed=4)).sum() + (zz * _rand(b, z, seed=5)).sum() + (mu * lv).sum()
+    loss.backward()
+    hg = h.cuda().requires_grad_()
+    o = Fn.vae_heads(hg, y.cuda(), eps.cuda(), *gmods)
+    lg = (o[0] * _rand(b, c, seed=4).cuda()).sum() + (o[3] * _rand(b, z, seed=5).cuda()).sum() + (o[1] * o[2]).sum()
+    lg.backward()
+    assert rel_err(o[0], y_hat) < 1e-5 and rel_err(o[3], zz) < 1e-5 and rel_err(hg.grad, hr.grad) < 1e-4
+    for m, g in zip(mods, gmods):
+        assert rel_err(g.weight.grad, m.weight.grad) < 1e-4 and rel_err(g.bias.grad, m.bias.grad) < 1e-4

@@ -230,3 +230,30 @@ def test_loss_and_reconstruction_error_curves_match_reference_with_dropout():
         assert de <= max(1e-2, 2 * spread_e), (a, de, spread_e)
     print("window: loss dev / ref spread, recon-error dev / ref spread:", [(a, f"{dl:.1e}/{sl:.1e}", f"{de:.1e}/{se:.1e}") for a, dl, sl, de, se in rows])
     assert E[-20:].mean() < 0.9 * E[:5].mean(), "the reconstruction error must have gone down"
+
+
+def test_learning_rate_change_reaches_a_captured_step():
+    """hyper-parameters were frozen into the captured graphs.  They now live in device memory: `opt.lr = ...`,
+    `param_groups[0]['lr'] = ...` (main.py:266-269) and formats.load_adam_state_dict change the NEXT replayed step."""
+    import meshvae_b200 as mvb
+    from meshvae_b200.engine import TrainEngine
+    B = 4
+    _, net, nn_ = _models(mvb, 0.0)
+    eng = TrainEngine(net, B, lr=1e-3, weight_decay=5e-4, x_gt_dtype=torch.float64, use_graph=True)
+    eng.capture(warmup=2)
+    x, y, eps = seeded_batch(B, nn_[0], 5)
+    args = (x.pin_memory(), x.double().pin_memory(), y.pin_memory())
+    eng.step(*args, eps_host=eps)
+    p0 = eng.opt.flat_p.clone()
+    eng.step(*args, eps_host=eps)
+    d1 = float((eng.opt.flat_p - p0).abs().max())
+    for g in eng.opt.param_groups:          # the reference's schedule loop, main.py:268-269
+        g["lr"] = 0.0
+    p1 = eng.opt.flat_p.clone()
+    eng.step(*args, eps_host=eps)
+    assert d1 > 0 and float((eng.opt.flat_p - p1).abs().max()) == 0.0, "lr = 0 must freeze the parameters of a replayed step"
+    eng.opt.set_lr(1e-3)
+    eng.step(*args, eps_host=eps)
+    assert float((eng.opt.flat_p - p1).abs().max()) > 0
+    eng.release()
+    assert not any(hasattr(p, "_mvb_grad_sink") for p in net.parameters())
