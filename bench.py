@@ -420,8 +420,15 @@ def layer_rooflines(mvb, net, nn_, batch, dev, peak_gbs, reps=12):
             x.requires_grad_()
         with torch.no_grad():
             xin = Fn.from_vertex_major(Fn.pack_input(x)) if first else x
-        y = net._layer(xin, conv, lvl, up=up, down=down)
-        gy = torch.randn_like(y)
+        # autograd replays a node's backward on the stream of its forward: the forward that the captured backward
+        # differentiates must itself have run on the capture stream
+        cap = torch.cuda.Stream()
+        cap.wait_stream(st)
+        with torch.cuda.stream(cap):
+            y = net._layer(xin, conv, lvl, up=up, down=down)
+            gy = torch.randn_like(y)
+        st.wait_stream(cap)
+        torch.cuda.synchronize()
         params = [conv.weight, conv.bias] + ([] if first else [x])
 
         def fwd():
@@ -432,15 +439,14 @@ def layer_rooflines(mvb, net, nn_, batch, dev, peak_gbs, reps=12):
             torch.autograd.grad(y, params, gy, retain_graph=True, allow_unused=True)      # (engine sinks: dW lands in the flat buffer)
         times = {}
         for tag, fn in (("fwd", fwd), ("bwd", bwd)):
-            side = torch.cuda.Stream()
-            side.wait_stream(st)
-            with torch.cuda.stream(side):
+            cap.wait_stream(st)
+            with torch.cuda.stream(cap):
                 for _ in range(3):
                     fn()
-            st.wait_stream(side)
+            st.wait_stream(cap)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=cap):
                 fn()
             ts = []
             for i in range(reps + 3):
@@ -470,7 +476,8 @@ def run_ours(args, rank, world, local_rank):
     mvb, net, A, nn_ = build_model(dev)
     from meshvae_b200.engine import TrainEngine
     B = args.batch
-    eng = TrainEngine(net, B, lr=1e-3, weight_decay=5e-4, x_gt_dtype=torch.float64, use_graph=not args.no_graph)
+    eng = TrainEngine(net, B, lr=1e-3, weight_decay=5e-4, x_gt_dtype=torch.float64, use_graph=not args.no_graph,
+                      graph_comm=not args.host_comm)
     eng.capture(warmup=3)
 
     # synthetic batch in pinned host memory (z-score-like vertices)
@@ -570,6 +577,9 @@ def run_ours(args, rank, world, local_rank):
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "flushed between timed steps (256 MiB write, outside the event pairs)",
                        "cuda_graph": not args.no_graph, "final_loss": last_loss,
+                       "step_graphs": (1 if eng.one_graph else (3 if eng.split else 2)) if not args.no_graph else 0,
+                       "collectives": None if world == 1 else ("NCCL all-reduce of the flat fp32 gradient in two buckets, "
+                                                               + ("captured inside the step graph" if eng.one_graph else "host-launched between graphs")),
                        "e2e_input": "double-buffered: each timed step copies the next batch from pinned host memory "
                                     "(on a copy stream, inside the event pair) while it computes the current one"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": eng.h2d_bytes(),
@@ -796,6 +806,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="meshes per GPU per step")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--host-comm", action="store_true",
+                    help="data parallel: all-reduces launched from the host between three graphs (round-1 scheme) instead of "
+                         "captured inside the one step graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -63,6 +63,8 @@ int mvb_tune(const char *spec);
  * mvb_side_join(stream), which makes `stream` wait for the pending chain, and (2) call it before reading any gradient
  * and before a stream capture ends.  Default off: every call joins before it returns. */
 int mvb_side_join(void *stream);
+/* the same for one lane of chains: 0 = convolution weight gradients, 1 = dense-layer weight gradients (mvb_linear_bwd) */
+int mvb_side_join_lane(void *stream, int lane);
 
 /* step-engine plumbing: cudaStreamWaitEvent(stream, event, cudaEventWaitExternal).  Legal during stream
  * capture (becomes an external event-wait node): each replay of the captured graph waits for the latest

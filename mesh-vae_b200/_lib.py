@@ -40,6 +40,7 @@ SIGNATURES = {
     "mvb_set_tensor_cores": (c_int, [c_int]),
     "mvb_tune": (c_int, [c_char_p]),
     "mvb_side_join": (c_int, [_vp]),
+    "mvb_side_join_lane": (c_int, [_vp, c_int]),
     "mvb_stream_wait_external_event": (c_int, [_vp, _vp]),
     "mvb_csr_from_coo_host": (c_int, [c_int64, c_int64, c_int64, _vp, _vp, _vp, c_int, _vp, _vp, _vp]),
     "mvb_spmm": (c_int, [c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_float, c_float, c_int64, _vp]),
@@ -113,10 +114,14 @@ def defer_side_chains(on: bool):
     tune(f"defer_wgrad={1 if on else 0}")
 
 
-def side_join():
-    """make the current stream wait for the pending side chain and release the parked tensors"""
-    check(lib.mvb_side_join(stream_ptr()), "mvb_side_join")
-    _deferred["keep"].clear()
+def side_join(lane=None):
+    """make the current stream wait for the pending side chains (of one lane, or of all: the parked tensors are then
+    released)"""
+    if lane is None:
+        check(lib.mvb_side_join(stream_ptr()), "mvb_side_join")
+        _deferred["keep"].clear()
+    else:
+        check(lib.mvb_side_join_lane(stream_ptr(), int(lane)), "mvb_side_join_lane")
 
 
 def ptr(t):

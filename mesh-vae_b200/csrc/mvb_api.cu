@@ -375,15 +375,19 @@ struct LazySide {
     cudaEvent_t fork = nullptr, join = nullptr;
     bool tried = false, ok = false, pending = false;
 };
-static LazySide g_lazy[64];
+static LazySide g_lazy[64][2];      // [device][lane]: lane 0 = convolution weight gradients, lane 1 = dense-layer weight gradients
 static std::mutex g_lazy_mu;
 static int g_defer_wgrad = 0;
 void set_defer_wgrad(int v) { g_defer_wgrad = v ? 1 : 0; }
+static int g_background_div = 0;        // deferred level-0 weight-gradient reduction: SMs per CTA, 0 = the usual two CTAs per SM
+                                        // (tuning: background_div; measured at 64 meshes: 0 -> 921 us per step, 1 -> 948, 2 -> 988:
+                                        // the slower reduction delays every chain queued behind it more than it spares the main stream)
+void set_background_div(int v) { g_background_div = v < 0 ? 0 : v; }
 
-static LazySide *lazy_side() {
+static LazySide *lazy_side(int lane) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    LazySide &s = g_lazy[dev];
+    LazySide &s = g_lazy[dev][lane & 1];
     if (!s.tried) {
         s.tried = true;
         // LOWEST priority: when a chain and a kernel of the caller's stream are ready together (the input-gradient
@@ -411,10 +415,10 @@ static void lazy_join_locked(LazySide *s, cudaStream_t st) {
 
 // Call AFTER the producer kernel of the chain has been enqueued on `st`.  Makes the side stream wait for that point of
 // `st`; returns the stream to enqueue the chain on, or NULL (not deferred / unavailable): run it on `st`.
-cudaStream_t lazy_fork(cudaStream_t st) {
+cudaStream_t lazy_fork(cudaStream_t st, int lane) {
     if (!g_defer_wgrad) return nullptr;
     std::lock_guard<std::mutex> lk(g_lazy_mu);
-    LazySide *s = lazy_side();
+    LazySide *s = lazy_side(lane);
     if (!s) return nullptr;
     if (cudaEventRecord(s->fork, st) != cudaSuccess || cudaStreamWaitEvent(s->stream, s->fork, 0) != cudaSuccess) {
         cudaGetLastError();
@@ -428,7 +432,8 @@ cudaStream_t lazy_fork(cudaStream_t st) {
 void lazy_done(cudaStream_t side, cudaStream_t st) {
     if (!side) return;
     std::lock_guard<std::mutex> lk(g_lazy_mu);
-    LazySide *s = lazy_side();
+    LazySide *s = lazy_side(0);
+    if (!s || s->stream != side) s = lazy_side(1);
     if (!s || s->stream != side) return;
     cudaEventRecord(s->join, s->stream);
     s->pending = true;
@@ -438,7 +443,16 @@ void lazy_done(cudaStream_t side, cudaStream_t st) {
 
 extern "C" int mvb_side_join(void *stream) {
     std::lock_guard<std::mutex> lk(mvb::g_lazy_mu);
-    mvb::lazy_join_locked(mvb::lazy_side(), (cudaStream_t)stream);
+    mvb::lazy_join_locked(mvb::lazy_side(0), (cudaStream_t)stream);
+    mvb::lazy_join_locked(mvb::lazy_side(1), (cudaStream_t)stream);
+    return MVB_OK;
+}
+
+// join only the chains of one lane (1 = the dense layers' weight gradients: the data-parallel engine reduces their
+// bucket while the convolution chains of lane 0 are still running)
+extern "C" int mvb_side_join_lane(void *stream, int lane) {
+    std::lock_guard<std::mutex> lk(mvb::g_lazy_mu);
+    mvb::lazy_join_locked(mvb::lazy_side(lane), (cudaStream_t)stream);
     return MVB_OK;
 }
 
@@ -689,6 +703,9 @@ static int cheb_bwd_adjoint(int N, int B, int Fin, int Fout, int K, int n_active
         wa.n_out = Fin;
         wa.partials = partA;
         wa.partial_bytes = partA_bytes;
+        // (tuning hook) deferred chain of a level too large for L2: fewer CTAs, so that the HBM-bound kernels of the
+        // critical path that follow keep more of the memory system - measured a net loss, off by default
+        wa.background = (lazy && rows_act * (int64_t)K * Fout * 4 > (int64_t)64 << 20) ? g_background_div : 0;
         rc = launch_wgrad_partials(wa, 0, &nA, &m4A, wst);
         if (rc) return rc;
     }
@@ -772,6 +789,7 @@ extern "C" int mvb_tune(const char *spec) {
         else if (!strcmp(key, "mesh_tc")) set_mesh_tc(v[0], v[1]);
         else if (!strcmp(key, "mesh_dbg")) set_mesh_dbg(v[0]);
         else if (!strcmp(key, "defer_wgrad")) set_defer_wgrad(v[0]);
+        else if (!strcmp(key, "background_div")) set_background_div(v[0]);
         else if (key[0]) return set_err(MVB_EINVAL, "mvb_tune: unknown key '%s'", key);
     }
     return MVB_OK;

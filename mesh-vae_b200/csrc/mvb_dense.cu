@@ -590,6 +590,31 @@ extern "C" int mvb_linear_bwd(int M, int K, int N, const float *x, int x_vm_f, c
         linear_bwd_kernel<VN_, VK_><<<nA + nB, 256, smem, (cudaStream_t)stream>>>(M, K, N, x, x_vm_f, W, y, gy, y_vm_f, relu, \
                                                                                   scale, dx, dW, db, nA, k_tiles, nc_b);     \
     } while (0)
+    // Deferred mode (step engine, mvb_tune "defer_wgrad=1"): the input-gradient tiles (role B) are what the backward
+    // pass waits for - they are launched alone on the caller's stream, and the weight / bias gradient tiles (role A) go
+    // to the deferred side chain (joined by mvb_side_join before the optimizer).  Otherwise one launch with both roles.
+    cudaStream_t lazy = (dx && nB) ? lazy_fork((cudaStream_t)stream, 1) : nullptr;
+#define MVB_LBWD_SPLIT(VN_, VK_, SLOT)                                                                                        \
+    do {                                                                                                                     \
+        rc = ensure_smem(linear_bwd_kernel<VN_, VK_>, smem, &granted[SLOT], "linear_bwd");                                   \
+        if (rc) break;                                                                                                       \
+        linear_bwd_kernel<VN_, VK_><<<nB, 256, smem, (cudaStream_t)stream>>>(M, K, N, x, x_vm_f, W, y, gy, y_vm_f, relu,      \
+                                                                             scale, dx, dW, db, 0, k_tiles, nc_b);           \
+        rc = check_launch("mvb_linear_bwd dx");                                                                              \
+        if (rc) break;                                                                                                       \
+        linear_bwd_kernel<VN_, VK_><<<nA, 256, smem, lazy>>>(M, K, N, x, x_vm_f, W, y, gy, y_vm_f, relu, scale, nullptr, dW,  \
+                                                             db, nA, k_tiles, nc_b);                                         \
+        rc = check_launch("mvb_linear_bwd dW");                                                                              \
+    } while (0)
+    if (lazy) {
+        if (vn && vk) MVB_LBWD_SPLIT(4, 4, 0);
+        else if (vn) MVB_LBWD_SPLIT(4, 1, 1);
+        else if (vk) MVB_LBWD_SPLIT(1, 4, 2);
+        else MVB_LBWD_SPLIT(1, 1, 3);
+        lazy_done(lazy, (cudaStream_t)stream);
+        return rc;
+    }
+#undef MVB_LBWD_SPLIT
     if (vn && vk) MVB_LBWD(4, 4, 0);
     else if (vn) MVB_LBWD(4, 1, 1);
     else if (vk) MVB_LBWD(1, 4, 2);

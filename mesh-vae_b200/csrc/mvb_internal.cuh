@@ -155,6 +155,10 @@ struct WgradArgs {
     const int32_t *row_sel;
     int sel_group;
     int64_t plane_rows;
+    // > 0: a reduction that runs as a deferred side chain next to kernels of the critical path - one CTA per
+    // `background` SMs... i.e. the grid is num_sms() / background instead of two CTAs per SM, so that it takes a
+    // fraction of the block slots and of the memory system instead of half of them
+    int background;
 };
 size_t wgrad_partial_bytes(int M, int n_out);
 int launch_wgrad_partials(const WgradArgs &a, int has_bias, int *nparts, int *m4_out, cudaStream_t st);
@@ -204,7 +208,7 @@ int launch_mesh_tc_bwd(int N, int B, int Fin, int Fout, int K, const int32_t *Lt
 int launch_layer_finalize(int B, int nw, int nb, const float *dwp, const float *dbp, float *dw, float *db, cudaStream_t st);
 
 // deferred side chains (mvb_api.cu): see lazy_fork / lazy_done / mvb_side_join
-cudaStream_t lazy_fork(cudaStream_t st);
+cudaStream_t lazy_fork(cudaStream_t st, int lane = 0);
 void lazy_done(cudaStream_t side, cudaStream_t st);
 
 // fork a per-thread side stream from `st` (NULL: no overlap) / make `st` wait for it again (mvb_api.cu)

@@ -816,7 +816,8 @@ int launch_wgrad_tc(const WgradArgs &a, int has_bias, int M4, int N4, int *npart
     t.tmem_cols = 32;
     const size_t smem = 1024 + 10 * 64 * 128 + 64;
     const int64_t ntiles = (a.rows + 63) / 64;
-    int64_t grid = (int64_t)num_sms() * 2;
+    int64_t grid = a.background > 0 ? (int64_t)num_sms() / a.background : (int64_t)num_sms() * 2;
+    if (grid < 1) grid = 1;
     if (grid > ntiles) grid = ntiles;
     if ((size_t)grid * M4 * N4 * sizeof(float) > a.partial_bytes) return set_err(MVB_EWORKSPACE, "tc_wgrad: workspace too small");
     int rc;

@@ -105,6 +105,7 @@ class TrainEngine:
         self.distributed = (self.world > 1) if distributed is None else distributed
         self.graph_comm = graph_comm            # data parallel: capture the all-reduces inside the step graph
         self.one_graph = False
+        self._capturing_one_graph = False
         self.n_vert = net.adjacency_matrices[0].shape[0]
         self.feat = net.filters[0]
         # which parameters receive gradients is a property of the graph (dec_lin_1 is dead): probe once
@@ -126,12 +127,20 @@ class TrainEngine:
         # final once the backward pass reaches the encoder's last pooled output - its all-reduce runs on NCCL's
         # stream while the encoder backward (a second graph) computes.
         self._enc_ids = {id(p) for p in getattr(net, "cheb", torch.nn.ModuleList()).parameters()}
-        late = [p for p in live if id(p) in self._enc_ids or (p.dim() == 3 and (p.shape[1] % 4 or p.shape[2] % 4))]
+        # (round 2) every convolution's weights go to the late bucket: their gradients come from the deferred
+        # weight-gradient side chains (joined once, at the end of the backward pass), and together they are ~100 KB -
+        # the early bucket then holds exactly the dense layers (99 % of the bytes), all produced on the main stream
+        # before the cut, and its all-reduce overlaps the whole encoder backward without an early join
+        conv_ids = self._enc_ids | {id(p) for p in getattr(net, "cheb_dec", torch.nn.ModuleList()).parameters()}
+        late = [p for p in live if id(p) in conv_ids or (p.dim() == 3 and (p.shape[1] % 4 or p.shape[2] % 4))]
         late_ids = {id(p) for p in late}
         live = late + [p for p in live if id(p) not in late_ids]
         self.opt = FlatAdam(live, lr=lr, weight_decay=weight_decay)
         self.split = self.opt.offsets[len(late)] if (self.distributed and use_graph and hasattr(net, "keep_encoder_conv_out")
                                                      and 0 < len(late) < len(live)) else 0
+        import os
+        if os.environ.get("MVB_DP_SPLIT") == "0":          # A/B: one all-reduce of the whole buffer at the end of the backward pass
+            self.split = 0
         if hasattr(net, "dropout_stream"):
             # fresh dropout masks on every graph replay: the fused dense kernels add Adam's device step
             # counter to their Philox offset; per-rank streams
@@ -215,11 +224,16 @@ class TrainEngine:
             self.kld, self.rec, self.correct = kld, rec, correct
             self.recon = recon.detach()         # [B,N,3] view of the decoder buffer (no autograd graph attached)
             self._fwd_out = None
-        _lib.defer_side_chains(True)          # weight-gradient chains of the mesh layers overlap the next layer (joined below)
+        _lib.defer_side_chains(True)          # weight-gradient chains of the conv layers run beside the following layers
         try:
             sel = self._backward_part(part, loss if part in (0, 1) else None)
         finally:
-            _lib.side_join()
+            # joined at the end of the backward pass; after part 1 only when a stream capture ends there (the
+            # three-graph scheme) - in the one-graph step the chains of the decoder keep running under the encoder backward
+            if part != 1 or not self._capturing_one_graph:
+                _lib.side_join()
+            else:
+                _lib.side_join(lane=1)          # the dense layers' dW / db (bucket 1) must be final before its all-reduce
             _lib.defer_side_chains(False)
         if sel:       # autograd-routed gradients into their views (all of them live in bucket 2)
             torch._foreach_copy_([v for _, v in sel], [p.grad for p, _ in sel])
@@ -295,6 +309,7 @@ class TrainEngine:
                 dist.all_reduce(warm)                       # communicator set-up outside the capture
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
+                self._capturing_one_graph = True
                 with torch.cuda.graph(g, stream=cap):
                     self._fwd()
                     check(lib.mvb_stream_wait_external_event(stream_ptr(), self._gt_ready.cuda_event), "mvb_stream_wait_external_event")
@@ -309,11 +324,13 @@ class TrainEngine:
                         self._loss_bwd(0)
                         dist.all_reduce(self.opt.flat_g, op=dist.ReduceOp.SUM)
                     self._optim()
+                self._capturing_one_graph = False
                 self.g_fb, self.one_graph = g, True
                 self.launches_per_step = lib.mvb_launch_count() - c0
                 torch.cuda.synchronize()
                 return
             except Exception as e:  # noqa: BLE001  (a build of torch / NCCL that cannot capture collectives): three graphs below
+                self._capturing_one_graph = False
                 import warnings
                 warnings.warn(f"TrainEngine: the data-parallel step could not be captured as one graph ({e}); "
                               "falling back to three graphs with host-launched all-reduces")

@@ -458,6 +458,11 @@ class _LinearFn(torch.autograd.Function):
         db = (sb if sb is not None else torch.empty(n, device=w.device, dtype=torch.float32)) if ctx.has_bias else None
         check(lib.mvb_linear_bwd(m, k, n, ptr(x), x_vm_f, ptr(w), ptr(y), ptr(gy), y_vm_f, 1 if relu else 0, p, ptr(dx), ptr(dw),
                                  ptr(db), stream_ptr()), "mvb_linear_bwd")
+        if _lib._deferred["on"] and dx is not None:
+            if sw is not None and (sb is not None or not ctx.has_bias):
+                _lib._deferred["keep"].append((x, w, y, gy, dw, db))        # the dW / db tiles may still be running on the side chain
+            else:
+                _lib.side_join()
         return dx, _ret(sw, dw), _ret(sb, db), None, None, None, None, None
 
 

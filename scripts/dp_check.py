@@ -46,5 +46,10 @@ rel = float((pd - ps).norm() / ps.norm())
 if rank == 0:
     print(f"worst relative loss deviation {worst:.2e}; parameters after 5 steps differ by {rel:.2e} (L2)")
     assert worst < 1e-4 and rel < 1e-3
-    print("DP_CHECK_OK")
+    print("DP_CHECK_OK", flush=True)
+# graphs that captured NCCL work must go before the communicator does
+sharded.release(); single.release()
+del sharded, single
+torch.cuda.synchronize()
+dist.barrier()
 dist.destroy_process_group()

@@ -97,8 +97,14 @@ def test_linear_dropout_properties(Fn):
     off.add_(1)
     y3 = Fn.linear(x, w, b, relu=True, p=p, rng=stream.site(0))
     assert not torch.equal(y, y3)
+    # with a device counter attached the host offset stays frozen (advancing both would give two steps the same sum);
+    # without one, advance() is what makes the next call draw a new mask
     stream.advance()
-    assert not torch.equal(y3, Fn.linear(x, w, b, relu=True, p=p, rng=stream.site(0)))
+    assert torch.equal(y3, Fn.linear(x, w, b, relu=True, p=p, rng=stream.site(0)))
+    stream.offset_dev = None
+    y4 = Fn.linear(x, w, b, relu=True, p=p, rng=stream.site(0))
+    stream.advance()
+    assert not torch.equal(y4, Fn.linear(x, w, b, relu=True, p=p, rng=stream.site(0)))
 
 
 @pytest.mark.parametrize("b,train", [(16, True), (64, True), (3, False)])
