@@ -295,6 +295,31 @@ int mvb_cheb_layer_bwd(int N, int B, int Fin, int Fout, int K, const int32_t *L_
                        const float *dy, float *dx, float *dweight, float *dbias, void *workspace,
                        size_t workspace_bytes, void *stream);
 
+/* ---- the same loop body at the levels that do NOT fit shared memory (level 0: 4998 vertices) ----
+ * pool(U) -> ChebConv_batch -> ReLU, models/cheb_VAE.py:284-285 (nn/conv.py:557-577, nn/pool.py:13-23), as ONE
+ * persistent launch per direction (csrc/mvb_stream_tc.cu): every CTA owns a fixed range of 128-(vertex, mesh)-pair
+ * tiles, produces each basis plane T_k for them with the arithmetic of mvb_spmm, hands the tile to tcgen05.mma through a
+ * shared-memory ring while it is still on chip (accumulators of all its tiles in TMEM across the K steps) and meets
+ * the other CTAs at a grid-wide barrier between steps - the basis is never re-read for the contraction.
+ *   x [n_in,B,16] (n_in == N unless U [N x n_in] is given), weight [K,16,16], y [N,B,16]; 16-wide features, K <= 8,
+ *   no row selection; mvb_cheb_stream_supported says whether (N, B) is covered (at least ~76 k (vertex, mesh) pairs and
+ *   few enough that a CTA's accumulators fit TMEM: B <= 121 at 4998 vertices) - otherwise use mvb_pool_* + mvb_cheb_*.
+ * Backward (adjoint form): G = dY*[y>0] and db, S_k = T_k(L^T) G, dT_0 = sum_k S_k W_k^T, dX = U^T dT_0 in the same
+ *   launch; dW through the streaming weight-gradient reduction (on the deferred side chain with mvb_tune
+ *   "defer_wgrad=1").  dweight / dbias OVERWRITTEN; dx may be NULL.  Workspaces: *_workspace_bytes; 16-byte aligned. */
+int mvb_cheb_stream_supported(int N, int B, int Fin, int Fout, int K, int n_in, int has_up, int n_out);
+size_t mvb_cheb_stream_fwd_workspace_bytes(int N, int B, int Fin, int Fout, int K, int has_up);
+int mvb_cheb_stream_fwd(int N, int B, int Fin, int Fout, int K, const int32_t *L_rowptr, const int32_t *L_colidx,
+                        const float *L_vals, int L_nnz, int n_in, const int32_t *U_rowptr, const int32_t *U_colidx,
+                        const float *U_vals, int U_nnz, const float *x, const float *weight, const float *bias, int relu,
+                        float *y, void *workspace, size_t workspace_bytes, void *stream);
+size_t mvb_cheb_stream_bwd_workspace_bytes(int N, int B, int Fin, int Fout, int K, int has_up);
+int mvb_cheb_stream_bwd(int N, int B, int Fin, int Fout, int K, const int32_t *Lt_rowptr, const int32_t *Lt_colidx,
+                        const float *Lt_vals, int L_nnz, int n_in, const int32_t *U_rowptr, const int32_t *U_colidx,
+                        const float *U_vals, const int32_t *Ut_rowptr, const int32_t *Ut_colidx, const float *Ut_vals,
+                        int U_nnz, const float *x, const float *weight, const float *y_for_relu, const float *dy, float *dx,
+                        float *dweight, float *dbias, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- next row f2: the dense bottleneck between the two mesh pyramids ------------------------
  * (models/cheb_VAE.py:149-168 layer definitions; :270-272 enc_lin; :253-258 classifier; :206-221
  *  z heads + reparameterisation; :276-281 dec_lin / dec_lin_2 - torch.nn.Linear + F.relu +

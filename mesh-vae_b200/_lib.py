@@ -70,6 +70,12 @@ SIGNATURES = {
     "mvb_cheb_layer_fwd": (c_int, [c_int] * 5 + [_vp, _vp, _vp, c_int, c_int, _vp, _vp, _vp, c_int, c_int, _vp, _vp, _vp, _vp, c_int, _vp, _vp]),
     "mvb_cheb_layer_bwd_workspace_bytes": (c_size_t, [c_int] * 6),
     "mvb_cheb_layer_bwd": (c_int, [c_int] * 5 + [_vp] * 6 + [c_int, c_int] + [_vp] * 6 + [c_int, c_int] + [_vp] * 9 + [c_size_t, _vp]),
+    "mvb_cheb_stream_supported": (c_int, [c_int] * 8),
+    "mvb_cheb_stream_fwd_workspace_bytes": (c_size_t, [c_int] * 6),
+    "mvb_cheb_stream_fwd": (c_int, [c_int] * 5 + [_vp, _vp, _vp, c_int, c_int, _vp, _vp, _vp, c_int, _vp, _vp, _vp, c_int, _vp, _vp,
+                                    c_size_t, _vp]),
+    "mvb_cheb_stream_bwd_workspace_bytes": (c_size_t, [c_int] * 6),
+    "mvb_cheb_stream_bwd": (c_int, [c_int] * 5 + [_vp, _vp, _vp, c_int, c_int] + [_vp] * 6 + [c_int] + [_vp] * 8 + [c_size_t, _vp]),
     "mvb_linear_fwd": (c_int, [c_int, c_int, c_int, _vp, c_int, _vp, _vp, c_int, c_float, c_uint64, _vp, c_int64, _vp, c_int, _vp]),
     "mvb_linear_bwd": (c_int, [c_int, c_int, c_int, _vp, c_int, _vp, _vp, _vp, c_int, c_int, c_float, _vp, _vp, _vp, _vp]),
     "mvb_vae_heads_fwd": (c_int, [c_int, c_int, c_int, c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, c_float, c_uint64, _vp,

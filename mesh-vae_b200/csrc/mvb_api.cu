@@ -755,6 +755,7 @@ extern "C" int mvb_stream_wait_external_event(void *stream, void *event) {
 //   overlap=0|1        side-stream fork inside mvb_cheb_bwd
 //   mesh_tc=e,c        tensor-core mesh layers on/off, CTAs per mesh (0 = automatic)
 //   defer_wgrad=0|1    weight-gradient chains of the mesh layers joined lazily (engine only; see mvb_side_join)
+//   stream_tc=e,sw     row-streaming fused level-0 layers (mvb_cheb_stream_*) on/off, meshes per slab (4 / 8 / 16, 0 = least work per CTA)
 //   mesh_dbg=bits      timing probes of the tensor-core mesh forward kernel (1 no MMAs, 2 no recurrence, 4 no epilogue):
 //                      results are then wrong - scripts/mesh_tc_probe.py only
 // ---------------------------------------------------------------------------------------------
@@ -788,6 +789,8 @@ extern "C" int mvb_tune(const char *spec) {
         else if (!strcmp(key, "overlap")) g_overlap = v[0] ? 1 : 0;
         else if (!strcmp(key, "mesh_tc")) set_mesh_tc(v[0], v[1]);
         else if (!strcmp(key, "mesh_dbg")) set_mesh_dbg(v[0]);
+        else if (!strcmp(key, "stream_tc")) set_stream_tc(v[0], nv > 1 ? v[1] : -1);
+        else if (!strcmp(key, "stream_nt")) set_stream_nt(v[0]);
         else if (!strcmp(key, "defer_wgrad")) set_defer_wgrad(v[0]);
         else if (!strcmp(key, "background_div")) set_background_div(v[0]);
         else if (key[0]) return set_err(MVB_EINVAL, "mvb_tune: unknown key '%s'", key);

@@ -557,7 +557,18 @@ def cheb_layer_supported(n: int, b: int, fin: int, fout: int, k: int, l_op: Mesh
         return False
     n_in = u_op.n_cols if u_op is not None else n
     n_out = d_op.n_rows if d_op is not None else n
-    return bool(lib.mvb_cheb_layer_supported(n, b, fin, fout, k, l_op.nnz, n_in, u_op.nnz if u_op is not None else 0, n_out))
+    if lib.mvb_cheb_layer_supported(n, b, fin, fout, k, l_op.nnz, n_in, u_op.nnz if u_op is not None else 0, n_out):
+        return True
+    return cheb_stream_supported(n, b, fin, fout, k, l_op, u_op, d_op)
+
+
+def cheb_stream_supported(n: int, b: int, fin: int, fout: int, k: int, l_op: MeshOperator, u_op: Optional[MeshOperator],
+                          d_op: Optional[MeshOperator]) -> bool:
+    """the row-streaming fused layer (mvb_cheb_stream_*): levels too large for shared memory, no row selection"""
+    if d_op is not None or l_op.n_active != n or l_op.n_rows != n:
+        return False
+    n_in = u_op.n_cols if u_op is not None else n
+    return bool(lib.mvb_cheb_stream_supported(n, b, fin, fout, k, n_in, 1 if u_op is not None else 0, n))
 
 
 class _ChebLayerFn(torch.autograd.Function):
@@ -622,6 +633,65 @@ class _ChebLayerFn(torch.autograd.Function):
         return dx, _ret(sw, dw), _ret(sb, db), None, None, None, None
 
 
+class _ChebStreamFn(torch.autograd.Function):
+    """mvb_cheb_stream_fwd / _bwd: [pool(U)] -> ChebConv -> ReLU at a level too large for shared memory (level 0), one
+    persistent launch per direction; saves only its input and output."""
+
+    @staticmethod
+    def forward(ctx, x_vm, weight, bias, l_op: MeshOperator, u_op, relu: bool):
+        _req_cuda(x_vm, "cheb_layer x")
+        _req_cuda(weight, "cheb_layer weight")
+        x_vm = x_vm.contiguous()
+        w = weight.contiguous()
+        n_in, b, fin = x_vm.shape
+        k, fin_w, fout = w.shape
+        n = l_op.n_rows
+        if fin_w != fin:
+            raise _lib.MvbError(f"cheb_layer: x has {fin} features, weight expects {fin_w}")
+        if (u_op.n_cols if u_op is not None else n) != n_in:
+            raise _lib.MvbError(f"cheb_layer: x has {n_in} vertices, the layer expects {u_op.n_cols if u_op is not None else n}")
+        bb = None if bias is None else bias.contiguous()
+        y = torch.empty((n, b, fout), device=x_vm.device, dtype=torch.float32)
+        u = u_op
+        ws_bytes = lib.mvb_cheb_stream_fwd_workspace_bytes(n, b, fin, fout, k, 1 if u is not None else 0)
+        ws = torch.empty(ws_bytes, device=w.device, dtype=torch.uint8)
+        check(lib.mvb_cheb_stream_fwd(n, b, fin, fout, k, ptr(l_op.rowptr), ptr(l_op.colidx), ptr(l_op.vals), l_op.nnz, n_in,
+                                      ptr(u.rowptr) if u else None, ptr(u.colidx) if u else None, ptr(u.vals) if u else None,
+                                      u.nnz if u else 0, ptr(x_vm), ptr(w), ptr(bb), 1 if relu else 0, ptr(y), ptr(ws), ws_bytes,
+                                      stream_ptr()), "mvb_cheb_stream_fwd")
+        ctx.ops = (l_op, u_op)
+        ctx.relu, ctx.has_bias = relu, bias is not None
+        ctx.sinks = (_sink(weight), _sink(bias))
+        ctx.save_for_backward(x_vm, w, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_vm, w, y = ctx.saved_tensors
+        l_op, u = ctx.ops
+        n_in, b, fin = x_vm.shape
+        k, _, fout = w.shape
+        n = l_op.n_rows
+        dy = dy.contiguous()
+        dx = torch.empty_like(x_vm) if ctx.needs_input_grad[0] else None
+        sw, sb = ctx.sinks
+        dw = _grad_out(sw, w)
+        db = (sb if sb is not None else torch.empty(fout, device=w.device, dtype=torch.float32)) if ctx.has_bias else None
+        ws_bytes = lib.mvb_cheb_stream_bwd_workspace_bytes(n, b, fin, fout, k, 1 if u is not None else 0)
+        ws = torch.empty(ws_bytes, device=w.device, dtype=torch.uint8)
+        check(lib.mvb_cheb_stream_bwd(n, b, fin, fout, k, ptr(l_op.rowptr_t), ptr(l_op.colidx_t), ptr(l_op.vals_t), l_op.nnz, n_in,
+                                      ptr(u.rowptr) if u else None, ptr(u.colidx) if u else None, ptr(u.vals) if u else None,
+                                      ptr(u.rowptr_t) if u else None, ptr(u.colidx_t) if u else None, ptr(u.vals_t) if u else None,
+                                      u.nnz if u else 0, ptr(x_vm), ptr(w), ptr(y) if ctx.relu else None, ptr(dy), ptr(dx), ptr(dw),
+                                      ptr(db), ptr(ws), ws_bytes, stream_ptr()), "mvb_cheb_stream_bwd")
+        if _lib._deferred["on"]:
+            if sw is not None and (sb is not None or not ctx.has_bias):
+                _lib._deferred["keep"].append((ws, x_vm, w, dy, dw, db))      # the side chain still reads ws / x and writes the sinks
+            else:
+                _lib.side_join()
+        return dx, _ret(sw, dw), _ret(sb, db), None, None, None
+
+
 def cheb_layer(x_vm, weight, bias, l_op: MeshOperator, u_op: Optional[MeshOperator] = None,
                d_op: Optional[MeshOperator] = None, relu: bool = True):
     """[U prologue] -> Chebyshev conv (+bias, ReLU) -> [D row selection] on vertex-major tensors: the fused
@@ -631,6 +701,9 @@ def cheb_layer(x_vm, weight, bias, l_op: MeshOperator, u_op: Optional[MeshOperat
     b, fin = x_vm.shape[1], x_vm.shape[2]
     k, _, fout = weight.shape
     if x_vm.is_cuda and cheb_layer_supported(n, b, fin, fout, k, l_op, u_op, d_op):
+        if cheb_stream_supported(n, b, fin, fout, k, l_op, u_op, d_op) and not lib.mvb_cheb_layer_supported(
+                n, b, fin, fout, k, l_op.nnz, x_vm.shape[0], u_op.nnz if u_op is not None else 0, n):
+            return _ChebStreamFn.apply(x_vm, weight, bias, l_op, u_op, relu)
         return _ChebLayerFn.apply(x_vm, weight, bias, l_op, u_op, d_op, relu)
     if u_op is not None:
         x_vm = pool(x_vm, u_op)

@@ -121,6 +121,60 @@ def _fused_layer_case(mvb, ops, kind, lvl, b, fin, fout, relu, bias, mode):
     assert rel_err(yg, ys) < TOL and rel_err(xg.grad, xs.grad) < TOL and rel_err(wg.grad, ws.grad) < TOL
 
 
+# level 0 (4998 vertices): the row-streaming fused layer (mvb_cheb_stream_*, csrc/mvb_stream_tc.cu) - one persistent launch
+# per direction behind the same cheb_layer call.  64 meshes = the benchmark shape; 24 / 20 meshes: fewer slabs, a ragged last
+# row block; plain = no up-sampling prologue.  sw = meshes per slab (8 / 16; mvb_tune
+# stream_tc=1,sw; 0 = automatic)
+STREAM_CASES = [("dec", 0, 64, 16, 16, True, True, 8), ("dec", 0, 64, 16, 16, True, True, 16), ("dec", 0, 24, 16, 16, True, False, 8),
+                ("plain", 0, 40, 16, 16, False, True, 0), ("plain", 0, 64, 16, 16, True, True, 0)]
+
+
+@pytest.mark.parametrize("kind,lvl,b,fin,fout,relu,bias,sw", STREAM_CASES)
+def test_stream_layer_matches_oracle_and_stepwise(mvb, ops, kind, lvl, b, fin, fout, relu, bias, sw):
+    A, D, U, nn_ = ops
+    dev = torch.device("cuda:0")
+    ei, norm = O.cheb_norm(A[lvl]._indices(), nn_[lvl])
+    l_op = mvb.operators.from_edges(ei.to(dev), norm.to(dev), nn_[lvl], dev)
+    u_op = mvb.operators.from_sparse(U[lvl].to(dev), dev) if kind == "dec" else None
+    mvb._lib.tune(f"stream_tc=1,{sw}")
+    try:
+        assert mvb.functional.cheb_stream_supported(nn_[lvl], b, fin, fout, 6, l_op, u_op, None)
+        _fused_layer_case(mvb, ops, kind, lvl, b, fin, fout, relu, bias, "mesh_tc=1,0")
+    finally:
+        mvb._lib.tune("stream_tc=0,16")
+
+
+def test_stream_layer_is_deterministic_and_can_be_switched_off(mvb, ops):
+    A, D, U, nn_ = ops
+    Fn = mvb.functional
+    dev = torch.device("cuda:0")
+    n = nn_[0]
+    ei, norm = O.cheb_norm(A[0]._indices(), n)
+    l_op = mvb.operators.from_edges(ei.to(dev), norm.to(dev), n, dev)
+    u_op = mvb.operators.from_sparse(U[0].to(dev), dev)
+    x = _rand(u_op.n_cols, 64, 16, seed=5).to(dev).requires_grad_()
+    w = _rand(6, 16, 16, seed=6, scale=0.1).to(dev).requires_grad_()
+    bias = _rand(16, seed=7, scale=0.1).to(dev).requires_grad_()
+    outs = []
+    mvb._lib.tune("stream_tc=1")           # opt-in (the default training step keeps the step-by-step kernels at this level)
+    try:
+        assert Fn.cheb_stream_supported(n, 64, 16, 16, 6, l_op, u_op, None)
+        for _ in range(3):
+            x.grad = w.grad = bias.grad = None
+            y = Fn.cheb_layer(x, w, bias, l_op, u_op, None, relu=True)
+            y.square().sum().backward()
+            outs.append((y.detach().clone(), x.grad.clone(), w.grad.clone(), bias.grad.clone()))
+    finally:
+        mvb._lib.tune("stream_tc=0")
+    for o in outs[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(outs[0], o))
+    # the recurrence is the step kernels' arithmetic: switched off, the composition path gives the same basis, and the
+    # outputs agree to the 3xTF32 rounding of the two contraction orders
+    assert not Fn.cheb_stream_supported(n, 64, 16, 16, 6, l_op, u_op, None)
+    y2 = Fn.cheb_layer(x.detach(), w.detach(), bias.detach(), l_op, u_op, None, relu=True)
+    assert rel_err(outs[0][0], y2) < 1e-5
+
+
 def test_fused_layer_is_deterministic_and_needs_no_input_grad(mvb, ops):
     A, D, U, nn_ = ops
     Fn = mvb.functional
