@@ -534,6 +534,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
+    log(f"rank {rank}: device-timed {dev_ms / args.steps:.4f} ms/step, end to end {e2e_ms / args.steps:.4f} ms/step (before the max over ranks)")
     t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -578,8 +579,13 @@ def run_ours(args, rank, world, local_rank):
                        "l2": "flushed between timed steps (256 MiB write, outside the event pairs)",
                        "cuda_graph": not args.no_graph, "final_loss": last_loss,
                        "step_graphs": (1 if eng.one_graph else (3 if eng.split else 2)) if not args.no_graph else 0,
-                       "collectives": None if world == 1 else ("NCCL all-reduce of the flat fp32 gradient in two buckets, "
-                                                               + ("captured inside the step graph" if eng.one_graph else "host-launched between graphs")),
+                       "collectives": None if world == 1 else (
+                           (f"none: mvb_dp_reduce_adam reads the peers' flat fp32 gradient buffers over NVLink ({eng.peer.backend} peer "
+                            "memory), sums them in rank order and applies Adam in the same launch; "
+                            + ("two buckets, the dense layers' under the encoder backward" if eng.split else "one bucket")
+                            + ", inside the step graph") if eng.peer is not None else
+                           ("NCCL all-reduce of the flat fp32 gradient in two buckets, "
+                            + ("captured inside the step graph" if eng.one_graph else "host-launched between graphs"))),
                        "e2e_input": "double-buffered: each timed step copies the next batch from pinned host memory "
                                     "(on a copy stream, inside the event pair) while it computes the current one"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": eng.h2d_bytes(),
@@ -775,7 +781,16 @@ def run_secondary(args, local_rank):
     clocks = sampler.stop()
     cpu = None
     if not args.no_cpu_baseline:
-        cpu = cpu_baseline_block("train" if args.workload == "dropin" else args.workload, steps=30)
+        if args.workload == "dropin":
+            # this process has the reference's module names bound to the native classes (compat/): the CPU arm - the same
+            # reference files on the leaf shims - runs in a process of its own
+            import subprocess
+            code = "import json, bench; print('CPU_BASELINE ' + json.dumps(bench.cpu_baseline_block('train', steps=30)))"
+            res = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=900)
+            tag = [ln for ln in res.stdout.splitlines() if ln.startswith("CPU_BASELINE ")]
+            cpu = json.loads(tag[-1][len("CPU_BASELINE "):]) if tag else {"unavailable": (res.stderr or res.stdout)[-300:]}
+        else:
+            cpu = cpu_baseline_block(args.workload, steps=30)
     work = {"infer": WORKLOAD_TEXT["infer"], "cls": WORKLOAD_TEXT["cls"],
             "dropin": "the reference's own cheb_VAE class (unchanged, imported on compat/) + accelerate() + torch.optim.Adam, eager "
                       "training step as main.py:67-85 runs it (H2D, forward, backward, optimizer, loss read-back), batch fp32 / x_gt fp64"}[args.workload]

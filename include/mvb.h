@@ -243,6 +243,33 @@ int mvb_adam_step(int64_t n, float *p, const float *g, float *m, float *v, int64
 int mvb_adam_step_hp(int64_t n, float *p, const float *g, float *m, float *v, int64_t *step, const float *hyper,
                      void *stream);
 
+/* ---- data parallel (new; the reference is single device): gradient exchange fused with the optimizer -------------
+ * One process per GPU; every rank keeps its flat fp32 gradient buffer and a 256-byte signal pad (zero at creation) in
+ * memory that its peers on the node have mapped (NVLink / NVSwitch peer access: torch symmetric memory, CUDA IPC, ... -
+ * the pointers are handed in as HOST arrays of `world` device pointers, entry `rank` = the local buffer).
+ *   mvb_dp_begin        at the head of a step, before anything writes the local gradient buffer: opens a new epoch once
+ *                       every peer has finished reading that buffer in the previous one (`channels` = how many exchanges a
+ *                       step makes, 1 or 2; every step must then use exactly the channels 0..channels-1 once each).
+ *   mvb_dp_reduce_adam  instead of all-reduce + mvb_adam_step_hp, for the elements [offset, offset + n) of the flat buffers
+ *                       (a gradient bucket; offset, n multiples of 4): tells the peers the local gradient is complete, waits
+ *                       for theirs, sums grads[0..world-1] in rank order (bit-identical on every rank, no atomics) straight
+ *                       out of the peers' memory and applies Adam (hyper as in mvb_adam_step_hp; fold 1/world into
+ *                       hyper[5]) to the local replica of p / m / v in the same pass; grad_sum_out (or NULL) receives the
+ *                       summed gradient.  tick = 1: the step counter is incremented first (the first exchange of a step).
+ *                       Two buckets on two channels may be in flight at once (the early one on a side stream under the
+ *                       rest of the backward pass); max_ctas > 0 caps the grid of such a background launch.
+ * state: mvb_dp_state_bytes() of LOCAL device memory, zero at creation (uint32 words: [0] epoch, [1] number of waits that
+ * gave up after ~30 s because a peer never signalled - the results are then invalid; a healthy run keeps it 0).  Every
+ * rank must issue the same sequence of begin / reduce calls.  Enqueue-only and CUDA-graph capturable (signals are epoch
+ * numbers that only grow). */
+int mvb_dp_max_world(void);
+size_t mvb_dp_pad_bytes(void);
+size_t mvb_dp_state_bytes(void);
+int mvb_dp_begin(int world, int rank, int channels, void *const *pads, void *state, void *stream);
+int mvb_dp_reduce_adam(int world, int rank, int channel, int64_t offset, int64_t n, float *p, void *const *grads, float *m, float *v,
+                       float *grad_sum_out, int64_t *step, int tick, const float *hyper, void *const *pads, void *state,
+                       int max_ctas, void *stream);
+
 /* ---- A3 + A5 fused on the step-by-step path: Chebyshev convolution + row selection -------------------------------
  * (the encoder loop body  x = relu(cheb[i](x, L)); x = pool(x, D)  models/cheb_VAE.py:264-265, at the levels too large
  *  for the mesh-resident kernels: level 0 of the template; D is a row selection, mesh_operations.py:72-85.)

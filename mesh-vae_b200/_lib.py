@@ -88,6 +88,11 @@ SIGNATURES = {
     "mvb_adam_step": (c_int, [c_int64, _vp, _vp, _vp, _vp, _vp, c_float, c_float, c_float, c_float, c_float, c_float,
                               _vp]),
     "mvb_adam_step_hp": (c_int, [c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mvb_dp_max_world": (c_int, []),
+    "mvb_dp_pad_bytes": (c_size_t, []),
+    "mvb_dp_state_bytes": (c_size_t, []),
+    "mvb_dp_begin": (c_int, [c_int, c_int, c_int, _vp, _vp, _vp]),
+    "mvb_dp_reduce_adam": (c_int, [c_int, c_int, c_int, c_int64, c_int64, _vp, _vp, _vp, _vp, _vp, _vp, c_int, _vp, _vp, _vp, c_int, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

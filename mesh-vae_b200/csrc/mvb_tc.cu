@@ -570,20 +570,32 @@ tc_wgrad_kernel(TcWgradArgs a) {
     // everything about a thread's pieces of a tile that does not depend on the tile - row, shared-memory offsets,
     // validity - is computed once: the per-tile code is then loads, the hi/lo split and stores (ncu: 11.2 M warp
     // instructions for 4998 narrow tiles before, two integer divisions and a swizzle computation per piece per tile)
+    // 16-wide planes (4 quads per row): a warp's 32 pieces are 8 rows x 4 quads.  In row-major lane order the 8 lanes
+    // of a quarter warp (2 rows x 4 quads) hit only TWO of the four 32-byte units of the BASE32B swizzle - every 16-byte
+    // store was a 2-way bank conflict (ncu r02b: 47 % of the shared wavefronts of tc_wgrad<6,4>).  Lane order
+    // (quad & 1, row & 3, quad >> 1, row >> 2) gives each quarter warp 4 rows x one 32-byte unit: all four units, no conflict;
+    // the global loads of the warp still cover the same contiguous 512 bytes.
+    auto perm16 = [](int i) {
+        const int l = i & 31;
+        return (i & ~31) | ((((l >> 4) & 1) * 4 + ((l >> 1) & 3)) << 2) | (((l >> 3) & 1) * 2 + (l & 1));
+    };
     int trow[LPT];                       // row of T piece j within the tile, -1 = no piece
+    int tidx[LPT];                       // its quad index inside the tile (row * Q4 + quad)
     uint32_t toff[NPV][LPT];
 #pragma unroll
     for (int j = 0; j < LPT; ++j) {
-        const int i = j * WG_NT + tid;
+        const int i = (Q4 == 4) ? perm16(j * WG_NT + tid) : j * WG_NT + tid;
+        tidx[j] = i;
         trow[j] = (FAST && i < 64 * Q4) ? i / Q4 : -1;
 #pragma unroll
         for (int p = 0; p < NPV; ++p) toff[p][j] = trow[j] >= 0 ? b32_off(trow[j], p * W + (i - trow[j] * Q4) * 4, blk) : 0u;
     }
-    int drow[DJ];
+    int drow[DJ], didx[DJ];
     uint32_t doff[DJ], doff_lo[DJ];
 #pragma unroll
     for (int j = 0; j < DJ; ++j) {
-        const int i = j * WG_NT + tid;
+        const int i = (dq4 == 4) ? perm16(j * WG_NT + tid) : j * WG_NT + tid;
+        didx[j] = i;
         drow[j] = (FAST && i < R * dq4) ? i / dq4 : -1;
         const int q = drow[j] >= 0 ? i - drow[j] * dq4 : 0;
         doff[j] = drow[j] >= 0 ? b32_off(drow[j], q * 4, blk) : 0u;
@@ -600,7 +612,7 @@ tc_wgrad_kernel(TcWgradArgs a) {
                 const float4 *b4 = reinterpret_cast<const float4 *>(p == 0 ? a.in0 : a.in_rest + (int64_t)(p - 1) * a.plane_rows * W);
 #pragma unroll
                 for (int j = 0; j < LPT; ++j) {
-                    const int i = j * WG_NT + tid;
+                    const int i = tidx[j];
                     pre[d][p * LPT + j] = (trow[j] >= 0 && trow[j] < nr) ? __ldg(b4 + src[j] * Q4 + (i - trow[j] * Q4)) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
@@ -610,7 +622,7 @@ tc_wgrad_kernel(TcWgradArgs a) {
             const float4 *s4 = reinterpret_cast<const float4 *>((p == 0 ? a.in0 : a.in_rest + (int64_t)(p - 1) * a.rows * W) + row0 * W);
 #pragma unroll
             for (int j = 0; j < LPT; ++j)
-                pre[d][p * LPT + j] = (trow[j] >= 0 && trow[j] < nr) ? __ldg(s4 + j * WG_NT + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
+                pre[d][p * LPT + j] = (trow[j] >= 0 && trow[j] < nr) ? __ldg(s4 + tidx[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         }
         const float4 *d4 = reinterpret_cast<const float4 *>(a.dy + row0 * a.n_out);
@@ -618,8 +630,8 @@ tc_wgrad_kernel(TcWgradArgs a) {
 #pragma unroll
         for (int j = 0; j < DJ; ++j) {
             const bool ok = drow[j] >= 0 && drow[j] < nr;
-            pred[d][j] = ok ? __ldg(d4 + j * WG_NT + tid) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.mask) prem[d][j] = ok ? __ldg(m4 + j * WG_NT + tid) : make_float4(1.f, 1.f, 1.f, 1.f);
+            pred[d][j] = ok ? __ldg(d4 + didx[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.mask) prem[d][j] = ok ? __ldg(m4 + didx[j]) : make_float4(1.f, 1.f, 1.f, 1.f);
         }
     };
     auto commit = [&](const int d) {

@@ -5,7 +5,7 @@ covered by world_size-2 `gloo` tests on CPU; on B200s the backend is NCCL over N
 Semantics: every rank holds a contiguous slice of the global batch; the loss is the mean over the
 batch (models/cheb_VAE.py:342), so the gradient of the global-batch mean loss is the average of
 the per-rank gradients when the slices are equal."""
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -69,3 +69,73 @@ def allreduce_sum_(flat: torch.Tensor, group=None) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     return flat
+
+
+class PeerBuffers:
+    """This rank's flat gradient buffer and signal pad in memory that every peer on the node has mapped, for the fused
+    exchange + optimizer launch (`mvb_dp_begin` / `mvb_dp_reduce_adam`, csrc/mvb_dp.cu).  Two ways to get there:
+    torch symmetric memory (`torch.distributed._symmetric_memory`: one rendezvous, no extra CUDA contexts) and, where
+    that is not available, CUDA IPC handles exchanged through the process group (`torch.multiprocessing.reductions`).
+    `backend`: "symm", "ipc" or None = try them in that order (env MVB_DP_PEER overrides).  Collective: every rank of
+    `group` must construct it at the same point."""
+
+    def __init__(self, n: int, device: torch.device, group=None, backend: Optional[str] = None):
+        import ctypes
+        import os
+        from ._lib import lib
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world > lib.mvb_dp_max_world():
+            raise RuntimeError(f"PeerBuffers: world size {self.world} > {lib.mvb_dp_max_world()}")
+        backend = os.environ.get("MVB_DP_PEER", backend)
+        pad_words = int(lib.mvb_dp_pad_bytes()) // 4
+        errors = []
+        self.backend = None
+        for b in ([backend] if backend else ["symm", "ipc"]):
+            try:
+                if b == "symm":
+                    self._keep = self._alloc_symm(n, pad_words, device)
+                elif b == "ipc":
+                    self._keep = self._alloc_ipc(n, pad_words, device)
+                else:
+                    raise ValueError(f"unknown peer-memory backend {b!r}")
+                self.backend = b
+                break
+            except Exception as e:  # noqa: BLE001
+                errors.append(f"{b}: {type(e).__name__}: {e}")
+        # every rank must have ended up on the same backend (or all fall back to NCCL together)
+        flags = [None] * self.world
+        dist.all_gather_object(flags, self.backend, group=self.group)
+        if any(f != flags[0] for f in flags) or self.backend is None:
+            raise RuntimeError("PeerBuffers: no common peer-memory backend (" + "; ".join(errors) + f"; ranks report {flags})")
+        self.flat_g, self.pad, grad_ptrs, pad_ptrs = self._keep[:4]
+        self.state = torch.zeros(int(lib.mvb_dp_state_bytes()) // 4, device=device, dtype=torch.int32)
+        arr = ctypes.c_void_p * self.world
+        self.grad_ptrs, self.pad_ptrs = arr(*grad_ptrs), arr(*pad_ptrs)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=self.group)          # every pad is zero and mapped before the first signal is sent
+
+    def _alloc_symm(self, n, pad_words, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        g = symm_mem.empty(n, dtype=torch.float32, device=device)
+        pad = symm_mem.empty(pad_words, dtype=torch.int32, device=device)
+        g.zero_()
+        pad.zero_()
+        hg = symm_mem.rendezvous(g, self.group)
+        hp = symm_mem.rendezvous(pad, self.group)
+        return g, pad, [int(p) for p in hg.buffer_ptrs], [int(p) for p in hp.buffer_ptrs], hg, hp
+
+    def _alloc_ipc(self, n, pad_words, device):
+        from torch.multiprocessing.reductions import reduce_tensor
+        g = torch.zeros(n, device=device, dtype=torch.float32)
+        pad = torch.zeros(pad_words, device=device, dtype=torch.int32)
+        torch.cuda.synchronize(device)
+        mine = (reduce_tensor(g), reduce_tensor(pad))
+        allh = [None] * self.world
+        dist.all_gather_object(allh, mine, group=self.group)
+        peers_g, peers_p = [], []
+        for r, ((fg, ag), (fp, ap)) in enumerate(allh):
+            peers_g.append(g if r == self.rank else fg(*ag))
+            peers_p.append(pad if r == self.rank else fp(*ap))
+        return g, pad, [t.data_ptr() for t in peers_g], [t.data_ptr() for t in peers_p], peers_g, peers_p

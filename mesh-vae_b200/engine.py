@@ -9,6 +9,7 @@ NVLink / NVSwitch between the backward graph and the optimizer graph; the 1/worl
 folded into the fused Adam kernel (`mvb_adam_step`).  `dec_lin_1` never receives a gradient
 (quirk 7) and is excluded from the flat buffers, exactly as torch's Adam skips it.
 """
+import os
 from typing import Optional
 
 import torch
@@ -38,7 +39,7 @@ class FlatAdam:
     ALIGN = 32          # elements: every parameter starts on a 128-byte boundary of the flat buffers, so that
                         # the kernels' 16-byte vector / cp.async paths apply to parameter and gradient views
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_buffer_factory=None):
         self.params = [p for p in params]
         dev = self.params[0].device
         self.offsets, self.n = dp.flat_layout(self.params, self.ALIGN)
@@ -48,7 +49,8 @@ class FlatAdam:
             k = p.numel()
             self.flat_p[o:o + k].copy_(p.detach().reshape(-1))
             p.data = self.flat_p[o:o + k].view_as(p)
-        self.flat_g = torch.zeros(self.n, device=dev, dtype=torch.float32)
+        # (data parallel: the gradient buffer may live in peer-mapped memory - dp.PeerBuffers - for the fused exchange)
+        self.flat_g = grad_buffer_factory(self.n) if grad_buffer_factory is not None else torch.zeros(self.n, device=dev, dtype=torch.float32)
         self.grad_views = dp.flat_views(self.flat_g, self.params, self.offsets)
         self.m = torch.zeros_like(self.flat_p)
         self.v = torch.zeros_like(self.flat_p)
@@ -89,6 +91,16 @@ class FlatAdam:
         """one multi-tensor copy of the per-parameter gradients into the flat exchange buffer"""
         dp.pack_grads(self.params, self.grad_views)
 
+    def step_peers(self, peer, grad_scale: float = 1.0, lo: int = 0, hi: Optional[int] = None, channel: int = 0, tick: bool = True,
+                   max_ctas: int = 0):
+        """all-reduce over the peers' gradient buffers + Adam in ONE launch (mvb_dp_reduce_adam) for the elements [lo, hi)
+        of the flat buffers (a gradient bucket)"""
+        self.grad_scale = grad_scale
+        hi = self.n if hi is None else hi
+        check(lib.mvb_dp_reduce_adam(peer.world, peer.rank, channel, lo, hi - lo, ptr(self.flat_p), peer.grad_ptrs, ptr(self.m),
+                                     ptr(self.v), None, ptr(self.step_count), 1 if tick else 0, ptr(self.hyper), peer.pad_ptrs,
+                                     ptr(peer.state), max_ctas, stream_ptr()), "mvb_dp_reduce_adam")
+
     def step(self, grad_scale: float = 1.0):
         self.grad_scale = grad_scale
         check(lib.mvb_adam_step_hp(self.n, ptr(self.flat_p), ptr(self.flat_g), ptr(self.m), ptr(self.v),
@@ -97,7 +109,7 @@ class FlatAdam:
 
 class TrainEngine:
     def __init__(self, net, batch: int, lr=1e-3, weight_decay=5e-4, x_gt_dtype=torch.float64, use_graph=True,
-                 distributed: Optional[bool] = None, graph_comm: bool = True):
+                 distributed: Optional[bool] = None, graph_comm: bool = True, fused_dp: Optional[bool] = None):
         self.net = net
         self.dev = next(net.parameters()).device
         self.batch = batch
@@ -135,10 +147,24 @@ class TrainEngine:
         late = [p for p in live if id(p) in conv_ids or (p.dim() == 3 and (p.shape[1] % 4 or p.shape[2] % 4))]
         late_ids = {id(p) for p in late}
         live = late + [p for p in live if id(p) not in late_ids]
-        self.opt = FlatAdam(live, lr=lr, weight_decay=weight_decay)
+        # Data parallel on one node: the gradient exchange and Adam are ONE launch that reads the peers' flat gradient
+        # buffers over NVLink (csrc/mvb_dp.cu) - no NCCL call in the step, no bucket split.  fused_dp=None: used when the
+        # process group is NCCL and the peer mapping succeeds on every rank, else the bucketed NCCL all-reduces below.
+        self.peer = None
+        want = fused_dp if fused_dp is not None else os.environ.get("MVB_FUSED_DP", "1") != "0"
+        if self.distributed and self.world > 1 and want and self.dev.type == "cuda" and dist.get_backend() == "nccl":
+            n_flat = dp.flat_layout(live, FlatAdam.ALIGN)[1]
+            try:
+                self.peer = dp.PeerBuffers(n_flat, self.dev)
+            except Exception as e:  # noqa: BLE001
+                if fused_dp:
+                    raise
+                import warnings
+                warnings.warn(f"TrainEngine: peer-memory gradient exchange unavailable ({e}); using NCCL all-reduces")
+        self.opt = FlatAdam(live, lr=lr, weight_decay=weight_decay,
+                            grad_buffer_factory=(lambda n: self.peer.flat_g) if self.peer is not None else None)
         self.split = self.opt.offsets[len(late)] if (self.distributed and use_graph and hasattr(net, "keep_encoder_conv_out")
                                                      and 0 < len(late) < len(live)) else 0
-        import os
         if os.environ.get("MVB_DP_SPLIT") == "0":          # A/B: one all-reduce of the whole buffer at the end of the backward pass
             self.split = 0
         if hasattr(net, "dropout_stream"):
@@ -170,6 +196,7 @@ class TrainEngine:
         self._stage = self._stage_flat = self._ev_staged = self._ev_consumed = self._h_small = None
         self._staged = False
         self._fwd_out = None
+        self._bg_ctas = 0
 
     def release(self):
         """Detach the engine from the model: remove the gradient sinks (while they are installed the backward kernels
@@ -204,6 +231,8 @@ class TrainEngine:
     # ---- device work of one step -------------------------------------------------------------
     def _fwd(self):
         """part A of the step: everything that does not need the ground-truth batch"""
+        if self.peer is not None:      # new epoch: the peers have finished reading this rank's gradient buffer
+            self._dp_begin()
         for p, _ in self.loose:
             p.grad = None
         self.net.keep_encoder_conv_out = bool(self.split)
@@ -263,8 +292,27 @@ class TrainEngine:
         """(mean kld, mean rec_loss, correct) of the last step - main.py:83-85 reads these per batch"""
         return float(self.kld.mean()), float(self.rec.mean()), int(self.correct)
 
+    def _dp_begin(self):
+        check(lib.mvb_dp_begin(self.peer.world, self.peer.rank, 2 if self.split else 1, self.peer.pad_ptrs, ptr(self.peer.state),
+                               stream_ptr()), "mvb_dp_begin")
+
     def _optim(self):
-        self.opt.step(1.0 / self.world)
+        if self.peer is None:
+            self.opt.step(1.0 / self.world)
+        elif self.split:        # the two gradient buckets, one after the other (warm-up and ragged steps; the captured step overlaps them)
+            self._optim_bucket(1)
+            self._optim_bucket(2)
+        else:
+            self.opt.step_peers(self.peer, 1.0 / self.world)
+
+    def _optim_bucket(self, which: int, background: bool = False):
+        """fused exchange + Adam of one gradient bucket: 1 = everything behind `split` (the dense layers - final once the
+        backward pass has reached the encoder), 2 = the convolutions in front of it"""
+        if which == 1:
+            self.opt.step_peers(self.peer, 1.0 / self.world, lo=self.split, hi=self.opt.n, channel=0, tick=True,
+                                max_ctas=self._bg_ctas if background else 0)
+        else:
+            self.opt.step_peers(self.peer, 1.0 / self.world, lo=0, hi=self.split, channel=1, tick=False)
 
     def capture(self, warmup: int = 3):
         """warm up on a side stream (lazy init, cuBLAS workspaces), then capture the graphs"""
@@ -299,7 +347,37 @@ class TrainEngine:
         # all captures on ONE stream: autograd replays a node's backward on the stream of its forward, so the
         # encoder backward (its own graph when the gradient buckets are split) must be captured on that stream
         cap = torch.cuda.Stream()
-        self.one_graph = not self.distributed
+        self.one_graph = not self.distributed or self.peer is not None
+        if self.peer is not None:
+            # data parallel through peer memory: the whole step - exchange included - is kernels of this library
+            dist.barrier()
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            self._bg_ctas = int(os.environ.get("MVB_DP_BG_CTAS", "74"))
+            with torch.cuda.graph(g, stream=cap):
+                self._fwd()
+                check(lib.mvb_stream_wait_external_event(stream_ptr(), self._gt_ready.cuda_event), "mvb_stream_wait_external_event")
+                if self.split:
+                    # bucket 1 (the dense layers, 99 % of the bytes) is exchanged and stepped on a side branch of the graph
+                    # while the encoder backward computes; the small bucket of the convolutions follows at the end
+                    self._capturing_one_graph = True
+                    try:
+                        self._loss_bwd(1)
+                        side.wait_stream(cap)
+                        with torch.cuda.stream(side):
+                            self._optim_bucket(1, background=True)
+                        self._loss_bwd(2)
+                    finally:
+                        self._capturing_one_graph = False
+                    cap.wait_stream(side)
+                    self._optim_bucket(2)
+                else:
+                    self._loss_bwd(0)
+                    self._optim()
+            self.g_fb = g
+            self.launches_per_step = lib.mvb_launch_count() - c0
+            torch.cuda.synchronize()
+            return
         if self.distributed and self.graph_comm:
             # Data parallel, ONE graph: the bucketed NCCL all-reduces are captured with the step (NCCL enqueues on its own
             # stream; fork / join become graph edges), so a step is a single replay - no host launch between backward,
@@ -368,7 +446,7 @@ class TrainEngine:
             if self._gt_ready is not None:
                 torch.cuda.current_stream().wait_event(self._gt_ready)
             self._loss_bwd()
-        if self.distributed:
+        if self.distributed and self.peer is None:
             if self.use_graph and self.split:
                 # bucket 1 is reduced on NCCL's stream while graph g_enc computes the encoder backward
                 w1 = dist.all_reduce(self.opt.flat_g[self.split:], op=dist.ReduceOp.SUM, async_op=True)
@@ -379,7 +457,7 @@ class TrainEngine:
             else:
                 dp.allreduce_sum_(self.opt.flat_g)
         if self.use_graph:
-            if self.distributed:
+            if self.distributed and self.peer is None:
                 self.g_opt.replay()
         else:
             self._optim()
@@ -473,6 +551,8 @@ class TrainEngine:
         the graph path issues two bucketed ones - loop.train_epoch decides from the global batch size); `grad_weight`
         = dp.ragged_weight(...) makes the average over ranks the gradient of the global-batch mean when the slices
         are unequal (0 for a rank that only holds a stand-in item)."""
+        if self.peer is not None:
+            self._dp_begin()
         for p, _ in self.loose:
             p.grad = None
         self.net.keep_encoder_conv_out = False
@@ -485,7 +565,8 @@ class TrainEngine:
         if self.distributed:
             if grad_weight != 1.0:
                 self.opt.flat_g.mul_(float(grad_weight))
-            dp.allreduce_sum_(self.opt.flat_g)
+            if self.peer is None:
+                dp.allreduce_sum_(self.opt.flat_g)
         self._optim()
         return loss.detach(), kld, rec, correct, recon.detach()
 

@@ -24,7 +24,9 @@ G = 8
 per = G // world
 sharded = TrainEngine(build(), per, distributed=True)
 sharded.capture(warmup=1)
-pass
+if rank == 0:
+    print("gradient exchange:", f"peer memory ({sharded.peer.backend}), fused with Adam (mvb_dp_reduce_adam)" if sharded.peer is not None
+          else "NCCL all-reduce", flush=True)
 single = TrainEngine(build(), G, distributed=False)
 single.world = 1
 single.capture(warmup=1)
@@ -43,7 +45,15 @@ for s in range(5):
 pd = torch.cat([p.detach().reshape(-1) for p in sharded.opt.params])
 ps = torch.cat([p.detach().reshape(-1) for p in single.opt.params])
 rel = float((pd - ps).norm() / ps.norm())
+# replicas: every rank must hold bit-identical parameters (ordered sums on every rank)
+reps = [torch.empty_like(sharded.opt.flat_p) for _ in range(world)]
+dist.all_gather(reps, sharded.opt.flat_p)
+same = all(torch.equal(reps[0], r) for r in reps[1:])
+if sharded.peer is not None:
+    assert int(sharded.peer.state[1]) == 0, "a wait for a peer's signal timed out"
 if rank == 0:
+    print(f"replicas bit-identical across ranks: {same}")
+    assert same
     print(f"worst relative loss deviation {worst:.2e}; parameters after 5 steps differ by {rel:.2e} (L2)")
     assert worst < 1e-4 and rel < 1e-3
     print("DP_CHECK_OK", flush=True)

@@ -14,7 +14,15 @@ from torch.profiler import profile, ProfilerActivity  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
 a = ap.parse_args()
-dev = torch.device("cuda:0")
+# under torchrun (WORLD_SIZE > 1): the data-parallel step of rank 0
+world = int(os.environ.get("WORLD_SIZE", "1"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+if world > 1:
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+dev = torch.device("cuda", local)
 mvb, net, A, nn_ = bench.build_model(dev)
 # tuning hooks for A/B runs: MVB_TUNE="tc_balance=1;tc_tuning=2,3;mesh_tc=0" (include/mvb.h: mvb_tune)
 if os.environ.get("MVB_TUNE"):
@@ -36,11 +44,21 @@ evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CU
 evs.sort(key=lambda e: e.time_range.start)
 # split into replays by the adam kernel
 steps, cur = [], []
+_seen_reduce = False
 for e in evs:
     cur.append(e)
-    if "adam_kernel" in e.name or "adam_hp_kernel" in e.name:
+    last = "dp_reduce_adam" if world > 1 and eng.peer is not None else "adam"
+    if (last == "adam" and ("adam_kernel" in e.name or "adam_hp_kernel" in e.name)) or (
+            last != "adam" and last in e.name and (not eng.split or _seen_reduce)):
+        _seen_reduce = False
         steps.append(cur)
         cur = []
+    elif "dp_reduce_adam" in e.name:
+        _seen_reduce = True
+if world > 1 and int(os.environ.get("RANK", "0")) != 0:
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.exit(0)
 st = steps[1] if len(steps) > 1 else steps[0]
 t0 = st[0].time_range.start
 end_prev = t0
@@ -61,3 +79,6 @@ print(f"# step span {end_prev - t0:.1f} us")
 print("# per-kernel totals (in-graph durations)")
 for k, (n, d) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"# {d:8.1f} us {n:3d}  {k}")
+if world > 1:
+    torch.cuda.synchronize()
+    dist.barrier()

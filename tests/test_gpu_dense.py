@@ -204,3 +204,59 @@ def test_vae_heads_beyond_one_launch_batch(Fn):
     assert rel_err(o[0], y_hat) < 1e-5 and rel_err(o[3], zz) < 1e-5 and rel_err(hg.grad, hr.grad) < 1e-4
     for m, g in zip(mods, gmods):
         assert rel_err(g.weight.grad, m.weight.grad) < 1e-4 and rel_err(g.bias.grad, m.bias.grad) < 1e-4
+
+
+# ---- data-parallel exchange fused with Adam (csrc/mvb_dp.cu): one GPU can check the arithmetic (world = 1) and the signal
+# protocol (two "ranks" = two buffer sets and two streams on the same device) ----
+def _dp_bufs(mvb, n, world, dev, seed):
+    import ctypes
+    g = torch.Generator().manual_seed(seed)
+    grads = [torch.randn(n, generator=g).to(dev) for _ in range(world)]
+    pads = [torch.zeros(int(mvb._lib.lib.mvb_dp_pad_bytes()) // 4, device=dev, dtype=torch.int32) for _ in range(world)]
+    arr = ctypes.c_void_p * world
+    return grads, pads, arr(*[t.data_ptr() for t in grads]), arr(*[t.data_ptr() for t in pads])
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_dp_reduce_adam_matches_allreduce_then_adam(world):
+    import meshvae_b200 as mvb
+    L, lib = mvb._lib, mvb._lib.lib
+    dev = torch.device("cuda:0")
+    n, cut = 4096 * 5 + 32, 1024
+    grads, pads, gp, pp = _dp_bufs(mvb, n, world, dev, 3)
+    hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 5e-4, 1.0 / world], device=dev)
+    g0 = torch.Generator().manual_seed(9)
+    p0 = torch.randn(n, generator=g0).to(dev)
+    # reference: ordered sum, then the single-GPU fused Adam
+    p_ref, m_ref, v_ref = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    step_ref = torch.zeros((), device=dev, dtype=torch.int64)
+    # ranks: replicas of p / m / v, one state each, one stream each
+    reps = [(p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0), torch.zeros((), device=dev, dtype=torch.int64),
+             torch.zeros(int(lib.mvb_dp_state_bytes()) // 4, device=dev, dtype=torch.int32), torch.cuda.Stream()) for _ in range(world)]
+    torch.cuda.synchronize()
+    for it in range(3):
+        for gr in grads:
+            gr.mul_(0.5).add_(0.1 * it)
+        gsum = grads[0].clone()
+        for gr in grads[1:]:
+            gsum += gr
+        L.check(lib.mvb_adam_step_hp(n, L.ptr(p_ref), L.ptr(gsum), L.ptr(m_ref), L.ptr(v_ref), L.ptr(step_ref), L.ptr(hyper),
+                                     L.stream_ptr()), "adam")
+        torch.cuda.synchronize()
+        for r, (p, m, v, st, state, stream) in enumerate(reps):
+            with torch.cuda.stream(stream):
+                # two gradient buckets on two channels, the way the captured step issues them
+                L.check(lib.mvb_dp_begin(world, r, 2, pp, L.ptr(state), stream.cuda_stream), "dp_begin")
+                L.check(lib.mvb_dp_reduce_adam(world, r, 0, cut, n - cut, L.ptr(p), gp, L.ptr(m), L.ptr(v), None, L.ptr(st), 1,
+                                               L.ptr(hyper), pp, L.ptr(state), 8, stream.cuda_stream), "dp_reduce_adam")
+                L.check(lib.mvb_dp_reduce_adam(world, r, 1, 0, cut, L.ptr(p), gp, L.ptr(m), L.ptr(v), None, L.ptr(st), 0,
+                                               L.ptr(hyper), pp, L.ptr(state), 0, stream.cuda_stream), "dp_reduce_adam")
+        torch.cuda.synchronize()
+        for p, m, v, st, state, _ in reps:
+            assert int(state[1]) == 0, "a wait for a peer's signal timed out"
+            assert int(state[0]) == it + 1 and int(st) == it + 1
+            # every rank sums in rank order: replicas are bit-identical to each other ...
+            assert torch.equal(p, reps[0][0]) and torch.equal(m, reps[0][1]) and torch.equal(v, reps[0][2])
+            # ... and agree with "ordered sum, then mvb_adam_step_hp" (the same arithmetic in another kernel)
+            assert torch.allclose(p, p_ref, rtol=1e-6, atol=1e-7) and torch.allclose(m, m_ref, rtol=1e-6, atol=1e-9)
+            assert torch.allclose(v, v_ref, rtol=1e-6, atol=1e-12)
