@@ -295,6 +295,8 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 def build_model(dev):
     import meshvae_b200 as mvb
+    if os.environ.get("MVB_TUNE"):          # A/B runs of the tuning hooks (include/mvb.h: mvb_tune); recorded in the line's config
+        mvb._lib.tune(os.environ["MVB_TUNE"])
     d = np.load(OPERATORS_NPZ)
     nn_ = [int(v) for v in d["num_nodes"]]
 
@@ -577,7 +579,7 @@ def run_ours(args, rank, world, local_rank):
                                    "4998-vertex template, K=6, filters 16,16,16,32,32, dropout 0.2, x_gt fp64",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "l2": "flushed between timed steps (256 MiB write, outside the event pairs)",
-                       "cuda_graph": not args.no_graph, "final_loss": last_loss,
+                       "cuda_graph": not args.no_graph, "final_loss": last_loss, "mvb_tune": os.environ.get("MVB_TUNE") or None,
                        "step_graphs": (1 if eng.one_graph else (3 if eng.split else 2)) if not args.no_graph else 0,
                        "collectives": None if world == 1 else (
                            (f"none: mvb_dp_reduce_adam reads the peers' flat fp32 gradient buffers over NVLink ({eng.peer.backend} peer "

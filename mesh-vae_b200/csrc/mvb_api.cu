@@ -791,6 +791,7 @@ extern "C" int mvb_tune(const char *spec) {
         else if (!strcmp(key, "mesh_dbg")) set_mesh_dbg(v[0]);
         else if (!strcmp(key, "stream_tc")) set_stream_tc(v[0], nv > 1 ? v[1] : -1);
         else if (!strcmp(key, "stream_nt")) set_stream_nt(v[0]);
+        else if (!strcmp(key, "wgrad_perm")) set_wgrad_perm(v[0]);
         else if (!strcmp(key, "defer_wgrad")) set_defer_wgrad(v[0]);
         else if (!strcmp(key, "background_div")) set_background_div(v[0]);
         else if (key[0]) return set_err(MVB_EINVAL, "mvb_tune: unknown key '%s'", key);

@@ -193,6 +193,7 @@ void set_mesh_tc(int enable, int c);
 void set_mesh_dbg(int v);
 void set_stream_tc(int v, int sw);
 void set_stream_nt(int v);
+void set_wgrad_perm(int v);
 
 // mesh-resident tensor-core layers (mvb_mesh_tc.cu): 1 = handled / supported, 0 = shape not covered, < 0 = error
 int mesh_tc_fwd_supported(int N, int B, int Fin, int Fout, int K, int Lnnz, int n_in, int n_out);

@@ -504,6 +504,7 @@ struct TcWgradArgs {
     const int32_t *row_sel;        // optional selection of the T rows (WgradArgs); dy / mask are dense over the selected rows
     int sel_group;
     int64_t plane_rows;
+    int perm;                      // conflict-free lane order for the 16-wide staging stores (mvb_tune wgrad_perm)
 };
 
 // byte offset of logical (row r, feature column col) in a BASE32B tile made of 32-column blocks of blk bytes
@@ -572,7 +573,7 @@ tc_wgrad_kernel(TcWgradArgs a) {
     // instructions for 4998 narrow tiles before, two integer divisions and a swizzle computation per piece per tile)
     // 16-wide planes (4 quads per row): a warp's 32 pieces are 8 rows x 4 quads.  In row-major lane order the 8 lanes
     // of a quarter warp (2 rows x 4 quads) hit only TWO of the four 32-byte units of the BASE32B swizzle - every 16-byte
-    // store was a 2-way bank conflict (ncu r02b: 47 % of the shared wavefronts of tc_wgrad<6,4>).  Lane order
+    // store is a 2-way bank conflict (ncu r02b: 47 % of the shared wavefronts of tc_wgrad<6,4>).  With a.perm the lane order
     // (quad & 1, row & 3, quad >> 1, row >> 2) gives each quarter warp 4 rows x one 32-byte unit: all four units, no conflict;
     // the global loads of the warp still cover the same contiguous 512 bytes.
     auto perm16 = [](int i) {
@@ -584,7 +585,7 @@ tc_wgrad_kernel(TcWgradArgs a) {
     uint32_t toff[NPV][LPT];
 #pragma unroll
     for (int j = 0; j < LPT; ++j) {
-        const int i = (Q4 == 4) ? perm16(j * WG_NT + tid) : j * WG_NT + tid;
+        const int i = (Q4 == 4 && a.perm) ? perm16(j * WG_NT + tid) : j * WG_NT + tid;
         tidx[j] = i;
         trow[j] = (FAST && i < 64 * Q4) ? i / Q4 : -1;
 #pragma unroll
@@ -594,7 +595,7 @@ tc_wgrad_kernel(TcWgradArgs a) {
     uint32_t doff[DJ], doff_lo[DJ];
 #pragma unroll
     for (int j = 0; j < DJ; ++j) {
-        const int i = (dq4 == 4) ? perm16(j * WG_NT + tid) : j * WG_NT + tid;
+        const int i = (dq4 == 4 && a.perm) ? perm16(j * WG_NT + tid) : j * WG_NT + tid;
         didx[j] = i;
         drow[j] = (FAST && i < R * dq4) ? i / dq4 : -1;
         const int q = drow[j] >= 0 ? i - drow[j] * dq4 : 0;
@@ -797,6 +798,10 @@ static int launch_wgrad_t(const TcWgradArgs &t, unsigned grid, size_t smem, cuda
     return check_launch("mvb tc_wgrad");
 }
 
+static int g_wgrad_perm = 0;        // measured (bench.py, same box, 2 x 300 steps each): 0.9181 / 0.9182 ms per step off, 0.9209 / 0.9389 on - the
+                                    // stores are not what paces the kernel; kept as a tuning hook
+void set_wgrad_perm(int v) { g_wgrad_perm = v ? 1 : 0; }
+
 // returns 1 if taken, 0 if unsupported, < 0 on error.  Partial layout matches the FFMA wgrad kernel.
 int launch_wgrad_tc(const WgradArgs &a, int has_bias, int M4, int N4, int *nparts, cudaStream_t st) {
     if (!g_tc_enabled) return 0;
@@ -826,6 +831,7 @@ int launch_wgrad_tc(const WgradArgs &a, int has_bias, int M4, int N4, int *npart
     t.N4 = N4;
     t.partials = a.partials;
     t.tmem_cols = 32;
+    t.perm = g_wgrad_perm;
     const size_t smem = 1024 + 10 * 64 * 128 + 64;
     const int64_t ntiles = (a.rows + 63) / 64;
     int64_t grid = a.background > 0 ? (int64_t)num_sms() / a.background : (int64_t)num_sms() * 2;
