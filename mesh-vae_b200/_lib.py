@@ -17,6 +17,8 @@ class MvbError(RuntimeError):
 
 
 def _load():
+    if os.environ.get("MVB_LIB"):          # A/B runs against another build of the same sources (scripts/): never built on the fly
+        return ctypes.CDLL(os.environ["MVB_LIB"])
     path = _build.LIB
     if not os.path.exists(path) or _build._stale():
         try:
