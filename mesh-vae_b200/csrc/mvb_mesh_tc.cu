@@ -29,7 +29,13 @@
 
 namespace mvb {
 
-constexpr int MT_NT = 1024;          // threads per CTA: the recurrence is a chain of shared-memory latencies
+#ifndef MVB_MT_NT
+#define MVB_MT_NT 768
+#endif
+// threads per CTA: the recurrence is a chain of shared-memory latencies, but every step also ends in a block barrier and the
+// gathers share one LSU pipe - same-box A/B of the whole step (scripts/trace_step.py): 1024 threads 923 us, 896: 907, 768: 906-908,
+// 640: 914, 512: 921; every mesh launch is 1-4 us shorter at 768 than at 1024 (-DMVB_MT_NT=... builds a variant for MVB_LIB)
+constexpr int MT_NT = MVB_MT_NT;
 constexpr int MT_NC = MT_NT - 32;    // ... of which the last warp only issues the MMAs (and so never delays a step)
 constexpr int MT_ISSUER = MT_NC;     // thread that issues tcgen05.mma / tcgen05.commit
 
