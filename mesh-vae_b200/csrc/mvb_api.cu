@@ -375,7 +375,15 @@ struct LazySide {
     cudaEvent_t fork = nullptr, join = nullptr;
     bool tried = false, ok = false, pending = false;
 };
-static LazySide g_lazy[64][2];      // [device][lane]: lane 0 = convolution weight gradients, lane 1 = dense-layer weight gradients
+constexpr int LAZY_SLOTS = 8;       // slot 1 = lane 1 (dense-layer weight gradients); slots 0, 2..7 = lane 0 (convolution weight gradients:
+                                    // successive chains go round robin over g_conv_lanes of them, so that chains can overlap each other)
+static LazySide g_lazy[64][LAZY_SLOTS];
+static int g_conv_lanes = 3;        // tuning: conv_lanes=1..7; same-box A/B (bench.py, 300 steps, second pass): 1 lane 0.9197 ms per step,
+                                    // 2: 0.9152, 3: 0.9116, 4: 0.9109, 5: 0.9111, 7: 0.9109 - the chains queued behind each other in the tail of the
+                                    // backward pass (the last layers' reductions) now run side by side
+static int g_conv_next[64] = {0};
+void set_conv_lanes(int v) { if (v >= 1 && v <= 7) g_conv_lanes = v; }
+static const int kConvSlot[7] = {0, 2, 3, 4, 5, 6, 7};
 static std::mutex g_lazy_mu;
 static int g_defer_wgrad = 0;
 void set_defer_wgrad(int v) { g_defer_wgrad = v ? 1 : 0; }
@@ -384,10 +392,10 @@ static int g_background_div = 0;        // deferred level-0 weight-gradient redu
                                         // the slower reduction delays every chain queued behind it more than it spares the main stream)
 void set_background_div(int v) { g_background_div = v < 0 ? 0 : v; }
 
-static LazySide *lazy_side(int lane) {
+static LazySide *lazy_side(int slot) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    LazySide &s = g_lazy[dev][lane & 1];
+    LazySide &s = g_lazy[dev][slot & (LAZY_SLOTS - 1)];
     if (!s.tried) {
         s.tried = true;
         // LOWEST priority: when a chain and a kernel of the caller's stream are ready together (the input-gradient
@@ -418,7 +426,14 @@ static void lazy_join_locked(LazySide *s, cudaStream_t st) {
 cudaStream_t lazy_fork(cudaStream_t st, int lane) {
     if (!g_defer_wgrad) return nullptr;
     std::lock_guard<std::mutex> lk(g_lazy_mu);
-    LazySide *s = lazy_side(lane);
+    int slot = 1;
+    if (lane == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+        slot = kConvSlot[g_conv_next[dev] % g_conv_lanes];
+        g_conv_next[dev] = (g_conv_next[dev] + 1) % g_conv_lanes;
+    }
+    LazySide *s = lazy_side(slot);
     if (!s) return nullptr;
     if (cudaEventRecord(s->fork, st) != cudaSuccess || cudaStreamWaitEvent(s->stream, s->fork, 0) != cudaSuccess) {
         cudaGetLastError();
@@ -432,9 +447,12 @@ cudaStream_t lazy_fork(cudaStream_t st, int lane) {
 void lazy_done(cudaStream_t side, cudaStream_t st) {
     if (!side) return;
     std::lock_guard<std::mutex> lk(g_lazy_mu);
-    LazySide *s = lazy_side(0);
-    if (!s || s->stream != side) s = lazy_side(1);
-    if (!s || s->stream != side) return;
+    LazySide *s = nullptr;
+    for (int slot = 0; slot < LAZY_SLOTS; ++slot) {
+        LazySide *c = lazy_side(slot);
+        if (c && c->stream == side) { s = c; break; }
+    }
+    if (!s) return;
     cudaEventRecord(s->join, s->stream);
     s->pending = true;
     if (!g_defer_wgrad) lazy_join_locked(s, st);
@@ -443,8 +461,7 @@ void lazy_done(cudaStream_t side, cudaStream_t st) {
 
 extern "C" int mvb_side_join(void *stream) {
     std::lock_guard<std::mutex> lk(mvb::g_lazy_mu);
-    mvb::lazy_join_locked(mvb::lazy_side(0), (cudaStream_t)stream);
-    mvb::lazy_join_locked(mvb::lazy_side(1), (cudaStream_t)stream);
+    for (int slot = 0; slot < mvb::LAZY_SLOTS; ++slot) mvb::lazy_join_locked(mvb::lazy_side(slot), (cudaStream_t)stream);
     return MVB_OK;
 }
 
@@ -452,7 +469,11 @@ extern "C" int mvb_side_join(void *stream) {
 // bucket while the convolution chains of lane 0 are still running)
 extern "C" int mvb_side_join_lane(void *stream, int lane) {
     std::lock_guard<std::mutex> lk(mvb::g_lazy_mu);
-    mvb::lazy_join_locked(mvb::lazy_side(lane), (cudaStream_t)stream);
+    if (lane == 1) {
+        mvb::lazy_join_locked(mvb::lazy_side(1), (cudaStream_t)stream);
+    } else {
+        for (int c = 0; c < 7; ++c) mvb::lazy_join_locked(mvb::lazy_side(mvb::kConvSlot[c]), (cudaStream_t)stream);
+    }
     return MVB_OK;
 }
 
@@ -792,6 +813,7 @@ extern "C" int mvb_tune(const char *spec) {
         else if (!strcmp(key, "stream_tc")) set_stream_tc(v[0], nv > 1 ? v[1] : -1);
         else if (!strcmp(key, "stream_nt")) set_stream_nt(v[0]);
         else if (!strcmp(key, "wgrad_perm")) set_wgrad_perm(v[0]);
+        else if (!strcmp(key, "conv_lanes")) set_conv_lanes(v[0]);
         else if (!strcmp(key, "defer_wgrad")) set_defer_wgrad(v[0]);
         else if (!strcmp(key, "background_div")) set_background_div(v[0]);
         else if (key[0]) return set_err(MVB_EINVAL, "mvb_tune: unknown key '%s'", key);
