@@ -42,6 +42,12 @@ int num_sms() {
 
 using namespace mvb;
 
+namespace mvb {
+static int g_pdl = 1;
+int pdl_enabled() { return g_pdl; }
+void set_pdl(int v) { g_pdl = v ? 1 : 0; }
+}  // namespace mvb
+
 extern "C" int mvb_version(void) { return MVB_VERSION; }
 extern "C" int mvb_sm_arch(void) { return 100; }
 extern "C" const char *mvb_last_error(void) { return err_buf(); }
@@ -814,6 +820,7 @@ extern "C" int mvb_tune(const char *spec) {
         else if (!strcmp(key, "stream_nt")) set_stream_nt(v[0]);
         else if (!strcmp(key, "wgrad_perm")) set_wgrad_perm(v[0]);
         else if (!strcmp(key, "conv_lanes")) set_conv_lanes(v[0]);
+        else if (!strcmp(key, "pdl")) set_pdl(v[0]);
         else if (!strcmp(key, "defer_wgrad")) set_defer_wgrad(v[0]);
         else if (!strcmp(key, "background_div")) set_background_div(v[0]);
         else if (key[0]) return set_err(MVB_EINVAL, "mvb_tune: unknown key '%s'", key);

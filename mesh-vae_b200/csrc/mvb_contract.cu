@@ -357,6 +357,8 @@ __global__ void __launch_bounds__(1024)
 wgrad_finalize_kernel(const float *__restrict__ partA, int nA, int M4A, const float *__restrict__ partB,
                       int nB, int M4B, int fin, int M, int n_out, int N4, int a_tr, int N4A, float *dweight,
                       float *dbias) {
+    pdl_trigger();
+    pdl_wait();
     // 32 outputs x 32 partial lanes per block: ~10 partials per thread instead of ~40 (each a dependent L2 round trip)
     __shared__ float red[32][33];
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -404,6 +406,8 @@ wgrad_finalize_kernel(const float *__restrict__ partA, int nA, int M4A, const fl
 __global__ void __launch_bounds__(256)
 mask_colsum_kernel(int64_t rows, int nq, const float4 *__restrict__ dy, const float4 *__restrict__ y,
                    float4 *__restrict__ g, float4 *__restrict__ part, int64_t rows_per_block) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float4 red[256];
     const int tid = threadIdx.x;
     const int q = tid % nq, rl = tid / nq, nrl = 256 / nq;
@@ -436,6 +440,8 @@ mask_colsum_kernel(int64_t rows, int nq, const float4 *__restrict__ dy, const fl
 // order, then a fixed shuffle tree - deterministic, and ~nblocks/32 dependent loads instead of nblocks
 __global__ void __launch_bounds__(256)
 colsum_finalize_kernel(int nblocks, int ncol, const float *__restrict__ part, float *__restrict__ db) {
+    pdl_trigger();
+    pdl_wait();
     const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= ncol) return;
     float s = 0.f;
@@ -461,11 +467,11 @@ int launch_mask_colsum(int64_t rows, int ncol, const float *dy, const float *y, 
                 "mask_colsum: %d columns / alignment not supported", ncol);
     const int nb = mask_colsum_blocks(rows);
     const int64_t rpb = (rows + nb - 1) / nb;
-    mask_colsum_kernel<<<nb, 256, 0, st>>>(rows, ncol / 4, (const float4 *)dy, (const float4 *)y, (float4 *)g,
+    launch_pdl(mask_colsum_kernel, dim3(nb), dim3(256), 0, st, rows, ncol / 4, (const float4 *)dy, (const float4 *)y, (float4 *)g,
                                            db ? (float4 *)part : nullptr, rpb);
     int rc = check_launch("mvb mask_colsum");
     if (rc || !db) return rc;
-    colsum_finalize_kernel<<<(ncol + 7) / 8, 256, 0, st>>>(nb, ncol, part, db);
+    launch_pdl(colsum_finalize_kernel, dim3((ncol + 7) / 8), dim3(256), 0, st, nb, ncol, part, db);
     return check_launch("mvb colsum finalize");
 }
 
@@ -550,6 +556,8 @@ __device__ __forceinline__ void fold_weights(float *Wf, const float *__restrict_
 __global__ void __launch_bounds__(256)
 fold_rows_fwd_kernel(int64_t rows, int K, int Fin, int Fout, const float *__restrict__ x, const float *__restrict__ w,
                      const float *__restrict__ bias, int relu, float *__restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float4 smem4[];
     float *Wf = reinterpret_cast<float *>(smem4);
     fold_weights(Wf, w, K, Fin, Fout, threadIdx.x, blockDim.x);
@@ -581,6 +589,8 @@ fold_rows_fwd_kernel(int64_t rows, int K, int Fin, int Fout, const float *__rest
 __global__ void __launch_bounds__(256)
 fold_rows_dx_kernel(int64_t rows, int K, int Fin, int Fout, const float *__restrict__ g, const float *__restrict__ w,
                     float *__restrict__ dx) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float4 smem4[];
     float *Wf = reinterpret_cast<float *>(smem4);
     fold_weights(Wf, w, K, Fin, Fout, threadIdx.x, blockDim.x);
@@ -613,6 +623,8 @@ fold_rows_dx_kernel(int64_t rows, int K, int Fin, int Fout, const float *__restr
 __global__ void __launch_bounds__(256)
 fold_rows_wgrad_kernel(int64_t rows, int Fin, int Fout, const float *__restrict__ x, const float *__restrict__ g,
                        float *__restrict__ partials) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float4 smem4[];
     float *red = reinterpret_cast<float *>(smem4);     // [lanes][nblk * 16]
     const int iq = Fin >> 2, oq = Fout >> 2, nblk = iq * oq;
@@ -658,13 +670,13 @@ static int fold_grid(int64_t threads) {
 int launch_fold_fwd(int64_t rows, int K, int Fin, int Fout, const float *x, const float *w, const float *bias, int relu,
                     float *out, cudaStream_t st) {
     if (!fold_ok(K, Fin, Fout, x, out, bias)) return 0;
-    fold_rows_fwd_kernel<<<fold_grid(rows * (Fout / 4)), 256, (size_t)Fin * Fout * 4, st>>>(rows, K, Fin, Fout, x, w, bias, relu, out);
+    launch_pdl(fold_rows_fwd_kernel, dim3(fold_grid(rows * (Fout / 4))), dim3(256), (size_t)Fin * Fout * 4, st, rows, K, Fin, Fout, x, w, bias, relu, out);
     const int rc = check_launch("mvb fold_rows_fwd");
     return rc ? rc : 1;
 }
 int launch_fold_dx(int64_t rows, int K, int Fin, int Fout, const float *g, const float *w, float *dx, cudaStream_t st) {
     if (!fold_ok(K, Fin, Fout, g, dx, nullptr)) return 0;
-    fold_rows_dx_kernel<<<fold_grid(rows * (Fin / 4)), 256, (size_t)Fin * Fout * 4, st>>>(rows, K, Fin, Fout, g, w, dx);
+    launch_pdl(fold_rows_dx_kernel, dim3(fold_grid(rows * (Fin / 4))), dim3(256), (size_t)Fin * Fout * 4, st, rows, K, Fin, Fout, g, w, dx);
     const int rc = check_launch("mvb fold_rows_dx");
     return rc ? rc : 1;
 }
@@ -679,7 +691,7 @@ int launch_fold_wgrad(int64_t rows, int Fin, int Fout, const float *x, const flo
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     if ((size_t)grid * Fin * Fout * sizeof(float) > partial_bytes) return 0;
-    fold_rows_wgrad_kernel<<<(unsigned)grid, 256, (size_t)lanes * nblk * 16 * 4, st>>>(rows, Fin, Fout, x, g, partials);
+    launch_pdl(fold_rows_wgrad_kernel, dim3((unsigned)grid), dim3(256), (size_t)lanes * nblk * 16 * 4, st, rows, Fin, Fout, x, g, partials);
     const int rc = check_launch("mvb fold_rows_wgrad");
     if (rc) return rc;
     *nparts = (int)grid;
@@ -692,8 +704,8 @@ int launch_wgrad_finalize(const float *partA, int nA, int M4A, const float *part
                           int fin, int M, int n_out, float *dweight, float *dbias, cudaStream_t st, int a_transposed) {
     const int total = (M + (dbias ? 1 : 0)) * n_out;
     const int N4 = round4(n_out);
-    wgrad_finalize_kernel<<<(total + 31) / 32, dim3(32, 32), 0, st>>>(partA, nA, M4A, partB, nB, M4B, fin, M, n_out,
-                                                                    N4, a_transposed, round4(fin), dweight, dbias);
+    launch_pdl(wgrad_finalize_kernel, dim3((total + 31) / 32), dim3(32, 32), 0, st, partA, nA, M4A, partB, nB, M4B, fin, M, n_out,
+               N4, a_transposed, round4(fin), dweight, dbias);
     return check_launch("mvb wgrad finalize");
 }
 

@@ -115,6 +115,8 @@ __global__ void __launch_bounds__(256)
 linear_fwd_kernel(int M, int K, int N, const float *__restrict__ x, int x_vmf, const float *__restrict__ W,
                   const float *__restrict__ bias, int relu, float p, uint64_t seed, const int64_t *off_dev,
                   int64_t off_host, float *__restrict__ y, int y_vmf, int KC) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float4 dsm4[];
     float *xs = reinterpret_cast<float *>(dsm4);     // [LF_TM][LD]
     const int LD = KC + 4;
@@ -175,6 +177,8 @@ __global__ void __launch_bounds__(256)
 linear_bwd_kernel(int M, int K, int N, const float *__restrict__ x, int x_vmf, const float *__restrict__ W,
                   const float *__restrict__ y, const float *__restrict__ gy, int y_vmf, int relu, float scale,
                   float *__restrict__ dx, float *__restrict__ dW, float *__restrict__ db, int nA, int k_tiles, int nc_b) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float4 dsm4[];
     float *sm = reinterpret_cast<float *>(dsm4);
     const int tid = threadIdx.x;
@@ -325,6 +329,8 @@ vae_heads_fwd_kernel(int B, int H, int Z, int C, const float *__restrict__ h, co
                      const float *__restrict__ bv, float p, uint64_t seed, const int64_t *off_dev, int64_t off_host,
                      float *__restrict__ y_hat, float *__restrict__ mu, float *__restrict__ logvar,
                      float *__restrict__ z_, float *__restrict__ zcat) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float4 dsm4[];
     const int ldw = C + H + 1;
     float *hs = reinterpret_cast<float *>(dsm4);   // [C + H]   cat(y, h) row
@@ -437,6 +443,8 @@ vae_heads_bwd_kernel(int B, int H, int Z, int C, const float *__restrict__ h, co
                      float p, uint64_t seed, const int64_t *off_dev, int64_t off_host, float *__restrict__ g_h,
                      float *__restrict__ dWc, float *__restrict__ dbc, float *__restrict__ dWm, float *__restrict__ dbm,
                      float *__restrict__ dWv, float *__restrict__ dbv, int nbg) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float4 dsm4[];
     float *sm = reinterpret_cast<float *>(dsm4);
     const int tid = threadIdx.x;
@@ -557,9 +565,9 @@ extern "C" int mvb_linear_fwd(int M, int K, int N, const float *x, int x_vm_f, c
     if (rc) return rc;
     dim3 grid((N + LF_TN - 1) / LF_TN, (M + LF_TM - 1) / LF_TM);
     if (vec)
-        linear_fwd_kernel<4><<<grid, 256, smem, (cudaStream_t)stream>>>(M, K, N, x, x_vm_f, W, bias, relu, p_drop, seed, offset_dev, offset_host, y, y_vm_f, KC);
+        launch_pdl(linear_fwd_kernel<4>, grid, dim3(256), smem, (cudaStream_t)stream, M, K, N, x, x_vm_f, W, bias, relu, p_drop, seed, offset_dev, offset_host, y, y_vm_f, KC);
     else
-        linear_fwd_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(M, K, N, x, x_vm_f, W, bias, relu, p_drop, seed, offset_dev, offset_host, y, y_vm_f, KC);
+        launch_pdl(linear_fwd_kernel<1>, grid, dim3(256), smem, (cudaStream_t)stream, M, K, N, x, x_vm_f, W, bias, relu, p_drop, seed, offset_dev, offset_host, y, y_vm_f, KC);
     return check_launch("mvb_linear_fwd");
 }
 
@@ -587,7 +595,7 @@ extern "C" int mvb_linear_bwd(int M, int K, int N, const float *x, int x_vm_f, c
     do {                                                                                                                     \
         rc = ensure_smem(linear_bwd_kernel<VN_, VK_>, smem, &granted[SLOT], "linear_bwd");                                   \
         if (rc) return rc;                                                                                                   \
-        linear_bwd_kernel<VN_, VK_><<<nA + nB, 256, smem, (cudaStream_t)stream>>>(M, K, N, x, x_vm_f, W, y, gy, y_vm_f, relu, \
+        launch_pdl(linear_bwd_kernel<VN_, VK_>, dim3(nA + nB), dim3(256), smem, (cudaStream_t)stream, M, K, N, x, x_vm_f, W, y, gy, y_vm_f, relu, \
                                                                                   scale, dx, dW, db, nA, k_tiles, nc_b);     \
     } while (0)
     // Deferred mode (step engine, mvb_tune "defer_wgrad=1"): the input-gradient tiles (role B) are what the backward
@@ -598,11 +606,11 @@ extern "C" int mvb_linear_bwd(int M, int K, int N, const float *x, int x_vm_f, c
     do {                                                                                                                     \
         rc = ensure_smem(linear_bwd_kernel<VN_, VK_>, smem, &granted[SLOT], "linear_bwd");                                   \
         if (rc) break;                                                                                                       \
-        linear_bwd_kernel<VN_, VK_><<<nB, 256, smem, (cudaStream_t)stream>>>(M, K, N, x, x_vm_f, W, y, gy, y_vm_f, relu,      \
+        launch_pdl(linear_bwd_kernel<VN_, VK_>, dim3(nB), dim3(256), smem, (cudaStream_t)stream, M, K, N, x, x_vm_f, W, y, gy, y_vm_f, relu,      \
                                                                              scale, dx, dW, db, 0, k_tiles, nc_b);           \
         rc = check_launch("mvb_linear_bwd dx");                                                                              \
         if (rc) break;                                                                                                       \
-        linear_bwd_kernel<VN_, VK_><<<nA, 256, smem, lazy>>>(M, K, N, x, x_vm_f, W, y, gy, y_vm_f, relu, scale, nullptr, dW,  \
+        launch_pdl(linear_bwd_kernel<VN_, VK_>, dim3(nA), dim3(256), smem, lazy, M, K, N, x, x_vm_f, W, y, gy, y_vm_f, relu, scale, nullptr, dW,  \
                                                              db, nA, k_tiles, nc_b);                                         \
         rc = check_launch("mvb_linear_bwd dW");                                                                              \
     } while (0)
@@ -637,7 +645,7 @@ extern "C" int mvb_vae_heads_fwd(int B, int H, int Z, int C, const float *h, con
     static DevFlags granted;
     int rc = ensure_smem(vae_heads_fwd_kernel, smem, &granted, "vae_heads_fwd");
     if (rc) return rc;
-    vae_heads_fwd_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(B, H, Z, C, h, y_onehot, eps, Wc, bc, Wm, bm, Wv, bv, p_drop,
+    launch_pdl(vae_heads_fwd_kernel, dim3(B), dim3(256), smem, (cudaStream_t)stream, B, H, Z, C, h, y_onehot, eps, Wc, bc, Wm, bm, Wv, bv, p_drop,
                                                                   seed, offset_dev, offset_host, y_hat, mu, logvar, z, zcat);
     return check_launch("mvb_vae_heads_fwd");
 }
@@ -664,7 +672,7 @@ extern "C" int mvb_vae_heads_bwd(int B, int H, int Z, int C, const float *h, con
     SmallIn gin;
     gin.y_hat = y_hat; gin.logvar = logvar; gin.eps = eps; gin.g_yhat = g_yhat; gin.g_mu = g_mu; gin.g_logvar = g_logvar;
     gin.g_z = g_z; gin.g_zcat = g_zcat;
-    vae_heads_bwd_kernel<<<nbg + ntile, 256, smem, (cudaStream_t)stream>>>(B, H, Z, C, h, y_onehot, Wc, Wm, Wv, gin, p_drop, seed,
+    launch_pdl(vae_heads_bwd_kernel, dim3(nbg + ntile), dim3(256), smem, (cudaStream_t)stream, B, H, Z, C, h, y_onehot, Wc, Wm, Wv, gin, p_drop, seed,
                                                                             offset_dev, offset_host, g_h, dWc, dbc, dWm, dbm, dWv,
                                                                             dbv, nbg);
     return check_launch("mvb_vae_heads_bwd");

@@ -32,6 +32,7 @@ inline int check_launch(const char *what) {
 }
 
 int num_sms();  // multiprocessor count of the CURRENT device, cached per device (148 on B200)
+int pdl_enabled();   // mvb_tune pdl=0/1: launch the kernels that have a pdl_wait() with the programmatic-serialization attribute
 
 // Function attributes (the opt-in for > 48 KB of dynamic shared memory) are per DEVICE: a process that drives several
 // GPUs must set them on each.  DevFlags keeps one bit / one size per device ordinal for a call site.
@@ -60,6 +61,31 @@ inline int smem_optin(KernelT kernel, size_t bytes, DevFlags &f, const char *wha
 }
 
 #ifdef __CUDACC__
+// Programmatic dependent launch (PDL): a kernel launched with the stream-serialization attribute may start while its
+// predecessor in the stream is still running - as soon as every CTA of the predecessor has executed pdl_trigger() (or
+// exited) - and runs its prologue (TMEM allocation, barrier init, operator / weight staging: data that no kernel of the
+// step writes) until pdl_wait(), which returns once the predecessor grid has completed and its writes are visible.
+// EVERYTHING that reads or writes a tensor of the step must come after pdl_wait().  Both are no-ops in an ordinary launch.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// launch with the programmatic-serialization attribute (kernels that begin with pdl_trigger() / pdl_wait())
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);          // errors surface through check_launch()
+}
+
 // global -> shared copy with U independent loads in flight per thread.  A plain
 // `for (i = tid; i < n; i += nthreads) dst[i] = src[i];` serialises on the load->store dependency
 // (one global-memory latency per iteration); small launch-latency-bound kernels spent most of their
@@ -193,6 +219,7 @@ void set_mesh_tc(int enable, int c);
 void set_mesh_dbg(int v);
 void set_stream_tc(int v, int sw);
 void set_stream_nt(int v);
+void set_pdl(int v);
 void set_wgrad_perm(int v);
 
 // mesh-resident tensor-core layers (mvb_mesh_tc.cu): 1 = handled / supported, 0 = shape not covered, < 0 = error

@@ -478,6 +478,8 @@ cheb_layer_bwd_kernel(LayerArgs a, LayerSmem S) {
 __global__ void __launch_bounds__(256)
 layer_finalize_kernel(int B, int nw, int nb, const float *__restrict__ dwp, const float *__restrict__ dbp,
                       float *__restrict__ dw, float *__restrict__ db) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float red[8][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int j = blockIdx.x * 32 + tx;
@@ -539,7 +541,7 @@ static int layer_check(int N, int B, int Fin, int Fout, int K, int Lnnz, int n_i
 
 int launch_layer_finalize(int B, int nw, int nb, const float *dwp, const float *dbp, float *dw, float *db, cudaStream_t st) {
     if (nw + nb <= 0) return MVB_OK;
-    layer_finalize_kernel<<<(nw + nb + 31) / 32, 256, 0, st>>>(B, nw, nb, dwp, dbp, dw, db);
+    launch_pdl(layer_finalize_kernel, dim3((nw + nb + 31) / 32), dim3(256), 0, st, B, nw, nb, dwp, dbp, dw, db);
     return check_launch("mvb layer finalize");
 }
 
@@ -661,7 +663,7 @@ extern "C" int mvb_cheb_layer_bwd(int N, int B, int Fin, int Fout, int K, const 
             rc = check_launch("mvb_cheb_layer_bwd dw");
         }
         if (!rc) {
-            layer_finalize_kernel<<<(nw + nb + 31) / 32, 256, 0, side>>>(B, nw, nb, a.dwp, a.dbp, dweight, dbias);
+            launch_pdl(layer_finalize_kernel, dim3((nw + nb + 31) / 32), dim3(256), 0, side, B, nw, nb, a.dwp, a.dbp, dweight, dbias);
             rc = check_launch("mvb_cheb_layer_bwd finalize");
         }
         side_join(side, st);          // rejoin on every path: a captured graph must not end forked

@@ -24,6 +24,8 @@ __global__ void __launch_bounds__(256)
 vae_rec_partial_kernel(int B, int N, int C, int ld, int VCH, int BCH, const float *__restrict__ recon,
                        const XT *__restrict__ xgt, float log_sigma, float sigma,
                        double *__restrict__ partial, float *__restrict__ dnll) {
+    pdl_trigger();
+    pdl_wait();
     typedef typename AccT<XT>::type AT;
     extern __shared__ double smem_d[];
     XT *Xs = reinterpret_cast<XT *>(smem_d);                     // [BCH][VCH*C]
@@ -110,6 +112,8 @@ vae_loss_finalize_kernel(int B, int Z, int ncls, int nchunks, const double *__re
                          const float *__restrict__ mu, const float *__restrict__ logvar,
                          const float *__restrict__ y_hat, const int64_t *__restrict__ y,
                          double *loss, float *kld, double *rec, int64_t *correct) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ double s_sum[1024];
     __shared__ int s_cnt[1024];
     const int tid = threadIdx.x;
@@ -193,6 +197,8 @@ __global__ void scale_by_gloss_kernel(int64_t n, const float *__restrict__ src,
 
 __global__ void scale4_by_gloss_kernel(int64_t n4, const float4 *__restrict__ src,
                                        const double *__restrict__ gloss, double inv_b, float4 *dst) {
+    pdl_trigger();
+    pdl_wait();
     const float s = (float)(*gloss * inv_b);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 v = __ldg(src + i);
@@ -206,6 +212,8 @@ __global__ void vae_loss_bwd_small_kernel(int B, int Z, int ncls, const float *_
                                           const int64_t *__restrict__ y,
                                           const double *__restrict__ gloss, float *d_mu,
                                           float *d_logvar, float *d_yhat) {
+    pdl_trigger();
+    pdl_wait();
     const float s = (float)(*gloss / (double)B);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B * Z) {
@@ -223,6 +231,8 @@ __global__ void vae_loss_bwd_small_kernel(int B, int Z, int ncls, const float *_
 // fill and padded copy) -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 pack_vertex_major_kernel(int B, int N, int C, int Cp, const float *__restrict__ x, float *__restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     // block = 32 vertices x 8 meshes through shared memory: reads coalesced along a mesh's vertices, writes along
     // a vertex's meshes
     __shared__ float tile[8][32 * 8 + 1];
@@ -470,12 +480,12 @@ extern "C" int mvb_vae_loss_fwd(int B, int N, int C, int Z, int ncls, const floa
     const float sigma = expf(log_sigma);
     double *partial = reinterpret_cast<double *>(workspace);
     if (x_is_f64)
-        vae_rec_partial_kernel<double><<<grid, 256, smem, st>>>(B, N, C, recon_ld, VCH, BCH, recon, (const double *)x_gt, log_sigma, sigma, partial, dnll);
+        launch_pdl(vae_rec_partial_kernel<double>, dim3(grid), dim3(256), smem, st, B, N, C, recon_ld, VCH, BCH, recon, (const double *)x_gt, log_sigma, sigma, partial, dnll);
     else
-        vae_rec_partial_kernel<float><<<grid, 256, smem, st>>>(B, N, C, recon_ld, VCH, BCH, recon, (const float *)x_gt, log_sigma, sigma, partial, dnll);
+        launch_pdl(vae_rec_partial_kernel<float>, dim3(grid), dim3(256), smem, st, B, N, C, recon_ld, VCH, BCH, recon, (const float *)x_gt, log_sigma, sigma, partial, dnll);
     int rc = check_launch("mvb_vae_loss_fwd partial");
     if (rc) return rc;
-    vae_loss_finalize_kernel<<<1, 1024, 0, st>>>(B, Z, ncls, nch, partial, mu, logvar, y_hat, y, loss, kld, rec, correct);
+    launch_pdl(vae_loss_finalize_kernel, dim3(1), dim3(1024), 0, st, B, Z, ncls, nch, partial, mu, logvar, y_hat, y, loss, kld, rec, correct);
     return check_launch("mvb_vae_loss_fwd finalize");
 }
 
@@ -489,7 +499,7 @@ extern "C" int mvb_vae_loss_bwd(int B, int N, int C, int Z, int ncls, const floa
         MVB_REQUIRE(dnll, "vae_loss_bwd: dnll is null");
         const int64_t n = (int64_t)N * B * C;
         if (n % 4 == 0 && aligned16(dnll) && aligned16(d_recon))
-            scale4_by_gloss_kernel<<<ew_grid(n / 4, 256), 256, 0, st>>>(n / 4, (const float4 *)dnll, gloss, 1.0 / B, (float4 *)d_recon);
+            launch_pdl(scale4_by_gloss_kernel, dim3(ew_grid(n / 4, 256)), dim3(256), 0, st, n / 4, (const float4 *)dnll, gloss, 1.0 / B, (float4 *)d_recon);
         else
             scale_by_gloss_kernel<<<ew_grid(n, 256), 256, 0, st>>>(n, dnll, gloss, 1.0 / B, d_recon);
         int rc = check_launch("mvb_vae_loss_bwd recon");
@@ -498,7 +508,7 @@ extern "C" int mvb_vae_loss_bwd(int B, int N, int C, int Z, int ncls, const floa
     if (d_mu || d_logvar || d_yhat) {
         MVB_REQUIRE(mu && logvar && y_hat && y, "vae_loss_bwd: null latent pointers");
         const int n = B * (Z > 1 ? Z : 1);
-        vae_loss_bwd_small_kernel<<<(n + 127) / 128, 128, 0, st>>>(B, Z, ncls, mu, logvar, y_hat, y, gloss, d_mu, d_logvar, d_yhat);
+        launch_pdl(vae_loss_bwd_small_kernel, dim3((n + 127) / 128), dim3(128), 0, st, B, Z, ncls, mu, logvar, y_hat, y, gloss, d_mu, d_logvar, d_yhat);
         return check_launch("mvb_vae_loss_bwd latent");
     }
     return MVB_OK;
@@ -594,6 +604,6 @@ extern "C" int mvb_epoch_meter_add(int B, const void *loss, int loss_is_f64, con
 
 extern "C" int mvb_pack_vertex_major(int B, int N, int C, int Cp, const float *x, float *out, void *stream) {
     MVB_REQUIRE(B > 0 && N > 0 && C > 0 && Cp >= C && C <= 8 && x && out, "pack_vertex_major: bad arguments");
-    mvb::pack_vertex_major_kernel<<<dim3((N + 31) / 32, (B + 7) / 8), 256, 0, (cudaStream_t)stream>>>(B, N, C, Cp, x, out);
+    mvb::launch_pdl(mvb::pack_vertex_major_kernel, dim3((N + 31) / 32, (B + 7) / 8), dim3(256), 0, (cudaStream_t)stream, B, N, C, Cp, x, out);
     return mvb::check_launch("mvb_pack_vertex_major");
 }

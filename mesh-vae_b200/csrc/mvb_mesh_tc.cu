@@ -276,6 +276,7 @@ cheb_mesh_tc_fwd_kernel(const MeshTcArgs a) {
     uint32_t *slot = reinterpret_cast<uint32_t *>(bar + 2);            // bar[0]: commits of even steps (all steps without lo2), bar[1]: odd
 
     prof_stamp(a.prof, 0);
+    pdl_trigger();
     if (warp == 0) tmem_alloc(slot, (uint32_t)a.tmem_cols);
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -300,6 +301,7 @@ cheb_mesh_tc_fwd_kernel(const MeshTcArgs a) {
         for (int v = tid; v < N; v += MT_NT) sts_i(inv + 4u * v, -1);
     }
     prof_stamp(a.prof, 3);
+    pdl_wait();          // everything above reads only the operator and the weights; x is the previous kernel's output
     // ---- T_0 into plane A (+ its lo part) ----
     const int64_t xrow = (int64_t)a.B * Fin;               // floats between consecutive vertices of one mesh
     const float *xb = a.x + (int64_t)b * Fin + c * WL;
@@ -512,6 +514,7 @@ cheb_mesh_tc_bwd_kernel(const MeshTcBwdArgs g) {
     uint64_t *bar = reinterpret_cast<uint64_t *>(smg + a.o_bar);
     uint32_t *slot = reinterpret_cast<uint32_t *>(bar + 2);            // bar[0]: commits of even steps (all steps without lo2), bar[1]: odd
 
+    pdl_trigger();
     if (warp == 0) tmem_alloc(slot, (uint32_t)a.tmem_cols);
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -531,6 +534,7 @@ cheb_mesh_tc_bwd_kernel(const MeshTcBwdArgs g) {
         sts_f(blo + off, l);
     }
     for (int v = tid; v < N; v += MT_NT) sts_i(inv + 4u * v, a.sel ? -1 : v);
+    pdl_wait();          // operator, weights and shared-memory set-up above; x / dy / y and every global write below
     // ---- T_0 = U x of this CTA's share of the input features, straight to global (operand of the weight gradient) ----
     if (a.Urp && g.T0) {
         const int FL = Fin / a.C, FQ = FL >> 2;
@@ -759,13 +763,15 @@ static int launch_mesh_fwd_t(const MeshTcArgs &a, cudaStream_t st) {
     cfg.blockDim = dim3(MT_NT);
     cfg.dynamicSmemBytes = (size_t)a.total + 1024;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)a.C;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, cheb_mesh_tc_fwd_kernel<WL>, a);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -837,13 +843,15 @@ static int launch_mesh_bwd_t(const MeshTcBwdArgs &g, cudaStream_t st) {
     cfg.blockDim = dim3(MT_NT);
     cfg.dynamicSmemBytes = (size_t)g.m.total + 1024;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)g.m.C;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, cheb_mesh_tc_bwd_kernel<WL>, g);
     if (e != cudaSuccess) {
         cudaGetLastError();

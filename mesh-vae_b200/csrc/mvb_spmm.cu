@@ -31,6 +31,8 @@ __global__ void __launch_bounds__(1024)
 spmm_v4_kernel(int n_rows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
                const float *__restrict__ vals, const float4 *__restrict__ x, float4 *y,
                const float4 *z, const float4 *w, float alpha, float beta, int nc4, int chunk) {
+    pdl_trigger();
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nc4) return;
     // a block walks `chunk` CONSECUTIVE rows of its column slab (blockDim.y rows at a time): the mesh
@@ -169,6 +171,8 @@ __global__ void __launch_bounds__(1024)
 cheb_recur_fwd_kernel(int N, int K, const int32_t *__restrict__ g_rowptr, const int32_t *__restrict__ g_colidx,
                       const float *__restrict__ g_vals, const float4 *__restrict__ x, float4 *__restrict__ basis,
                       int nc4, int nnz_smem) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float4 sbuf[];
     float4 *cur = sbuf;                  // T_{k-1}
     float4 *old = sbuf + (size_t)N * CS4;  // T_{k-2}, overwritten by T_k
@@ -348,11 +352,11 @@ int launch_cheb_recur_fwd(int N, int nnz, int K, const int32_t *rowptr, const in
     if (cs4 == 2) {
         if (smem_optin(cheb_recur_fwd_kernel<2>, 200 * 1024, optin2, "cheb_recur_fwd_kernel")) e = cudaErrorInvalidValue;
         if (e == cudaSuccess)
-            cheb_recur_fwd_kernel<2><<<grid, g_recur_threads, smem, st>>>(N, K, rowptr, colidx, vals, (const float4 *)x, (float4 *)basis, nc4, nnz_smem);
+            launch_pdl(cheb_recur_fwd_kernel<2>, dim3(grid), dim3(g_recur_threads), smem, st, N, K, rowptr, colidx, vals, (const float4 *)x, (float4 *)basis, nc4, nnz_smem);
     } else {
         if (smem_optin(cheb_recur_fwd_kernel<1>, 200 * 1024, optin1, "cheb_recur_fwd_kernel")) e = cudaErrorInvalidValue;
         if (e == cudaSuccess)
-            cheb_recur_fwd_kernel<1><<<grid, g_recur_threads, smem, st>>>(N, K, rowptr, colidx, vals, (const float4 *)x, (float4 *)basis, nc4, nnz_smem);
+            launch_pdl(cheb_recur_fwd_kernel<1>, dim3(grid), dim3(g_recur_threads), smem, st, N, K, rowptr, colidx, vals, (const float4 *)x, (float4 *)basis, nc4, nnz_smem);
     }
     if (e != cudaSuccess) return set_err(MVB_ECUDA, "cheb_recur_fwd: %s", cudaGetErrorString(e));
     int rc = check_launch("mvb cheb_recur_fwd");
@@ -440,9 +444,9 @@ int launch_spmm(int n_rows, int n_src_rows, const int32_t *rowptr, const int32_t
 #define MVB_SPMM_LAUNCH(HZ, HW)                                                                                         \
     do {                                                                                                                \
         if (idx32)                                                                                                      \
-            spmm_v4_kernel<HZ, HW, uint32_t><<<grid, block, 0, st>>>(n_rows, rowptr, colidx, vals, x4, y4, z4, w4, alpha, beta, nc4, chunk); \
+            launch_pdl(spmm_v4_kernel<HZ, HW, uint32_t>, grid, block, 0, st, n_rows, rowptr, colidx, vals, x4, y4, z4, w4, alpha, beta, nc4, chunk); \
         else                                                                                                            \
-            spmm_v4_kernel<HZ, HW, int64_t><<<grid, block, 0, st>>>(n_rows, rowptr, colidx, vals, x4, y4, z4, w4, alpha, beta, nc4, chunk);  \
+            launch_pdl(spmm_v4_kernel<HZ, HW, int64_t>, grid, block, 0, st, n_rows, rowptr, colidx, vals, x4, y4, z4, w4, alpha, beta, nc4, chunk);  \
     } while (0)
         if (z && w)
             MVB_SPMM_LAUNCH(true, true);

@@ -199,6 +199,7 @@ tc_rowgemm_kernel(TcRowArgs a) {
     uint64_t *bar = reinterpret_cast<uint64_t *>(Blo + NPB * b_plane);
     uint32_t *slot = reinterpret_cast<uint32_t *>(bar + 1);
 
+    pdl_trigger();
     if (warp == 0) tmem_alloc(slot, (uint32_t)a.tmem_cols);
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -209,10 +210,11 @@ tc_rowgemm_kernel(TcRowArgs a) {
             reinterpret_cast<float4 *>(Ahi)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
     }
-    stage_b_operand(a, Bhi, Blo, b_plane, row_bytes, tid, blockDim.x);
+    stage_b_operand(a, Bhi, Blo, b_plane, row_bytes, tid, blockDim.x);          // weights: no kernel of the step writes them
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();          // the planes are the previous kernels' output
     const uint32_t tmem_base = *slot;
     const uint32_t idesc = make_idesc(128, a.nn16, 0, 0);
     const uint32_t layout_type = (row_bytes == 128) ? 2u : 4u;
@@ -378,7 +380,7 @@ static int launch_rowgemm_t(const TcRowArgs &t, unsigned grid, size_t smem, cuda
         const int rc_attr = smem_optin(tc_rowgemm_kernel<W, NP, PG>, 200 * 1024, optin, "tc_rowgemm");
         if (rc_attr) return rc_attr;
     }
-    tc_rowgemm_kernel<W, NP, PG><<<grid, 128, smem, st>>>(t);
+    launch_pdl(tc_rowgemm_kernel<W, NP, PG>, dim3(grid), dim3(128), smem, st, t);
     return check_launch("mvb tc_rowgemm");
 }
 
@@ -537,6 +539,7 @@ tc_wgrad_kernel(TcWgradArgs a) {
     uint64_t *bar = reinterpret_cast<uint64_t *>(Dlo + blk);
     uint32_t *slot = reinterpret_cast<uint32_t *>(bar + 1);
 
+    pdl_trigger();
     if (warp == 0) tmem_alloc(slot, (uint32_t)a.tmem_cols);
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -553,6 +556,7 @@ tc_wgrad_kernel(TcWgradArgs a) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();          // shared-memory and TMEM set-up above; the planes / dY are the previous kernels' output
     const uint32_t tmem_base = *slot;
     // N-STACKING (Fout <= 16): the lo parts of dY go into columns 16..31 of the same 128-byte B rows, so ONE MMA with
     // N = 32 yields A.[B_hi | B_lo]; two MMAs per K step (A_hi, A_lo) instead of three give all four hi/lo products, the
@@ -794,7 +798,7 @@ static int launch_wgrad_t(const TcWgradArgs &t, unsigned grid, size_t smem, cuda
         const int rc_attr = smem_optin(tc_wgrad_kernel<NPF, Q4>, 200 * 1024, optin, "tc_wgrad");
         if (rc_attr) return rc_attr;
     }
-    tc_wgrad_kernel<NPF, Q4><<<grid, WG_NT, smem, st>>>(t);
+    launch_pdl(tc_wgrad_kernel<NPF, Q4>, dim3(grid), dim3(WG_NT), smem, st, t);
     return check_launch("mvb tc_wgrad");
 }
 
