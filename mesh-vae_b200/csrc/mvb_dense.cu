@@ -116,7 +116,6 @@ linear_fwd_kernel(int M, int K, int N, const float *__restrict__ x, int x_vmf, c
                   const float *__restrict__ bias, int relu, float p, uint64_t seed, const int64_t *off_dev,
                   int64_t off_host, float *__restrict__ y, int y_vmf, int KC) {
     pdl_trigger();
-    pdl_wait();
     extern __shared__ float4 dsm4[];
     float *xs = reinterpret_cast<float *>(dsm4);     // [LF_TM][LD]
     const int LD = KC + 4;
@@ -131,8 +130,9 @@ linear_fwd_kernel(int M, int K, int N, const float *__restrict__ x, int x_vmf, c
         const int kc = min(KC, K - k0);
         const int kc4 = (kc + 3) & ~3;
         if (k0) __syncthreads();
-        stage_async<VEC>(xs, LD, LF_TM, rows, kc4, kc, xv, m0, k0, tid, 256);
         stage_async<VEC>(ws, LD, LF_TN, cols, kc4, kc, wv, n0, k0, tid, 256);
+        if (k0 == 0) pdl_wait();          // the first weight tile is in flight before the previous kernel has finished; x is its output
+        stage_async<VEC>(xs, LD, LF_TM, rows, kc4, kc, xv, m0, k0, tid, 256);
         cp_async_wait_all();
         __syncthreads();
         const float4 *w4 = reinterpret_cast<const float4 *>(ws + n * LD);
@@ -330,7 +330,6 @@ vae_heads_fwd_kernel(int B, int H, int Z, int C, const float *__restrict__ h, co
                      float *__restrict__ y_hat, float *__restrict__ mu, float *__restrict__ logvar,
                      float *__restrict__ z_, float *__restrict__ zcat) {
     pdl_trigger();
-    pdl_wait();
     extern __shared__ float4 dsm4[];
     const int ldw = C + H + 1;
     float *hs = reinterpret_cast<float *>(dsm4);   // [C + H]   cat(y, h) row
@@ -338,7 +337,8 @@ vae_heads_fwd_kernel(int B, int H, int Z, int C, const float *__restrict__ h, co
     float *wsm = hd + (C + H);                     // [C + 2Z][ldw]
     __shared__ float outs[HEADS_MAX_OUT];
     const int b = blockIdx.x, tid = threadIdx.x;
-    stage_head_weights(wsm, ldw, H, Z, C, Wc, Wm, Wv, tid, blockDim.x);
+    stage_head_weights(wsm, ldw, H, Z, C, Wc, Wm, Wv, tid, blockDim.x);      // weights: in flight before the previous kernel has finished
+    pdl_wait();
     const uint64_t off = (uint64_t)(off_host + (off_dev ? *off_dev : 0));
     const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
     for (int j = tid; j < C + H; j += blockDim.x) {
@@ -444,12 +444,10 @@ vae_heads_bwd_kernel(int B, int H, int Z, int C, const float *__restrict__ h, co
                      float *__restrict__ dWc, float *__restrict__ dbc, float *__restrict__ dWm, float *__restrict__ dbm,
                      float *__restrict__ dWv, float *__restrict__ dbv, int nbg) {
     pdl_trigger();
-    pdl_wait();
     extern __shared__ float4 dsm4[];
     float *sm = reinterpret_cast<float *>(dsm4);
     const int tid = threadIdx.x;
     const int nout = C + 2 * Z;
-    const uint64_t off = (uint64_t)(off_host + (off_dev ? *off_dev : 0));
     const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
     if ((int)blockIdx.x < nbg) {
         const int ldw = C + H + 1;
@@ -458,8 +456,10 @@ vae_heads_bwd_kernel(int B, int H, int Z, int C, const float *__restrict__ h, co
         float *small = gs + ((HB_ROWS * nout + 3) & ~3);
         const int b0 = blockIdx.x * HB_ROWS;
         const int nr = min(HB_ROWS, B - b0);
+        stage_head_weights(wsm, ldw, H, Z, C, Wc, Wm, Wv, tid, blockDim.x);      // weights: in flight before the previous kernel has finished
+        pdl_wait();
+        const uint64_t off = (uint64_t)(off_host + (off_dev ? *off_dev : 0));
         const SmallIn si = stage_small_inputs(small, b0, nr, Z, C, gin, tid, blockDim.x);
-        stage_head_weights(wsm, ldw, H, Z, C, Wc, Wm, Wv, tid, blockDim.x);
         cp_async_wait_all();
         __syncthreads();
         for (int i = tid; i < HB_ROWS * nout; i += blockDim.x) {
@@ -481,6 +481,8 @@ vae_heads_bwd_kernel(int B, int H, int Z, int C, const float *__restrict__ h, co
         return;
     }
     // ---- weight gradients ----
+    pdl_wait();
+    const uint64_t off = (uint64_t)(off_host + (off_dev ? *off_dev : 0));
     float *gs = sm;                                    // [B][nout]
     float *ht = sm + B * nout;                         // [B][33]: columns j0..j0+31 of cat(y, h, 1)
     float *hdt = ht + B * 33;                          // same, with the classifier's dropout mask

@@ -33,6 +33,7 @@ adam_kernel(int64_t n, float *__restrict__ p, const float *__restrict__ g, float
 __global__ void __launch_bounds__(256)
 adam_hp_kernel(int64_t n, float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
                float *__restrict__ v, const int64_t *__restrict__ step, const float *__restrict__ hp) {
+    pdl_wait();          // (no trigger: nothing may start early next to the kernel that rewrites the weights)
     const float lr = hp[0], beta1 = hp[1], beta2 = hp[2], eps = hp[3], wd = hp[4], gscale = hp[5];
     const float t = (float)(*step);
     const float bc1 = 1.f - powf(beta1, t);
@@ -64,7 +65,7 @@ extern "C" int mvb_adam_step_hp(int64_t n, float *p, const float *g, float *m, f
     int64_t blocks = (n + 255) / 256;
     const int64_t cap = (int64_t)num_sms() * 8;
     if (blocks > cap) blocks = cap;
-    adam_hp_kernel<<<(unsigned)blocks, 256, 0, st>>>(n, p, g, m, v, step, hyper);
+    launch_pdl(adam_hp_kernel, dim3((unsigned)blocks), dim3(256), 0, st, n, p, g, m, v, step, hyper);
     return check_launch("mvb_adam_step_hp");
 }
 
