@@ -111,14 +111,20 @@ dp_reduce_adam_kernel(int world, int rank, int channel, int64_t off, int64_t n, 
         const int64_t e4 = 4 * (i0 + i);
         // all peers' quads in flight at once (the reads cross NVLink: latency, not arithmetic, paces this loop), then the
         // sum in rank order
-        float4 gr[DP_MAX_WORLD];
+        // eight peers at a time (keeps the kernel at ~64 registers: it runs next to the encoder backward)
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r0 = 0; r0 < world; r0 += 8) {
+            float4 gr[8];
 #pragma unroll
-        for (int r = 0; r < DP_MAX_WORLD; ++r)
-            if (r < world) gr[r] = ld_peer4(ptrs.grads[r] + e4);
-        float4 g = gr[0];
+            for (int r = 0; r < 8; ++r)
+                if (r0 + r < world) gr[r] = ld_peer4(ptrs.grads[r0 + r] + e4);
 #pragma unroll
-        for (int r = 1; r < DP_MAX_WORLD; ++r)
-            if (r < world) { g.x += gr[r].x; g.y += gr[r].y; g.z += gr[r].z; g.w += gr[r].w; }
+            for (int r = 0; r < 8; ++r)
+                if (r0 + r < world) {
+                    if (r0 + r == 0) g = gr[0];
+                    else { g.x += gr[r].x; g.y += gr[r].y; g.z += gr[r].z; g.w += gr[r].w; }
+                }
+        }
         float4 pi = *reinterpret_cast<const float4 *>(p + e4);
         float4 mi = *reinterpret_cast<const float4 *>(m + e4);
         float4 vi = *reinterpret_cast<const float4 *>(v + e4);

@@ -161,6 +161,11 @@ class TrainEngine:
                     raise
                 import warnings
                 warnings.warn(f"TrainEngine: peer-memory gradient exchange unavailable ({e}); using NCCL all-reduces")
+        if self.distributed and self.world > 1 and os.environ.get("MVB_DP_PDL", "0") != "1":
+            # programmatic dependent launch helps the single-GPU graph (0.914 -> 0.895 ms) but costs the data-parallel one
+            # (2 GPUs, same box: 0.9913 ms with it, 0.9627 ms without - the pre-launched CTAs that sit in griddepcontrol.wait
+            # take block slots next to the background exchange branch): off for N > 1
+            _lib.tune("pdl=0")
         self.opt = FlatAdam(live, lr=lr, weight_decay=weight_decay,
                             grad_buffer_factory=(lambda n: self.peer.flat_g) if self.peer is not None else None)
         self.split = self.opt.offsets[len(late)] if (self.distributed and use_graph and hasattr(net, "keep_encoder_conv_out")
@@ -353,7 +358,7 @@ class TrainEngine:
             dist.barrier()
             g = torch.cuda.CUDAGraph()
             side = torch.cuda.Stream()
-            self._bg_ctas = int(os.environ.get("MVB_DP_BG_CTAS", "74"))
+            self._bg_ctas = int(os.environ.get("MVB_DP_BG_CTAS", "40"))          # 8 GPUs: 16 -> 0.984 ms, 40 -> 0.965, 74 -> 0.974, 148 -> 0.973
             with torch.cuda.graph(g, stream=cap):
                 self._fwd()
                 check(lib.mvb_stream_wait_external_event(stream_ptr(), self._gt_ready.cuda_event), "mvb_stream_wait_external_event")
