@@ -117,6 +117,10 @@ def tune(spec: str):
     check(lib.mvb_tune(spec.encode()), "mvb_tune")
 
 
+if os.environ.get("MVB_TUNE"):          # A/B runs of the tuning hooks (tests, bench, scripts alike)
+    tune(os.environ["MVB_TUNE"])
+
+
 # Deferred side chains (include/mvb.h: mvb_side_join): while on, the tensors a chain still reads are parked here until
 # the join, so that the caching allocator cannot hand their memory to a later kernel of the main stream
 _deferred = {"on": False, "keep": []}

@@ -809,6 +809,7 @@ extern "C" int mvb_tune(const char *spec) {
         if (*p == ';') ++p;
         if (!strcmp(key, "tc_tuning")) { if (v[0]) set_tc_pg6(v[0]); if (v[1]) set_tc_cap(v[1]); }
         else if (!strcmp(key, "tc_balance")) set_tc_balance(v[0]);
+        else if (!strcmp(key, "tc_tma")) set_tc_tma(v[0], v[1]);
         else if (!strcmp(key, "layer_tuning")) set_layer_tuning(v[0], v[1]);
         else if (!strcmp(key, "fused_recurrence")) set_recur_fused(v[0]);
         else if (!strcmp(key, "spmm_shape")) set_spmm_shape(v[0], v[1]);

@@ -211,6 +211,7 @@ int launch_wgrad_tc(const WgradArgs &a, int has_bias, int M4, int N4, int *npart
 void set_tc_pg6(int v);
 void set_tc_cap(int v);
 void set_tc_balance(int v);
+void set_tc_tma(int v, int nb);
 void set_layer_tuning(int v, int conc);
 void set_recur_fused(int v);
 void set_spmm_shape(int tx, int chunk);

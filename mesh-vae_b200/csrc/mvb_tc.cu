@@ -15,12 +15,14 @@
 // and D += A_hi B_hi + A_lo B_hi + A_hi B_lo  (dropped term ~2^-22).  Tensor throughput is >20x what
 // these HBM-bound contractions need, so the 3x MMA count is free.
 //
-// Operands are staged global -> registers -> shared (the split needs the register pass, so TMA
-// would not remove it) directly into the canonical SWIZZLE_64B / SWIZZLE_128B layouts the UMMA
+// Operands are staged global -> registers -> shared directly into the canonical SWIZZLE_64B / SWIZZLE_128B layouts the UMMA
 // shared-memory descriptors expect: a tile row is 64 B (Fin = 16) or 128 B (Fin = 32) and its
 // 16-byte chunk index is XORed with address bits [7,9) / [7,10), which also makes the staging
-// stores bank-conflict free.
+// stores bank-conflict free.  A TMA-fed variant of the row GEMM exists (tc_rowgemm_tma_kernel below: the raw fp32 tile
+// loaded by cp.async.bulk.tensor IS the hi operand, only lo is computed) - measured slower than the register path
+// (it needs a block barrier per plane instead of per plane pair), opt-in.
 #include <stdlib.h>
+#include <cuda.h>
 #include "mvb_internal.cuh"
 #include "mvb_tcgen05.cuh"
 
@@ -367,6 +369,194 @@ tc_rowgemm_kernel(TcRowArgs a) {
     if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Row GEMM with TMA-fed operands (16-wide planes, no mask / row selection): kind::tf32 reads only the upper 19 bits of an
+// operand, so the RAW fp32 tile is the `hi` operand as it stands - cp.async.bulk.tensor writes it straight into the K-major
+// SWIZZLE_64B UMMA layout (the TMA swizzle mode and the descriptor's swizzle mode are the same XOR), no register pass; only
+// lo = x - trunc(x) is computed, shared memory to shared memory.  One plane (128 rows x 64 bytes = 8 KB) per iteration:
+//   ring of NB hi tiles filled by TMA NB-1 iterations ahead (mbarrier complete_tx), two lo tiles; per iteration
+//   wait(full) -> convert -> barrier -> one thread issues the 6 MMAs of the plane and commits to the lo tile's mbarrier ->
+//   the tile freed by the PREVIOUS iteration's MMAs is refilled; the accumulator stays in TMEM across the planes of a row tile.
+// ---------------------------------------------------------------------------------------------
+struct TcTmaMaps {
+    CUtensorMap m0;       // plane 0: [rows][16]
+    CUtensorMap m1;       // planes 1..NP-1, contiguous: [(NP-1) * rows][16]
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+template <int NB>
+__global__ void __launch_bounds__(128)
+tc_rowgemm_tma_kernel(TcRowArgs a, const __grid_constant__ TcTmaMaps maps) {
+    extern __shared__ __align__(1024) char smem_raw[];
+    char *smem = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NP = a.in_planes;
+    constexpr int R = 128, A_TILE = R * 64;
+    const int b_plane = a.nn16 * 64;
+    char *Ahi = smem;                                   // [NB][8 KB]
+    char *Alo = Ahi + NB * A_TILE;                      // [2][8 KB]
+    char *Bhi = Alo + 2 * A_TILE;                       // [NP][b_plane]
+    char *Blo = Bhi + NP * b_plane;
+    uint64_t *full = reinterpret_cast<uint64_t *>(Blo + NP * b_plane);      // [NB]
+    uint64_t *mbar = full + NB;                                            // [2]: MMAs that read lo tile b (and their hi tile) are done
+    uint32_t *slot = reinterpret_cast<uint32_t *>(mbar + 2);
+
+    pdl_trigger();
+    if (warp == 0) tmem_alloc(slot, (uint32_t)a.tmem_cols);
+    if (tid == 0) {
+        for (int i = 0; i < NB; ++i) mbar_init(full + i, 1);
+        mbar_init(mbar, 1);
+        mbar_init(mbar + 1, 1);
+        fence_barrier_init();
+    }
+    stage_b_operand(a, Bhi, Blo, b_plane, 64, tid, blockDim.x);          // weights: no kernel of the step writes them
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    pdl_wait();          // the planes are the previous kernels' output
+    const uint32_t tmem_base = *slot;
+    const uint32_t idesc = make_idesc(128, a.nn16, 0, 0);
+    const int64_t ntiles = (a.rows + R - 1) / R;
+    const int64_t my_tiles = ((int64_t)blockIdx.x < ntiles) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t n_iters = my_tiles * NP;
+    const int row = warp * 32 + lane;                   // D row (TMEM lane) this thread reads back
+
+    // iteration it = (tile it / NP of this CTA, plane it % NP)
+    auto issue_load = [&](int64_t it) {
+        const int p = (int)(it % NP);
+        const int64_t row0 = ((int64_t)blockIdx.x + (it / NP) * gridDim.x) * R;
+        uint64_t *fb = full + (it % NB);
+        mbar_expect_tx(fb, (uint32_t)A_TILE);
+        if (p == 0) tma_load_2d(smem_u32(Ahi + (it % NB) * A_TILE), &maps.m0, 0, (int)row0, fb);
+        else tma_load_2d(smem_u32(Ahi + (it % NB) * A_TILE), &maps.m1, 0, (int)((int64_t)(p - 1) * a.rows + row0), fb);
+    };
+    if (tid == 0)
+        for (int64_t it = 0; it < NB - 1 && it < n_iters; ++it) issue_load(it);
+
+    // this thread's four pieces of a tile (row, 16-byte chunk): swizzled offsets, tile-invariant
+    uint32_t soff[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = j * 128 + tid;
+        soff[j] = swz_off(i >> 2, i & 3, 64);
+    }
+    for (int64_t it = 0; it < n_iters; ++it) {
+        const int p = (int)(it % NP), lb = (int)(it & 1), hb = (int)(it % NB);
+        if (it >= 2) mbar_wait(mbar + lb, (uint32_t)(((it - 2) >> 1) & 1));        // the MMAs of iteration it - 2 have read lo tile lb
+        mbar_wait(full + hb, (uint32_t)((it / NB) & 1));                           // the raw tile has landed
+        const char *hi = Ahi + hb * A_TILE;
+        char *lo = Alo + lb * A_TILE;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 v = *reinterpret_cast<const float4 *>(hi + soff[j]);
+            float4 h, l;
+            split4(v, h, l);
+            *reinterpret_cast<float4 *>(lo + soff[j]) = l;
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const uint64_t ah = make_desc(smem_u32(hi) + j * 32, 16, 512, 4u), al = make_desc(smem_u32(lo) + j * 32, 16, 512, 4u);
+                const uint64_t bh = make_desc(smem_u32(Bhi + p * b_plane) + j * 32, 16, 512, 4u);
+                const uint64_t bl = make_desc(smem_u32(Blo + p * b_plane) + j * 32, 16, 512, 4u);
+                umma_tf32(tmem_base, al, bh, idesc, (p > 0 || j > 0) ? 1u : 0u);      // small terms first
+                umma_tf32(tmem_base, ah, bl, idesc, 1u);
+                umma_tf32(tmem_base, ah, bh, idesc, 1u);
+            }
+            umma_commit(mbar + lb);
+            // refill the hi tile that the PREVIOUS iteration's MMAs have finished with (iteration it + NB - 1)
+            const int64_t nx = it + NB - 1;
+            if (nx < n_iters) {
+                if (it >= 1) mbar_wait(mbar + (lb ^ 1), (uint32_t)(((it - 1) >> 1) & 1));
+                issue_load(nx);
+            }
+        }
+        if (p == NP - 1) {       // the row tile is complete: every MMA issued so far is covered by this commit
+            mbar_wait(mbar + lb, (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            const int64_t row0 = ((int64_t)blockIdx.x + (it / NP) * gridDim.x) * R;
+            const int nr = (int)((a.rows - row0) < R ? (a.rows - row0) : R);
+            row_epilogue(a, tmem_base, warp, row, nr, row0);
+            tc_fence_before();   // order this tile's TMEM reads before the barrier that precedes the next MMA
+        }
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+}
+
+static int g_tc_tma = 0;            // mvb_tune tc_tma=0/1[,hi tiles in the ring: 3 or 4].  Off by default: same-box A/B of the step (bench.py,
+                                    // two passes): register-staged kernel 0.8920 / 0.8918 ms, TMA-fed 0.9049 / 0.9054 ms (ring of 3, four CTAs per SM),
+                                    // 0.9066 / 0.9068 ms (ring of 4, three CTAs per SM); results identical (same products, same order)
+static int g_tc_tma_nb = 4;
+void set_tc_tma(int v, int nb) {
+    g_tc_tma = v ? 1 : 0;
+    if (nb == 3 || nb == 4) g_tc_tma_nb = nb;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+static bool make_plane_map(CUtensorMap *m, const float *base, int64_t nrows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t gdim[2] = {16, (cuuint64_t)nrows};
+    const cuuint64_t gstride[1] = {64};
+    const cuuint32_t box[2] = {16, 128};
+    const cuuint32_t estride[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// 1 = launched, 0 = not covered
+static int launch_rowgemm_tma(const TcRowArgs &t, cudaStream_t st) {
+    if (!g_tc_tma || t.in_w != 16 || t.in_planes < 2 || t.in_planes > 8 || t.mask || t.row_sel || t.w_fold > 1) return 0;
+    if (t.rows < 128 * 64 || (int64_t)t.in_planes * t.rows >= ((int64_t)1 << 31)) return 0;
+    TcTmaMaps maps;
+    if (!make_plane_map(&maps.m0, t.in0, t.rows) || !make_plane_map(&maps.m1, t.in_rest, (int64_t)(t.in_planes - 1) * t.rows)) return 0;
+    const int NB = g_tc_tma_nb;
+    const size_t smem = 1024 + (size_t)(NB + 2) * 8192 + 2 * (size_t)t.in_planes * t.nn16 * 64 + (NB + 2) * 8 + 16;
+    static DevFlags optin3, optin4;
+    if (NB == 3 ? smem_optin(tc_rowgemm_tma_kernel<3>, 200 * 1024, optin3, "tc_rowgemm_tma") : smem_optin(tc_rowgemm_tma_kernel<4>, 200 * 1024, optin4, "tc_rowgemm_tma")) return 0;
+    int per_sm = (int)((220 * 1024) / smem);
+    if (per_sm > 512 / t.tmem_cols) per_sm = 512 / t.tmem_cols;
+    if (per_sm > 6) per_sm = 6;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t ntiles = (t.rows + 127) / 128;
+    int64_t grid = (int64_t)num_sms() * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    if (NB == 3) launch_pdl(tc_rowgemm_tma_kernel<3>, dim3((unsigned)grid), dim3(128), smem, st, t, maps);
+    else launch_pdl(tc_rowgemm_tma_kernel<4>, dim3((unsigned)grid), dim3(128), smem, st, t, maps);
+    const int rc = check_launch("mvb tc_rowgemm_tma");
+    return rc ? rc : 1;
+}
+
 static int pow2_cols(int n) {
     int c = 32;
     while (c < n) c <<= 1;
@@ -425,6 +615,10 @@ int launch_contract_tc(const ContractArgs &a, cudaStream_t st) {
     t.tmem_cols = pow2_cols(nn16);
     t.tile_w = (packed || w == 4) ? (Kd <= 16 ? 16 : 32) : w;
     t.tile_planes = (packed || w == 4) ? 1 : a.in_planes;
+    if (!packed && w == 16) {          // TMA-fed variant (mvb_tune tc_tma=1)
+        const int rt = launch_rowgemm_tma(t, st);
+        if (rt != 0) return rt;
+    }
     // plane groups (A tiles staged at a time): 3 of 6 / 2 of 4 planes for 16-wide planes, 1 of 2-3 for 32-wide
     int pg = t.tile_planes;
     if (w == 16 && a.in_planes == 6) pg = g_tc_pg6;
