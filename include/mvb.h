@@ -52,9 +52,11 @@ int64_t mvb_launch_count(void);
  * disabled, the strict-fp32 FFMA kernels run everywhere.  Returns the previous setting. */
 int mvb_set_tensor_cores(int enable);
 /* Tuning hooks for A/B measurement runs (scripts/, tests) - not part of the operator API.  spec is a list
- * "key=a[,b];key=..." (keys: tc_tuning, tc_balance, layer_tuning, fused_recurrence, spmm_shape, spmm_mode, overlap,
- * mesh_tc; documented next to mvb_tune in csrc/mvb_api.cu).  Results are bit-identical for every setting of the
- * grid-shape keys; mesh_tc / fused_recurrence select between implementations tested against each other. */
+ * "key=a[,b];key=..." (keys: tc_tuning, tc_balance, tc_tma, layer_tuning, fused_recurrence, spmm_shape, spmm_mode, overlap,
+ * mesh_tc, mesh_dbg, stream_tc, stream_nt, conv_lanes, pdl, wgrad_perm, defer_wgrad, background_div; documented next to
+ * mvb_tune in csrc/mvb_api.cu).  Results are bit-identical for every setting of the grid-shape / launch keys; mesh_tc /
+ * fused_recurrence / stream_tc / tc_tma select between implementations tested against each other.  The mvb Python package
+ * applies the environment variable MVB_TUNE through this call when it is imported. */
 int mvb_tune(const char *spec);
 /* Deferred side chains: with mvb_tune("defer_wgrad=1") the weight-gradient reductions of mvb_cheb_layer_bwd run on an
  * internal per-device side stream (as does the weight-gradient branch of mvb_cheb_bwd) and are NOT joined into the
@@ -324,13 +326,14 @@ int mvb_cheb_layer_bwd(int N, int B, int Fin, int Fout, int K, const int32_t *L_
 
 /* ---- the same loop body at the levels that do NOT fit shared memory (level 0: 4998 vertices) ----
  * pool(U) -> ChebConv_batch -> ReLU, models/cheb_VAE.py:284-285 (nn/conv.py:557-577, nn/pool.py:13-23), as ONE
- * persistent launch per direction (csrc/mvb_stream_tc.cu): every CTA owns a fixed range of 128-(vertex, mesh)-pair
- * tiles, produces each basis plane T_k for them with the arithmetic of mvb_spmm, hands the tile to tcgen05.mma through a
+ * persistent launch per direction (csrc/mvb_stream_tc.cu): every CTA owns a block of rows x a slab of 8 / 16 meshes (tiles of
+ * 128 (vertex, mesh) pairs), produces each basis plane T_k for them with the arithmetic of mvb_spmm, hands the tile to tcgen05.mma through a
  * shared-memory ring while it is still on chip (accumulators of all its tiles in TMEM across the K steps) and meets
  * the other CTAs at a grid-wide barrier between steps - the basis is never re-read for the contraction.
  *   x [n_in,B,16] (n_in == N unless U [N x n_in] is given), weight [K,16,16], y [N,B,16]; 16-wide features, K <= 8,
- *   no row selection; mvb_cheb_stream_supported says whether (N, B) is covered (at least ~76 k (vertex, mesh) pairs and
- *   few enough that a CTA's accumulators fit TMEM: B <= 121 at 4998 vertices) - otherwise use mvb_pool_* + mvb_cheb_*.
+ *   no row selection; mvb_cheb_stream_supported says whether (N, B) is covered (opt-in: mvb_tune "stream_tc=1"; B a
+ *   multiple of 8, at least ~76 k (vertex, mesh) pairs, and few enough that a CTA's accumulators fit TMEM: B <= ~112 at
+ *   4998 vertices) - otherwise use mvb_pool_* + mvb_cheb_*.
  * Backward (adjoint form): G = dY*[y>0] and db, S_k = T_k(L^T) G, dT_0 = sum_k S_k W_k^T, dX = U^T dT_0 in the same
  *   launch; dW through the streaming weight-gradient reduction (on the deferred side chain with mvb_tune
  *   "defer_wgrad=1").  dweight / dbias OVERWRITTEN; dx may be NULL.  Workspaces: *_workspace_bytes; 16-byte aligned. */
