@@ -782,7 +782,13 @@ extern "C" int mvb_stream_wait_external_event(void *stream, void *event) {
 //   overlap=0|1        side-stream fork inside mvb_cheb_bwd
 //   mesh_tc=e,c        tensor-core mesh layers on/off, CTAs per mesh (0 = automatic)
 //   defer_wgrad=0|1    weight-gradient chains of the mesh layers joined lazily (engine only; see mvb_side_join)
-//   stream_tc=e,sw     row-streaming fused level-0 layers (mvb_cheb_stream_*) on/off, meshes per slab (4 / 8 / 16, 0 = least work per CTA)
+//   stream_tc=e,sw     row-streaming fused level-0 layers (mvb_cheb_stream_*) on/off, meshes per slab (8 / 16, 0 = least work per CTA)
+//   stream_nt=n        threads per CTA of that kernel (1024 / 768)
+//   tc_tma=e,ring      TMA-fed row GEMM for the 16-wide planes on/off, hi tiles in the ring (3 / 4)
+//   conv_lanes=n       side streams the deferred convolution weight-gradient chains rotate over (1..7, default 3)
+//   pdl=0|1            programmatic dependent launch of the step's kernels (default on; the engine switches it off for N > 1)
+//   wgrad_perm=0|1     conflict-free lane order of the staging stores in tc_wgrad (default off)
+//   background_div=d   grid of the deferred level-0 weight-gradient reduction: one CTA per d SMs (0 = two per SM)
 //   mesh_dbg=bits      timing probes of the tensor-core mesh forward kernel (1 no MMAs, 2 no recurrence, 4 no epilogue):
 //                      results are then wrong - scripts/mesh_tc_probe.py only
 // ---------------------------------------------------------------------------------------------
