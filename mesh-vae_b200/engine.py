@@ -161,10 +161,14 @@ class TrainEngine:
                     raise
                 import warnings
                 warnings.warn(f"TrainEngine: peer-memory gradient exchange unavailable ({e}); using NCCL all-reduces")
-        if self.distributed and self.world > 1 and os.environ.get("MVB_DP_PDL", "0") != "1":
-            # programmatic dependent launch helps the single-GPU graph (0.914 -> 0.895 ms) but costs the data-parallel one
-            # (2 GPUs, same box: 0.9913 ms with it, 0.9627 ms without - the pre-launched CTAs that sit in griddepcontrol.wait
-            # take block slots next to the background exchange branch): off for N > 1
+        if self.distributed and self.world > 1 and (self.peer is None or os.environ.get("MVB_DP_PDL", "1") == "0"):
+            # Programmatic dependent launch and the data-parallel graph (2 GPUs, same box, ms per step): with the exchange
+            # branch on an ordinary-priority stream 0.9913 with PDL / 0.9627 without (the CTAs parked in griddepcontrol.wait take
+            # the block slots the exchange kernel needs); with the branch on a HIGHEST-priority stream 0.9424 with PDL (the mesh
+            # kernels' CTAs are already resident when the exchange launches, and its few CTAs win the slots that free up) but
+            # 1.07-1.54 without (the exchange CTAs are placed first, one per SM, and every mesh kernel - one CTA per WHOLE SM -
+            # waits for them).  So: PDL stays on with the peer-memory exchange (MVB_DP_PDL=0 switches it off) and goes off
+            # for the NCCL fallback, whose kernels run on NCCL's own ordinary-priority stream.
             _lib.tune("pdl=0")
         self.opt = FlatAdam(live, lr=lr, weight_decay=weight_decay,
                             grad_buffer_factory=(lambda n: self.peer.flat_g) if self.peer is not None else None)
@@ -357,7 +361,8 @@ class TrainEngine:
             # data parallel through peer memory: the whole step - exchange included - is kernels of this library
             dist.barrier()
             g = torch.cuda.CUDAGraph()
-            side = torch.cuda.Stream()
+            # (highest priority with PDL on - see __init__; ordinary priority when PDL is off)
+            side = torch.cuda.Stream(priority=-1) if os.environ.get("MVB_DP_PDL", "1") != "0" else torch.cuda.Stream()
             self._bg_ctas = int(os.environ.get("MVB_DP_BG_CTAS", "40"))          # 8 GPUs: 16 -> 0.984 ms, 40 -> 0.965, 74 -> 0.974, 148 -> 0.973
             with torch.cuda.graph(g, stream=cap):
                 self._fwd()
